@@ -1,0 +1,180 @@
+"""Batch-object API the train step consumes, without PyG.
+
+The reference step (train.py:25-51) touches exactly this surface of a PyG
+`HeteroDataBatch`: `.cuda()` (in place, train.py:28), `.x_dict`, `.edge_index_dict`,
+`["path"].batch`, `["path"].y`, `["path"].x.shape[0]` (train.py:34,38,50); `load_model` reads
+`dataset[0]['link']['x'].shape[1]` (train.py:117-119); the loader is iterated and `len()`-ed
+(train.py:24-25).  PyG's collate (`Batch.from_data_list`, reached through
+`torch_geometric.loader.DataLoader`, dataset.py:242) concatenates node tensors on dim 0 and
+`edge_index` on dim 1 with per-node-type offsets, in sample order — reproduced here bit-exactly
+(SURVEY §8(a) A0).
+
+Host-side only: no arithmetic on features happens here.
+"""
+from __future__ import annotations
+
+import torch
+
+# Relation order of the reference's HeteroData (dataset.py:112-117).
+EDGE_TYPES = (
+    ("path", "uses", "link"),
+    ("link", "includes", "path"),
+    ("link", "connects", "node"),
+    ("node", "has", "link"),
+    ("path", "is_connected", "node"),
+    ("node", "is_used", "path"),
+)
+# The four relations HetroGIN wires into HeteroConv (models.py:286-290).
+CONV_EDGE_TYPES = EDGE_TYPES[:4]
+
+
+class Store(dict):
+    """dict with attribute access (`store.x` == `store['x']`), like a PyG storage."""
+
+    __slots__ = ()
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name) from None
+
+    def __setattr__(self, name, value):
+        self[name] = value
+
+    def __delattr__(self, name):
+        del self[name]
+
+
+class HeteroData:
+    """Typed graph container: `d['path'].x`, `d['path','uses','link'].edge_index`."""
+
+    def __init__(self):
+        self.__dict__["_nodes"] = {}
+        self.__dict__["_edges"] = {}
+
+    # -- stores ---------------------------------------------------------------------------
+    def __getitem__(self, key) -> Store:
+        if isinstance(key, (tuple, list)):
+            return self._edges.setdefault(tuple(key), Store())
+        return self._nodes.setdefault(key, Store())
+
+    @property
+    def node_types(self):
+        return list(self._nodes)
+
+    @property
+    def edge_types(self):
+        return list(self._edges)
+
+    def _gather(self, attr):
+        found = {k: s[attr] for k, s in self._nodes.items() if attr in s}
+        found.update({k: s[attr] for k, s in self._edges.items() if attr in s})
+        return found
+
+    @property
+    def x_dict(self):
+        return self._gather("x")
+
+    @property
+    def edge_index_dict(self):
+        return self._gather("edge_index")
+
+    def __getattr__(self, name):
+        if name.endswith("_dict"):
+            return self._gather(name[: -len("_dict")])
+        raise AttributeError(name)
+
+    # -- movement (in place, returns self: `sample.cuda()` at train.py:28) -----------------
+    def apply_(self, fn):
+        for store in list(self._nodes.values()) + list(self._edges.values()):
+            for k, v in store.items():
+                if isinstance(v, torch.Tensor):
+                    store[k] = fn(v)
+        return self
+
+    def to(self, device, non_blocking=False):
+        return self.apply_(lambda t: t.to(device, non_blocking=non_blocking))
+
+    def cuda(self, non_blocking=False):
+        return self.to("cuda", non_blocking=non_blocking)
+
+    def cpu(self):
+        return self.to("cpu")
+
+    def pin_memory(self):
+        return self.apply_(lambda t: t if t.is_pinned() else t.pin_memory())
+
+    def nbytes(self):
+        total = 0
+        for store in list(self._nodes.values()) + list(self._edges.values()):
+            for v in store.values():
+                if isinstance(v, torch.Tensor):
+                    total += v.numel() * v.element_size()
+        return total
+
+
+class Batch(HeteroData):
+    """Block-diagonal concatenation of samples (PyG `Batch.from_data_list` semantics)."""
+
+    @classmethod
+    def from_data_list(cls, samples, index_dtype=None, edge_types=None):
+        """`index_dtype=None` keeps the samples' dtype (int64 in the reference,
+        generateFiles.py:172-181); `torch.int32` narrows on the host so that only 4-byte
+        indices cross PCIe.  `edge_types` restricts the relations that are collated (the
+        reference ships all six, of which HetroGIN reads four)."""
+        out = cls()
+        first = samples[0]
+        base = {}
+        for nt in first.node_types:
+            counts = [s[nt]["x"].shape[0] for s in samples]
+            starts = [0]
+            for c in counts:
+                starts.append(starts[-1] + c)
+            base[nt] = starts
+            store = out[nt]
+            for key in first[nt].keys():
+                store[key] = torch.cat([s[nt][key] for s in samples], dim=0)
+            store["batch"] = torch.repeat_interleave(
+                torch.arange(len(samples), dtype=torch.int64), torch.tensor(counts, dtype=torch.int64))
+            store["ptr"] = torch.tensor(starts, dtype=torch.int64)
+        for et in (first.edge_types if edge_types is None else edge_types):
+            src, _, dst = et
+            pieces = []
+            for i, s in enumerate(samples):
+                ei = s[et]["edge_index"]
+                shift = torch.tensor([[base[src][i]], [base[dst][i]]], dtype=ei.dtype)
+                pieces.append(ei + shift)
+            ei = torch.cat(pieces, dim=1)
+            if index_dtype is not None:
+                ei = ei.to(index_dtype)
+            out[et]["edge_index"] = ei
+        out.__dict__["num_graphs"] = len(samples)
+        return out
+
+
+class DataLoader:
+    """Minimal stand-in for `torch_geometric.loader.DataLoader(ds, batch_size, shuffle)`
+    (dataset.py:242-244): single-threaded (`num_workers=0` in the reference), keeps the last
+    partial batch, reshuffles every epoch with `generator`."""
+
+    def __init__(self, dataset, batch_size=1, shuffle=False, generator=None, index_dtype=None,
+                 edge_types=None, pin_memory=False):
+        self.dataset = dataset
+        self.batch_size = int(batch_size)
+        self.shuffle = shuffle
+        self.generator = generator
+        self.index_dtype = index_dtype
+        self.edge_types = edge_types
+        self.pin_memory = pin_memory
+
+    def __len__(self):
+        return (len(self.dataset) + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        n = len(self.dataset)
+        order = torch.randperm(n, generator=self.generator).tolist() if self.shuffle else list(range(n))
+        for lo in range(0, n, self.batch_size):
+            batch = Batch.from_data_list([self.dataset[i] for i in order[lo:lo + self.batch_size]],
+                                         index_dtype=self.index_dtype, edge_types=self.edge_types)
+            yield batch.pin_memory() if self.pin_memory else batch
