@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py — HeteroGIN train-step throughput on B200 (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfgC|cfgA|cfgD] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of synthetic datanet-shaped samples:
+CSR build -> L heterogeneous GIN layers -> readout -> sqrt(MAPE) -> backward -> Adam
+(train.py:27-44).  Prints ONE JSON line on rank 0.
+
+  value     graphs/s with the batch already resident in HBM when the timed region starts
+  e2e       graphs/s through the public API with HOST (pinned) batches: H2D of the step's
+            inputs + step + D2H read of the loss inside the timed region
+  roofline  live CUDA-event timing of the aggregation kernel (hgin_gin_combine) over the timed
+            region against the measured HBM peak of MEASURED_PEAKS.json
+  cpu_baseline  the oracle port of the reference's CPU path on this box's host cores
+
+`--impl reference` times the reference's own CPU implementation of the path (the oracle port:
+the reference is pure Python on PyG, which cannot be installed here — DESIGN.md) on a bounded
+sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # config.json defaults (emb 8, 1 layer, readout [128,32]) at the reference's train batch of 8
+    "cfgA": dict(batch=8, emb=8, layers=1, mlp=[128, 32], desc="configs[1]: config.json model, batch 8 of 50-node topologies"),
+    # the large single-GPU configuration: 1024 topologies / step, hidden 128, 4 GIN layers
+    "cfgC": dict(batch=1024, emb=128, layers=4, mlp=[128, 32], desc="configs[2]: 1024 topologies/step, hidden 128, 4 GIN layers"),
+}
+METRIC = "HeteroGIN train graphs/sec"
+
+
+def model_kwargs(w):
+    return dict(node_embedding_size=w["emb"], message_passing_layers=w["layers"], dropout=0.0, concat_path=True,
+                bl_features=False, divided_features=False, global_feats=False, mlp_layers=list(w["mlp"]),
+                act="torch.nn.PReLU()", mlp_head_act=None, mlp_bn=False)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return p["hbm_gbs"], p.get("bf16_tflops_sustained", p["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def result(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def make_host_batches(w, count, rank, pin):
+    from gnn_link_prediction_b200.data import Batch, CONV_EDGE_TYPES
+    from gnn_link_prediction_b200.synthetic import SyntheticDataset
+    ds = SyntheticDataset(w["batch"] * count, num_topologies=16, seed=1997 + 100003 * rank)
+    batches = []
+    for b in range(count):
+        samples = [ds[b * w["batch"] + i] for i in range(w["batch"])]
+        batch = Batch.from_data_list(samples, index_dtype=torch.int32, edge_types=CONV_EDGE_TYPES)
+        batches.append(batch.pin_memory() if pin else batch)
+    return batches
+
+
+def batch_counts(batch):
+    from gnn_link_prediction_b200.data import CONV_EDGE_TYPES
+    edges = sum(batch[et].edge_index.shape[1] for et in CONV_EDGE_TYPES)
+    return batch.num_graphs, edges
+
+
+def copy_batch_to_device(host):
+    """What a user does per step: `sample.cuda()` (train.py:28) — a fresh device copy of every tensor."""
+    from gnn_link_prediction_b200.data import Batch
+    dev = Batch()
+    for nt in host.node_types:
+        for k, v in host[nt].items():
+            dev[nt][k] = v.cuda(non_blocking=True)
+    for et in host.edge_types:
+        dev[et].edge_index = host[et].edge_index.cuda(non_blocking=True)
+    dev.__dict__["num_graphs"] = host.num_graphs
+    return dev
+
+
+def cpu_reference_run(w, sample_graphs, steps, warmup, threads=None):
+    """The reference's CPU path (oracle port) on a bounded sample: `sample_graphs` topologies per step."""
+    from oracle import hgin_oracle
+    from gnn_link_prediction_b200.data import Batch
+    from gnn_link_prediction_b200.synthetic import SyntheticDataset
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
+    ds = SyntheticDataset(sample_graphs, num_topologies=min(16, sample_graphs))
+    batch = Batch.from_data_list([ds[i] for i in range(sample_graphs)])
+    torch.manual_seed(1997)
+    model = hgin_oracle.HetroGIN(input_channels={"link": 7, "path": 7, "node": 3}, **model_kwargs(w))
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0)
+    model.train()
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        hgin_oracle.train_step(model, opt, batch)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return {"value": sample_graphs * steps / total, "unit": "graphs/s", "cores": cores, "kind": "port",
+            "sample": f"{sample_graphs} topologies/step x {steps} steps (+{warmup} warm-up), fwd+bwd+Adam, "
+                      f"torch {torch.__version__} CPU, {cores} threads of {os.cpu_count()} cores",
+            "ms_per_step": 1e3 * total / steps}
+
+
+def run_reference(args, w, rank):
+    if rank != 0:
+        return
+    sample = 8 if args.workload == "cfgA" else 16
+    steps = max(1, min(args.steps, 5))
+    r = cpu_reference_run(w, sample, steps, min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "graphs/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "desc": w["desc"], "emb": w["emb"], "layers": w["layers"],
+                       "batch_per_step": sample},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def timed_steps(step_fn, steps, flush_buf):
+    """K steps, each bracketed by its own CUDA events on the current stream; with `flush_buf` the
+    L2 is flushed (a >L2 buffer is overwritten) between steps, outside the per-step interval."""
+    evs = []
+    for i in range(steps):
+        if flush_buf is not None:
+            flush_buf.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step_fn(i)
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in evs]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfgC", choices=sorted(WORKLOADS) + ["cfgD"])
+    ap.add_argument("--math", default="fp32", choices=["fp32", "tf32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.workload == "cfgD":
+        import bench_conv
+        return bench_conv.main(args)
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, w, rank)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from gnn_link_prediction_b200 import ops
+    from gnn_link_prediction_b200.models import HetroGIN, MATH_FP32, MATH_TF32
+    from gnn_link_prediction_b200.profiling import KernelTimer
+    from gnn_link_prediction_b200.train import TrainStep
+
+    args.warmup = max(args.warmup, 3)
+    n_host = 2
+    host = make_host_batches(w, n_host, rank, pin=True)
+    graphs, edges = batch_counts(host[0])
+    h2d_bytes = host[0].nbytes()
+
+    torch.manual_seed(1997)
+    model = HetroGIN(input_channels={"link": 7, "path": 7, "node": 3}, **model_kwargs(w)).cuda().train()
+    model.set_math_mode(MATH_TF32 if args.math == "tf32" else MATH_FP32)
+    step = TrainStep(model, lr=1e-3, distributed=world > 1)
+    dev_batches = [copy_batch_to_device(h) for h in host]
+    torch.cuda.synchronize()
+
+    small = args.workload == "cfgA"   # working set << L2: flush between timed steps
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda") if small else None
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm ("value") ----------------------------------------------------------
+    def resident_step(i):
+        step(dev_batches[i % n_host])
+
+    for i in range(args.warmup):
+        resident_step(i)
+    timer = KernelTimer()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ops.TIMER = timer
+    t_wall = time.perf_counter()
+    per_step = timed_steps(resident_step, args.steps, flush)
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    ops.TIMER = None
+    clocks = sampler.result()
+    kernels = timer.summary()
+    resident_ms = sum(per_step)
+
+    # ---- end-to-end arm ("e2e"): pinned host batch -> H2D -> step -> D2H loss ----------------------
+    losses = []
+
+    def e2e_step(i):
+        dev = copy_batch_to_device(host[i % n_host])
+        losses.append(step(dev).cpu())   # D2H read of [mape, sqrt(mape)] — synchronises the step
+
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    e2e_per_step = timed_steps(e2e_step, args.steps, flush)
+    barrier()
+    e2e_ms = sum(e2e_per_step)
+
+    # max over ranks (device time)
+    t = torch.tensor([resident_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    resident_ms, e2e_ms = (float(v) for v in t.tolist())
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    hbm_peak, tf_peak, basis = measured_peaks()
+    agg = kernels.get("gin_combine", {"ms": 0.0, "launches": 0, "roofline_bytes": 0, "alg_bytes": 0, "compulsory_bytes": 0})
+    total_kernel_ms = sum(k["ms"] for k in kernels.values()) or 1.0
+    roofline = None
+    if agg["launches"]:
+        achieved = agg["roofline_bytes"] / (agg["ms"] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "hgin_gin_combine", "achieved": achieved, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_basis": basis,
+                    "bytes": "compulsory (source tables fit L2) unless table > L2, SURVEY 8(d)",
+                    "launches": agg["launches"], "avg_launch_ms": agg["ms"] / agg["launches"],
+                    "share_of_step": agg["ms"] / total_kernel_ms,
+                    "achieved_algorithmic_GBs": agg["alg_bytes"] / (agg["ms"] * 1e-3) / 1e9}
+    breakdown = {name: {"ms_per_step": k["ms"] / args.steps, "launches_per_step": k["launches"] / args.steps,
+                        **({"TFLOPs": k["flops"] / (k["ms"] * 1e-3) / 1e12} if "flops" in k and k["ms"] > 0 else {}),
+                        **({"GBs": k["bytes"] / (k["ms"] * 1e-3) / 1e9} if "bytes" in k and k["ms"] > 0 else {})}
+                 for name, k in kernels.items()}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        sample = 8 if small else 16
+        r = cpu_reference_run(w, sample, 3, 1)
+        cpu_baseline = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    launches = sum(k.get("kernels", k["launches"]) for k in kernels.values())
+    value = graphs * world * args.steps / (resident_ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": "graphs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": resident_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if args.math == "fp32" else "tf32", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": w["desc"], "emb": w["emb"], "layers": w["layers"],
+                   "graphs_per_gpu_per_step": graphs, "edges_per_gpu_per_step": edges,
+                   "l2": "flushed between timed steps" if small else "inputs+activations larger than L2",
+                   "parallelism": f"dp{world} (samples sharded, NCCL sum-allreduce of one flat grad bucket)"},
+        "edges_per_s": edges * world * args.steps / (resident_ms * 1e-3),
+        "e2e": {"value": graphs * world * args.steps / (e2e_ms * 1e-3), "unit": "graphs/s",
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches, "abi_calls": sum(k["launches"] for k in kernels.values()),
+        "wall_s_resident": t_wall,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "kernels": breakdown,
+        "loss_first_last": [float(losses[0][0]), float(losses[-1][0])],
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,229 @@
+// K1 / K4 — segmented neighbour sum over CSR rows fused with the GIN self term.
+//
+// Forward  (models.py:208-215):  h[d] = sum_{e in row d} x_src[col[e]]  (+|concat)  (1+eps) * x_dst[d]
+// Backward (autograd of the same, train.py:43): the identical kernel over the TRANSPOSED CSR
+//          gathers dh rows into dx_src, fused with the (1+eps)*dh self branch and, through
+//          `accumulate`, with the sum over relations that share a node type.
+//
+// Roofline: HBM.  Algorithmic bytes per row = sum_e (F*4 + 4) + 4 + F_self*4 + F_out*4
+// (SURVEY §8(d)).  No atomics, no materialised x_j: each row is owned by one group of LPR
+// lanes that walks its neighbours left to right (CSR order == stable edge order, so the fp32
+// result is bit-identical to the CPU reference's scatter_add_), each lane carrying VEC
+// consecutive features so that a full warp issues one 512-byte row read per neighbour at F=128.
+// Neighbour indices are fetched LPR at a time with one coalesced load and handed round by
+// shuffle; the gathers of a batch are issued back to back (UNROLL in flight) before the
+// dependent adds.
+#include "hgin_common.cuh"
+
+namespace hgin {
+namespace {
+
+template <int VEC>
+struct Pack;
+template <>
+struct Pack<1> {
+    float v[1];
+};
+template <>
+struct Pack<4> {
+    float v[4];
+};
+
+template <int VEC>
+__device__ __forceinline__ Pack<VEC> load_pack(const float *p) {
+    Pack<VEC> r;
+    if constexpr (VEC == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+        r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+    } else {
+        r.v[0] = __ldg(p);
+    }
+    return r;
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_pack(float *p, const Pack<VEC> &r) {
+    if constexpr (VEC == 4) {
+        *reinterpret_cast<float4 *>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    } else {
+        p[0] = r.v[0];
+    }
+}
+
+// LPR lanes per row, VEC features per lane per chunk, NC chunks per lane:
+// covers f_src <= LPR * VEC * NC.
+template <int VEC, int LPR, int NC>
+__global__ void __launch_bounds__(256, (VEC * NC <= 4) ? 4 : 1)
+gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                   const float *__restrict__ x_src, int64_t ld_src, int f_src,
+                   const float *__restrict__ x_self, int64_t ld_self, int f_self,
+                   const float *__restrict__ eps_ptr, int self_mode, int accumulate,
+                   float *__restrict__ out, int64_t ld_out) {
+    // gathers in flight per lane before the dependent adds; bounded by the batch (LPR) and by
+    // the register budget when a lane carries several chunks
+    constexpr int UNROLL_MAX = (NC >= 4) ? 2 : ((NC == 2) ? 4 : 8);
+    constexpr int UNROLL = (LPR < UNROLL_MAX) ? LPR : UNROLL_MAX;
+    constexpr int ROWS_PER_WARP = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % LPR;   // lane inside the row group
+    const int grp = lane / LPR;   // row group inside the warp
+    const unsigned full = 0xffffffffu;
+    // fl(1 + eps): the reference computes (1 + self.eps) as an fp32 tensor op (models.py:213/215).
+    const float ope = __fadd_rn(1.0f, eps_ptr ? __ldg(eps_ptr) : 0.0f);
+
+    const int64_t warp_id = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t num_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+
+    for (int64_t row0 = warp_id * ROWS_PER_WARP; row0 < num_rows; row0 += num_warps * ROWS_PER_WARP) {
+        const int64_t row = row0 + grp;
+        const bool live = row < num_rows;
+        int32_t beg = 0, len = 0;
+        if (live) {
+            beg = __ldg(rowptr + row);
+            len = __ldg(rowptr + row + 1) - beg;
+        }
+        // warp-uniform trip count so the shuffles below are always convergent
+        int32_t max_len = len;
+#pragma unroll
+        for (int o = 16; o >= LPR; o >>= 1) max_len = max(max_len, __shfl_xor_sync(full, max_len, o));
+
+        Pack<VEC> acc[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[c].v[i] = 0.0f;
+
+        for (int32_t base = 0; base < max_len; base += LPR) {
+            // one coalesced index load per group, LPR neighbours at a time
+            const int32_t mine = (base + sub < len) ? __ldg(col + beg + base + sub) : -1;
+            const int32_t batch = min(LPR, max_len - base);
+            for (int32_t j0 = 0; j0 < batch; j0 += UNROLL) {
+                Pack<VEC> v[UNROLL][NC];
+                int32_t nb[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    // (j0+u) % LPR keeps the source lane in range; out-of-batch slots are masked by nb < 0
+                    const int32_t s = __shfl_sync(full, mine, grp * LPR + ((j0 + u) % LPR));
+                    nb[u] = (j0 + u < batch) ? s : -1;
+                }
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        const int f = (c * LPR + sub) * VEC;
+                        if (nb[u] >= 0 && f < f_src) {
+                            v[u][c] = load_pack<VEC>(x_src + static_cast<int64_t>(nb[u]) * ld_src + f);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) v[u][c].v[i] = 0.0f;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    if (nb[u] >= 0) {  // strictly left-to-right; skipped slots add nothing (not even +0)
+#pragma unroll
+                        for (int c = 0; c < NC; ++c)
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) acc[c].v[i] = __fadd_rn(acc[c].v[i], v[u][c].v[i]);
+                    }
+                }
+            }
+        }
+
+        if (!live) continue;
+        float *orow = out + row * ld_out;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const int f = (c * LPR + sub) * VEC;
+            if (f >= f_src) continue;
+            Pack<VEC> r = acc[c];
+            if (self_mode == HGIN_SELF_ADD) {
+                const Pack<VEC> xs = load_pack<VEC>(x_self + row * ld_self + f);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) r.v[i] = __fadd_rn(r.v[i], __fmul_rn(ope, xs.v[i]));
+            }
+            if (accumulate) {
+                const Pack<VEC> old = load_pack<VEC>(orow + f);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) r.v[i] = __fadd_rn(old.v[i], r.v[i]);
+            }
+            store_pack<VEC>(orow + f, r);
+        }
+        if (self_mode == HGIN_SELF_CONCAT) {
+            // [agg | (1+eps) x_self]: the self block starts at column f_src (rarely 16B aligned) -> scalar
+            for (int f = sub; f < f_self; f += LPR) {
+                float t = __fmul_rn(ope, __ldg(x_self + row * ld_self + f));
+                if (accumulate) t = __fadd_rn(orow[f_src + f], t);
+                orow[f_src + f] = t;
+            }
+        }
+    }
+}
+
+template <int VEC, int LPR, int NC>
+void launch(int64_t num_rows, const int32_t *rowptr, const int32_t *col, const float *x_src, int64_t ld_src,
+            int f_src, const float *x_self, int64_t ld_self, int f_self, const float *eps, int self_mode,
+            int accumulate, float *out, int64_t ld_out, cudaStream_t s) {
+    constexpr int rows_per_cta = (256 / 32) * (32 / LPR);
+    // Grid-stride over rows with whole waves of CTAs: enough CTAs (32 per SM) that the hardware
+    // scheduler evens out the heavy-tailed row lengths of the path->link relation.
+    const int grid = grid_for(num_rows, rows_per_cta, 32);
+    gin_combine_kernel<VEC, LPR, NC><<<grid, 256, 0, s>>>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self,
+                                                          ld_self, f_self, eps, self_mode, accumulate, out, ld_out);
+}
+
+}  // namespace
+}  // namespace hgin
+
+extern "C" int32_t hgin_gin_combine(int64_t num_rows, const int32_t *rowptr, const int32_t *col, const float *x_src,
+                                    int64_t ld_src, int32_t f_src, const float *x_self, int64_t ld_self,
+                                    int32_t f_self, const float *eps, int32_t self_mode, int32_t accumulate,
+                                    float *out, int64_t ld_out, void *stream) {
+    using namespace hgin;
+    HGIN_CHECK_ARG(num_rows >= 0 && num_rows < INT32_MAX, "hgin_gin_combine: bad num_rows %lld", (long long)num_rows);
+    HGIN_CHECK_ARG(f_src > 0 && f_src <= 512, "hgin_gin_combine: f_src must be in [1,512], got %d", f_src);
+    HGIN_CHECK_ARG(self_mode >= HGIN_SELF_NONE && self_mode <= HGIN_SELF_CONCAT, "hgin_gin_combine: bad self_mode %d",
+                   self_mode);
+    HGIN_CHECK_ARG(self_mode == HGIN_SELF_NONE || x_self != nullptr, "hgin_gin_combine: x_self is null");
+    HGIN_CHECK_ARG(self_mode != HGIN_SELF_ADD || f_self == f_src, "hgin_gin_combine: SELF_ADD needs f_self == f_src");
+    HGIN_CHECK_ARG(self_mode != HGIN_SELF_CONCAT || f_self > 0, "hgin_gin_combine: SELF_CONCAT needs f_self > 0");
+    if (num_rows == 0) return HGIN_OK;
+    HGIN_CHECK_ARG(rowptr && col && x_src && out, "hgin_gin_combine: null pointer");
+    const int width = f_src + (self_mode == HGIN_SELF_CONCAT ? f_self : 0);
+    HGIN_CHECK_ARG(ld_src >= f_src && ld_out >= width, "hgin_gin_combine: leading dimension too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+    // 128-bit lanes need every row start 16-byte aligned.
+    bool vec4 = (f_src % 4 == 0) && (ld_src % 4 == 0) && (ld_out % 4 == 0) && aligned16(x_src) && aligned16(out);
+    if (self_mode == HGIN_SELF_ADD) vec4 = vec4 && (ld_self % 4 == 0) && aligned16(x_self);
+
+#define HGIN_LAUNCH(V, L, N)                                                                                    \
+    launch<V, L, N>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode,      \
+                    accumulate, out, ld_out, s)
+    if (vec4) {
+        const int chunks = f_src / 4;
+        if (chunks <= 1) HGIN_LAUNCH(4, 1, 1);
+        else if (chunks <= 2) HGIN_LAUNCH(4, 2, 1);
+        else if (chunks <= 4) HGIN_LAUNCH(4, 4, 1);
+        else if (chunks <= 8) HGIN_LAUNCH(4, 8, 1);
+        else if (chunks <= 16) HGIN_LAUNCH(4, 16, 1);
+        else if (chunks <= 32) HGIN_LAUNCH(4, 32, 1);
+        else if (chunks <= 64) HGIN_LAUNCH(4, 32, 2);
+        else HGIN_LAUNCH(4, 32, 4);
+    } else {
+        if (f_src <= 1) HGIN_LAUNCH(1, 1, 1);
+        else if (f_src <= 2) HGIN_LAUNCH(1, 2, 1);
+        else if (f_src <= 4) HGIN_LAUNCH(1, 4, 1);
+        else if (f_src <= 8) HGIN_LAUNCH(1, 8, 1);
+        else if (f_src <= 16) HGIN_LAUNCH(1, 16, 1);
+        else if (f_src <= 32) HGIN_LAUNCH(1, 32, 1);
+        else if (f_src <= 64) HGIN_LAUNCH(1, 32, 2);
+        else if (f_src <= 128) HGIN_LAUNCH(1, 32, 4);
+        else if (f_src <= 256) HGIN_LAUNCH(1, 32, 8);
+        else HGIN_LAUNCH(1, 32, 16);
+    }
+#undef HGIN_LAUNCH
+    HGIN_CHECK_LAUNCH("hgin_gin_combine");
+    return HGIN_OK;
+}

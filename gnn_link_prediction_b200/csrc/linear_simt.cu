@@ -1,0 +1,399 @@
+// K2 / K3 — dense layer forward and backward, fp32 SIMT path (HGIN_MATH_FP32).
+//
+// Forward  (models.py:217, 236-239; readout models.py:366-374):   z = [x1|x2] W^T + b, out (+)= act(z)
+// Backward (autograd, train.py:43):   dz = g * act'(z);  dx = dz W;  dW = dz^T [x1|x2];  db = sum dz;
+//                                     dalpha = sum g*min(z,0);  d(eps) = sum dx_self * x_dst.
+// All reductions over rows are two-stage and deterministic: every CTA writes its partial to the
+// caller's workspace and a second kernel adds the partials in CTA order.
+#include "gemm_simt.cuh"
+
+namespace hgin {
+namespace {
+
+using simt::BK;
+using simt::THREADS;
+
+// ---- operand accessors ------------------------------------------------------------------------
+struct ConcatRows {  // element (m, k) of [x1 | x2]
+    const float *x1; int64_t ld1; int k1;
+    const float *x2; int64_t ld2; int k2;
+    int64_t rows;
+    __device__ __forceinline__ float operator()(int64_t m, int64_t k) const {
+        if (m >= rows) return 0.0f;
+        if (k < k1) return __ldg(x1 + m * ld1 + k);
+        if (k < k1 + k2) return __ldg(x2 + m * ld2 + (k - k1));
+        return 0.0f;
+    }
+};
+
+struct WeightRows {  // element (n, k) of W[n][k]
+    const float *W; int n, k;
+    __device__ __forceinline__ float operator()(int64_t j, int64_t kk) const {
+        return (j < n && kk < k) ? __ldg(W + j * k + kk) : 0.0f;
+    }
+};
+
+struct WeightCols {  // element (c, nn) = W[nn][c0 + c]: output index contiguous, contraction over rows of W
+    const float *W; int n, k, c0, c1;
+    __device__ __forceinline__ float operator()(int64_t c, int64_t nn) const {
+        return (c0 + c < c1 && nn < n) ? __ldg(W + nn * k + c0 + c) : 0.0f;
+    }
+};
+
+struct GradZ {  // element (m, nn) of dz = g * act'(z)
+    const float *g; int64_t ldg;
+    const float *z; int64_t ldz;
+    int64_t rows; int n; int act; float alpha;
+    __device__ __forceinline__ float operator()(int64_t m, int64_t nn) const {
+        if (m >= rows || nn >= n) return 0.0f;
+        const float gv = __ldg(g + m * ldg + nn);
+        if (act == HGIN_ACT_NONE) return gv;
+        return act_backward(gv, __ldg(z + m * ldz + nn), act, alpha);
+    }
+};
+
+struct GradZT {  // element (nn, m) of dz^T, also accumulating dalpha on the side
+    GradZ dz;
+    float *dalpha_acc;  // thread-local
+    bool want_alpha;
+    __device__ __forceinline__ float operator()(int64_t nn, int64_t m) const {
+        if (m >= dz.rows || nn >= dz.n) return 0.0f;
+        const float gv = __ldg(dz.g + m * dz.ldg + nn);
+        if (dz.act == HGIN_ACT_NONE) return gv;
+        const float zv = __ldg(dz.z + m * dz.ldz + nn);
+        if (want_alpha && !(zv > 0.0f)) *dalpha_acc += gv * zv;   // at::prelu_backward: x > 0 ? 0 : x*g
+        return act_backward(gv, zv, dz.act, dz.alpha);
+    }
+};
+
+struct ConcatColsT {  // element (k, m) of [x1 | x2 | 1]^T — the ones column yields db
+    ConcatRows x;
+    __device__ __forceinline__ float operator()(int64_t k, int64_t m) const {
+        if (m >= x.rows) return 0.0f;
+        if (k == x.k1 + x.k2) return 1.0f;
+        return x(m, k);
+    }
+};
+
+// ---- forward ----------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(THREADS)
+linear_fwd_kernel(ConcatRows fa, WeightRows fb, const float *__restrict__ bias, int act,
+                  const float *__restrict__ alpha_ptr, float *__restrict__ z, int64_t ldz,
+                  float *__restrict__ out, int64_t ldo, int accumulate_out, int vec_ok) {
+    __shared__ __align__(16) float smem[T::SMEM_FLOATS];
+    const int64_t m0 = static_cast<int64_t>(blockIdx.x) * T::BM;
+    const int n0 = blockIdx.y * T::BN;
+    float acc[T::TM][T::TN];
+#pragma unroll
+    for (int i = 0; i < T::TM; ++i)
+#pragma unroll
+        for (int j = 0; j < T::TN; ++j) acc[i][j] = 0.0f;
+    simt::mainloop<T, true, true>(acc, fa, fb, m0, n0, 0, fb.k, smem);
+
+    const float alpha = (act == HGIN_ACT_PRELU) ? __ldg(alpha_ptr) : 0.0f;
+    const int tx = threadIdx.x % T::TX, ty = threadIdx.x / T::TX;
+#pragma unroll
+    for (int i = 0; i < T::TM; ++i) {
+        const int64_t m = m0 + T::row_of(ty, i);
+        if (m >= fa.rows) continue;
+#pragma unroll
+        for (int gj = 0; gj < T::GN; ++gj) {
+            const int nb = n0 + T::col_of(tx, gj * T::VN);
+            float zv[T::VN], ov[T::VN];
+#pragma unroll
+            for (int j = 0; j < T::VN; ++j) {
+                const int n = nb + j;
+                zv[j] = acc[i][gj * T::VN + j] + ((bias && n < fb.n) ? __ldg(bias + n) : 0.0f);
+                ov[j] = act_forward(zv[j], act, alpha);
+            }
+            if (T::VN == 4 && vec_ok && nb + 3 < fb.n) {
+                if (z) *reinterpret_cast<float4 *>(z + m * ldz + nb) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+                if (out) {
+                    float4 *po = reinterpret_cast<float4 *>(out + m * ldo + nb);
+                    if (accumulate_out) {
+                        const float4 old = *po;
+                        ov[0] += old.x; ov[1] += old.y; ov[2] += old.z; ov[3] += old.w;
+                    }
+                    *po = make_float4(ov[0], ov[1], ov[2], ov[3]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < T::VN; ++j) {
+                    const int n = nb + j;
+                    if (n >= fb.n) continue;
+                    if (z) z[m * ldz + n] = zv[j];
+                    if (out) out[m * ldo + n] = accumulate_out ? out[m * ldo + n] + ov[j] : ov[j];
+                }
+            }
+        }
+    }
+}
+
+// ---- input gradient: dx[:, c0:c1] = (dz W)[:, c0:c1], optional dot with dot_x ------------------
+template <class T>
+__global__ void __launch_bounds__(THREADS)
+linear_bwd_dx_kernel(GradZ fa, const float *__restrict__ alpha_ptr, WeightCols fb, float *__restrict__ dx,
+                     int64_t lddx, const float *__restrict__ dot_x, int64_t ld_dot,
+                     float *__restrict__ dot_partials, int vec_ok) {
+    __shared__ __align__(16) float smem[T::SMEM_FLOATS];
+    __shared__ float red[32];
+    fa.alpha = (fa.act == HGIN_ACT_PRELU) ? __ldg(alpha_ptr) : 0.0f;  // slope lives in device memory
+    const int64_t m0 = static_cast<int64_t>(blockIdx.x) * T::BM;
+    const int n0 = blockIdx.y * T::BN;  // offset inside [c0, c1)
+    const int width = fb.c1 - fb.c0;
+    float acc[T::TM][T::TN];
+#pragma unroll
+    for (int i = 0; i < T::TM; ++i)
+#pragma unroll
+        for (int j = 0; j < T::TN; ++j) acc[i][j] = 0.0f;
+    simt::mainloop<T, true, false>(acc, fa, fb, m0, n0, 0, fb.n, smem);
+
+    const int tx = threadIdx.x % T::TX, ty = threadIdx.x / T::TX;
+    float dot = 0.0f;
+#pragma unroll
+    for (int i = 0; i < T::TM; ++i) {
+        const int64_t m = m0 + T::row_of(ty, i);
+        if (m >= fa.rows) continue;
+#pragma unroll
+        for (int gj = 0; gj < T::GN; ++gj) {
+            const int cb = n0 + T::col_of(tx, gj * T::VN);
+            if (dot_x) {
+#pragma unroll
+                for (int j = 0; j < T::VN; ++j)
+                    if (cb + j < width) dot += acc[i][gj * T::VN + j] * __ldg(dot_x + m * ld_dot + cb + j);
+            }
+            if (!dx) continue;
+            if (T::VN == 4 && vec_ok && cb + 3 < width) {
+                *reinterpret_cast<float4 *>(dx + m * lddx + cb) =
+                    make_float4(acc[i][gj * 4 + 0], acc[i][gj * 4 + 1], acc[i][gj * 4 + 2], acc[i][gj * 4 + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < T::VN; ++j)
+                    if (cb + j < width) dx[m * lddx + cb + j] = acc[i][gj * T::VN + j];
+            }
+        }
+    }
+    if (dot_partials) {
+        dot = block_sum(dot, red);
+        if (threadIdx.x == 0) dot_partials[blockIdx.y * gridDim.x + blockIdx.x] = dot;
+    }
+}
+
+// ---- weight gradient: partial[cta][n][k] over this CTA's row range; k == K is the bias column --
+template <class T>
+__global__ void __launch_bounds__(THREADS)
+linear_bwd_dw_kernel(GradZ dzf, const float *__restrict__ alpha_ptr, ConcatRows xf, int want_alpha,
+                     int64_t rows_per_cta, float *__restrict__ partials /* [gridDim.x][n][kp] */,
+                     float *__restrict__ alpha_partials) {
+    __shared__ __align__(16) float smem[T::SMEM_FLOATS];
+    __shared__ float red[32];
+    dzf.alpha = (dzf.act == HGIN_ACT_PRELU) ? __ldg(alpha_ptr) : 0.0f;
+    const int kp = xf.k1 + xf.k2 + 1;
+    const int nn0 = blockIdx.y * T::BM;  // output row  = n index
+    const int kk0 = blockIdx.z * T::BN;  // output col  = k index (incl. ones column)
+    const int64_t mbeg = static_cast<int64_t>(blockIdx.x) * rows_per_cta;
+    const int64_t mend = min(mbeg + rows_per_cta, dzf.rows);
+    float dalpha = 0.0f;
+    GradZT fa{dzf, &dalpha, want_alpha && blockIdx.z == 0};
+    ConcatColsT fb{xf};
+    float acc[T::TM][T::TN];
+#pragma unroll
+    for (int i = 0; i < T::TM; ++i)
+#pragma unroll
+        for (int j = 0; j < T::TN; ++j) acc[i][j] = 0.0f;
+    // accessors bound rows by dzf.rows / xf.rows; restrict to this CTA's range
+    fa.dz.rows = mend;
+    fb.x.rows = mend;
+    if (mbeg < mend) simt::mainloop<T, false, false>(acc, fa, fb, nn0, kk0, mbeg, mend, smem);
+
+    const int tx = threadIdx.x % T::TX, ty = threadIdx.x / T::TX;
+    float *dst = partials + static_cast<int64_t>(blockIdx.x) * dzf.n * kp;
+#pragma unroll
+    for (int i = 0; i < T::TM; ++i) {
+        const int n = nn0 + T::row_of(ty, i);
+        if (n >= dzf.n) continue;
+#pragma unroll
+        for (int j = 0; j < T::TN; ++j) {
+            const int k = kk0 + T::col_of(tx, j);
+            if (k < kp) dst[static_cast<int64_t>(n) * kp + k] = acc[i][j];
+        }
+    }
+    if (alpha_partials && blockIdx.z == 0) {
+        dalpha = block_sum(dalpha, red);
+        if (threadIdx.x == 0) alpha_partials[blockIdx.y * gridDim.x + blockIdx.x] = dalpha;
+    }
+}
+
+// out[i] = sum_p partials[p][i] in fixed order; columns split into dW / db.
+__global__ void __launch_bounds__(256)
+reduce_dw_kernel(const float *__restrict__ partials, int num_partials, int n, int kp, float *__restrict__ dW,
+                 float *__restrict__ db) {
+    const int64_t total = static_cast<int64_t>(n) * kp;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float s = 0.0f;
+        for (int p = 0; p < num_partials; ++p) s += partials[static_cast<int64_t>(p) * total + i];
+        const int row = static_cast<int>(i / kp), k = static_cast<int>(i % kp);
+        if (k == kp - 1) {
+            if (db) db[row] = s;
+        } else if (dW) {
+            dW[static_cast<int64_t>(row) * (kp - 1) + k] = s;
+        }
+    }
+}
+
+// Deterministic sum of `count` floats into out[0] (single CTA, fixed tree).
+__global__ void __launch_bounds__(1024) reduce_scalar_kernel(const float *__restrict__ v, int64_t count,
+                                                             float *__restrict__ out) {
+    __shared__ float red[32];
+    float s = 0.0f;
+    for (int64_t i = threadIdx.x; i < count; i += blockDim.x) s += v[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+using T128 = simt::Tile<128, 128, 8, 8>;
+using T64 = simt::Tile<128, 64, 8, 4>;
+using T32 = simt::Tile<128, 32, 4, 4>;
+using T16 = simt::Tile<128, 16, 4, 2>;
+using T8 = simt::Tile<128, 8, 4, 1>;
+
+constexpr int kDwSplit = kNumSMs * 2;  // row ranges of the weight-gradient pass
+
+inline int64_t dw_splits(int64_t rows) {
+    int64_t s = ceil_div(rows, 512);
+    if (s < 1) s = 1;
+    return s < kDwSplit ? s : kDwSplit;
+}
+
+}  // namespace
+}  // namespace hgin
+
+extern "C" int32_t hgin_linear_fwd(int64_t rows, const float *x1, int64_t ld1, int32_t k1, const float *x2,
+                                   int64_t ld2, int32_t k2, const float *W, const float *bias, int32_t n,
+                                   int32_t act, const float *alpha, float *z, int64_t ldz, float *out, int64_t ldo,
+                                   int32_t accumulate_out, int32_t math_mode, void *stream) {
+    using namespace hgin;
+    HGIN_CHECK_ARG(rows >= 0 && k1 > 0 && k2 >= 0 && n > 0, "hgin_linear_fwd: bad sizes rows=%lld k1=%d k2=%d n=%d",
+                   (long long)rows, k1, k2, n);
+    HGIN_CHECK_ARG(act >= HGIN_ACT_NONE && act <= HGIN_ACT_RELU, "hgin_linear_fwd: bad act %d", act);
+    HGIN_CHECK_ARG(act != HGIN_ACT_PRELU || alpha, "hgin_linear_fwd: PReLU needs alpha");
+    HGIN_CHECK_ARG(math_mode == HGIN_MATH_FP32, "hgin_linear_fwd: math_mode %d not available in this build", math_mode);
+    if (rows == 0) return HGIN_OK;
+    HGIN_CHECK_ARG(x1 && W && (k2 == 0 || x2) && (z || out), "hgin_linear_fwd: null pointer");
+    HGIN_CHECK_ARG(ld1 >= k1 && (k2 == 0 || ld2 >= k2) && (!z || ldz >= n) && (!out || ldo >= n),
+                   "hgin_linear_fwd: leading dimension too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ConcatRows fa{x1, ld1, k1, x2, ld2, k2, rows};
+    WeightRows fb{W, n, k1 + k2};
+    const int vec_ok = (!z || (ldz % 4 == 0 && aligned16(z))) && (!out || (ldo % 4 == 0 && aligned16(out)));
+    const unsigned gx = static_cast<unsigned>(ceil_div(rows, 128));
+#define HGIN_FWD(T)                                                                                             \
+    linear_fwd_kernel<T><<<dim3(gx, static_cast<unsigned>(ceil_div(n, T::BN))), THREADS, 0, s>>>(               \
+        fa, fb, bias, act, alpha, z, ldz, out, ldo, accumulate_out, vec_ok)
+    if (n > 64) HGIN_FWD(T128);
+    else if (n > 32) HGIN_FWD(T64);
+    else if (n > 16) HGIN_FWD(T32);
+    else if (n > 8) HGIN_FWD(T16);
+    else HGIN_FWD(T8);
+#undef HGIN_FWD
+    HGIN_CHECK_LAUNCH("hgin_linear_fwd");
+    return HGIN_OK;
+}
+
+extern "C" int64_t hgin_linear_bwd_workspace_bytes(int64_t rows, int32_t k, int32_t n) {
+    using namespace hgin;
+    if (rows < 0 || k <= 0 || n <= 0) return -1;
+    const int64_t dw = dw_splits(rows) * n * (k + 1) * 4;
+    const int64_t scal = (ceil_div(rows, 128) * ceil_div(k > n ? k : n, 8) + dw_splits(rows) * ceil_div(n, 128)) * 4;
+    return align_up(dw, 256) + align_up(scal, 256) + 512;
+}
+
+extern "C" int32_t hgin_linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, int64_t ldz,
+                                   int32_t act, const float *alpha, const float *x1, int64_t ld1, int32_t k1,
+                                   const float *x2, int64_t ld2, int32_t k2, const float *W, int32_t n, int32_t c0,
+                                   int32_t c1, float *dx, int64_t lddx, const float *dot_x, int64_t ld_dot,
+                                   float *ddot, float *dW, float *db, float *dalpha, void *workspace,
+                                   int64_t workspace_bytes, int32_t math_mode, void *stream) {
+    using namespace hgin;
+    const int k = k1 + k2;
+    HGIN_CHECK_ARG(rows >= 0 && k1 > 0 && k2 >= 0 && n > 0, "hgin_linear_bwd: bad sizes");
+    HGIN_CHECK_ARG(act >= HGIN_ACT_NONE && act <= HGIN_ACT_RELU, "hgin_linear_bwd: bad act %d", act);
+    HGIN_CHECK_ARG(act == HGIN_ACT_NONE || z, "hgin_linear_bwd: activation backward needs z");
+    HGIN_CHECK_ARG(act != HGIN_ACT_PRELU || alpha, "hgin_linear_bwd: PReLU needs alpha");
+    HGIN_CHECK_ARG(0 <= c0 && c0 <= c1 && c1 <= k, "hgin_linear_bwd: bad column range [%d,%d) of %d", c0, c1, k);
+    HGIN_CHECK_ARG(math_mode == HGIN_MATH_FP32, "hgin_linear_bwd: math_mode %d not available in this build", math_mode);
+    HGIN_CHECK_ARG(!ddot || dot_x, "hgin_linear_bwd: ddot needs dot_x");
+    HGIN_CHECK_ARG(g && W && x1 && (k2 == 0 || x2), "hgin_linear_bwd: null pointer");
+    const int64_t need = hgin_linear_bwd_workspace_bytes(rows, k, n);
+    if (workspace_bytes < need || !workspace)
+        return fail(HGIN_ERR_WORKSPACE_TOO_SMALL, "hgin_linear_bwd: workspace %lld < %lld bytes",
+                    (long long)workspace_bytes, (long long)need);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int64_t splits = dw_splits(rows);
+    float *dw_partials = static_cast<float *>(workspace);
+    float *scal = reinterpret_cast<float *>(static_cast<char *>(workspace) + align_up(splits * n * (k + 1) * 4, 256));
+
+    if (rows == 0) {  // empty batch: all reductions are zero
+        if (dW) cudaMemsetAsync(dW, 0, sizeof(float) * n * k, s);
+        if (db) cudaMemsetAsync(db, 0, sizeof(float) * n, s);
+        if (dalpha) cudaMemsetAsync(dalpha, 0, sizeof(float), s);
+        if (ddot) cudaMemsetAsync(ddot, 0, sizeof(float), s);
+        return HGIN_OK;
+    }
+
+    // The PReLU slope stays in device memory (kernels read it through `alpha`), so a captured
+    // graph replays with the current value.
+    GradZ dzf{g, ldg, z, ldz, rows, n, act, 0.0f};
+
+    // ---- input gradient ----
+    const int width = c1 - c0;
+    if (width > 0 && (dx || ddot)) {
+        WeightCols fb{W, n, k, c0, c1};
+        const unsigned gx = static_cast<unsigned>(ceil_div(rows, 128));
+        const int vec_ok = !dx || (lddx % 4 == 0 && aligned16(dx));
+        float *dot_partials = ddot ? scal : nullptr;
+        unsigned gy = 1;
+#define HGIN_DX(T)                                                                                              \
+    gy = static_cast<unsigned>(ceil_div(width, T::BN));                                                         \
+    linear_bwd_dx_kernel<T><<<dim3(gx, gy), THREADS, 0, s>>>(dzf, alpha, fb, dx, lddx, dot_x, ld_dot,           \
+                                                             dot_partials, vec_ok)
+        if (width > 64) { HGIN_DX(T128); }
+        else if (width > 32) { HGIN_DX(T64); }
+        else if (width > 16) { HGIN_DX(T32); }
+        else if (width > 8) { HGIN_DX(T16); }
+        else { HGIN_DX(T8); }
+#undef HGIN_DX
+        if (ddot) reduce_scalar_kernel<<<1, 1024, 0, s>>>(dot_partials, static_cast<int64_t>(gx) * gy, ddot);
+    } else if (ddot) {
+        cudaMemsetAsync(ddot, 0, sizeof(float), s);
+    }
+
+    // ---- weight / bias / slope gradients ----
+    if (dW || db || dalpha) {
+        ConcatRows xf{x1, ld1, k1, x2, ld2, k2, rows};
+        const int64_t rows_per_cta = align_up(ceil_div(rows, splits), BK);
+        const unsigned gx = static_cast<unsigned>(ceil_div(rows, rows_per_cta));
+        const unsigned gy = static_cast<unsigned>(ceil_div(n, 128));
+        float *alpha_partials = (dalpha && act == HGIN_ACT_PRELU) ? scal : nullptr;
+        const int kp = k + 1;
+#define HGIN_DW(T)                                                                                              \
+    linear_bwd_dw_kernel<T><<<dim3(gx, gy, static_cast<unsigned>(ceil_div(kp, T::BN))), THREADS, 0, s>>>(       \
+        dzf, alpha, xf, alpha_partials != nullptr, rows_per_cta, dw_partials, alpha_partials)
+        if (kp > 64) HGIN_DW(T128);
+        else if (kp > 32) HGIN_DW(T64);
+        else if (kp > 16) HGIN_DW(T32);
+        else if (kp > 8) HGIN_DW(T16);
+        else HGIN_DW(T8);
+#undef HGIN_DW
+        reduce_dw_kernel<<<grid_for(static_cast<int64_t>(n) * kp, 256, 4), 256, 0, s>>>(dw_partials, static_cast<int>(gx),
+                                                                                      n, kp, dW, db);
+        if (dalpha) {
+            if (alpha_partials) reduce_scalar_kernel<<<1, 1024, 0, s>>>(alpha_partials, static_cast<int64_t>(gx) * gy, dalpha);
+            else cudaMemsetAsync(dalpha, 0, sizeof(float), s);
+        }
+    }
+    HGIN_CHECK_LAUNCH("hgin_linear_bwd");
+    return HGIN_OK;
+}

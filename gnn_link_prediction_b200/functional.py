@@ -1,0 +1,218 @@
+"""Autograd glue between the module mirror (models.py) and the CUDA kernels (ops.py).
+
+Two `torch.autograd.Function`s cover the whole hot path:
+
+* `HeteroConvFn`  — one heterogeneous GIN layer over a set of relations (what PyG's
+  `HeteroConv({...: GINLayer}, aggr='sum')` does at models.py:356): per relation K1 (neighbour
+  sum + self term) -> K2 (Linear + PReLU, accumulated into the destination type's buffer = the
+  'sum' merge); backward K3 per relation, then ONE transposed-CSR gather per node type that
+  also folds in the `(1+eps)*dh` self branches (K4).
+* `LinearActFn`   — one readout layer `act([x1|x2] W^T + b)` (models.py:366-374).
+
+Autograd only sees tensors in / tensors out; saved activations are `h` (MLP input) and `z`
+(pre-activation) per relation.  Parameters that feed no live output keep `grad=None`, exactly as
+the reference's autograd leaves them.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .ops import ACT_NONE, ACT_PRELU, ACT_RELU, MATH_FP32, SELF_ADD, SELF_CONCAT, SELF_NONE, HginError
+
+
+class GraphCSR:
+    """Per-batch adjacency in kernel layout: for every relation a destination-sorted CSR (forward
+    aggregation) and, on demand, the source-sorted transpose (backward gather).  Built on the GPU
+    by K0 from the COO `edge_index_dict` the reference passes around (train.py:34)."""
+
+    def __init__(self, edge_index_dict, num_nodes):
+        self.edge_index_dict = dict(edge_index_dict)
+        self.num_nodes = dict(num_nodes)
+        self._by_dst, self._by_src = {}, {}
+
+    # mapping protocol, so a GraphCSR can be passed wherever an edge_index_dict is expected
+    def items(self):
+        return self.edge_index_dict.items()
+
+    def keys(self):
+        return self.edge_index_dict.keys()
+
+    def __contains__(self, et):
+        return et in self.edge_index_dict
+
+    def __getitem__(self, et):
+        return self.edge_index_dict[et]
+
+    def fwd(self, et) -> ops.CSR:
+        if et not in self._by_dst:
+            self._by_dst[et] = ops.csr_build(self.edge_index_dict[et], self.num_nodes[et[0]],
+                                             self.num_nodes[et[2]], by="dst")
+        return self._by_dst[et]
+
+    def bwd(self, et) -> ops.CSR:
+        if et not in self._by_src:
+            self._by_src[et] = ops.csr_build(self.edge_index_dict[et], self.num_nodes[et[0]],
+                                             self.num_nodes[et[2]], by="src")
+        return self._by_src[et]
+
+    def validate(self):
+        for c in list(self._by_dst.values()) + list(self._by_src.values()):
+            c.validate()
+        return self
+
+
+class RelationSpec:
+    """Static description of one relation's GIN layer inside a HeteroConvFn call."""
+
+    __slots__ = ("et", "src", "dst", "concat", "act")
+
+    def __init__(self, et, concat, act):
+        self.et, self.src, self.dst = tuple(et), et[0], et[-1]
+        self.concat, self.act = bool(concat), act
+
+
+class HeteroConvFn(torch.autograd.Function):
+    """args: specs, graph, types, math_mode, x[types...], then (W, b, alpha, eps) per spec.
+    returns one tensor per destination type, in order of first appearance."""
+
+    @staticmethod
+    def forward(ctx, specs, graph, types, math_mode, *tensors):
+        nt = len(types)
+        xs = dict(zip(types, tensors[:nt]))
+        params = tensors[nt:]
+        training = any(ctx.needs_input_grad)
+        outs, saved = {}, []
+        for i, sp in enumerate(specs):
+            W, b, alpha, eps = params[4 * i:4 * i + 4]
+            x_src, x_dst = xs[sp.src], xs[sp.dst]
+            h = ops.gin_combine(graph.fwd(sp.et), x_src, x_dst, eps, SELF_CONCAT if sp.concat else SELF_ADD)
+            z, o = ops.linear_fwd(h, W, b, act=sp.act, alpha=alpha, want_z=training and sp.act != ACT_NONE,
+                                  out=outs.get(sp.dst), accumulate_out=sp.dst in outs, math_mode=math_mode)
+            outs[sp.dst] = o
+            saved += [h if training else None, z]
+            if training and ctx.needs_input_grad[4 + types.index(sp.src)]:
+                graph.bwd(sp.et)  # build the transposed CSR alongside the forward work
+        ctx.specs, ctx.graph, ctx.types, ctx.math_mode = specs, graph, types, math_mode
+        ctx.out_types = list(outs)
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(*tensors, *saved)
+        return tuple(outs[t] for t in ctx.out_types)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        specs, graph, types = ctx.specs, ctx.graph, ctx.types
+        nt, ns = len(types), len(specs)
+        tensors = ctx.saved_tensors
+        xs = dict(zip(types, tensors[:nt]))
+        params = tensors[nt:nt + 4 * ns]
+        saved = tensors[nt + 4 * ns:]
+        need = ctx.needs_input_grad[4:]
+        need_x = dict(zip(types, need[:nt]))
+        g_out = dict(zip(ctx.out_types, gouts))
+        grads_p = [None] * (4 * ns)
+        gather_terms = {t: [] for t in types}   # (transposed csr, dh_agg)
+        self_terms = {t: [] for t in types}     # (dh_self, eps)
+
+        for i, sp in enumerate(specs):
+            g = g_out.get(sp.dst)
+            if g is None:
+                continue
+            if g.stride(-1) != 1:
+                g = g.contiguous()
+            W, b, alpha, eps = params[4 * i:4 * i + 4]
+            h, z = saved[2 * i], saved[2 * i + 1]
+            nW, nb, nalpha, neps = need[nt + 4 * i:nt + 4 * i + 4]
+            x_src, x_dst = xs[sp.src], xs[sp.dst]
+            fs = x_src.shape[1]
+            k = h.shape[1]
+            want_agg, want_self = need_x[sp.src], need_x[sp.dst]
+            common = dict(act=sp.act, alpha=alpha, math_mode=ctx.math_mode)
+            if sp.concat:
+                r = ops.linear_bwd(g, z, h, W, dx_cols=(fs, k), want_dx=want_self, dot_x=x_dst if neps else None,
+                                   want_dw=nW, want_db=bool(nb), want_dalpha=bool(nalpha), **common)
+                dh_self = r["dx"]
+                dh_agg = None
+                if want_agg:
+                    dh_agg = ops.linear_bwd(g, z, h, W, dx_cols=(0, fs), want_dx=True, want_dw=False, want_db=False,
+                                            **common)["dx"]
+            else:
+                r = ops.linear_bwd(g, z, h, W, dx_cols=(0, k), want_dx=want_agg or want_self,
+                                   dot_x=x_dst if neps else None, want_dw=nW, want_db=bool(nb),
+                                   want_dalpha=bool(nalpha), **common)
+                dh_agg = dh_self = r["dx"]
+            grads_p[4 * i:4 * i + 4] = [r["dW"], r["db"],
+                                        None if r["dalpha"] is None else r["dalpha"].view_as(alpha),
+                                        None if r["ddot"] is None else r["ddot"].view_as(eps)]
+            if want_agg:
+                gather_terms[sp.src].append((graph.bwd(sp.et), dh_agg))
+            if want_self:
+                self_terms[sp.dst].append((dh_self, eps))
+
+        grads_x = []
+        for t in types:
+            dx = None
+            selfs = self_terms[t]
+            for csr_t, dh in gather_terms[t]:
+                if selfs:  # fold one (1+eps)*dh self branch into this gather pass
+                    s_dh, s_eps = selfs.pop(0)
+                    dx = ops.gin_combine(csr_t, dh, s_dh, s_eps, SELF_ADD, out=dx, accumulate=dx is not None)
+                else:
+                    dx = ops.gin_combine(csr_t, dh, None, None, SELF_NONE, out=dx, accumulate=dx is not None)
+            for s_dh, s_eps in selfs:  # self branches with no gather to ride on
+                term = s_dh * (1 + s_eps) if s_eps is not None else s_dh
+                dx = term if dx is None else dx.add_(term)
+            grads_x.append(dx)
+        return (None, None, None, None, *grads_x, *grads_p)
+
+
+class LinearActFn(torch.autograd.Function):
+    """out = act([x1 | x2] W^T + b)."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, W, b, alpha, act, math_mode):
+        training = any(ctx.needs_input_grad)
+        z, out = ops.linear_fwd(x1, W, b, x2=x2, act=act, alpha=alpha, want_z=training and act != ACT_NONE,
+                                math_mode=math_mode)
+        ctx.act, ctx.math_mode = act, math_mode
+        ctx.save_for_backward(x1, x2, W, alpha, z)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x1, x2, W, alpha, z = ctx.saved_tensors
+        n1, n2, nW, nb, nalpha = ctx.needs_input_grad[:5]
+        if g.stride(-1) != 1:
+            g = g.contiguous()
+        k1 = x1.shape[1]
+        k = W.shape[1]
+        c0, c1 = (0 if n1 else k1), (k if n2 else k1)
+        r = ops.linear_bwd(g, z, x1, W, x2=x2, act=ctx.act, alpha=alpha, dx_cols=(c0, c1), want_dx=n1 or n2,
+                           want_dw=nW, want_db=bool(nb), want_dalpha=bool(nalpha), math_mode=ctx.math_mode)
+        dx = r["dx"]
+        dx1 = dx[:, :k1 - c0] if n1 else None
+        dx2 = dx[:, k1 - c0:] if n2 else None
+        dalpha = None if r["dalpha"] is None else r["dalpha"].view_as(alpha)
+        return dx1, dx2, r["dW"], r["db"], dalpha, None, None
+
+
+def activation_of(module):
+    """(ACT_* code, slope parameter) for the activations the kernels fuse."""
+    if module is None or isinstance(module, torch.nn.Identity):
+        return ACT_NONE, None
+    if isinstance(module, torch.nn.PReLU):
+        if module.weight.numel() != 1:
+            raise NotImplementedError("only the single-slope torch.nn.PReLU() of the reference is fused")
+        return ACT_PRELU, module.weight
+    if isinstance(module, torch.nn.ReLU):
+        return ACT_RELU, None
+    raise NotImplementedError(f"activation {type(module).__name__} has no fused kernel (PReLU, ReLU, Identity do)")
+
+
+def linear_act_of(seq):
+    """Decompose `Sequential(Linear[, act])` (models.py:236-239, 317-330) into kernel arguments."""
+    mods = list(seq) if isinstance(seq, torch.nn.Sequential) else [seq]
+    if not mods or not isinstance(mods[0], torch.nn.Linear) or len(mods) > 2:
+        raise NotImplementedError("fused path expects Sequential(Linear[, activation]); got " + repr(seq))
+    act, alpha = activation_of(mods[1] if len(mods) == 2 else None)
+    return mods[0].weight, mods[0].bias, act, alpha

@@ -1,0 +1,249 @@
+"""Module mirror of the reference's HeteroGIN path — same class names, constructor and `forward`
+signatures, attribute tree and `state_dict` keys as `/root/reference/models.py:180-376` (plus the
+PyG `HeteroConv` container it instantiates, models.py:286-298) — with every tensor operation
+routed to the sm_100a kernels in libhgin.so.  A reference user swaps
+
+    from models import HetroGIN            ->   from gnn_link_prediction_b200.models import HetroGIN
+
+and keeps `train.py`'s step unchanged: `model(sample.x_dict, sample.edge_index_dict,
+sample["path"].batch)` (train.py:34) returns `f32[N_path, 1]` with an autograd graph.
+
+Differences from the reference, all deliberate and documented in DESIGN.md:
+* relations whose output cannot reach the readout are not evaluated (the reference computes and
+  discards them); their parameters keep `grad=None` either way;
+* `dropout > 0` in training mode, `mlp_bn=True`, `global_feats=True` and activations other than
+  PReLU/ReLU/None raise `NotImplementedError` instead of silently running something else;
+* inputs must be CUDA tensors: there is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Any
+
+import torch
+from torch import Tensor
+
+from . import functional as F_
+from .functional import GraphCSR, HeteroConvFn, LinearActFn, RelationSpec
+from .ops import MATH_FP32, MATH_TF32  # noqa: F401
+
+
+def reset(value: Any):
+    """models.py:162-167."""
+    if hasattr(value, "reset_parameters"):
+        value.reset_parameters()
+    else:
+        for child in value.children() if hasattr(value, "children") else []:
+            reset(child)
+
+
+class GINConv(torch.nn.Module):
+    """models.py:180-228.  `forward(x, edge_index)` with `x` a tensor or a `(x_src, x_dst)` pair and
+    `edge_index` a `[2,E]` COO tensor; `nn` must be `Sequential(Linear[, PReLU|ReLU])`."""
+
+    def __init__(self, nn, eps: float = 0.0, train_eps: bool = False, concat: bool = False, **kwargs):
+        aggr = kwargs.pop("aggr", "add")
+        if aggr not in ("add", "sum"):
+            raise NotImplementedError(f"aggr={aggr!r}: the reference path uses sum aggregation (models.py:186)")
+        if kwargs:
+            raise TypeError(f"unsupported MessagePassing arguments: {sorted(kwargs)}")
+        super().__init__()
+        self.aggr = "add"
+        self.nn = nn
+        self.initial_eps = eps
+        self.concat = concat
+        self.math_mode = MATH_FP32
+        if train_eps:
+            self.eps = torch.nn.Parameter(torch.Tensor([eps]))
+        else:
+            self.register_buffer("eps", torch.Tensor([eps]))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        reset(self.nn)
+        self.eps.data.fill_(self.initial_eps)
+
+    def kernel_args(self):
+        W, b, act, alpha = F_.linear_act_of(self.nn)
+        return W, b, alpha, self.eps, act
+
+    def forward(self, x, edge_index, size=None):
+        if isinstance(x, Tensor):
+            types, xs, et = ("n",), (x,), ("n", "to", "n")
+        else:
+            types, xs, et = ("src", "dst"), (x[0], x[1]), ("src", "to", "dst")
+            if xs[1] is None:
+                raise NotImplementedError("x = (x_src, None) is not used by the reference path")
+        num = {t: v.shape[0] for t, v in zip(types, xs)}
+        if size is not None and (size[0] not in (None, num[et[0]]) or size[1] not in (None, num[et[2]])):
+            raise ValueError(f"size {size} does not match the feature matrices {num}")
+        graph = edge_index if isinstance(edge_index, GraphCSR) else GraphCSR({et: edge_index}, num)
+        W, b, alpha, eps, act = self.kernel_args()
+        (out,) = HeteroConvFn.apply([RelationSpec(et, self.concat, act)], graph, types, self.math_mode, *xs,
+                                    W, b, alpha, eps)
+        return out
+
+    def __repr__(self):
+        return "{}(nn={})".format(self.__class__.__name__, self.nn)
+
+
+class GINLayer(torch.nn.Module):
+    """models.py:231-245: `mlp = Linear(in, out) -> PReLU()`, aliased as `conv.nn`; eps learnable."""
+
+    def __init__(self, in_channels: int, out_channels: int, concat: bool = False) -> None:
+        super().__init__()
+        self.mlp = torch.nn.Sequential(torch.nn.Linear(in_channels, out_channels), torch.nn.PReLU())
+        self.conv = GINConv(self.mlp, eps=0, train_eps=True, concat=concat)
+
+    def forward(self, x, edge_index):
+        return self.conv(x, edge_index)
+
+
+class HeteroConv(torch.nn.Module):
+    """The subset of PyG 2.0.2 `HeteroConv` the reference uses (models.py:286-298, 356): a dict of
+    per-relation GIN layers, outputs of relations with the same destination type summed.  All live
+    relations of the layer run inside ONE autograd node so that the merge and the per-node-type
+    backward gathers are fused."""
+
+    def __init__(self, convs: dict, aggr: str = "sum"):
+        super().__init__()
+        if aggr not in ("sum", "add"):
+            raise NotImplementedError(f"HeteroConv aggr={aggr!r}: the reference uses 'sum' (models.py:290)")
+        for k, v in convs.items():
+            if not isinstance(v, (GINLayer, GINConv)):
+                raise NotImplementedError(f"relation {k}: only GINLayer/GINConv modules have fused kernels")
+        self.convs = torch.nn.ModuleDict({"__".join(k): v for k, v in convs.items()})
+        self.aggr = aggr
+        self.math_mode = MATH_FP32
+
+    def reset_parameters(self):
+        for conv in self.convs.values():
+            conv.reset_parameters()
+
+    def forward(self, x_dict, edge_index_dict, only=None):
+        """`only`: optional collection of edge types to evaluate (dead-branch pruning by HetroGIN)."""
+        graph = edge_index_dict if isinstance(edge_index_dict, GraphCSR) else GraphCSR(
+            edge_index_dict, {t: v.shape[0] for t, v in x_dict.items()})
+        specs, params = [], []
+        for et in graph.keys():                      # insertion order of the batch's relations
+            key = "__".join(et)
+            if key not in self.convs or (only is not None and tuple(et) not in only):
+                continue
+            m = self.convs[key]
+            conv = m.conv if isinstance(m, GINLayer) else m
+            W, b, alpha, eps, act = conv.kernel_args()
+            specs.append(RelationSpec(et, conv.concat, act))
+            params += [W, b, alpha, eps]
+        if not specs:
+            return {}
+        types = tuple(dict.fromkeys(t for sp in specs for t in (sp.src, sp.dst)))
+        outs = HeteroConvFn.apply(specs, graph, types, self.math_mode, *[x_dict[t] for t in types], *params)
+        out_types = list(dict.fromkeys(sp.dst for sp in specs))
+        return dict(zip(out_types, outs))
+
+
+class HetroGIN(torch.nn.Module):
+    """models.py:248-376 (sic: the reference spells it HetroGIN)."""
+
+    RELATIONS = (("path", "uses", "link"), ("link", "includes", "path"),
+                 ("link", "connects", "node"), ("node", "has", "link"))
+
+    def __init__(self, input_channels: dict, node_embedding_size: int, message_passing_layers: int, dropout: float,
+                 concat_path: bool, bl_features: bool, divided_features: bool, global_feats: bool,
+                 mlp_layers: list, act, mlp_head_act, mlp_bn: bool):
+        super().__init__()
+        if global_feats:
+            raise NotImplementedError("global_feats=True (models.py:347-352) has no fused kernel yet")
+        if mlp_bn:
+            raise NotImplementedError("mlp_bn=True (models.py:303-313) has no fused kernel yet")
+        self.num_layers = message_passing_layers
+        self.concat_path = concat_path
+        self.bl_features = bl_features
+        self.divided_features = divided_features
+        self.mlp_layers = mlp_layers
+        self.dropout = dropout
+        self.global_feats = global_feats
+        self.math_mode = MATH_FP32
+
+        # channel arithmetic, in place on the caller's dict exactly as models.py:260-269 does
+        if not self.divided_features:
+            input_channels["path"] = input_channels["path"] - 3
+            input_channels["link"] = input_channels["link"] - 1
+            if not self.bl_features:
+                input_channels["path"] = input_channels["path"] - 1
+                input_channels["link"] = input_channels["link"] - 3
+        elif not self.bl_features:
+            input_channels["path"] = input_channels["path"] - 1
+            input_channels["link"] = input_channels["link"] - 3
+        self.global_feats_size = 0
+        self.concat_size = input_channels["path"] if concat_path else 0
+
+        emb = node_embedding_size
+        self.convs = torch.nn.ModuleList()
+        self.readout = torch.nn.ModuleList()
+        # construction order = RNG consumption order of the reference (models.py:286-298)
+        self.convs.append(HeteroConv({r: GINLayer(input_channels[r[0]] + input_channels[r[2]], emb, concat=True)
+                                      for r in self.RELATIONS}, aggr="sum"))
+        for _ in range(self.num_layers - 1):
+            self.convs.append(HeteroConv({r: GINLayer(emb, emb) for r in self.RELATIONS}, aggr="sum"))
+
+        act = eval(act)                                 # one shared activation object (models.py:301)
+        F_.activation_of(act)                           # fail at construction if it cannot be fused
+        width = emb + self.concat_size + self.global_feats_size
+        for w in mlp_layers:
+            self.readout.append(torch.nn.Sequential(torch.nn.Linear(width, w), act))
+            width = w
+        if mlp_head_act is None:
+            self.readout.append(torch.nn.Sequential(torch.nn.Linear(mlp_layers[-1], 1)))
+        else:
+            head = eval(mlp_head_act)
+            F_.activation_of(head)
+            self.readout.append(torch.nn.Sequential(torch.nn.Linear(mlp_layers[-1], 1), head))
+
+    def set_math_mode(self, mode):
+        """MATH_FP32 (parity) or MATH_TF32 (tensor cores) for every dense layer of the model."""
+        self.math_mode = mode
+        for m in self.modules():
+            if isinstance(m, (HeteroConv, GINConv)):
+                m.math_mode = mode
+        return self
+
+    def live_relations(self, edge_types):
+        """Per layer, the relations whose output can reach the readout (which reads only
+        x_dict['path'], models.py:362-371): walk back from {'path'}."""
+        present = [tuple(et) for et in edge_types if "__".join(et) in self.convs[0].convs]
+        needed = {"path"}
+        live = [None] * self.num_layers
+        for li in reversed(range(self.num_layers)):
+            live[li] = [et for et in present if et[2] in needed]
+            needed = {t for et in live[li] for t in (et[0], et[2])}
+        return live
+
+    def forward(self, x_dict, edge_index_dict, path_batch=None):
+        if self.training and self.dropout > 0:
+            raise NotImplementedError("dropout > 0 in training mode: RNG parity with the reference is impossible "
+                                      "by construction; config.json uses DROPOUT=0.0")
+        # feature slicing, rebinding the caller's dict like models.py:333-342
+        if not self.divided_features:
+            x_dict["path"] = torch.cat([x_dict["path"][:, 0:3], x_dict["path"][:, 6].reshape(-1, 1)], axis=1)
+            x_dict["link"] = torch.cat([x_dict["link"][:, 0:3], x_dict["link"][:, 4:7]], axis=1)
+            if not self.bl_features:
+                x_dict["path"] = x_dict["path"][:, 0:3]
+                x_dict["link"] = x_dict["link"][:, 0:3]
+        elif not self.bl_features:
+            x_dict["path"] = x_dict["path"][:, 0:6]
+            x_dict["link"] = x_dict["link"][:, 0:3]
+        origin_path = x_dict["path"]
+
+        graph = edge_index_dict if isinstance(edge_index_dict, GraphCSR) else GraphCSR(
+            edge_index_dict, {t: v.shape[0] for t, v in x_dict.items()})
+        live = self.live_relations(graph.keys())
+        for i in range(self.num_layers):
+            x_dict = self.convs[i](x_dict, graph, only=live[i])
+            # dropout(p=0) / eval mode is the identity (models.py:358-359)
+
+        x1 = x_dict["path"]
+        x2 = origin_path if self.concat_path else None
+        for i, layer in enumerate(self.readout):
+            W, b, act, alpha = F_.linear_act_of(layer)
+            x1 = LinearActFn.apply(x1, x2 if i == 0 else None, W, b, alpha, act, self.math_mode)
+        return x1

@@ -1,0 +1,263 @@
+"""Tensor-level wrappers over the C ABI (include/hgin.h).
+
+PyTorch is used here for device memory, streams and nothing else: every function validates its
+tensors (CUDA, fp32/int32, unit inner stride), allocates outputs/workspaces with `torch.empty`,
+passes raw pointers + the current stream to libhgin.so and raises `HginError` on a non-zero
+status.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .profiling import L2_BYTES, combine_bytes
+from ._lib import (ACT_NONE, ACT_PRELU, ACT_RELU, MATH_FP32, MATH_TF32, SELF_ADD, SELF_CONCAT,  # noqa: F401
+                   SELF_NONE, HginError, check)
+
+
+TIMER = None  # set to a profiling.KernelTimer by bench.py to attribute time per kernel
+
+
+class _NoRegion:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_REGION = _NoRegion()
+
+
+def _region(name, **meta):
+    return TIMER.region(name, **meta) if TIMER is not None and TIMER.enabled else _NO_REGION
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32_matrix(t, name):
+    if t is None:
+        return 0, 0
+    if not t.is_cuda:
+        raise HginError(f"{name}: expected a CUDA tensor (there is no CPU fallback), got device {t.device}")
+    if t.dtype != torch.float32 or t.dim() != 2:
+        raise HginError(f"{name}: expected a 2-D float32 tensor, got {tuple(t.shape)} {t.dtype}")
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        raise HginError(f"{name}: inner stride must be 1, got strides {t.stride()}")
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+    if ld < t.shape[1]:
+        raise HginError(f"{name}: row stride {ld} < width {t.shape[1]} (overlapping rows)")
+    return t.data_ptr(), ld
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _scalar(t, name):
+    if t is None:
+        return 0
+    if not t.is_cuda or t.dtype != torch.float32 or t.numel() != 1:
+        raise HginError(f"{name}: expected a 1-element CUDA float32 tensor")
+    return t.data_ptr()
+
+
+class CSR:
+    """Row-sorted adjacency: rows own their neighbour lists in stable edge order."""
+
+    __slots__ = ("rowptr", "col", "perm", "status", "num_rows", "num_cols", "num_edges")
+
+    def __init__(self, rowptr, col, perm, status, num_rows, num_cols, num_edges):
+        self.rowptr, self.col, self.perm, self.status = rowptr, col, perm, status
+        self.num_rows, self.num_cols, self.num_edges = num_rows, num_cols, num_edges
+
+    def validate(self):
+        """Synchronising check of the out-of-range flag set by hgin_csr_build."""
+        if int(self.status.item()) != 0:
+            raise IndexError("edge_index holds node ids outside [0, num_src) x [0, num_dst)")
+        return self
+
+
+def csr_build(edge_index, num_src, num_dst, by="dst", want_perm=False):
+    """K0.  edge_index: CUDA int64/int32 [2,E] (row 0 = source ids, row 1 = destination ids).
+    by='dst' -> forward CSR (rows = destinations, cols = sources);
+    by='src' -> transposed CSR (rows = sources, cols = destinations)."""
+    if not edge_index.is_cuda:
+        raise HginError("csr_build: edge_index must live on the GPU (there is no CPU fallback)")
+    if edge_index.dim() != 2 or edge_index.shape[0] != 2 or edge_index.dtype not in (torch.int64, torch.int32):
+        raise HginError(f"csr_build: expected int64/int32 [2,E], got {tuple(edge_index.shape)} {edge_index.dtype}")
+    E = edge_index.shape[1]
+    if E > 0 and edge_index.stride(1) != 1:
+        edge_index = edge_index.contiguous()
+    ld_edge = edge_index.stride(0) if E > 0 else 0
+    sort_row = 1 if by == "dst" else 0
+    rows, cols = (num_dst, num_src) if sort_row else (num_src, num_dst)
+    dev = edge_index.device
+    lib = _lib.load()
+    rowptr = torch.empty(rows + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(E, dtype=torch.int32, device=dev)
+    perm = torch.empty(E, dtype=torch.int32, device=dev) if want_perm else None
+    status = torch.empty(1, dtype=torch.int32, device=dev)
+    ws_bytes = lib.hgin_csr_workspace_bytes(E, rows)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    n_kernels = (3 if E > 0 else 0) + (1 if rows + 1 <= 4096 else 3)
+    with _region("csr_build", kernels=n_kernels, bytes=E * (2 * edge_index.element_size() + 16) + rows * 12):
+        check(lib.hgin_csr_build(edge_index.data_ptr(), edge_index.element_size(), E, max(ld_edge, E), sort_row,
+                                 rows, cols, rowptr.data_ptr(), _ptr(col), _ptr(perm), status.data_ptr(),
+                                 ws.data_ptr(), ws_bytes, _stream()), "hgin_csr_build")
+    return CSR(rowptr, col, perm, status, rows, cols, E)
+
+
+def gin_combine(csr, x_src, x_self=None, eps=None, self_mode=SELF_NONE, out=None, accumulate=False):
+    """K1/K4.  out[r] (+)= sum_{e in row r} x_src[col[e]]  {+ | concat}  (1+eps) * x_self[r]."""
+    ps, lds = _f32_matrix(x_src, "gin_combine.x_src")
+    pf, ldf = _f32_matrix(x_self, "gin_combine.x_self")
+    if x_src.shape[0] != csr.num_cols:
+        raise HginError(f"gin_combine: x_src has {x_src.shape[0]} rows, CSR expects {csr.num_cols}")
+    if x_self is not None and x_self.shape[0] != csr.num_rows:
+        raise HginError(f"gin_combine: x_self has {x_self.shape[0]} rows, CSR has {csr.num_rows}")
+    f_src = x_src.shape[1]
+    f_self = 0 if x_self is None else x_self.shape[1]
+    width = f_src + (f_self if self_mode == SELF_CONCAT else 0)
+    if out is None:
+        if accumulate:
+            raise HginError("gin_combine: accumulate needs an existing `out`")
+        out = torch.empty(csr.num_rows, width, dtype=torch.float32, device=x_src.device)
+    po, ldo = _f32_matrix(out, "gin_combine.out")
+    if tuple(out.shape) != (csr.num_rows, width):
+        raise HginError(f"gin_combine: out is {tuple(out.shape)}, expected {(csr.num_rows, width)}")
+    alg, comp = combine_bytes(csr.num_rows, csr.num_cols, csr.num_edges, f_src,
+                              f_self if self_mode != SELF_NONE else 0, width * (2 if accumulate else 1))
+    big = csr.num_cols * f_src * 4 > L2_BYTES
+    with _region("gin_combine", kernels=1, alg_bytes=alg, compulsory_bytes=comp,
+                 roofline_bytes=alg if big else comp):
+        check(_lib.load().hgin_gin_combine(csr.num_rows, csr.rowptr.data_ptr(), _ptr(csr.col), ps, lds, f_src, pf,
+                                           ldf, f_self, _scalar(eps, "gin_combine.eps"), self_mode,
+                                           1 if accumulate else 0, po, ldo, _stream()), "hgin_gin_combine")
+    return out
+
+
+def linear_fwd(x1, W, bias=None, x2=None, act=ACT_NONE, alpha=None, want_z=True, out=None, accumulate_out=False,
+               math_mode=MATH_FP32):
+    """K2.  z = [x1|x2] W^T + b;  out (+)= act(z).  Returns (z or None, out)."""
+    p1, ld1 = _f32_matrix(x1, "linear_fwd.x1")
+    p2, ld2 = _f32_matrix(x2, "linear_fwd.x2")
+    rows, k1 = x1.shape
+    k2 = 0 if x2 is None else x2.shape[1]
+    n = W.shape[0]
+    if not (W.is_cuda and W.dtype == torch.float32 and W.is_contiguous() and W.shape[1] == k1 + k2):
+        raise HginError(f"linear_fwd: W must be contiguous CUDA float32 [n,{k1 + k2}], got {tuple(W.shape)}")
+    if x2 is not None and x2.shape[0] != rows:
+        raise HginError("linear_fwd: x1 and x2 row counts differ")
+    dev = x1.device
+    z = torch.empty(rows, n, dtype=torch.float32, device=dev) if want_z else None
+    if out is None:
+        if accumulate_out:
+            raise HginError("linear_fwd: accumulate_out needs an existing `out`")
+        out = torch.empty(rows, n, dtype=torch.float32, device=dev)
+    pz, ldz = _f32_matrix(z, "linear_fwd.z")
+    po, ldo = _f32_matrix(out, "linear_fwd.out")
+    if tuple(out.shape) != (rows, n):
+        raise HginError(f"linear_fwd: out is {tuple(out.shape)}, expected {(rows, n)}")
+    with _region("linear_fwd", kernels=1, flops=2 * rows * (k1 + k2) * n,
+                 bytes=4 * rows * (k1 + k2 + n * ((1 if want_z else 0) + (2 if accumulate_out else 1)))):
+        check(_lib.load().hgin_linear_fwd(rows, p1, ld1, k1, p2, ld2, k2, W.data_ptr(), _ptr(bias), n, act,
+                                          _scalar(alpha, "linear_fwd.alpha"), pz, ldz, po, ldo,
+                                          1 if accumulate_out else 0, math_mode, _stream()), "hgin_linear_fwd")
+    return z, out
+
+
+def linear_bwd(g, z, x1, W, x2=None, act=ACT_NONE, alpha=None, dx_cols=None, want_dx=True, dot_x=None,
+               want_dw=True, want_db=True, want_dalpha=False, math_mode=MATH_FP32):
+    """K3.  Returns dict(dx, ddot, dW, db, dalpha) with None for what was not requested.
+    dx_cols=(c0,c1) restricts the input gradient to those columns of [x1|x2]."""
+    pg, ldg = _f32_matrix(g, "linear_bwd.g")
+    pz, ldz = _f32_matrix(z, "linear_bwd.z")
+    p1, ld1 = _f32_matrix(x1, "linear_bwd.x1")
+    p2, ld2 = _f32_matrix(x2, "linear_bwd.x2")
+    pd, ldd = _f32_matrix(dot_x, "linear_bwd.dot_x")
+    rows, k1 = x1.shape
+    k2 = 0 if x2 is None else x2.shape[1]
+    k = k1 + k2
+    n = W.shape[0]
+    if tuple(g.shape) != (rows, n):
+        raise HginError(f"linear_bwd: g is {tuple(g.shape)}, expected {(rows, n)}")
+    c0, c1 = (0, k) if dx_cols is None else dx_cols
+    if not (want_dx or dot_x is not None):
+        c1 = c0
+    dev = g.device
+    dx = torch.empty(rows, c1 - c0, dtype=torch.float32, device=dev) if (want_dx and c1 > c0) else None
+    pdx, lddx = _f32_matrix(dx, "linear_bwd.dx")
+    if dot_x is not None and tuple(dot_x.shape) != (rows, c1 - c0):
+        raise HginError(f"linear_bwd: dot_x is {tuple(dot_x.shape)}, expected {(rows, c1 - c0)}")
+    ddot = torch.empty(1, dtype=torch.float32, device=dev) if dot_x is not None else None
+    dW = torch.empty(n, k, dtype=torch.float32, device=dev) if want_dw else None
+    db = torch.empty(n, dtype=torch.float32, device=dev) if want_db else None
+    dalpha = torch.empty(1, dtype=torch.float32, device=dev) if want_dalpha else None
+    lib = _lib.load()
+    ws_bytes = lib.hgin_linear_bwd_workspace_bytes(rows, k, n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    flops = 2 * rows * n * ((c1 - c0) + (k + 1 if (want_dw or want_db or want_dalpha) else 0))
+    reduces = want_dw or want_db or want_dalpha
+    n_kernels = ((1 + (1 if ddot is not None else 0)) if c1 > c0 else 0) + \
+        ((2 + (1 if (want_dalpha and act == ACT_PRELU) else 0)) if reduces else 0)
+    with _region("linear_bwd", kernels=n_kernels, flops=flops,
+                 bytes=4 * rows * (2 * n * (2 if c1 > c0 else 1) + k + (c1 - c0))):
+        check(lib.hgin_linear_bwd(rows, pg, ldg, pz, ldz, act, _scalar(alpha, "linear_bwd.alpha"), p1, ld1, k1, p2,
+                                  ld2, k2, W.data_ptr(), n, c0, c1, pdx, lddx, pd, ldd, _ptr(ddot), _ptr(dW),
+                                  _ptr(db), _ptr(dalpha), ws.data_ptr(), ws_bytes, math_mode, _stream()),
+              "hgin_linear_bwd")
+    return {"dx": dx, "ddot": ddot, "dW": dW, "db": db, "dalpha": dalpha}
+
+
+def mape_sum(pred, y):
+    """sums = [sum |(pred - y)/y|, n]  (train.py:13 before the mean)."""
+    pred = pred.reshape(-1)
+    y = y.reshape(-1)
+    if not (pred.is_cuda and y.is_cuda and pred.dtype == y.dtype == torch.float32 and pred.numel() == y.numel()):
+        raise HginError("mape_sum: pred and y must be CUDA float32 of equal size")
+    pred, y = pred.contiguous(), y.contiguous()
+    n = pred.numel()
+    lib = _lib.load()
+    sums = torch.empty(2, dtype=torch.float32, device=pred.device)
+    ws_bytes = lib.hgin_reduce_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pred.device)
+    with _region("loss", kernels=2):
+        check(lib.hgin_mape_sum(n, pred.data_ptr(), y.data_ptr(), sums.data_ptr(), ws.data_ptr(), ws_bytes,
+                                _stream()), "hgin_mape_sum")
+    return sums
+
+
+def sqrt_mape_bwd(pred, y, sums, gscale=1.0):
+    """Returns (loss_out=[mape, sqrt(mape)], dpred) for the GLOBAL sums (all-reduced by the caller)."""
+    shape = pred.shape
+    pred = pred.reshape(-1).contiguous()
+    y = y.reshape(-1).contiguous()
+    n = pred.numel()
+    loss_out = torch.empty(2, dtype=torch.float32, device=pred.device)
+    dpred = torch.empty(n, dtype=torch.float32, device=pred.device)
+    with _region("loss", kernels=1):
+        check(_lib.load().hgin_sqrt_mape_bwd(n, pred.data_ptr(), y.data_ptr(), sums.data_ptr(), float(gscale),
+                                             loss_out.data_ptr(), dpred.data_ptr(), _stream()),
+              "hgin_sqrt_mape_bwd")
+    return loss_out, dpred.view(shape)
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
+              decoupled=False):
+    """In-place Adam/AdamW on flat fp32 buffers; `step` is a CUDA int32[1] holding the 1-based step."""
+    n = param.numel()
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n):
+            raise HginError("adam_step: flat contiguous CUDA float32 buffers of equal size expected")
+    with _region("adam", kernels=1):
+        check(_lib.load().hgin_adam_step(n, param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(),
+                                         exp_avg_sq.data_ptr(), step.data_ptr(), lr, beta1, beta2, eps, weight_decay,
+                                         1 if decoupled else 0, _stream()), "hgin_adam_step")
+
+
+def increment(counter):
+    with _region("adam", kernels=1):
+        check(_lib.load().hgin_increment(counter.data_ptr(), _stream()), "hgin_increment")

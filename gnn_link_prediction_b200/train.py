@@ -1,0 +1,148 @@
+"""The reference's train step (train.py:12-148), kept signature-for-signature, plus `TrainStep`:
+the same step with the loss, the gradient bucket and the optimizer on this package's kernels and
+with sample-sharded data parallelism.
+
+Drop-in surface (what `/root/reference/train.py` exports and `main.py` / its own loops call):
+`mape`, `train_one_epoch`, `test`, `load_model`, `load_optmizer` (sic).  Logging to wandb and the
+tqdm bars are not part of the hot path and are left to the caller.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .models import HetroGIN
+
+
+def mape(preds, actuals):
+    """train.py:12-13."""
+    return 100.0 * torch.mean(torch.abs((preds - actuals) / actuals))
+
+
+def load_model(config, datasets):
+    """train.py:116-137 (GIN branch).  `datasets["train"][0][t]['x'].shape[1]` gives the widths."""
+    first = datasets["train"][0]
+    input_channels = {"link": first["link"]["x"].shape[1], "path": first["path"]["x"].shape[1],
+                      "node": first["node"]["x"].shape[1]}
+    if config["MODEL"] == "GIN":
+        return HetroGIN(input_channels=input_channels, node_embedding_size=config["NODE_EMBEDDING_SIZE"],
+                        message_passing_layers=config["MP_LAYERS"], dropout=config["DROPOUT"],
+                        concat_path=config["CONCAT_PATH"], bl_features=config["BL_FEATURES"],
+                        divided_features=config["DIVIDED_FEATURES"], global_feats=config["GLOBAL_FEATS"],
+                        mlp_layers=config["MLP_LAYERS"], act=config["MLP_ACT"], mlp_bn=config["MLP_BN"],
+                        mlp_head_act=config["MLP_HEAD_ACT"])
+    if config["MODEL"] == "GAT":
+        raise NotImplementedError("HetroGAT (models.py:380-506) is outside the accelerated HeteroGIN path")
+    raise IOError("Model not implemented")  # train.py:135
+
+
+def load_optmizer(config, model):
+    """train.py:140-148."""
+    kw = dict(lr=config["LEARNING_RATE"], params=model.parameters(), weight_decay=config["WEIGHT_DECAY"])
+    if config["OPTIMIZER"] == "adam":
+        return torch.optim.Adam(**kw)
+    if config["OPTIMIZER"] == "adamW":
+        return torch.optim.AdamW(**kw)
+    if config["OPTIMIZER"] == "sgd":
+        return torch.optim.SGD(**kw)
+
+
+def train_one_epoch(epoch, loss_func, opt, dataloader, model, k=None):
+    """train.py:16-67 without tqdm/wandb.  Returns (mean loss_value, node-weighted MAPE)."""
+    running_loss, step = 0.0, 0
+    running_loss_mape, step_mape = 0.0, 0
+    for sample in dataloader:
+        with torch.set_grad_enabled(True):
+            sample.cuda()
+            opt.zero_grad()
+            out = model(sample.x_dict, sample.edge_index_dict, sample["path"].batch)
+            label = sample["path"].y.reshape(-1, 1)
+            loss_value = loss_func(out, label)
+            loss = torch.sqrt(loss_value)
+            loss.backward()
+            opt.step()
+            running_loss += loss_value.detach()
+            step += 1
+            running_loss_mape += mape(out.detach(), label).item() * sample["path"].x.shape[0]
+            step_mape += sample["path"].x.shape[0]
+    return float(running_loss / max(step, 1)), running_loss_mape / max(step_mape, 1)
+
+
+def test(epoch, loss_func, dataloader, model, mode="Validation", k=None):
+    """train.py:70-113 without tqdm/wandb.  Returns the mean loss."""
+    running_loss, step = 0.0, 0
+    with torch.no_grad():
+        for sample in dataloader:
+            sample.cuda()
+            out = model(sample.x_dict, sample.edge_index_dict, sample["path"].batch)
+            label = sample["path"].y.reshape(-1, 1)
+            running_loss += loss_func(out, label).item()
+            step += 1
+    return running_loss / max(step, 1)
+
+
+class TrainStep:
+    """One optimisation step of train.py:31-44 with everything after the model on this package's
+    kernels: fused sqrt(MAPE) forward/backward, one flat gradient bucket, Adam on the flat bucket.
+
+    Data parallelism: every rank runs its own shard of samples; the loss
+    statistics `(sum|err/y|, N_path)` are all-reduced BEFORE backward so every rank differentiates
+    the same global `sqrt(100 * S / N)`, then the flat gradient bucket is all-reduced with SUM (no
+    division by world size).  The result equals the single-process step on the concatenated batch.
+
+    Parameters that cannot receive a gradient (dead relations) stay out of the bucket
+    and are never touched by the optimizer, as in the reference where their `.grad` is None.
+    """
+
+    def __init__(self, model: HetroGIN, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                 optimizer="adam", process_group=None, distributed=None):
+        if optimizer not in ("adam", "adamW"):
+            raise NotImplementedError("TrainStep fuses Adam/AdamW; use train_one_epoch with torch.optim.SGD")
+        self.model = model
+        self.hyper = dict(lr=lr, beta1=betas[0], beta2=betas[1], eps=eps, weight_decay=weight_decay,
+                          decoupled=optimizer == "adamW")
+        self.pg = process_group
+        self.distributed = (torch.distributed.is_available() and torch.distributed.is_initialized()
+                            if distributed is None else distributed)
+        live_mods = set()
+        for li, rels in enumerate(model.live_relations(HetroGIN.RELATIONS)):
+            for et in rels:
+                live_mods.add(model.convs[li].convs["__".join(et)])
+        live_ids = {id(p) for m in live_mods for p in m.parameters()} | {id(p) for p in model.readout.parameters()}
+        self.live = [p for p in model.parameters() if id(p) in live_ids and p.requires_grad]
+        dev = self.live[0].device
+        if dev.type != "cuda":
+            raise ops.HginError("TrainStep: move the model to the GPU first (there is no CPU path)")
+        n = sum(p.numel() for p in self.live)
+        self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in self.live:                      # parameters become views of the flat bucket
+                self.flat_p[off:off + p.numel()].copy_(p.reshape(-1))
+                p.data = self.flat_p[off:off + p.numel()].view_as(p)
+                off += p.numel()
+
+    def _allreduce(self, t):
+        if self.distributed:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+
+    def __call__(self, batch):
+        """`batch` already resident on the GPU.  Returns a CUDA tensor [mape, sqrt(mape)] (global)."""
+        model = self.model
+        for p in self.live:
+            p.grad = None
+        out = model(batch.x_dict, batch.edge_index_dict, batch["path"].batch)
+        y = batch["path"].y
+        sums = ops.mape_sum(out.detach(), y)
+        self._allreduce(sums)
+        loss_out, dpred = ops.sqrt_mape_bwd(out.detach(), y, sums)
+        out.backward(dpred)
+        torch.cat([p.grad.reshape(-1) for p in self.live], out=self.flat_g)
+        self._allreduce(self.flat_g)
+        ops.increment(self.step_count)
+        ops.adam_step(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, self.step_count, **self.hyper)
+        return loss_out

@@ -1,0 +1,162 @@
+/* hgin.h — C ABI of libhgin.so: the HeteroGIN message-passing hot path on B200 (sm_100a).
+ *
+ * This is the LOWER drop-in boundary of SURVEY §8(b).  The reference is pure Python and has no
+ * FFI of its own; what it binds today are the PyTorch/PyG operator calls listed per entry point
+ * below (file:line into /root/reference).  A maintainer replaces those calls with a ctypes stub
+ * over this header (INTEGRATION.md shows it); gnn_link_prediction_b200/_lib.py is that stub.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; all buffers (inputs,
+ *     outputs, saved-for-backward, workspaces) are allocated and owned by the caller.  The
+ *     library allocates nothing, frees nothing and keeps no state between calls.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises,
+ *     so every entry point is legal inside CUDA-graph capture.
+ *   - return value: HGIN_OK (0) or a negative hgin_status; hgin_last_error() returns a
+ *     thread-local message for the last failing call.  No exceptions, no aborts.
+ *   - matrices are fp32 row-major with an explicit leading dimension `ld*` in ELEMENTS;
+ *     indices cross the ABI as int32 CSR (built once per batch by hgin_csr_build).
+ */
+#ifndef HGIN_H_
+#define HGIN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HGIN_VERSION 100 /* major*100 + minor */
+
+typedef enum hgin_status {
+    HGIN_OK = 0,
+    HGIN_ERR_INVALID_ARGUMENT = -1,
+    HGIN_ERR_WORKSPACE_TOO_SMALL = -2,
+    HGIN_ERR_CUDA = -3,
+    HGIN_ERR_UNSUPPORTED = -4
+} hgin_status;
+
+/* self-term modes of hgin_gin_combine */
+#define HGIN_SELF_NONE 0   /* out = agg                                   */
+#define HGIN_SELF_ADD 1    /* out = fl(agg + fl(fl(1+eps) * x_self))      models.py:215 */
+#define HGIN_SELF_CONCAT 2 /* out = [agg | fl(fl(1+eps) * x_self)]        models.py:213 */
+
+/* activations of hgin_linear_* */
+#define HGIN_ACT_NONE 0
+#define HGIN_ACT_PRELU 1 /* single shared slope, torch.nn.PReLU() (models.py:238, config.json:27) */
+#define HGIN_ACT_RELU 2
+
+/* math modes of hgin_linear_* */
+#define HGIN_MATH_FP32 0 /* SIMT fp32 FMA: parity mode, rel 1e-5 against the CPU reference */
+#define HGIN_MATH_TF32 1 /* tcgen05 kind::tf32 tensor-core tiles, fp32 accumulate in TMEM */
+
+int32_t hgin_version(void);
+const char *hgin_last_error(void);
+
+/* ---- K0: destination-sorted CSR (and its transpose) from a COO edge list --------------------
+ * Replaces: nothing in the reference (PyG keeps COO and uses atomics); fixes the summation
+ * order of `scatter_add_` (models.py:208 -> torch_scatter.scatter) so that K1 is deterministic.
+ * Contract, integer-exact:
+ *     key  = edge_index[sort_row], other = edge_index[1 - sort_row]
+ *     perm = argsort(key, stable);  rowptr = exclusive_cumsum(bincount(key, num_rows));
+ *     col  = other[perm]
+ * sort_row = 1 gives the forward CSR (rows = destination nodes), sort_row = 0 the transposed
+ * CSR used by the backward gather (rows = source nodes).
+ *   edge_index : [2, num_edges], index_bytes = 8 (int64, as the reference ships it,
+ *                generateFiles.py:172-181) or 4 (int32); row r starts at element r*ld_edge.
+ *   rowptr     : int32 [num_rows + 1];  col : int32 [num_edges];  perm : int32 [num_edges] or NULL.
+ *   status     : int32 [1], set to 1 if any index is outside [0,num_rows) x [0,num_cols); such
+ *                edges are dropped.  The caller reads it when it chooses to (no sync here).
+ *   workspace  : hgin_csr_workspace_bytes(num_edges, num_rows) bytes.
+ */
+int64_t hgin_csr_workspace_bytes(int64_t num_edges, int64_t num_rows);
+int32_t hgin_csr_build(const void *edge_index, int32_t index_bytes, int64_t num_edges,
+                       int64_t ld_edge, int32_t sort_row, int64_t num_rows, int64_t num_cols,
+                       int32_t *rowptr, int32_t *col, int32_t *perm, int32_t *status,
+                       void *workspace, int64_t workspace_bytes, void *stream);
+
+/* ---- K1 / K4: segmented neighbour sum over CSR rows, fused with the GIN self term -----------
+ * Replaces (forward): GINConv.forward up to the MLP input, models.py:208-215 —
+ *   propagate = x_src.index_select(0, edge_index[0]) + scatter_add_ over edge_index[1],
+ *   then `(1 + eps) * x_r` and `cat` / in-place `+=`.
+ * Replaces (backward): autograd of the same — index_select.backward (index_add_) as a gather
+ *   over the TRANSPOSED CSR, fused with `(1+eps) * dh` for the self branch and with the sum over
+ *   relations that share a node type (`accumulate`).
+ * Per row r (one warp or sub-warp per row; neighbours added left to right in CSR order, fp32,
+ * no atomics — bit-exact with the CPU reference):
+ *     agg[f]  = sum_{e in [rowptr[r], rowptr[r+1])} x_src[col[e]*ld_src + f]        f < f_src
+ *     out row = per `self_mode` above; `accumulate` != 0 adds the result to `out` instead.
+ * eps: device pointer to the learnable scalar (models.py:191-194) or NULL for eps = 0.
+ * HGIN_SELF_ADD needs f_self == f_src.  x_self may be NULL only with HGIN_SELF_NONE.
+ */
+int32_t hgin_gin_combine(int64_t num_rows, const int32_t *rowptr, const int32_t *col,
+                         const float *x_src, int64_t ld_src, int32_t f_src,
+                         const float *x_self, int64_t ld_self, int32_t f_self,
+                         const float *eps, int32_t self_mode, int32_t accumulate,
+                         float *out, int64_t ld_out, void *stream);
+
+/* ---- K2: dense layer forward  z = [x1 | x2] W^T + b,  out (+)= act(z) ------------------------
+ * Replaces: GINLayer.mlp = Linear + PReLU (models.py:236-239, applied at models.py:217), the
+ * HeteroConv 'sum' merge over relations with the same destination type (models.py:286-298 ->
+ * PyG group(): stack().sum(0)) through `accumulate_out`, and the readout layers including
+ * `torch.cat((x_dict['path'], origin_input['path']), 1)` (models.py:366, 373-374) through the
+ * two-source input [x1 | x2].
+ *   x1 [rows,k1], x2 [rows,k2] (x2 may be NULL with k2 = 0);  W [n, k1+k2] row-major (torch
+ *   Linear.weight);  bias [n] or NULL;  alpha: device scalar for PRELU.
+ *   z   [rows,n] or NULL — pre-activation, saved for backward;
+ *   out [rows,n] or NULL — act(z), overwritten or accumulated.
+ */
+int32_t hgin_linear_fwd(int64_t rows, const float *x1, int64_t ld1, int32_t k1,
+                        const float *x2, int64_t ld2, int32_t k2, const float *W,
+                        const float *bias, int32_t n, int32_t act, const float *alpha,
+                        float *z, int64_t ldz, float *out, int64_t ldo, int32_t accumulate_out,
+                        int32_t math_mode, void *stream);
+
+/* ---- K3: dense layer backward ---------------------------------------------------------------
+ * Replaces: autograd of the above (train.py:43): with dz = g * act'(z),
+ *     dx[:, c0:c1] = (dz W)[:, c0:c1]      -> dx   [rows, c1-c0]  (NULL to skip the store)
+ *     dW = dz^T [x1 | x2]                  -> dW   [n, k1+k2]
+ *     db = sum_rows dz                     -> db   [n]            (NULL to skip)
+ *     dalpha = sum g * min(z,0) (PReLU)    -> dalpha [1]          (NULL to skip)
+ *     ddot = sum dx[:, c0:c1] * dot_x      -> ddot [1]            (NULL to skip) — this is
+ *            d(eps) = sum dh_self * x_dst of GINConv (models.py:213/215).
+ * dW/db/dalpha/ddot are OVERWRITTEN (reductions are two-stage and deterministic: per-CTA
+ * partials in `workspace`, summed in a fixed order).  Set dW = NULL to skip the weight pass,
+ * c1 == c0 to skip the input pass.
+ */
+int64_t hgin_linear_bwd_workspace_bytes(int64_t rows, int32_t k, int32_t n);
+int32_t hgin_linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, int64_t ldz,
+                        int32_t act, const float *alpha, const float *x1, int64_t ld1, int32_t k1,
+                        const float *x2, int64_t ld2, int32_t k2, const float *W, int32_t n,
+                        int32_t c0, int32_t c1, float *dx, int64_t lddx, const float *dot_x,
+                        int64_t ld_dot, float *ddot, float *dW, float *db, float *dalpha,
+                        void *workspace, int64_t workspace_bytes, int32_t math_mode, void *stream);
+
+/* ---- loss: sqrt(MAPE) (train.py:12-13, 40-42) -----------------------------------------------
+ * hgin_mape_sum:       sums[0] = sum_i |(pred_i - y_i) / y_i|,  sums[1] = n  (fp32, two-stage,
+ *                      deterministic).  Multi-GPU: the caller all-reduces `sums`.
+ * hgin_sqrt_mape_bwd:  with S = sums[0], N = sums[1] (global), L = sqrt(100 S / N):
+ *                      loss_out[0] = 100 S / N, loss_out[1] = L,
+ *                      dpred_i = gscale * 50 * sign((pred_i - y_i) / y_i) / (y_i * N * L).
+ */
+int64_t hgin_reduce_workspace_bytes(int64_t n);
+int32_t hgin_mape_sum(int64_t n, const float *pred, const float *y, float *sums, void *workspace,
+                      int64_t workspace_bytes, void *stream);
+int32_t hgin_sqrt_mape_bwd(int64_t n, const float *pred, const float *y, const float *sums,
+                           float gscale, float *loss_out, float *dpred, void *stream);
+
+/* ---- optimizer: Adam / AdamW on one flat fp32 bucket (train.py:44, 140-148) ------------------
+ * torch.optim.Adam semantics (amsgrad off, maximize off): `step` is the 1-based step count read
+ * from device memory (int32 [1]) so that the call is CUDA-graph replayable; the kernel does not
+ * advance it (hgin_increment does).  decoupled != 0 selects AdamW.
+ */
+int32_t hgin_adam_step(int64_t n, float *param, const float *grad, float *exp_avg,
+                       float *exp_avg_sq, const int32_t *step, double lr, double beta1,
+                       double beta2, double eps, double weight_decay, int32_t decoupled,
+                       void *stream);
+int32_t hgin_increment(int32_t *counter, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HGIN_H_ */

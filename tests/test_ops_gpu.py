@@ -1,0 +1,227 @@
+"""Kernel-level parity: every C-ABI entry point against the CPU oracle on the same seeded inputs.
+Integer work and the fp32 aggregation are compared bit-for-bit; GEMM-shaped work within the fp32
+tolerance written in each test."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+from gnn_link_prediction_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_edges(ns, nd, e, seed, sort_src=False):
+    g = torch.Generator().manual_seed(seed)
+    ei = torch.stack([torch.randint(0, ns, (e,), generator=g), torch.randint(0, nd, (e,), generator=g)])
+    if sort_src and e:
+        ei = ei[:, torch.argsort(ei[0], stable=True)]
+    return ei
+
+
+CSR_SHAPES = [(1000, 300, 20000), (50, 2000, 7000), (7, 5, 0), (1, 1, 40), (3000, 10, 50000), (100000, 9000, 400000),
+              (5, 70000, 33)]
+
+
+@pytest.mark.parametrize("ns,nd,e", CSR_SHAPES)
+@pytest.mark.parametrize("dtype", [torch.int64, torch.int32])
+@pytest.mark.parametrize("by", ["dst", "src"])
+def test_csr_build_bit_exact(ns, nd, e, dtype, by):
+    ei = _rand_edges(ns, nd, e, seed=ns + e, sort_src=(e % 2 == 0))
+    csr = ops.csr_build(ei.to(dtype).cuda(), ns, nd, by=by, want_perm=True).validate()
+    src = ei if by == "dst" else ei.flip(0).contiguous()
+    rows, cols = (nd, ns) if by == "dst" else (ns, nd)
+    rowptr, col, perm = c_oracle.csr_build(src.numpy(), cols, rows)
+    assert np.array_equal(csr.rowptr.cpu().numpy(), rowptr)
+    assert np.array_equal(csr.col.cpu().numpy(), col)
+    assert np.array_equal(csr.perm.cpu().numpy(), perm)
+    # and against torch's own stable argsort, independently of the C oracle
+    key = ei[1] if by == "dst" else ei[0]
+    other = ei[0] if by == "dst" else ei[1]
+    p = torch.argsort(key, stable=True)
+    assert torch.equal(csr.col.cpu().long(), other[p])
+
+
+def test_csr_build_long_rows_and_strided_input():
+    # one hub row with 5000 entries exercises the rank-counting branch; input is a strided view
+    ns, nd = 6000, 40
+    ei = _rand_edges(ns, nd, 30000, seed=3)
+    ei[1, :5000] = 7
+    big = torch.zeros(2, 40000, dtype=torch.int64)
+    big[:, :30000] = ei
+    dev = big.cuda()[:, :30000]
+    csr = ops.csr_build(dev, ns, nd).validate()
+    rowptr, col, _ = c_oracle.csr_build(ei.numpy(), ns, nd)
+    assert np.array_equal(csr.rowptr.cpu().numpy(), rowptr) and np.array_equal(csr.col.cpu().numpy(), col)
+
+
+def test_csr_build_flags_out_of_range():
+    ei = torch.tensor([[0, 5, 1], [0, 1, 9]])
+    csr = ops.csr_build(ei.cuda(), 3, 2)
+    with pytest.raises(IndexError):
+        csr.validate()
+    assert csr.rowptr.cpu().tolist() == [0, 1, 1]   # only the valid edge (0 -> 0) is kept
+
+
+COMBINE_SHAPES = [  # ns, nd, e, f
+    (1000, 300, 20000, 128), (50, 2000, 7000, 3), (500, 500, 60000, 8), (10, 5, 0, 4), (300, 200, 9000, 16),
+    (300, 200, 9000, 64), (200, 100, 3000, 256), (200, 100, 3000, 5), (200, 100, 3000, 33), (64, 64, 4000, 100),
+    (40, 4000, 9000, 32), (2000, 7, 30000, 128)]
+
+
+@pytest.mark.parametrize("ns,nd,e,f", COMBINE_SHAPES)
+@pytest.mark.parametrize("mode", ["add", "concat", "none"])
+def test_gin_combine_bit_exact(ns, nd, e, f, mode):
+    ei = _rand_edges(ns, nd, e, seed=e + f, sort_src=True)
+    g = torch.Generator().manual_seed(f)
+    xs = torch.randn(ns, f, generator=g)
+    xd = torch.randn(nd, f if mode == "add" else 3, generator=g)
+    eps = 0.37
+    rowptr, col, _ = c_oracle.csr_build(ei.numpy(), ns, nd)
+    want = c_oracle.gin_combine(rowptr, col, xs.numpy(), None if mode == "none" else xd.numpy(), eps, mode == "concat")
+    csr = ops.csr_build(ei.cuda(), ns, nd)
+    self_mode = {"add": ops.SELF_ADD, "concat": ops.SELF_CONCAT, "none": ops.SELF_NONE}[mode]
+    got = ops.gin_combine(csr, xs.cuda(), None if mode == "none" else xd.cuda(),
+                          torch.tensor([eps]).cuda() if mode != "none" else None, self_mode)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_gin_combine_strided_inputs_and_accumulate():
+    # layer-0 layout: 3 columns of a 7-wide row (ld = 7), as models.py:336-338 slices them
+    ns, nd, e = 400, 150, 5000
+    ei = _rand_edges(ns, nd, e, seed=11, sort_src=True)
+    g = torch.Generator().manual_seed(1)
+    xs7, xd7 = torch.randn(ns, 7, generator=g), torch.randn(nd, 7, generator=g)
+    rowptr, col, _ = c_oracle.csr_build(ei.numpy(), ns, nd)
+    want = c_oracle.gin_combine(rowptr, col, xs7[:, 0:3].numpy(), xd7[:, 0:3].numpy(), 0.0, True)
+    csr = ops.csr_build(ei.cuda(), ns, nd)
+    got = ops.gin_combine(csr, xs7.cuda()[:, 0:3], xd7.cuda()[:, 0:3], torch.zeros(1).cuda(), ops.SELF_CONCAT)
+    assert np.array_equal(got.cpu().numpy(), want)
+    # accumulate: out += agg, fp32 add of the two bit-exact parts
+    base = torch.randn(nd, 6, generator=g)
+    acc = base.clone().cuda()
+    ops.gin_combine(csr, xs7.cuda()[:, 0:3], xd7.cuda()[:, 0:3], torch.zeros(1).cuda(), ops.SELF_CONCAT, out=acc,
+                    accumulate=True)
+    assert np.array_equal(acc.cpu().numpy(), base.numpy() + want)
+
+
+def test_transposed_gather_matches_index_add_backward():
+    ns, nd, e, f = 700, 300, 12000, 128
+    ei = _rand_edges(ns, nd, e, seed=5, sort_src=True)
+    gout = torch.randn(nd, f, generator=torch.Generator().manual_seed(2))
+    xs = torch.zeros(ns, f, requires_grad=True)
+    msg = xs.index_select(0, ei[0])
+    torch.zeros(nd, f).scatter_add_(0, ei[1].view(-1, 1).expand_as(msg), msg).backward(gout)
+    csr_t = ops.csr_build(ei.cuda(), ns, nd, by="src")
+    got = ops.gin_combine(csr_t, gout.cuda())
+    assert torch.equal(got.cpu(), xs.grad)
+
+
+LINEAR_SHAPES = [  # rows, k1, k2, n
+    (1000, 6, 0, 8), (777, 8, 0, 8), (1500, 128, 3, 128), (900, 128, 0, 32), (333, 32, 0, 1), (2000, 11, 0, 128),
+    (129, 16, 0, 16), (5, 3, 2, 7), (4100, 64, 0, 64), (300, 200, 0, 150)]
+# fp32 GEMM against an fp64 reference: error ~ sqrt(k) * 2^-24 * |x||w|; the CPU reference's own
+# sgemm differs from fp64 by the same amount, so this is the "rel 1e-5" bar of the north star.
+RTOL, ATOL = 2e-5, 2e-5
+
+
+@pytest.mark.parametrize("rows,k1,k2,n", LINEAR_SHAPES)
+@pytest.mark.parametrize("act", [ops.ACT_PRELU, ops.ACT_NONE, ops.ACT_RELU])
+def test_linear_fwd(rows, k1, k2, n, act):
+    g = torch.Generator().manual_seed(rows + n)
+    x1, x2 = torch.randn(rows, k1, generator=g), (torch.randn(rows, k2, generator=g) if k2 else None)
+    W, b = torch.randn(n, k1 + k2, generator=g) / (k1 + k2) ** 0.5, torch.randn(n, generator=g)
+    alpha = torch.tensor([0.25])
+    x = x1 if x2 is None else torch.cat((x1, x2), 1)
+    z_ref = x.double() @ W.double().t() + b.double()
+    o_ref = {ops.ACT_PRELU: torch.where(z_ref > 0, z_ref, 0.25 * z_ref), ops.ACT_NONE: z_ref,
+             ops.ACT_RELU: z_ref.clamp(min=0)}[act]
+    z, o = ops.linear_fwd(x1.cuda(), W.cuda(), b.cuda(), x2=None if x2 is None else x2.cuda(), act=act,
+                          alpha=alpha.cuda())
+    torch.testing.assert_close(z.cpu().double(), z_ref, rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(o.cpu().double(), o_ref, rtol=RTOL, atol=ATOL)
+    # merge: out += act(z) (HeteroConv 'sum')
+    prev = torch.randn(rows, n, generator=g)
+    acc = prev.clone().cuda()
+    ops.linear_fwd(x1.cuda(), W.cuda(), b.cuda(), x2=None if x2 is None else x2.cuda(), act=act, alpha=alpha.cuda(),
+                   out=acc, accumulate_out=True, want_z=False)
+    torch.testing.assert_close(acc.cpu().double(), prev.double() + o_ref, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("rows,k1,k2,n", LINEAR_SHAPES)
+@pytest.mark.parametrize("act", [ops.ACT_PRELU, ops.ACT_NONE])
+def test_linear_bwd(rows, k1, k2, n, act):
+    g = torch.Generator().manual_seed(rows * 3 + n)
+    k = k1 + k2
+    x = torch.randn(rows, k, generator=g, dtype=torch.float64, requires_grad=True)
+    W = (torch.randn(n, k, generator=g, dtype=torch.float64) / k ** 0.5).requires_grad_(True)
+    b = torch.randn(n, generator=g, dtype=torch.float64, requires_grad=True)
+    alpha = torch.tensor([0.25], dtype=torch.float64, requires_grad=True)
+    dot_x = torch.randn(rows, k, generator=g, dtype=torch.float64)
+    z_ref = x @ W.t() + b
+    o_ref = torch.nn.functional.prelu(z_ref, alpha) if act == ops.ACT_PRELU else z_ref
+    gout = torch.randn(rows, n, generator=g, dtype=torch.float64)
+    o_ref.backward(gout)
+    f32 = lambda t: t.detach().float().cuda()
+    x1, x2 = f32(x[:, :k1]).contiguous(), (f32(x[:, k1:]).contiguous() if k2 else None)
+    r = ops.linear_bwd(f32(gout), f32(z_ref), x1, f32(W), x2=x2, act=act, alpha=f32(alpha), dot_x=f32(dot_x),
+                       want_dalpha=act == ops.ACT_PRELU)
+    scale = rows ** 0.5
+    torch.testing.assert_close(r["dx"].cpu().double(), x.grad, rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(r["dW"].cpu().double(), W.grad, rtol=RTOL, atol=ATOL * scale)
+    torch.testing.assert_close(r["db"].cpu().double(), b.grad, rtol=RTOL, atol=ATOL * scale)
+    torch.testing.assert_close(r["ddot"].cpu().double(), (x.grad * dot_x).sum().view(1), rtol=1e-4, atol=ATOL * scale * k ** 0.5)
+    if act == ops.ACT_PRELU:
+        torch.testing.assert_close(r["dalpha"].cpu().double(), alpha.grad, rtol=1e-4, atol=ATOL * scale * n ** 0.5)
+    # column-restricted input gradient (layer-0 self block) without storing dx
+    c0 = k // 2
+    r2 = ops.linear_bwd(f32(gout), f32(z_ref), x1, f32(W), x2=x2, act=act, alpha=f32(alpha), dx_cols=(c0, k),
+                        want_dx=False, dot_x=f32(dot_x[:, c0:]).contiguous(), want_dw=False, want_db=False)
+    assert r2["dx"] is None and r2["dW"] is None
+    torch.testing.assert_close(r2["ddot"].cpu().double(), (x.grad[:, c0:] * dot_x[:, c0:]).sum().view(1), rtol=1e-4,
+                               atol=ATOL * scale * k ** 0.5)
+
+
+def test_linear_bwd_is_deterministic():
+    g = torch.Generator().manual_seed(0)
+    rows, k, n = 50000, 128, 128
+    x, W = torch.randn(rows, k, generator=g).cuda(), torch.randn(n, k, generator=g).cuda()
+    z, gout = torch.randn(rows, n, generator=g).cuda(), torch.randn(rows, n, generator=g).cuda()
+    a = torch.tensor([0.25]).cuda()
+    r1 = ops.linear_bwd(gout, z, x, W, act=ops.ACT_PRELU, alpha=a, want_dalpha=True)
+    r2 = ops.linear_bwd(gout, z, x, W, act=ops.ACT_PRELU, alpha=a, want_dalpha=True)
+    for key in ("dx", "dW", "db", "dalpha"):
+        assert torch.equal(r1[key], r2[key]), key
+
+
+@pytest.mark.parametrize("n", [1, 1000, 250000])
+def test_sqrt_mape_loss(n):
+    g = torch.Generator().manual_seed(n)
+    pred = torch.randn(n, 1, generator=g, dtype=torch.float64, requires_grad=True)
+    y = 0.1 + 9 * torch.rand(n, generator=g, dtype=torch.float64)
+    mape = 100.0 * torch.mean(torch.abs((pred - y.view(-1, 1)) / y.view(-1, 1)))   # train.py:13
+    loss = torch.sqrt(mape)                                                      # train.py:42
+    loss.backward()
+    sums = ops.mape_sum(pred.detach().float().cuda(), y.float().cuda())
+    assert float(sums[1]) == n
+    loss_out, dpred = ops.sqrt_mape_bwd(pred.detach().float().cuda(), y.float().cuda(), sums)
+    torch.testing.assert_close(loss_out.cpu().double(), torch.stack([mape.detach(), loss.detach()]), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(dpred.cpu().double(), pred.grad, rtol=1e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize("decoupled,wd", [(False, 0.0), (False, 0.01), (True, 0.01)])
+def test_adam_matches_torch_optim(decoupled, wd):
+    g = torch.Generator().manual_seed(4)
+    p0 = torch.randn(5000, generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = (torch.optim.AdamW if decoupled else torch.optim.Adam)([ref], lr=1e-3, weight_decay=wd)
+    p, m, v = p0.clone().cuda(), torch.zeros(5000).cuda(), torch.zeros(5000).cuda()
+    step = torch.zeros(1, dtype=torch.int32).cuda()
+    for _ in range(6):
+        grad = torch.randn(5000, generator=g)
+        ref.grad = grad.clone()
+        opt.step()
+        ops.increment(step)
+        ops.adam_step(p, grad.cuda(), m, v, step, 1e-3, 0.9, 0.999, 1e-8, wd, decoupled)
+    assert int(step.item()) == 6
+    torch.testing.assert_close(p.cpu(), ref.detach(), rtol=1e-6, atol=1e-7)
