@@ -26,9 +26,10 @@ SIGNATURES = {
     "hgin_csr_workspace_bytes": (_i64, [_i64, _i64]),
     "hgin_csr_build": (_i32, [_ptr, _i32, _i64, _i64, _i32, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
     "hgin_gin_combine": (_i32, [_i64, _ptr, _ptr, _ptr, _i64, _i32, _ptr, _i64, _i32, _ptr, _i32, _i32, _ptr, _i64, _ptr]),
+    "hgin_linear_fwd_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32]),
     "hgin_linear_fwd": (_i32, [_i64, _ptr, _i64, _i32, _ptr, _i64, _i32, _ptr, _ptr, _i32, _i32, _ptr, _ptr, _i64,
-                               _ptr, _i64, _i32, _i32, _ptr]),
-    "hgin_linear_bwd_workspace_bytes": (_i64, [_i64, _i32, _i32]),
+                               _ptr, _i64, _i32, _ptr, _i64, _i32, _ptr]),
+    "hgin_linear_bwd_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32]),
     "hgin_linear_bwd": (_i32, [_i64, _ptr, _i64, _ptr, _i64, _i32, _ptr, _ptr, _i64, _i32, _ptr, _i64, _i32, _ptr,
                                _i32, _i32, _i32, _ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32,
                                _ptr]),
@@ -37,6 +38,7 @@ SIGNATURES = {
     "hgin_sqrt_mape_bwd": (_i32, [_i64, _ptr, _ptr, _ptr, _f32, _ptr, _ptr, _ptr]),
     "hgin_adam_step": (_i32, [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _f64, _f64, _f64, _f64, _f64, _i32, _ptr]),
     "hgin_increment": (_i32, [_ptr, _ptr]),
+    "hgin_debug_gemm_tn": (_i32, [_i64, _ptr, _i32, _ptr, _i32, _ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _ptr]),
 }
 
 _lib = None

@@ -189,7 +189,8 @@ extern "C" int32_t hgin_gin_combine(int64_t num_rows, const int32_t *rowptr, con
     HGIN_CHECK_ARG(self_mode != HGIN_SELF_ADD || f_self == f_src, "hgin_gin_combine: SELF_ADD needs f_self == f_src");
     HGIN_CHECK_ARG(self_mode != HGIN_SELF_CONCAT || f_self > 0, "hgin_gin_combine: SELF_CONCAT needs f_self > 0");
     if (num_rows == 0) return HGIN_OK;
-    HGIN_CHECK_ARG(rowptr && col && x_src && out, "hgin_gin_combine: null pointer");
+    // `col` may be null for an edgeless relation (every row empty): it is never dereferenced then.
+    HGIN_CHECK_ARG(rowptr && x_src && out, "hgin_gin_combine: null pointer");
     const int width = f_src + (self_mode == HGIN_SELF_CONCAT ? f_self : 0);
     HGIN_CHECK_ARG(ld_src >= f_src && ld_out >= width, "hgin_gin_combine: leading dimension too small");
     cudaStream_t s = static_cast<cudaStream_t>(stream);

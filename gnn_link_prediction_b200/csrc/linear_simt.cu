@@ -6,6 +6,7 @@
 // All reductions over rows are two-stage and deterministic: every CTA writes its partial to the
 // caller's workspace and a second kernel adds the partials in CTA order.
 #include "gemm_simt.cuh"
+#include "linear_tc_api.h"
 
 namespace hgin {
 namespace {
@@ -270,21 +271,33 @@ inline int64_t dw_splits(int64_t rows) {
 }  // namespace
 }  // namespace hgin
 
+extern "C" int64_t hgin_linear_fwd_workspace_bytes(int64_t rows, int32_t k, int32_t n, int32_t math_mode) {
+    if (rows < 0 || k <= 0 || n <= 0) return -1;
+    return math_mode == HGIN_MATH_TF32 ? hgin::tcgemm::fwd_workspace_bytes(k, n) : 0;
+}
+
 extern "C" int32_t hgin_linear_fwd(int64_t rows, const float *x1, int64_t ld1, int32_t k1, const float *x2,
                                    int64_t ld2, int32_t k2, const float *W, const float *bias, int32_t n,
                                    int32_t act, const float *alpha, float *z, int64_t ldz, float *out, int64_t ldo,
-                                   int32_t accumulate_out, int32_t math_mode, void *stream) {
+                                   int32_t accumulate_out, void *workspace, int64_t workspace_bytes,
+                                   int32_t math_mode, void *stream) {
     using namespace hgin;
     HGIN_CHECK_ARG(rows >= 0 && k1 > 0 && k2 >= 0 && n > 0, "hgin_linear_fwd: bad sizes rows=%lld k1=%d k2=%d n=%d",
                    (long long)rows, k1, k2, n);
     HGIN_CHECK_ARG(act >= HGIN_ACT_NONE && act <= HGIN_ACT_RELU, "hgin_linear_fwd: bad act %d", act);
     HGIN_CHECK_ARG(act != HGIN_ACT_PRELU || alpha, "hgin_linear_fwd: PReLU needs alpha");
-    HGIN_CHECK_ARG(math_mode == HGIN_MATH_FP32, "hgin_linear_fwd: math_mode %d not available in this build", math_mode);
+    HGIN_CHECK_ARG(math_mode == HGIN_MATH_FP32 || math_mode == HGIN_MATH_TF32, "hgin_linear_fwd: bad math_mode %d", math_mode);
     if (rows == 0) return HGIN_OK;
     HGIN_CHECK_ARG(x1 && W && (k2 == 0 || x2) && (z || out), "hgin_linear_fwd: null pointer");
     HGIN_CHECK_ARG(ld1 >= k1 && (k2 == 0 || ld2 >= k2) && (!z || ldz >= n) && (!out || ldo >= n),
                    "hgin_linear_fwd: leading dimension too small");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (math_mode == HGIN_MATH_TF32 && tcgemm::fwd_eligible(rows, x1, ld1, k1, k2, n, z, ldz, out, ldo)) {
+        if (!workspace || workspace_bytes < tcgemm::fwd_workspace_bytes(k1 + k2, n))
+            return fail(HGIN_ERR_WORKSPACE_TOO_SMALL, "hgin_linear_fwd: workspace too small for the tf32 path");
+        return tcgemm::linear_fwd(rows, x1, ld1, k1, x2, ld2, k2, W, bias, n, act, alpha, z, ldz, out, ldo,
+                                  accumulate_out, workspace, s);
+    }
     ConcatRows fa{x1, ld1, k1, x2, ld2, k2, rows};
     WeightRows fb{W, n, k1 + k2};
     const int vec_ok = (!z || (ldz % 4 == 0 && aligned16(z))) && (!out || (ldo % 4 == 0 && aligned16(out)));
@@ -302,12 +315,19 @@ extern "C" int32_t hgin_linear_fwd(int64_t rows, const float *x1, int64_t ld1, i
     return HGIN_OK;
 }
 
-extern "C" int64_t hgin_linear_bwd_workspace_bytes(int64_t rows, int32_t k, int32_t n) {
+static int64_t simt_bwd_workspace_bytes(int64_t rows, int32_t k, int32_t n) {
     using namespace hgin;
-    if (rows < 0 || k <= 0 || n <= 0) return -1;
     const int64_t dw = dw_splits(rows) * n * (k + 1) * 4;
     const int64_t scal = (ceil_div(rows, 128) * ceil_div(k > n ? k : n, 8) + dw_splits(rows) * ceil_div(n, 128)) * 4;
     return align_up(dw, 256) + align_up(scal, 256) + 512;
+}
+
+extern "C" int64_t hgin_linear_bwd_workspace_bytes(int64_t rows, int32_t k, int32_t n, int32_t math_mode) {
+    if (rows < 0 || k <= 0 || n <= 0) return -1;
+    const int64_t simt = simt_bwd_workspace_bytes(rows, k, n);
+    if (math_mode != HGIN_MATH_TF32) return simt;
+    const int64_t tc = hgin::tcgemm::bwd_workspace_bytes(rows, k, k < 4 ? k : 4, n);
+    return simt > tc ? simt : tc;
 }
 
 extern "C" int32_t hgin_linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, int64_t ldz,
@@ -323,10 +343,10 @@ extern "C" int32_t hgin_linear_bwd(int64_t rows, const float *g, int64_t ldg, co
     HGIN_CHECK_ARG(act == HGIN_ACT_NONE || z, "hgin_linear_bwd: activation backward needs z");
     HGIN_CHECK_ARG(act != HGIN_ACT_PRELU || alpha, "hgin_linear_bwd: PReLU needs alpha");
     HGIN_CHECK_ARG(0 <= c0 && c0 <= c1 && c1 <= k, "hgin_linear_bwd: bad column range [%d,%d) of %d", c0, c1, k);
-    HGIN_CHECK_ARG(math_mode == HGIN_MATH_FP32, "hgin_linear_bwd: math_mode %d not available in this build", math_mode);
+    HGIN_CHECK_ARG(math_mode == HGIN_MATH_FP32 || math_mode == HGIN_MATH_TF32, "hgin_linear_bwd: bad math_mode %d", math_mode);
     HGIN_CHECK_ARG(!ddot || dot_x, "hgin_linear_bwd: ddot needs dot_x");
     HGIN_CHECK_ARG(g && W && x1 && (k2 == 0 || x2), "hgin_linear_bwd: null pointer");
-    const int64_t need = hgin_linear_bwd_workspace_bytes(rows, k, n);
+    const int64_t need = hgin_linear_bwd_workspace_bytes(rows, k, n, math_mode);
     if (workspace_bytes < need || !workspace)
         return fail(HGIN_ERR_WORKSPACE_TOO_SMALL, "hgin_linear_bwd: workspace %lld < %lld bytes",
                     (long long)workspace_bytes, (long long)need);
@@ -335,6 +355,12 @@ extern "C" int32_t hgin_linear_bwd(int64_t rows, const float *g, int64_t ldg, co
     float *dw_partials = static_cast<float *>(workspace);
     float *scal = reinterpret_cast<float *>(static_cast<char *>(workspace) + align_up(splits * n * (k + 1) * 4, 256));
 
+    if (math_mode == HGIN_MATH_TF32 && rows > 0 &&
+        tcgemm::bwd_eligible(rows, g, ldg, z, ldz, act, x1, ld1, k1, k2, n, c0, c1, dx, lddx, dot_x, ld_dot)) {
+        return tcgemm::linear_bwd(rows, g, ldg, z, ldz, act, alpha, x1, ld1, k1, x2, ld2, k2, W, n, c0, c1, dx, lddx,
+                                  dot_x, ld_dot, ddot, dW, db, dalpha, workspace, nullptr,
+                                  static_cast<cudaStream_t>(stream));
+    }
     if (rows == 0) {  // empty batch: all reductions are zero
         if (dW) cudaMemsetAsync(dW, 0, sizeof(float) * n * k, s);
         if (db) cudaMemsetAsync(db, 0, sizeof(float) * n, s);
@@ -396,4 +422,20 @@ extern "C" int32_t hgin_linear_bwd(int64_t rows, const float *g, int64_t ldg, co
     }
     HGIN_CHECK_LAUNCH("hgin_linear_bwd");
     return HGIN_OK;
+}
+
+extern "C" int32_t hgin_debug_gemm_tn(int64_t rows, const float *a, int32_t n, const float *b, int32_t k, float *out,
+                                      void *workspace, int64_t workspace_bytes, int32_t tma_swizzle, int32_t lbo,
+                                      int32_t sbo, int32_t layout_type, int32_t k_step_bytes, void *stream) {
+    using namespace hgin;
+    HGIN_CHECK_ARG(rows > 0 && a && b && out && n >= 16 && n <= 128 && n % 16 == 0 && k >= 16 && k <= 128 && k % 16 == 0,
+                   "hgin_debug_gemm_tn: bad arguments");
+    if (!workspace || workspace_bytes < tcgemm::bwd_workspace_bytes(rows, k, 0, n))
+        return fail(HGIN_ERR_WORKSPACE_TOO_SMALL, "hgin_debug_gemm_tn: workspace too small");
+    tcgemm::TnDebug d{tma_swizzle < 0 ? 4 : tma_swizzle, lbo < 0 ? 4096 : lbo, sbo < 0 ? 512 : sbo,
+                      layout_type < 0 ? 1 : layout_type, k_step_bytes < 0 ? 1024 : k_step_bytes};
+    // dz = a (no activation), dW = a^T b
+    return tcgemm::linear_bwd(rows, a, n, nullptr, 0, HGIN_ACT_NONE, nullptr, b, k, k, nullptr, 0, 0, out /*W unused*/, n,
+                              0, 0, nullptr, 0, nullptr, 0, nullptr, out, nullptr, nullptr, workspace, &d,
+                              static_cast<cudaStream_t>(stream));
 }

@@ -1,0 +1,349 @@
+// Host side of the tensor-core dense-layer path (HGIN_MATH_TF32): TMA tensor maps, the small
+// helper kernels (dz = g * act'(z) with fused db / dalpha / tail-dW reductions, weight repacking)
+// and the dispatch used by hgin_linear_fwd / hgin_linear_bwd.  Kernels: linear_tc.cuh.
+#include "linear_tc.cuh"
+
+namespace hgin {
+namespace tcgemm {
+
+// ---- TMA tensor maps ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// fp32 matrix [outer x inner], row pitch ld elements, box [box_outer x box_inner].
+static bool make_map(CUtensorMap *m, const float *base, int64_t inner, int64_t outer, int64_t ld, int box_inner,
+                     int box_outer, CUtensorMapSwizzle swz) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static bool tma_ok(const float *p, int64_t ld) { return p && aligned16(p) && ld % 4 == 0; }
+
+// ---- helper kernels -------------------------------------------------------------------------------
+// dst[r][c] = src[r * ld + c0 + c]   (repack W[:, c0:c0+cols] to a dense, 16B-aligned matrix)
+__global__ void __launch_bounds__(256) pack_cols_kernel(const float *__restrict__ src, int rows, int ld, int c0,
+                                                        int cols, float *__restrict__ dst) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * cols; i += gridDim.x * blockDim.x)
+        dst[i] = __ldg(src + static_cast<int64_t>(i / cols) * ld + c0 + i % cols);
+}
+// dst[c][r] = src[r * ld + c0 + c]   (W^T restricted to columns [c0, c0+cols): K-major B of the dx GEMM)
+__global__ void __launch_bounds__(256) transpose_cols_kernel(const float *__restrict__ src, int rows, int ld, int c0,
+                                                             int cols, float *__restrict__ dst) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * cols; i += gridDim.x * blockDim.x) {
+        const int c = i / rows, r = i % rows;
+        dst[i] = __ldg(src + static_cast<int64_t>(r) * ld + c0 + c);
+    }
+}
+
+// dz = g * act'(z) written densely [rows x n]; per-CTA partials of
+//   db[nn] = sum_m dz,  tail[nn][t] = sum_m dz * x2[m][t] (t < k2 <= 4),  dalpha = sum g * min(z, 0).
+// Partial layout: part[cta][nn][k2 + 1] with the LAST column = db (same convention as the SIMT
+// weight-gradient partials), alpha_part[cta].
+constexpr int DZ_THREADS = 256;
+__global__ void __launch_bounds__(DZ_THREADS)
+dz_prepare_kernel(int64_t rows, int n, const float *__restrict__ g, int64_t ldg, const float *__restrict__ z,
+                  int64_t ldz, int act, const float *__restrict__ alpha_ptr, const float *__restrict__ x2,
+                  int64_t ld2, int k2, float *__restrict__ dz, float *__restrict__ part,
+                  float *__restrict__ alpha_part, int want_sums) {
+    extern __shared__ float sm[];  // [slots][n][5] for the cross-slot combine
+    __shared__ float red[32];
+    const int tpr = n / 4;                       // threads per row (float4 each)
+    const int slots = DZ_THREADS / tpr;          // rows processed per iteration
+    const int slot = threadIdx.x / tpr;
+    const int cg = threadIdx.x % tpr;            // column group -> columns 4cg .. 4cg+3
+    const bool active = slot < slots;
+    const float alpha = (act == HGIN_ACT_PRELU) ? __ldg(alpha_ptr) : 0.0f;
+    float db[4] = {0.f, 0.f, 0.f, 0.f};
+    float tail[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) tail[i][t] = 0.f;
+    float dalpha = 0.f;
+    if (active) {
+        for (int64_t m = static_cast<int64_t>(blockIdx.x) * slots + slot; m < rows;
+             m += static_cast<int64_t>(gridDim.x) * slots) {
+            const float4 gv = __ldg(reinterpret_cast<const float4 *>(g + m * ldg) + cg);
+            float d[4] = {gv.x, gv.y, gv.z, gv.w};
+            if (act != HGIN_ACT_NONE) {
+                const float4 zv4 = __ldg(reinterpret_cast<const float4 *>(z + m * ldz) + cg);
+                const float zv[4] = {zv4.x, zv4.y, zv4.z, zv4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (act == HGIN_ACT_PRELU && !(zv[i] > 0.f)) dalpha += d[i] * zv[i];
+                    d[i] = act_backward(d[i], zv[i], act, alpha);
+                }
+            }
+            reinterpret_cast<float4 *>(dz + m * n)[cg] = make_float4(d[0], d[1], d[2], d[3]);
+            if (want_sums) {
+                float xv[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int t = 0; t < k2; ++t) xv[t] = __ldg(x2 + m * ld2 + t);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    db[i] += d[i];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) tail[i][t] = fmaf(d[i], xv[t], tail[i][t]);
+                }
+            }
+        }
+    }
+    if (!want_sums) return;
+    // combine the row slots of this CTA in a fixed order
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float *dst = sm + (static_cast<int64_t>(slot) * n + cg * 4 + i) * 5;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) dst[t] = tail[i][t];
+            dst[4] = db[i];
+        }
+    }
+    __syncthreads();
+    const int kp = k2 + 1;
+    for (int i = threadIdx.x; i < n * kp; i += DZ_THREADS) {
+        const int nn = i / kp, t = i % kp;
+        const int src_t = (t == k2) ? 4 : t;
+        float s = 0.f;
+        for (int sl = 0; sl < slots; ++sl) s += sm[(static_cast<int64_t>(sl) * n + nn) * 5 + src_t];
+        part[(static_cast<int64_t>(blockIdx.x) * n + nn) * kp + t] = s;
+    }
+    dalpha = block_sum(dalpha, red);
+    if (threadIdx.x == 0 && alpha_part) alpha_part[blockIdx.x] = dalpha;
+}
+
+// out[nn][col0 + k] (ld = ldw) = sum_p part[p][nn][k] for k < kcols; the optional extra column
+// (index kcols) goes to db.
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float *__restrict__ part, int num_part, int n, int kcols, int has_db_col,
+                       float *__restrict__ dW, int ldw, int col0, float *__restrict__ db) {
+    const int kp = kcols + (has_db_col ? 1 : 0);
+    const int64_t total = static_cast<int64_t>(n) * kp;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int pp = 0;
+        for (; pp + 3 < num_part; pp += 4) {   // four independent chains, fixed association
+            s0 += part[static_cast<int64_t>(pp) * total + i];
+            s1 += part[static_cast<int64_t>(pp + 1) * total + i];
+            s2 += part[static_cast<int64_t>(pp + 2) * total + i];
+            s3 += part[static_cast<int64_t>(pp + 3) * total + i];
+        }
+        for (; pp < num_part; ++pp) s0 += part[static_cast<int64_t>(pp) * total + i];
+        const float s = (s0 + s1) + (s2 + s3);
+        const int nn = static_cast<int>(i / kp), k = static_cast<int>(i % kp);
+        if (has_db_col && k == kcols) {
+            if (db) db[nn] = s;
+        } else if (dW) {
+            dW[static_cast<int64_t>(nn) * ldw + col0 + k] = s;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024) reduce_scalar_tc_kernel(const float *__restrict__ v, int count,
+                                                                float *__restrict__ out) {
+    __shared__ float red[32];
+    float s = 0.0f;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) s += v[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+// ---- eligibility ----------------------------------------------------------------------------------
+bool fwd_eligible(int64_t rows, const float *x1, int64_t ld1, int k1, int k2, int n, const float *z, int64_t ldz,
+                  const float *out, int64_t ldo) {
+    return rows >= BM && k1 >= 16 && k1 <= 128 && k1 % 4 == 0 && k2 <= 4 && n >= 16 && n <= 128 && n % 16 == 0 &&
+           tma_ok(x1, ld1) && (!z || tma_ok(z, ldz)) && (!out || tma_ok(out, ldo)) && encode_fn() != nullptr;
+}
+
+bool bwd_eligible(int64_t rows, const float *g, int64_t ldg, const float *z, int64_t ldz, int act, const float *x1,
+                  int64_t ld1, int k1, int k2, int n, int c0, int c1, const float *dx, int64_t lddx,
+                  const float *dot_x, int64_t ld_dot) {
+    const int width = c1 - c0;
+    const bool dx_ok = width == 0 || (width >= 16 && width <= 128 && width % 16 == 0 && (!dx || tma_ok(dx, lddx)) &&
+                                      (!dot_x || tma_ok(dot_x, ld_dot)));
+    return rows >= BM && k1 >= 16 && k1 <= 128 && k1 % 16 == 0 && k2 <= 4 && n >= 16 && n <= 128 && n % 16 == 0 &&
+           tma_ok(g, ldg) && (act == HGIN_ACT_NONE || tma_ok(z, ldz)) && tma_ok(x1, ld1) && dx_ok &&
+           encode_fn() != nullptr;
+}
+
+static int dz_ctas() { return kNumSMs * 4; }
+
+int64_t fwd_workspace_bytes(int k1, int n) { return align_up(static_cast<int64_t>(n) * k1 * 4, 1024) + 1024; }
+
+int64_t bwd_workspace_bytes(int64_t rows, int k1, int k2, int n) {
+    int64_t b = 0;
+    b += align_up(rows * n * 4, 1024);                                     // dz
+    b += align_up(static_cast<int64_t>(128) * n * 4, 1024);                // W^T slice
+    b += align_up(static_cast<int64_t>(dz_ctas()) * n * (k2 + 1) * 4, 1024);  // db / tail partials
+    b += align_up(static_cast<int64_t>(dz_ctas()) * 4, 1024);              // dalpha partials
+    b += align_up(static_cast<int64_t>(kNumSMs) * n * k1 * 4, 1024);       // dW partials
+    b += align_up(static_cast<int64_t>(kNumSMs) * 4, 1024);                // dot partials
+    return b + 1024;
+}
+
+static bool g_attr_set = false;
+static int32_t set_attrs() {
+    if (g_attr_set) return HGIN_OK;
+    cudaError_t e = cudaFuncSetAttribute(gemm_nt_kernel<EPI_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, NtSmem::total);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_nt_kernel<EPI_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, NtSmem::total);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TnSmem::total);
+    if (e != cudaSuccess) return fail(HGIN_ERR_CUDA, "tensor-core kernels: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    g_attr_set = true;
+    return HGIN_OK;
+}
+
+static char *carve(char *&p, int64_t bytes) {
+    char *r = p;
+    p += align_up(bytes, 1024);
+    return r;
+}
+
+// ---- forward --------------------------------------------------------------------------------------
+int32_t linear_fwd(int64_t rows, const float *x1, int64_t ld1, int k1, const float *x2, int64_t ld2, int k2,
+                   const float *W, const float *bias, int n, int act, const float *alpha, float *z, int64_t ldz,
+                   float *out, int64_t ldo, int accumulate_out, void *workspace, cudaStream_t s) {
+    if (int32_t rc = set_attrs()) return rc;
+    const int k = k1 + k2;
+    char *ws = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+    float *Wp = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(n) * k1 * 4));
+    pack_cols_kernel<<<grid_for(n * k1, 256, 1), 256, 0, s>>>(W, n, k, 0, k1, Wp);
+
+    CUtensorMap tm_a, tm_b, tm_o, tm_z, tm_e;
+    bool ok = make_map(&tm_a, x1, k1, rows, ld1, KB, BM, CU_TENSOR_MAP_SWIZZLE_128B) &&
+              make_map(&tm_b, Wp, k1, n, k1, KB, n, CU_TENSOR_MAP_SWIZZLE_128B);
+    float *o_base = out ? out : z;
+    const int64_t o_ld = out ? ldo : ldz;
+    ok = ok && make_map(&tm_o, o_base, n, rows, o_ld, 32, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    ok = ok && make_map(&tm_z, z ? z : o_base, n, rows, z ? ldz : o_ld, 32, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    ok = ok && make_map(&tm_e, o_base, n, rows, o_ld, 32, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (!ok) return fail(HGIN_ERR_CUDA, "hgin_linear_fwd(tf32): cuTensorMapEncodeTiled failed");
+
+    NtParams p{};
+    p.rows = rows;
+    p.num_tiles = static_cast<int>(ceil_div(rows, BM));
+    p.num_kb = static_cast<int>(ceil_div(k1, KB));
+    p.n = n;
+    p.bias = bias;
+    p.alpha = alpha;
+    p.act = act;
+    p.x2 = x2;
+    p.ld2 = ld2;
+    p.k2 = k2;
+    p.w_tail = W + k1;
+    p.ldw = k;
+    p.want_z = z != nullptr;
+    p.want_out = out != nullptr;
+    p.use_e = (out != nullptr && accumulate_out) ? 1 : 0;
+    p.dot_partials = nullptr;
+    const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+    gemm_nt_kernel<EPI_FWD><<<grid, THREADS, NtSmem::total, s>>>(tm_a, tm_b, tm_o, tm_z, tm_e, p);
+    HGIN_CHECK_LAUNCH("hgin_linear_fwd(tf32)");
+    return HGIN_OK;
+}
+
+// ---- backward -------------------------------------------------------------------------------------
+int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, int64_t ldz, int act,
+                   const float *alpha, const float *x1, int64_t ld1, int k1, const float *x2, int64_t ld2, int k2,
+                   const float *W, int n, int c0, int c1, float *dx, int64_t lddx, const float *dot_x,
+                   int64_t ld_dot, float *ddot, float *dW, float *db, float *dalpha, void *workspace,
+                   const TnDebug *dbg, cudaStream_t s) {
+    if (int32_t rc = set_attrs()) return rc;
+    const int k = k1 + k2;
+    char *ws = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+    float *dz = reinterpret_cast<float *>(carve(ws, rows * n * 4));
+    float *Wt = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(128) * n * 4));
+    float *sum_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(dz_ctas()) * n * (k2 + 1) * 4));
+    float *alpha_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(dz_ctas()) * 4));
+    float *dw_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(kNumSMs) * n * k1 * 4));
+    float *dot_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(kNumSMs) * 4));
+
+    // 1. dz and the cheap reductions that ride on it
+    const int want_sums = (dW || db || dalpha) ? 1 : 0;
+    const bool want_alpha = dalpha && act == HGIN_ACT_PRELU;
+    const int tpr = n / 4, slots = DZ_THREADS / tpr;
+    const int ctas = static_cast<int>(ceil_div(rows, slots) < dz_ctas() ? ceil_div(rows, slots) : dz_ctas());
+    dz_prepare_kernel<<<ctas, DZ_THREADS, static_cast<size_t>(slots) * n * 5 * 4, s>>>(
+        rows, n, g, ldg, z, ldz, act, alpha, x2, ld2, k2, dz, sum_part, want_alpha ? alpha_part : nullptr, want_sums);
+    if (want_sums && (db || (dW && k2 > 0)))
+        reduce_partials_kernel<<<grid_for(n * (k2 + 1), 256, 1), 256, 0, s>>>(sum_part, ctas, n, k2, 1, dW, k, k1, db);
+    if (dalpha) {
+        if (want_alpha) reduce_scalar_tc_kernel<<<1, 1024, 0, s>>>(alpha_part, ctas, dalpha);
+        else cudaMemsetAsync(dalpha, 0, sizeof(float), s);
+    }
+
+    // 2. input gradient: dx[:, c0:c1] = dz * W[:, c0:c1]
+    const int width = c1 - c0;
+    if (width > 0 && (dx || ddot)) {
+        transpose_cols_kernel<<<grid_for(n * width, 256, 1), 256, 0, s>>>(W, n, k, c0, width, Wt);
+        CUtensorMap tm_a, tm_b, tm_o, tm_e;
+        bool ok = make_map(&tm_a, dz, n, rows, n, KB, BM, CU_TENSOR_MAP_SWIZZLE_128B) &&
+                  make_map(&tm_b, Wt, n, width, n, KB, width, CU_TENSOR_MAP_SWIZZLE_128B);
+        // without a dx destination the store map still needs a valid (never written) target
+        ok = ok && make_map(&tm_o, dx ? dx : dz, dx ? width : n, rows, dx ? lddx : n, 32, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+        ok = ok && make_map(&tm_e, dot_x ? dot_x : dz, dot_x ? width : n, rows, dot_x ? ld_dot : n, 32, BM,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
+        if (!ok) return fail(HGIN_ERR_CUDA, "hgin_linear_bwd(tf32): cuTensorMapEncodeTiled failed (dx)");
+        NtParams p{};
+        p.rows = rows;
+        p.num_tiles = static_cast<int>(ceil_div(rows, BM));
+        p.num_kb = static_cast<int>(ceil_div(n, KB));
+        p.n = width;
+        p.act = HGIN_ACT_NONE;
+        p.want_out = dx != nullptr;
+        p.use_e = ddot != nullptr;
+        p.dot_partials = ddot ? dot_part : nullptr;
+        const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+        gemm_nt_kernel<EPI_DX><<<grid, THREADS, NtSmem::total, s>>>(tm_a, tm_b, tm_o, tm_o, tm_e, p);
+        if (ddot) reduce_scalar_tc_kernel<<<1, 1024, 0, s>>>(dot_part, grid, ddot);
+    } else if (ddot) {
+        cudaMemsetAsync(ddot, 0, sizeof(float), s);
+    }
+
+    // 3. weight gradient: dW[:, :k1] = dz^T x1
+    if (dW) {
+        const CUtensorMapSwizzle swz = dbg ? static_cast<CUtensorMapSwizzle>(dbg->tma_swizzle) : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+        CUtensorMap tm_a, tm_b;
+        bool ok = make_map(&tm_a, dz, n, rows, n, 32, TN_ROWS, swz) && make_map(&tm_b, x1, k1, rows, ld1, 32, TN_ROWS, swz);
+        if (!ok) return fail(HGIN_ERR_CUDA, "hgin_linear_bwd(tf32): cuTensorMapEncodeTiled failed (dW)");
+        TnParams p{};
+        p.rows = rows;
+        p.rows_per_cta = align_up(ceil_div(rows, kNumSMs), TN_ROWS);
+        p.n = n;
+        p.k = k1;
+        p.partials = dw_part;
+        p.lbo = dbg ? dbg->lbo : TN_BOX_BYTES;
+        p.sbo = dbg ? dbg->sbo : 512;
+        p.layout_type = dbg ? dbg->layout_type : 1;
+        p.k_step_bytes = dbg ? dbg->k_step_bytes : 1024;
+        const int grid = static_cast<int>(ceil_div(rows, p.rows_per_cta));
+        gemm_tn_kernel<<<grid, THREADS, TnSmem::total, s>>>(tm_a, tm_b, p);
+        reduce_partials_kernel<<<grid_for(n * k1, 256, 2), 256, 0, s>>>(dw_part, grid, n, k1, 0, dW, k, 0, nullptr);
+    }
+    HGIN_CHECK_LAUNCH("hgin_linear_bwd(tf32)");
+    return HGIN_OK;
+}
+
+}  // namespace tcgemm
+}  // namespace hgin

@@ -1,0 +1,36 @@
+// Host entry points of the tensor-core dense-layer path (defined in linear_tc.cu), called by the
+// C-ABI functions in linear_simt.cu when math_mode == HGIN_MATH_TF32 and the shapes qualify.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hgin {
+namespace tcgemm {
+
+struct TnDebug {   // overrides of the MN-major descriptor fields (hgin_debug_gemm_tn)
+    int tma_swizzle;
+    int lbo;
+    int sbo;
+    int layout_type;
+    int k_step_bytes;
+};
+
+bool fwd_eligible(int64_t rows, const float *x1, int64_t ld1, int k1, int k2, int n, const float *z, int64_t ldz,
+                  const float *out, int64_t ldo);
+bool bwd_eligible(int64_t rows, const float *g, int64_t ldg, const float *z, int64_t ldz, int act, const float *x1,
+                  int64_t ld1, int k1, int k2, int n, int c0, int c1, const float *dx, int64_t lddx,
+                  const float *dot_x, int64_t ld_dot);
+int64_t fwd_workspace_bytes(int k1, int n);
+int64_t bwd_workspace_bytes(int64_t rows, int k1, int k2, int n);
+int32_t linear_fwd(int64_t rows, const float *x1, int64_t ld1, int k1, const float *x2, int64_t ld2, int k2,
+                   const float *W, const float *bias, int n, int act, const float *alpha, float *z, int64_t ldz,
+                   float *out, int64_t ldo, int accumulate_out, void *workspace, cudaStream_t s);
+int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, int64_t ldz, int act,
+                   const float *alpha, const float *x1, int64_t ld1, int k1, const float *x2, int64_t ld2, int k2,
+                   const float *W, int n, int c0, int c1, float *dx, int64_t lddx, const float *dot_x,
+                   int64_t ld_dot, float *ddot, float *dW, float *db, float *dalpha, void *workspace,
+                   const TnDebug *dbg, cudaStream_t s);
+
+}  // namespace tcgemm
+}  // namespace hgin

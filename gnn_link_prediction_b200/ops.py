@@ -161,11 +161,14 @@ def linear_fwd(x1, W, bias=None, x2=None, act=ACT_NONE, alpha=None, want_z=True,
     po, ldo = _f32_matrix(out, "linear_fwd.out")
     if tuple(out.shape) != (rows, n):
         raise HginError(f"linear_fwd: out is {tuple(out.shape)}, expected {(rows, n)}")
-    with _region("linear_fwd", kernels=1, flops=2 * rows * (k1 + k2) * n,
+    lib = _lib.load()
+    ws_bytes = lib.hgin_linear_fwd_workspace_bytes(rows, k1 + k2, n, math_mode)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes > 0 else None
+    with _region("linear_fwd", kernels=1 + (1 if ws_bytes else 0), flops=2 * rows * (k1 + k2) * n,
                  bytes=4 * rows * (k1 + k2 + n * ((1 if want_z else 0) + (2 if accumulate_out else 1)))):
-        check(_lib.load().hgin_linear_fwd(rows, p1, ld1, k1, p2, ld2, k2, W.data_ptr(), _ptr(bias), n, act,
-                                          _scalar(alpha, "linear_fwd.alpha"), pz, ldz, po, ldo,
-                                          1 if accumulate_out else 0, math_mode, _stream()), "hgin_linear_fwd")
+        check(lib.hgin_linear_fwd(rows, p1, ld1, k1, p2, ld2, k2, W.data_ptr(), _ptr(bias), n, act,
+                                  _scalar(alpha, "linear_fwd.alpha"), pz, ldz, po, ldo, 1 if accumulate_out else 0,
+                                  _ptr(ws), ws_bytes, math_mode, _stream()), "hgin_linear_fwd")
     return z, out
 
 
@@ -197,7 +200,7 @@ def linear_bwd(g, z, x1, W, x2=None, act=ACT_NONE, alpha=None, dx_cols=None, wan
     db = torch.empty(n, dtype=torch.float32, device=dev) if want_db else None
     dalpha = torch.empty(1, dtype=torch.float32, device=dev) if want_dalpha else None
     lib = _lib.load()
-    ws_bytes = lib.hgin_linear_bwd_workspace_bytes(rows, k, n)
+    ws_bytes = lib.hgin_linear_bwd_workspace_bytes(rows, k, n, math_mode)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     flops = 2 * rows * n * ((c1 - c0) + (k + 1 if (want_dw or want_db or want_dalpha) else 0))
     reduces = want_dw or want_db or want_dalpha
@@ -210,6 +213,19 @@ def linear_bwd(g, z, x1, W, x2=None, act=ACT_NONE, alpha=None, dx_cols=None, wan
                                   _ptr(db), _ptr(dalpha), ws.data_ptr(), ws_bytes, math_mode, _stream()),
               "hgin_linear_bwd")
     return {"dx": dx, "ddot": ddot, "dW": dW, "db": db, "dalpha": dalpha}
+
+
+def debug_gemm_tn(a, b, tma_swizzle=-1, lbo=-1, sbo=-1, layout_type=-1, k_step_bytes=-1):
+    """Diagnostics: a[rows,n]^T @ b[rows,k] through the tcgen05 MN-major kernel (hgin_debug_gemm_tn)."""
+    rows, n = a.shape
+    k = b.shape[1]
+    lib = _lib.load()
+    out = torch.empty(n, k, dtype=torch.float32, device=a.device)
+    ws_bytes = lib.hgin_linear_bwd_workspace_bytes(rows, k, n, MATH_TF32)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
+    check(lib.hgin_debug_gemm_tn(rows, a.data_ptr(), n, b.data_ptr(), k, out.data_ptr(), ws.data_ptr(), ws_bytes,
+                                 tma_swizzle, lbo, sbo, layout_type, k_step_bytes, _stream()), "hgin_debug_gemm_tn")
+    return out
 
 
 def mape_sum(pred, y):

@@ -105,12 +105,16 @@ int32_t hgin_gin_combine(int64_t num_rows, const int32_t *rowptr, const int32_t 
  *   Linear.weight);  bias [n] or NULL;  alpha: device scalar for PRELU.
  *   z   [rows,n] or NULL — pre-activation, saved for backward;
  *   out [rows,n] or NULL — act(z), overwritten or accumulated.
+ * math_mode HGIN_MATH_TF32 runs the tcgen05 kernel when the shapes are GEMM-sized (16 <= k1 <= 128,
+ * k1 % 4 == 0, k2 <= 4, n % 16 == 0, n <= 128, rows >= 128, 16-byte aligned rows) and the fp32 SIMT
+ * kernel otherwise; workspace: hgin_linear_fwd_workspace_bytes (0 bytes / NULL allowed for FP32).
  */
+int64_t hgin_linear_fwd_workspace_bytes(int64_t rows, int32_t k, int32_t n, int32_t math_mode);
 int32_t hgin_linear_fwd(int64_t rows, const float *x1, int64_t ld1, int32_t k1,
                         const float *x2, int64_t ld2, int32_t k2, const float *W,
                         const float *bias, int32_t n, int32_t act, const float *alpha,
                         float *z, int64_t ldz, float *out, int64_t ldo, int32_t accumulate_out,
-                        int32_t math_mode, void *stream);
+                        void *workspace, int64_t workspace_bytes, int32_t math_mode, void *stream);
 
 /* ---- K3: dense layer backward ---------------------------------------------------------------
  * Replaces: autograd of the above (train.py:43): with dz = g * act'(z),
@@ -124,7 +128,7 @@ int32_t hgin_linear_fwd(int64_t rows, const float *x1, int64_t ld1, int32_t k1,
  * partials in `workspace`, summed in a fixed order).  Set dW = NULL to skip the weight pass,
  * c1 == c0 to skip the input pass.
  */
-int64_t hgin_linear_bwd_workspace_bytes(int64_t rows, int32_t k, int32_t n);
+int64_t hgin_linear_bwd_workspace_bytes(int64_t rows, int32_t k, int32_t n, int32_t math_mode);
 int32_t hgin_linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, int64_t ldz,
                         int32_t act, const float *alpha, const float *x1, int64_t ld1, int32_t k1,
                         const float *x2, int64_t ld2, int32_t k2, const float *W, int32_t n,
@@ -155,6 +159,17 @@ int32_t hgin_adam_step(int64_t n, float *param, const float *grad, float *exp_av
                        double beta2, double eps, double weight_decay, int32_t decoupled,
                        void *stream);
 int32_t hgin_increment(int32_t *counter, void *stream);
+
+/* ---- diagnostics ------------------------------------------------------------------------------
+ * out[n,k] = a[rows,n]^T * b[rows,k] through the tcgen05 MN-major weight-gradient kernel with the
+ * UMMA shared-memory descriptor fields given explicitly (tests pin the layout with it):
+ * tma_swizzle = CUtensorMapSwizzle value, lbo / sbo / k_step_bytes in bytes, layout_type = UMMA
+ * layout type.  Pass -1 for any field to use the library default.
+ */
+int32_t hgin_debug_gemm_tn(int64_t rows, const float *a, int32_t n, const float *b, int32_t k,
+                           float *out, void *workspace, int64_t workspace_bytes, int32_t tma_swizzle,
+                           int32_t lbo, int32_t sbo, int32_t layout_type, int32_t k_step_bytes,
+                           void *stream);
 
 #ifdef __cplusplus
 }

@@ -195,3 +195,33 @@ def test_unsupported_configurations_fail_loudly():
     dev = Batch.from_data_list([ds[0]]).cuda()
     with pytest.raises(NotImplementedError):
         m(dev.x_dict, dev.edge_index_dict, None)
+
+
+@pytest.mark.parametrize("emb,layers,batch", [(128, 4, 4), (64, 2, 3)])
+def test_tf32_tensor_core_mode_against_oracle(emb, layers, batch):
+    """HGIN_MATH_TF32 (tcgen05 kind::tf32 GEMMs, fp32 aggregation): the north star's reduced-precision
+    bar, rel 1e-2, on scores and gradients."""
+    from gnn_link_prediction_b200.models import MATH_TF32
+    ds = SyntheticDataset(batch, num_topologies=2)
+    samples = [ds[i] for i in range(batch)]
+    cpu_batch = Batch.from_data_list(samples)
+    kw = dict(node_embedding_size=emb, message_passing_layers=layers, dropout=0.0, concat_path=True,
+              bl_features=False, divided_features=False, global_feats=False, mlp_layers=[128, 32],
+              act="torch.nn.PReLU()", mlp_head_act=None, mlp_bn=False)
+    torch.manual_seed(7)
+    ref = hgin_oracle.HetroGIN(input_channels={"link": 7, "path": 7, "node": 3}, **kw)
+    m = HetroGIN(input_channels={"link": 7, "path": 7, "node": 3}, **kw)
+    m.load_state_dict(ref.state_dict())
+    m.cuda().train().set_math_mode(MATH_TF32)
+    y = cpu_batch["path"].y.reshape(-1, 1)
+    o_ref = ref(cpu_batch.x_dict, cpu_batch.edge_index_dict, None)
+    torch.sqrt(hgin_oracle.mape(o_ref, y)).backward()
+    dev = Batch.from_data_list(samples, index_dtype=torch.int32, edge_types=CONV_EDGE_TYPES).cuda()
+    o = m(dev.x_dict, dev.edge_index_dict, dev["path"].batch)
+    close(o, o_ref, rtol=1e-2, atol_rel=1e-2)
+    torch.sqrt(mape(o, dev["path"].y.reshape(-1, 1))).backward()
+    g_ref = {k: p.grad for k, p in ref.named_parameters()}
+    for k, p in m.named_parameters():
+        assert (p.grad is None) == (g_ref[k] is None), k
+        if p.grad is not None:
+            close(p.grad, g_ref[k], rtol=1e-2, atol_rel=1e-2)

@@ -225,3 +225,74 @@ def test_adam_matches_torch_optim(decoupled, wd):
         ops.adam_step(p, grad.cuda(), m, v, step, 1e-3, 0.9, 0.999, 1e-8, wd, decoupled)
     assert int(step.item()) == 6
     torch.testing.assert_close(p.cpu(), ref.detach(), rtol=1e-6, atol=1e-7)
+
+
+# ---- tensor-core path (HGIN_MATH_TF32): tcgen05 kind::tf32, fp32 accumulation ---------------------
+# tf32 keeps 10 mantissa bits: products carry ~2^-11 relative error, so the bar is the north
+# star's "1e-2 under reduced-precision GEMMs" with margin: rtol 5e-3, atol 5e-3 * max|ref|.
+TC_SHAPES = [  # rows, k1, k2, n
+    (4096, 128, 0, 128), (1000, 128, 3, 128), (130, 128, 0, 32), (20000, 64, 0, 128), (777, 32, 0, 16),
+    (5000, 128, 0, 64), (3001, 96, 2, 48)]
+
+
+def _tc_close(got, want, atol_rel=5e-3):
+    torch.testing.assert_close(got.cpu().double(), want, rtol=5e-3, atol=atol_rel * float(want.abs().max()) + 1e-9)
+
+
+@pytest.mark.parametrize("rows,k1,k2,n", TC_SHAPES)
+@pytest.mark.parametrize("act", [ops.ACT_PRELU, ops.ACT_NONE])
+def test_linear_fwd_tf32(rows, k1, k2, n, act):
+    g = torch.Generator().manual_seed(rows + n)
+    x1, x2 = torch.randn(rows, k1, generator=g), (torch.randn(rows, k2, generator=g) if k2 else None)
+    W, b = torch.randn(n, k1 + k2, generator=g) / (k1 + k2) ** 0.5, torch.randn(n, generator=g)
+    alpha = torch.tensor([0.25])
+    x = x1 if x2 is None else torch.cat((x1, x2), 1)
+    z_ref = x.double() @ W.double().t() + b.double()
+    o_ref = torch.where(z_ref > 0, z_ref, 0.25 * z_ref) if act == ops.ACT_PRELU else z_ref
+    z, o = ops.linear_fwd(x1.cuda(), W.cuda(), b.cuda(), x2=None if x2 is None else x2.cuda(), act=act,
+                          alpha=alpha.cuda(), math_mode=ops.MATH_TF32)
+    _tc_close(z, z_ref)
+    _tc_close(o, o_ref)
+    prev = torch.randn(rows, n, generator=g)
+    acc = prev.clone().cuda()
+    ops.linear_fwd(x1.cuda(), W.cuda(), b.cuda(), x2=None if x2 is None else x2.cuda(), act=act, alpha=alpha.cuda(),
+                   out=acc, accumulate_out=True, want_z=False, math_mode=ops.MATH_TF32)
+    _tc_close(acc, prev.double() + o_ref)
+
+
+@pytest.mark.parametrize("rows,k1,k2,n", [s for s in TC_SHAPES if s[1] % 16 == 0])
+@pytest.mark.parametrize("act", [ops.ACT_PRELU, ops.ACT_NONE])
+def test_linear_bwd_tf32(rows, k1, k2, n, act):
+    g = torch.Generator().manual_seed(rows * 3 + n)
+    k = k1 + k2
+    x = torch.randn(rows, k, generator=g, dtype=torch.float64, requires_grad=True)
+    W = (torch.randn(n, k, generator=g, dtype=torch.float64) / k ** 0.5).requires_grad_(True)
+    b = torch.randn(n, generator=g, dtype=torch.float64, requires_grad=True)
+    alpha = torch.tensor([0.25], dtype=torch.float64, requires_grad=True)
+    dot_x = torch.randn(rows, k1, generator=g, dtype=torch.float64)
+    z_ref = x @ W.t() + b
+    o_ref = torch.nn.functional.prelu(z_ref, alpha) if act == ops.ACT_PRELU else z_ref
+    gout = torch.randn(rows, n, generator=g, dtype=torch.float64)
+    o_ref.backward(gout)
+    f32 = lambda t: t.detach().float().cuda()
+    x1, x2 = f32(x[:, :k1]).contiguous(), (f32(x[:, k1:]).contiguous() if k2 else None)
+    r = ops.linear_bwd(f32(gout), f32(z_ref), x1, f32(W), x2=x2, act=act, alpha=f32(alpha), dx_cols=(0, k1),
+                       dot_x=f32(dot_x), want_dalpha=act == ops.ACT_PRELU, math_mode=ops.MATH_TF32)
+    _tc_close(r["dx"], x.grad[:, :k1])
+    _tc_close(r["dW"], W.grad)
+    _tc_close(r["db"], b.grad, atol_rel=1e-4)
+    _tc_close(r["ddot"], (x.grad[:, :k1] * dot_x).sum().view(1), atol_rel=2e-2)
+    if act == ops.ACT_PRELU:
+        _tc_close(r["dalpha"], alpha.grad, atol_rel=1e-4)
+    r2 = ops.linear_bwd(f32(gout), f32(z_ref), x1, f32(W), x2=x2, act=act, alpha=f32(alpha), dx_cols=(0, k1),
+                        math_mode=ops.MATH_TF32)
+    for key in ("dx", "dW", "db"):
+        assert torch.equal(r[key], r2[key]), f"{key} not deterministic"
+
+
+def test_tn_descriptor_default_is_exact_layout():
+    """The MN-major descriptor defaults must reproduce a^T b (tools/sweep_tn_descriptor.py finds them)."""
+    g = torch.Generator().manual_seed(1)
+    a, b = torch.randn(4096, 128, generator=g).cuda(), torch.randn(4096, 128, generator=g).cuda()
+    ref = a.double().t() @ b.double()
+    _tc_close(ops.debug_gemm_tn(a, b), ref.cpu())
