@@ -7,6 +7,7 @@
 // caller's workspace and a second kernel adds the partials in CTA order.
 #include "gemm_simt.cuh"
 #include "linear_tc_api.h"
+#include "linear_thin_api.h"
 
 namespace hgin {
 namespace {
@@ -182,7 +183,9 @@ linear_bwd_dx_kernel(GradZ fa, const float *__restrict__ alpha_ptr, WeightCols f
 }
 
 // ---- weight gradient: partial[cta][n][k] over this CTA's row range; k == K is the bias column --
-template <class T>
+// SWAP = false: tile rows index n (dz columns), tile columns index k; SWAP = true: the roles are
+// exchanged so that a tiny n (the 32 -> 1 readout head) sits on the narrow BN side of the tile.
+template <class T, bool SWAP>
 __global__ void __launch_bounds__(THREADS)
 linear_bwd_dw_kernel(GradZ dzf, const float *__restrict__ alpha_ptr, ConcatRows xf, int want_alpha,
                      int64_t rows_per_cta, float *__restrict__ partials /* [gridDim.x][n][kp] */,
@@ -191,38 +194,40 @@ linear_bwd_dw_kernel(GradZ dzf, const float *__restrict__ alpha_ptr, ConcatRows 
     __shared__ float red[32];
     dzf.alpha = (dzf.act == HGIN_ACT_PRELU) ? __ldg(alpha_ptr) : 0.0f;
     const int kp = xf.k1 + xf.k2 + 1;
-    const int nn0 = blockIdx.y * T::BM;  // output row  = n index
-    const int kk0 = blockIdx.z * T::BN;  // output col  = k index (incl. ones column)
+    const int r0 = blockIdx.y * T::BM;   // tile-row offset (n if !SWAP, k if SWAP)
+    const int q0 = blockIdx.z * T::BN;   // tile-col offset (k if !SWAP, n if SWAP)
     const int64_t mbeg = static_cast<int64_t>(blockIdx.x) * rows_per_cta;
     const int64_t mend = min(mbeg + rows_per_cta, dzf.rows);
     float dalpha = 0.0f;
-    GradZT fa{dzf, &dalpha, want_alpha && blockIdx.z == 0};
-    ConcatColsT fb{xf};
+    // each dz element must feed dalpha exactly once per row range: only the first tile on the x side
+    const bool alpha_here = want_alpha && (SWAP ? blockIdx.y == 0 : blockIdx.z == 0);
+    GradZT fz{dzf, &dalpha, alpha_here};
+    ConcatColsT fx{xf};
     float acc[T::TM][T::TN];
 #pragma unroll
     for (int i = 0; i < T::TM; ++i)
 #pragma unroll
         for (int j = 0; j < T::TN; ++j) acc[i][j] = 0.0f;
-    // accessors bound rows by dzf.rows / xf.rows; restrict to this CTA's range
-    fa.dz.rows = mend;
-    fb.x.rows = mend;
-    if (mbeg < mend) simt::mainloop<T, false, false>(acc, fa, fb, nn0, kk0, mbeg, mend, smem);
-
+    fz.dz.rows = mend;   // accessors bound rows by .rows: restrict to this CTA's range
+    fx.x.rows = mend;
+    if (mbeg < mend) {
+        if (SWAP) simt::mainloop<T, false, false>(acc, fx, fz, r0, q0, mbeg, mend, smem);
+        else simt::mainloop<T, false, false>(acc, fz, fx, r0, q0, mbeg, mend, smem);
+    }
     const int tx = threadIdx.x % T::TX, ty = threadIdx.x / T::TX;
     float *dst = partials + static_cast<int64_t>(blockIdx.x) * dzf.n * kp;
 #pragma unroll
     for (int i = 0; i < T::TM; ++i) {
-        const int n = nn0 + T::row_of(ty, i);
-        if (n >= dzf.n) continue;
 #pragma unroll
         for (int j = 0; j < T::TN; ++j) {
-            const int k = kk0 + T::col_of(tx, j);
-            if (k < kp) dst[static_cast<int64_t>(n) * kp + k] = acc[i][j];
+            const int rr = r0 + T::row_of(ty, i), qq = q0 + T::col_of(tx, j);
+            const int n = SWAP ? qq : rr, k = SWAP ? rr : qq;
+            if (n < dzf.n && k < kp) dst[static_cast<int64_t>(n) * kp + k] = acc[i][j];
         }
     }
-    if (alpha_partials && blockIdx.z == 0) {
+    if (alpha_partials && alpha_here) {
         dalpha = block_sum(dalpha, red);
-        if (threadIdx.x == 0) alpha_partials[blockIdx.y * gridDim.x + blockIdx.x] = dalpha;
+        if (threadIdx.x == 0) alpha_partials[(SWAP ? blockIdx.z : blockIdx.y) * gridDim.x + blockIdx.x] = dalpha;
     }
 }
 
@@ -292,6 +297,8 @@ extern "C" int32_t hgin_linear_fwd(int64_t rows, const float *x1, int64_t ld1, i
     HGIN_CHECK_ARG(ld1 >= k1 && (k2 == 0 || ld2 >= k2) && (!z || ldz >= n) && (!out || ldo >= n),
                    "hgin_linear_fwd: leading dimension too small");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (thin::fwd_eligible(x1, k1, k2, n, z, ldz, out, ldo))
+        return thin::linear_fwd(rows, x1, ld1, k1, W, bias, n, act, alpha, z, ldz, out, ldo, accumulate_out, s);
     if (math_mode == HGIN_MATH_TF32 && tcgemm::fwd_eligible(rows, x1, ld1, k1, k2, n, z, ldz, out, ldo)) {
         if (!workspace || workspace_bytes < tcgemm::fwd_workspace_bytes(k1 + k2, n))
             return fail(HGIN_ERR_WORKSPACE_TOO_SMALL, "hgin_linear_fwd: workspace too small for the tf32 path");
@@ -318,8 +325,10 @@ extern "C" int32_t hgin_linear_fwd(int64_t rows, const float *x1, int64_t ld1, i
 static int64_t simt_bwd_workspace_bytes(int64_t rows, int32_t k, int32_t n) {
     using namespace hgin;
     const int64_t dw = dw_splits(rows) * n * (k + 1) * 4;
-    const int64_t scal = (ceil_div(rows, 128) * ceil_div(k > n ? k : n, 8) + dw_splits(rows) * ceil_div(n, 128)) * 4;
-    return align_up(dw, 256) + align_up(scal, 256) + 512;
+    const int64_t scal = (ceil_div(rows, 128) * ceil_div(k > n ? k : n, 8) + dw_splits(rows) * (ceil_div(n, 8) + 1)) * 4;
+    const int64_t simt = align_up(dw, 256) + align_up(scal, 256) + 512;
+    const int64_t th = thin::bwd_workspace_bytes(n, k);
+    return simt > th ? simt : th;
 }
 
 extern "C" int64_t hgin_linear_bwd_workspace_bytes(int64_t rows, int32_t k, int32_t n, int32_t math_mode) {
@@ -355,6 +364,9 @@ extern "C" int32_t hgin_linear_bwd(int64_t rows, const float *g, int64_t ldg, co
     float *dw_partials = static_cast<float *>(workspace);
     float *scal = reinterpret_cast<float *>(static_cast<char *>(workspace) + align_up(splits * n * (k + 1) * 4, 256));
 
+    if (rows > 0 && thin::bwd_eligible(g, ldg, z, ldz, act, k1, k2, n, c0, c1, dx, dot_x))
+        return thin::linear_bwd(rows, g, ldg, z, ldz, act, alpha, x1, ld1, k1, W, n, c0, c1, dot_x, ld_dot, ddot, dW, db,
+                                dalpha, workspace, static_cast<cudaStream_t>(stream));
     if (math_mode == HGIN_MATH_TF32 && rows > 0 &&
         tcgemm::bwd_eligible(rows, g, ldg, z, ldz, act, x1, ld1, k1, k2, n, c0, c1, dx, lddx, dot_x, ld_dot)) {
         return tcgemm::linear_bwd(rows, g, ldg, z, ldz, act, alpha, x1, ld1, k1, x2, ld2, k2, W, n, c0, c1, dx, lddx,
@@ -401,22 +413,31 @@ extern "C" int32_t hgin_linear_bwd(int64_t rows, const float *g, int64_t ldg, co
         ConcatRows xf{x1, ld1, k1, x2, ld2, k2, rows};
         const int64_t rows_per_cta = align_up(ceil_div(rows, splits), BK);
         const unsigned gx = static_cast<unsigned>(ceil_div(rows, rows_per_cta));
-        const unsigned gy = static_cast<unsigned>(ceil_div(n, 128));
         float *alpha_partials = (dalpha && act == HGIN_ACT_PRELU) ? scal : nullptr;
         const int kp = k + 1;
+        const bool swap = n <= 16 && kp > n;   // tiny n: put it on the narrow side of the tile
+        const int wide = swap ? kp : n, narrow = swap ? n : kp;
+        const unsigned gy = static_cast<unsigned>(ceil_div(wide, 128));
+        unsigned gz = 1;
 #define HGIN_DW(T)                                                                                              \
-    linear_bwd_dw_kernel<T><<<dim3(gx, gy, static_cast<unsigned>(ceil_div(kp, T::BN))), THREADS, 0, s>>>(       \
-        dzf, alpha, xf, alpha_partials != nullptr, rows_per_cta, dw_partials, alpha_partials)
-        if (kp > 64) HGIN_DW(T128);
-        else if (kp > 32) HGIN_DW(T64);
-        else if (kp > 16) HGIN_DW(T32);
-        else if (kp > 8) HGIN_DW(T16);
-        else HGIN_DW(T8);
+    gz = static_cast<unsigned>(ceil_div(narrow, T::BN));                                                        \
+    if (swap)                                                                                                   \
+        linear_bwd_dw_kernel<T, true><<<dim3(gx, gy, gz), THREADS, 0, s>>>(dzf, alpha, xf, alpha_partials != nullptr, \
+                                                                           rows_per_cta, dw_partials, alpha_partials); \
+    else                                                                                                        \
+        linear_bwd_dw_kernel<T, false><<<dim3(gx, gy, gz), THREADS, 0, s>>>(dzf, alpha, xf, alpha_partials != nullptr, \
+                                                                            rows_per_cta, dw_partials, alpha_partials)
+        if (narrow > 64) { HGIN_DW(T128); }
+        else if (narrow > 32) { HGIN_DW(T64); }
+        else if (narrow > 16) { HGIN_DW(T32); }
+        else if (narrow > 8) { HGIN_DW(T16); }
+        else { HGIN_DW(T8); }
 #undef HGIN_DW
+        const unsigned alpha_count = gx * (swap ? gz : gy);
         reduce_dw_kernel<<<grid_for(static_cast<int64_t>(n) * kp, 256, 4), 256, 0, s>>>(dw_partials, static_cast<int>(gx),
                                                                                       n, kp, dW, db);
         if (dalpha) {
-            if (alpha_partials) reduce_scalar_kernel<<<1, 1024, 0, s>>>(alpha_partials, static_cast<int64_t>(gx) * gy, dalpha);
+            if (alpha_partials) reduce_scalar_kernel<<<1, 1024, 0, s>>>(alpha_partials, alpha_count, dalpha);
             else cudaMemsetAsync(dalpha, 0, sizeof(float), s);
         }
     }

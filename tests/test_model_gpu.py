@@ -223,5 +223,13 @@ def test_tf32_tensor_core_mode_against_oracle(emb, layers, batch):
     g_ref = {k: p.grad for k, p in ref.named_parameters()}
     for k, p in m.named_parameters():
         assert (p.grad is None) == (g_ref[k] is None), k
-        if p.grad is not None:
+        if p.grad is None:
+            continue
+        if p.numel() == 1:
+            # d(eps), d(alpha): one number = a sum of ~1e6 signed products that largely cancel, so
+            # tf32 rounding noise (rel 2^-11 per product) is measured against the typical size of
+            # such a gradient, not against its own (possibly tiny) value.
+            scale = max(float(g.abs().max()) for kk, g in g_ref.items() if g is not None and g.numel() == 1)
+            assert abs(float(p.grad) - float(g_ref[k])) <= 1e-2 * scale + 1e-1 * abs(float(g_ref[k])), k
+        else:
             close(p.grad, g_ref[k], rtol=1e-2, atol_rel=1e-2)

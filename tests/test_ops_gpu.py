@@ -296,3 +296,56 @@ def test_tn_descriptor_default_is_exact_layout():
     a, b = torch.randn(4096, 128, generator=g).cuda(), torch.randn(4096, 128, generator=g).cuda()
     ref = a.double().t() @ b.double()
     _tc_close(ops.debug_gemm_tn(a, b), ref.cpu())
+
+
+# ---- thin-contraction kernels (K <= 8): GIN layer 0 and the emb-8 default config -------------------
+@pytest.mark.parametrize("rows,k,n,d0", [(5000, 6, 128, 3), (19600, 6, 8, 3), (1601, 8, 8, 0), (333, 3, 64, 1),
+                                         (70000, 6, 128, 3), (1, 6, 16, 3)])
+@pytest.mark.parametrize("act", [ops.ACT_PRELU, ops.ACT_NONE])
+def test_thin_layer_forward_backward(rows, k, n, d0, act):
+    """One pass computes dW, db, dalpha and d(eps) = sum (dz W)[:, d0:] * dot_x without dx."""
+    g = torch.Generator().manual_seed(rows + n + k)
+    x = torch.randn(rows, k, generator=g, dtype=torch.float64, requires_grad=True)
+    W = (torch.randn(n, k, generator=g, dtype=torch.float64) / k ** 0.5).requires_grad_(True)
+    b = torch.randn(n, generator=g, dtype=torch.float64, requires_grad=True)
+    alpha = torch.tensor([0.25], dtype=torch.float64, requires_grad=True)
+    dot_x = torch.randn(rows, k - d0, generator=g, dtype=torch.float64)
+    z_ref = x @ W.t() + b
+    o_ref = torch.nn.functional.prelu(z_ref, alpha) if act == ops.ACT_PRELU else z_ref
+    gout = torch.randn(rows, n, generator=g, dtype=torch.float64)
+    o_ref.backward(gout)
+    f32 = lambda t: t.detach().float().cuda()
+    z, o = ops.linear_fwd(f32(x), f32(W), f32(b), act=act, alpha=f32(alpha))
+    torch.testing.assert_close(z.cpu().double(), z_ref.detach(), rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(o.cpu().double(), o_ref.detach(), rtol=RTOL, atol=ATOL)
+    r = ops.linear_bwd(f32(gout), z, f32(x), f32(W), act=act, alpha=f32(alpha), dx_cols=(d0, k), want_dx=False,
+                       dot_x=f32(dot_x), want_dalpha=act == ops.ACT_PRELU)
+    scale = rows ** 0.5
+    assert r["dx"] is None
+    torch.testing.assert_close(r["dW"].cpu().double(), W.grad, rtol=RTOL, atol=ATOL * scale)
+    torch.testing.assert_close(r["db"].cpu().double(), b.grad, rtol=RTOL, atol=ATOL * scale)
+    torch.testing.assert_close(r["ddot"].cpu().double(), (x.grad[:, d0:] * dot_x).sum().view(1), rtol=1e-4,
+                               atol=ATOL * scale * (n * k) ** 0.5)
+    if act == ops.ACT_PRELU:
+        torch.testing.assert_close(r["dalpha"].cpu().double(), alpha.grad, rtol=1e-4, atol=ATOL * scale * n ** 0.5)
+    r2 = ops.linear_bwd(f32(gout), z, f32(x), f32(W), act=act, alpha=f32(alpha), dx_cols=(d0, k), want_dx=False,
+                        dot_x=f32(dot_x), want_dalpha=act == ops.ACT_PRELU)
+    for key in ("dW", "db", "ddot"):
+        assert torch.equal(r[key], r2[key]), key
+
+
+def test_head_layer_weight_gradient_swapped_tile():
+    """32 -> 1 readout head: n = 1 sits on the narrow side of the weight-gradient tile."""
+    g = torch.Generator().manual_seed(9)
+    rows, k, n = 30000, 32, 1
+    x = torch.randn(rows, k, generator=g, dtype=torch.float64)
+    W = torch.randn(n, k, generator=g, dtype=torch.float64, requires_grad=True)
+    b = torch.randn(n, generator=g, dtype=torch.float64, requires_grad=True)
+    gout = torch.randn(rows, n, generator=g, dtype=torch.float64)
+    xr = x.clone().requires_grad_(True)
+    (xr @ W.t() + b).backward(gout)
+    f32 = lambda t: t.detach().float().cuda()
+    r = ops.linear_bwd(f32(gout), None, f32(x), f32(W), act=ops.ACT_NONE)
+    torch.testing.assert_close(r["dW"].cpu().double(), W.grad, rtol=RTOL, atol=ATOL * rows ** 0.5)
+    torch.testing.assert_close(r["db"].cpu().double(), b.grad, rtol=RTOL, atol=ATOL * rows ** 0.5)
+    torch.testing.assert_close(r["dx"].cpu().double(), xr.grad, rtol=RTOL, atol=ATOL)
