@@ -13,6 +13,8 @@
 // Neighbour indices are fetched LPR at a time with one coalesced load and handed round by
 // shuffle; the gathers of a batch are issued back to back (UNROLL in flight) before the
 // dependent adds.
+#include <stdlib.h>
+
 #include "hgin_common.cuh"
 
 namespace hgin {
@@ -52,8 +54,8 @@ __device__ __forceinline__ void store_pack(float *p, const Pack<VEC> &r) {
 
 // LPR lanes per row, VEC features per lane per chunk, NC chunks per lane:
 // covers f_src <= LPR * VEC * NC.
-template <int VEC, int LPR, int NC>
-__global__ void __launch_bounds__(256, (VEC * NC <= 4) ? 4 : 1)
+template <int VEC, int LPR, int NC, bool CONTIG, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                    const float *__restrict__ x_src, int64_t ld_src, int f_src,
                    const float *__restrict__ x_self, int64_t ld_self, int f_self,
@@ -71,16 +73,60 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
     // fl(1 + eps): the reference computes (1 + self.eps) as an fp32 tensor op (models.py:213/215).
     const float ope = __fadd_rn(1.0f, eps_ptr ? __ldg(eps_ptr) : 0.0f);
 
-    const int64_t warp_id = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const int64_t num_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    // Row -> warp mapping.
+    // CONTIG (short rows): each CTA owns a CONTIGUOUS block of rows, its warps interleaving inside it.
+    //   Batched datanet graphs are block-diagonal with contiguous ids, so neighbouring rows gather
+    //   from the same few hundred source rows (one topology: 200 link rows = 100 KB), which then stay
+    //   resident in this SM's L1 instead of being re-fetched from L2 ~36 times each.
+    // otherwise (long, heavy-tailed rows): rows are dealt round-robin over all warps of the grid so
+    //   that the tail is spread evenly.
+    const int warps_per_cta = blockDim.x >> 5;
+    int64_t cta_beg, cta_end, stride;
+    if (CONTIG) {
+        const int64_t unit = static_cast<int64_t>(warps_per_cta) * ROWS_PER_WARP;
+        const int64_t rows_per_cta = ((num_rows + gridDim.x - 1) / gridDim.x + unit - 1) / unit * unit;
+        cta_beg = static_cast<int64_t>(blockIdx.x) * rows_per_cta;
+        cta_end = min(cta_beg + rows_per_cta, num_rows);
+        stride = unit;
+    } else {
+        cta_beg = static_cast<int64_t>(blockIdx.x) * warps_per_cta * ROWS_PER_WARP;
+        cta_end = num_rows;
+        stride = static_cast<int64_t>(gridDim.x) * warps_per_cta * ROWS_PER_WARP;
+    }
 
-    for (int64_t row0 = warp_id * ROWS_PER_WARP; row0 < num_rows; row0 += num_warps * ROWS_PER_WARP) {
+    // Software pipeline over this warp's rows.  The dependent chain rowptr -> col -> x_src[col] costs
+    // three memory latencies; with ~3 neighbours per row (link->path) that chain, not bandwidth,
+    // bounds the kernel.  So the row bounds are fetched two iterations ahead and the first batch of
+    // neighbour indices one iteration ahead, leaving only the gather itself exposed.
+    int64_t row0 = cta_beg + static_cast<int64_t>(threadIdx.x >> 5) * ROWS_PER_WARP;
+    auto load_bounds = [&](int64_t r0, int32_t &b, int32_t &l) {
+        const int64_t r = r0 + grp;
+        b = 0;
+        l = 0;
+        if (r < cta_end) {
+            b = __ldg(rowptr + r);
+            l = __ldg(rowptr + r + 1) - b;
+        }
+    };
+    int32_t beg, len, nbeg, nlen;
+    load_bounds(row0, beg, len);
+    load_bounds(row0 + stride, nbeg, nlen);
+    int32_t mine = (sub < len) ? __ldg(col + beg + sub) : -1;
+
+    for (; row0 < cta_end; row0 += stride) {
         const int64_t row = row0 + grp;
-        const bool live = row < num_rows;
-        int32_t beg = 0, len = 0;
-        if (live) {
-            beg = __ldg(rowptr + row);
-            len = __ldg(rowptr + row + 1) - beg;
+        const bool live = row < cta_end;
+        // issue the prefetches for the following rows before touching this row's data
+        const int32_t nmine = (sub < nlen) ? __ldg(col + nbeg + sub) : -1;
+        int32_t nnbeg, nnlen;
+        load_bounds(row0 + 2 * stride, nnbeg, nnlen);
+        Pack<VEC> self_v[NC];
+        if (self_mode == HGIN_SELF_ADD && live) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int f = (c * LPR + sub) * VEC;
+                if (f < f_src) self_v[c] = load_pack<VEC>(x_self + row * ld_self + f);
+            }
         }
         // warp-uniform trip count so the shuffles below are always convergent
         int32_t max_len = len;
@@ -94,8 +140,8 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
             for (int i = 0; i < VEC; ++i) acc[c].v[i] = 0.0f;
 
         for (int32_t base = 0; base < max_len; base += LPR) {
-            // one coalesced index load per group, LPR neighbours at a time
-            const int32_t mine = (base + sub < len) ? __ldg(col + beg + base + sub) : -1;
+            // one coalesced index load per group, LPR neighbours at a time (the first batch was prefetched)
+            if (base > 0) mine = (base + sub < len) ? __ldg(col + beg + base + sub) : -1;
             const int32_t batch = min(LPR, max_len - base);
             for (int32_t j0 = 0; j0 < batch; j0 += UNROLL) {
                 Pack<VEC> v[UNROLL][NC];
@@ -131,37 +177,39 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
             }
         }
 
-        if (!live) continue;
-        float *orow = out + row * ld_out;
+        if (live) {
+            float *orow = out + row * ld_out;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            const int f = (c * LPR + sub) * VEC;
-            if (f >= f_src) continue;
-            Pack<VEC> r = acc[c];
-            if (self_mode == HGIN_SELF_ADD) {
-                const Pack<VEC> xs = load_pack<VEC>(x_self + row * ld_self + f);
+            for (int c = 0; c < NC; ++c) {
+                const int f = (c * LPR + sub) * VEC;
+                if (f >= f_src) continue;
+                Pack<VEC> r = acc[c];
+                if (self_mode == HGIN_SELF_ADD) {
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) r.v[i] = __fadd_rn(r.v[i], __fmul_rn(ope, xs.v[i]));
+                    for (int i = 0; i < VEC; ++i) r.v[i] = __fadd_rn(r.v[i], __fmul_rn(ope, self_v[c].v[i]));
+                }
+                if (accumulate) {
+                    const Pack<VEC> old = load_pack<VEC>(orow + f);
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) r.v[i] = __fadd_rn(old.v[i], r.v[i]);
+                }
+                store_pack<VEC>(orow + f, r);
             }
-            if (accumulate) {
-                const Pack<VEC> old = load_pack<VEC>(orow + f);
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) r.v[i] = __fadd_rn(old.v[i], r.v[i]);
+            if (self_mode == HGIN_SELF_CONCAT) {
+                // [agg | (1+eps) x_self]: the self block starts at column f_src (rarely 16B aligned) -> scalar
+                for (int f = sub; f < f_self; f += LPR) {
+                    float t = __fmul_rn(ope, __ldg(x_self + row * ld_self + f));
+                    if (accumulate) t = __fadd_rn(orow[f_src + f], t);
+                    orow[f_src + f] = t;
+                }
             }
-            store_pack<VEC>(orow + f, r);
         }
-        if (self_mode == HGIN_SELF_CONCAT) {
-            // [agg | (1+eps) x_self]: the self block starts at column f_src (rarely 16B aligned) -> scalar
-            for (int f = sub; f < f_self; f += LPR) {
-                float t = __fmul_rn(ope, __ldg(x_self + row * ld_self + f));
-                if (accumulate) t = __fadd_rn(orow[f_src + f], t);
-                orow[f_src + f] = t;
-            }
-        }
+        beg = nbeg; len = nlen; mine = nmine;
+        nbeg = nnbeg; nlen = nnlen;
     }
 }
 
-template <int VEC, int LPR, int NC>
+template <int VEC, int LPR, int NC, bool CONTIG = false, int MINB = ((VEC * NC <= 4) ? 4 : 1)>
 void launch(int64_t num_rows, const int32_t *rowptr, const int32_t *col, const float *x_src, int64_t ld_src,
             int f_src, const float *x_self, int64_t ld_self, int f_self, const float *eps, int self_mode,
             int accumulate, float *out, int64_t ld_out, cudaStream_t s) {
@@ -169,15 +217,15 @@ void launch(int64_t num_rows, const int32_t *rowptr, const int32_t *col, const f
     // Grid-stride over rows with whole waves of CTAs: enough CTAs (32 per SM) that the hardware
     // scheduler evens out the heavy-tailed row lengths of the path->link relation.
     const int grid = grid_for(num_rows, rows_per_cta, 32);
-    gin_combine_kernel<VEC, LPR, NC><<<grid, 256, 0, s>>>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self,
+    gin_combine_kernel<VEC, LPR, NC, CONTIG, MINB><<<grid, 256, 0, s>>>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self,
                                                           ld_self, f_self, eps, self_mode, accumulate, out, ld_out);
 }
 
 }  // namespace
 }  // namespace hgin
 
-extern "C" int32_t hgin_gin_combine(int64_t num_rows, const int32_t *rowptr, const int32_t *col, const float *x_src,
-                                    int64_t ld_src, int32_t f_src, const float *x_self, int64_t ld_self,
+extern "C" int32_t hgin_gin_combine(int64_t num_rows, const int32_t *rowptr, const int32_t *col, int64_t num_edges,
+                                    const float *x_src, int64_t ld_src, int32_t f_src, const float *x_self, int64_t ld_self,
                                     int32_t f_self, const float *eps, int32_t self_mode, int32_t accumulate,
                                     float *out, int64_t ld_out, void *stream) {
     using namespace hgin;
@@ -202,9 +250,22 @@ extern "C" int32_t hgin_gin_combine(int64_t num_rows, const int32_t *rowptr, con
 #define HGIN_LAUNCH(V, L, N)                                                                                    \
     launch<V, L, N>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode,      \
                     accumulate, out, ld_out, s)
+    // Lanes per row: a full warp per row suits long rows (path->link, ~36 neighbours); for short
+    // rows (link->path, ~3 neighbours) the per-row latency chain rowptr -> col -> gather dominates,
+    // so several rows share a warp and each lane carries more 128-bit chunks.
+    const double avg_len = (num_edges >= 0 && num_rows > 0) ? static_cast<double>(num_edges) / num_rows : 1e9;
+    static const int force_lpr = getenv("HGIN_COMBINE_LPR") ? atoi(getenv("HGIN_COMBINE_LPR")) : 0;
     if (vec4) {
         const int chunks = f_src / 4;
-        if (chunks <= 1) HGIN_LAUNCH(4, 1, 1);
+        // Measured on B200 (profiles/): 2.5 M rows x ~3 neighbours, F = 128: warp/row 1.10 ms ->
+        // half-warp/row + contiguous CTA ranges + pipelined indices 0.60 ms; long rows keep warp/row.
+        int lpr = chunks <= 32 ? chunks : 32;
+        const bool short_rows = avg_len <= 8.0;
+        if ((chunks == 32 || chunks == 16) && short_rows) lpr = chunks / 2;
+        if (force_lpr > 0 && (chunks == 32 || chunks == 16) && (force_lpr == chunks || force_lpr == chunks / 2)) lpr = force_lpr;
+        if (chunks == 32 && lpr == 16) launch<4, 16, 2, true, 4>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, accumulate, out, ld_out, s);
+        else if (chunks == 16 && lpr == 8) launch<4, 8, 2, true, 4>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, accumulate, out, ld_out, s);
+        else if (chunks <= 1) HGIN_LAUNCH(4, 1, 1);
         else if (chunks <= 2) HGIN_LAUNCH(4, 2, 1);
         else if (chunks <= 4) HGIN_LAUNCH(4, 4, 1);
         else if (chunks <= 8) HGIN_LAUNCH(4, 8, 1);

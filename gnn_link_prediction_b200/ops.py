@@ -133,7 +133,7 @@ def gin_combine(csr, x_src, x_self=None, eps=None, self_mode=SELF_NONE, out=None
     big = csr.num_cols * f_src * 4 > L2_BYTES
     with _region("gin_combine", kernels=1, alg_bytes=alg, compulsory_bytes=comp,
                  roofline_bytes=alg if big else comp):
-        check(_lib.load().hgin_gin_combine(csr.num_rows, csr.rowptr.data_ptr(), _ptr(csr.col), ps, lds, f_src, pf,
+        check(_lib.load().hgin_gin_combine(csr.num_rows, csr.rowptr.data_ptr(), _ptr(csr.col), csr.num_edges, ps, lds, f_src, pf,
                                            ldf, f_self, _scalar(eps, "gin_combine.eps"), self_mode,
                                            1 if accumulate else 0, po, ldo, _stream()), "hgin_gin_combine")
     return out

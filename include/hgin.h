@@ -86,11 +86,13 @@ int32_t hgin_csr_build(const void *edge_index, int32_t index_bytes, int64_t num_
  * no atomics — bit-exact with the CPU reference):
  *     agg[f]  = sum_{e in [rowptr[r], rowptr[r+1])} x_src[col[e]*ld_src + f]        f < f_src
  *     out row = per `self_mode` above; `accumulate` != 0 adds the result to `out` instead.
+ * num_edges: rowptr[num_rows] as known to the host (scheduling hint only: picks lanes per row
+ * from the mean row length; pass -1 if unknown).
  * eps: device pointer to the learnable scalar (models.py:191-194) or NULL for eps = 0.
  * HGIN_SELF_ADD needs f_self == f_src.  x_self may be NULL only with HGIN_SELF_NONE.
  */
 int32_t hgin_gin_combine(int64_t num_rows, const int32_t *rowptr, const int32_t *col,
-                         const float *x_src, int64_t ld_src, int32_t f_src,
+                         int64_t num_edges, const float *x_src, int64_t ld_src, int32_t f_src,
                          const float *x_self, int64_t ld_self, int32_t f_self,
                          const float *eps, int32_t self_mode, int32_t accumulate,
                          float *out, int64_t ld_out, void *stream);

@@ -31,7 +31,7 @@ def test_argument_errors_do_not_need_a_gpu(built):
     assert built.hgin_csr_workspace_bytes(-1, 4) == -1
     rc = built.hgin_csr_build(None, 3, 0, 0, 1, 0, 0, None, None, None, None, None, 0, None)
     assert rc == -1 and b"index_bytes" in built.hgin_last_error()
-    rc = built.hgin_gin_combine(4, None, None, None, 0, 0, None, 0, 0, None, 0, 0, None, 0, None)
+    rc = built.hgin_gin_combine(4, None, None, -1, None, 0, 0, None, 0, 0, None, 0, 0, None, 0, None)
     assert rc == -1 and b"f_src" in built.hgin_last_error()
     with pytest.raises(_lib.HginError):
         _lib.check(rc, "hgin_gin_combine")
