@@ -186,7 +186,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfgC", choices=sorted(WORKLOADS) + ["cfgD"])
-    ap.add_argument("--math", default="fp32", choices=["fp32", "tf32"])
+    ap.add_argument("--math", default=None, choices=["fp32", "tf32"],
+                    help="dense-layer arithmetic; default tf32 tensor cores for cfgC (BASELINE configs[2] allows "
+                         "reduced-precision MLP GEMMs), fp32 for cfgA")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -197,14 +199,16 @@ def main():
         import bench_conv
         return bench_conv.main(args)
     w = WORKLOADS[args.workload]
+    if args.math is None:
+        args.math = "tf32" if args.workload == "cfgC" else "fp32"
     if args.impl == "reference":
         return run_reference(args, w, rank)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from gnn_link_prediction_b200.parallel import Communicator
+    comm = Communicator.from_env("nccl")
     from gnn_link_prediction_b200 import ops
     from gnn_link_prediction_b200.models import HetroGIN, MATH_FP32, MATH_TF32
     from gnn_link_prediction_b200.profiling import KernelTimer
@@ -219,7 +223,7 @@ def main():
     torch.manual_seed(1997)
     model = HetroGIN(input_channels={"link": 7, "path": 7, "node": 3}, **model_kwargs(w)).cuda().train()
     model.set_math_mode(MATH_TF32 if args.math == "tf32" else MATH_FP32)
-    step = TrainStep(model, lr=1e-3, distributed=world > 1)
+    step = TrainStep(model, lr=1e-3, communicator=comm)
     dev_batches = [copy_batch_to_device(h) for h in host]
     torch.cuda.synchronize()
 
@@ -227,8 +231,7 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda") if small else None
 
     def barrier():
-        if world > 1:
-            torch.distributed.barrier()
+        comm.barrier()
         torch.cuda.synchronize()
 
     # ---- device-resident arm ("value") ----------------------------------------------------------
@@ -267,8 +270,7 @@ def main():
 
     # max over ranks (device time)
     t = torch.tensor([resident_ms, e2e_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    comm.all_reduce_max_(t)
     resident_ms, e2e_ms = (float(v) for v in t.tolist())
     if rank != 0:
         if world > 1:
@@ -303,7 +305,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "graphs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": resident_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32" if args.math == "fp32" else "tf32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32" if args.math == "fp32" else "tf32 (dense layers; f32 aggregation and accumulation)", "data": "synthetic",
         "config": {"workload": args.workload, "desc": w["desc"], "emb": w["emb"], "layers": w["layers"],
                    "graphs_per_gpu_per_step": graphs, "edges_per_gpu_per_step": edges,
                    "l2": "flushed between timed steps" if small else "inputs+activations larger than L2",

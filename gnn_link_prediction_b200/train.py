@@ -12,6 +12,7 @@ import torch
 
 from . import ops
 from .models import HetroGIN
+from .parallel import Communicator
 
 
 def mape(preds, actuals):
@@ -95,15 +96,13 @@ class TrainStep:
     """
 
     def __init__(self, model: HetroGIN, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
-                 optimizer="adam", process_group=None, distributed=None):
+                 optimizer="adam", communicator=None):
         if optimizer not in ("adam", "adamW"):
             raise NotImplementedError("TrainStep fuses Adam/AdamW; use train_one_epoch with torch.optim.SGD")
         self.model = model
         self.hyper = dict(lr=lr, beta1=betas[0], beta2=betas[1], eps=eps, weight_decay=weight_decay,
                           decoupled=optimizer == "adamW")
-        self.pg = process_group
-        self.distributed = (torch.distributed.is_available() and torch.distributed.is_initialized()
-                            if distributed is None else distributed)
+        self.comm = communicator if communicator is not None else Communicator()
         live_mods = set()
         for li, rels in enumerate(model.live_relations(HetroGIN.RELATIONS)):
             for et in rels:
@@ -126,10 +125,6 @@ class TrainStep:
                 p.data = self.flat_p[off:off + p.numel()].view_as(p)
                 off += p.numel()
 
-    def _allreduce(self, t):
-        if self.distributed:
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.pg)
-
     def __call__(self, batch):
         """`batch` already resident on the GPU.  Returns a CUDA tensor [mape, sqrt(mape)] (global)."""
         model = self.model
@@ -138,11 +133,11 @@ class TrainStep:
         out = model(batch.x_dict, batch.edge_index_dict, batch["path"].batch)
         y = batch["path"].y
         sums = ops.mape_sum(out.detach(), y)
-        self._allreduce(sums)
+        self.comm.all_reduce_sum_(sums)          # global (S, N): every rank differentiates the same loss
         loss_out, dpred = ops.sqrt_mape_bwd(out.detach(), y, sums)
         out.backward(dpred)
         torch.cat([p.grad.reshape(-1) for p in self.live], out=self.flat_g)
-        self._allreduce(self.flat_g)
+        self.comm.all_reduce_sum_(self.flat_g)   # SUM of partial gradients (no division by world size)
         ops.increment(self.step_count)
         ops.adam_step(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, self.step_count, **self.hyper)
         return loss_out
