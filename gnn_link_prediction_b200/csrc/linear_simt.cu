@@ -297,6 +297,8 @@ extern "C" int32_t hgin_linear_fwd(int64_t rows, const float *x1, int64_t ld1, i
     HGIN_CHECK_ARG(ld1 >= k1 && (k2 == 0 || ld2 >= k2) && (!z || ldz >= n) && (!out || ldo >= n),
                    "hgin_linear_fwd: leading dimension too small");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (thin::head_fwd_eligible(x1, ld1, k1, k2, n) && aligned16(W))
+        return thin::head_fwd(rows, x1, ld1, k1, W, bias, act, alpha, z, ldz, out, ldo, accumulate_out, s);
     if (thin::fwd_eligible(x1, k1, k2, n, z, ldz, out, ldo))
         return thin::linear_fwd(rows, x1, ld1, k1, W, bias, n, act, alpha, z, ldz, out, ldo, accumulate_out, s);
     if (math_mode == HGIN_MATH_TF32 && tcgemm::fwd_eligible(rows, x1, ld1, k1, k2, n, z, ldz, out, ldo)) {
@@ -364,6 +366,9 @@ extern "C" int32_t hgin_linear_bwd(int64_t rows, const float *g, int64_t ldg, co
     float *dw_partials = static_cast<float *>(workspace);
     float *scal = reinterpret_cast<float *>(static_cast<char *>(workspace) + align_up(splits * n * (k + 1) * 4, 256));
 
+    if (rows > 0 && thin::head_bwd_eligible(x1, ld1, k1, k2, n, c0, c1, dx, lddx, dot_x, W) && !ddot)
+        return thin::head_bwd(rows, g, ldg, z, ldz, act, alpha, x1, ld1, k1, W, dx, lddx, dW, db, dalpha, workspace,
+                              static_cast<cudaStream_t>(stream));
     if (rows > 0 && thin::bwd_eligible(g, ldg, z, ldz, act, k1, k2, n, c0, c1, dx, dot_x))
         return thin::linear_bwd(rows, g, ldg, z, ldz, act, alpha, x1, ld1, k1, W, n, c0, c1, dot_x, ld_dot, ddot, dW, db,
                                 dalpha, workspace, static_cast<cudaStream_t>(stream));

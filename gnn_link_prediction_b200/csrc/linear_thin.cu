@@ -144,37 +144,48 @@ thin_bwd_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, const fl
     if (threadIdx.x == 0 && alpha_part) alpha_part[blockIdx.x] = da;
 }
 
-// dW / db from the partials; ddot = sum_{n,c} W[n][c0+c] * T[n][c]; dalpha = sum of alpha partials.
-__global__ void __launch_bounds__(1024)
-thin_finalize_kernel(const float *__restrict__ part, int num_part, int n, int k, int d, const float *__restrict__ W,
-                     int c0, float *__restrict__ dW, float *__restrict__ db, float *__restrict__ ddot,
-                     const float *__restrict__ alpha_part, float *__restrict__ dalpha) {
-    __shared__ float red[32];
+// Stage 2a (grid): out[i] = sum over CTAs of part[cta][i] (fixed association); columns [0,k) -> dW,
+// [k,k+d) -> tbuf (T = dz^T dot_x), k+d -> db.
+__global__ void __launch_bounds__(256)
+thin_finalize_kernel(const float *__restrict__ part, int num_part, int n, int k, int d, float *__restrict__ dW,
+                     float *__restrict__ db, float *__restrict__ tbuf) {
     const int kp = k + d + 1;
     const int total = n * kp;
-    float dot = 0.0f;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;   // four independent chains, fixed association
-        int p = 0;
-        for (; p + 3 < num_part; p += 4) {
-            s0 += part[static_cast<int64_t>(p) * total + i];
-            s1 += part[static_cast<int64_t>(p + 1) * total + i];
-            s2 += part[static_cast<int64_t>(p + 2) * total + i];
-            s3 += part[static_cast<int64_t>(p + 3) * total + i];
-        }
-        for (; p < num_part; ++p) s0 += part[static_cast<int64_t>(p) * total + i];
-        const float s = (s0 + s1) + (s2 + s3);
-        const int nn = i / kp, c = i % kp;
-        if (c < k) {
-            if (dW) dW[nn * k + c] = s;
-        } else if (c < k + d) {
-            dot = fmaf(__ldg(W + nn * k + c0 + (c - k)), s, dot);
-        } else if (db) {
-            db[nn] = s;
-        }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;   // four independent chains, fixed association
+    int p = 0;
+    for (; p + 3 < num_part; p += 4) {
+        s0 += part[static_cast<int64_t>(p) * total + i];
+        s1 += part[static_cast<int64_t>(p + 1) * total + i];
+        s2 += part[static_cast<int64_t>(p + 2) * total + i];
+        s3 += part[static_cast<int64_t>(p + 3) * total + i];
     }
-    dot = block_sum(dot, red);
-    if (threadIdx.x == 0 && ddot) ddot[0] = dot;
+    for (; p < num_part; ++p) s0 += part[static_cast<int64_t>(p) * total + i];
+    const float s = (s0 + s1) + (s2 + s3);
+    const int nn = i / kp, c = i % kp;
+    if (c < k) {
+        if (dW) dW[nn * k + c] = s;
+    } else if (c < k + d) {
+        tbuf[nn * d + (c - k)] = s;
+    } else if (db) {
+        db[nn] = s;
+    }
+}
+
+// Stage 2b (one CTA): ddot = sum_{n,c} W[n][c0+c] * T[n][c];  dalpha = sum of the CTA partials.
+__global__ void __launch_bounds__(256)
+thin_scalars_kernel(const float *__restrict__ tbuf, int n, int k, int d, const float *__restrict__ W, int c0,
+                    float *__restrict__ ddot, const float *__restrict__ alpha_part, int num_part,
+                    float *__restrict__ dalpha) {
+    __shared__ float red[32];
+    if (ddot) {
+        float dot = 0.0f;
+        for (int i = threadIdx.x; i < n * d; i += blockDim.x)
+            dot = fmaf(__ldg(W + (i / d) * k + c0 + i % d), tbuf[i], dot);
+        dot = block_sum(dot, red);
+        if (threadIdx.x == 0) ddot[0] = dot;
+    }
     if (dalpha) {
         float s = 0.0f;
         if (alpha_part)
@@ -182,6 +193,85 @@ thin_finalize_kernel(const float *__restrict__ part, int num_part, int n, int k,
         s = block_sum(s, red);
         if (threadIdx.x == 0) dalpha[0] = s;
     }
+}
+
+// ---- readout head: n = 1 output column (models.py:328), k <= 128 ---------------------------------
+// k/4 lanes per row, each owning 4 input columns: forward is a segmented dot product, backward
+// streams g, z, x once and produces dx = dz * w, dW = sum_m dz x, db, dalpha.
+__global__ void __launch_bounds__(THREADS)
+head_fwd_kernel(int64_t rows, const float *__restrict__ x, int64_t ldx, int k, const float *__restrict__ W,
+                const float *__restrict__ bias, int act, const float *__restrict__ alpha_ptr, float *__restrict__ z,
+                int64_t ldz, float *__restrict__ out, int64_t ldo, int accumulate_out) {
+    const int lpr = k >> 2;
+    const int cg = threadIdx.x % lpr;
+    const int64_t slots = (static_cast<int64_t>(gridDim.x) * THREADS) / lpr;
+    const int64_t slot = (static_cast<int64_t>(blockIdx.x) * THREADS + threadIdx.x) / lpr;
+    const float4 w = __ldg(reinterpret_cast<const float4 *>(W) + cg);
+    const float b = bias ? __ldg(bias) : 0.0f;
+    const float alpha = act == HGIN_ACT_PRELU ? __ldg(alpha_ptr) : 0.0f;
+    const int64_t iters = (rows + slots - 1) / slots;   // warp-uniform trip count for the shuffles
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t m = it * slots + slot;
+        float s = 0.0f;
+        if (m < rows) {
+            const float4 xv = __ldg(reinterpret_cast<const float4 *>(x + m * ldx) + cg);
+            s = fmaf(xv.x, w.x, fmaf(xv.y, w.y, fmaf(xv.z, w.z, xv.w * w.w)));
+        }
+        for (int o = lpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (m < rows && cg == 0) {
+            const float zz = s + b;
+            if (z) z[m * ldz] = zz;
+            if (out) {
+                const float o = act_forward(zz, act, alpha);
+                out[m * ldo] = accumulate_out ? out[m * ldo] + o : o;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(THREADS)
+head_bwd_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, const float *__restrict__ z, int64_t ldz,
+                int act, const float *__restrict__ alpha_ptr, const float *__restrict__ x, int64_t ldx, int k,
+                const float *__restrict__ W, float *__restrict__ dx, int64_t lddx, float *__restrict__ part,
+                float *__restrict__ alpha_part) {
+    __shared__ float sm[THREADS * 5];
+    __shared__ float red[32];
+    const int lpr = k >> 2;
+    const int cg = threadIdx.x % lpr;
+    const int grp = threadIdx.x / lpr;
+    const int slots_per_cta = THREADS / lpr;
+    const int64_t slots = static_cast<int64_t>(gridDim.x) * slots_per_cta;
+    const float4 w = __ldg(reinterpret_cast<const float4 *>(W) + cg);
+    const float alpha = act == HGIN_ACT_PRELU ? __ldg(alpha_ptr) : 0.0f;
+    float aw[4] = {0.f, 0.f, 0.f, 0.f}, adb = 0.0f, adal = 0.0f;
+    for (int64_t m = static_cast<int64_t>(blockIdx.x) * slots_per_cta + grp; m < rows; m += slots) {
+        float dz = __ldg(g + m * ldg);
+        if (act != HGIN_ACT_NONE) {
+            const float zv = __ldg(z + m * ldz);
+            if (cg == 0 && act == HGIN_ACT_PRELU && !(zv > 0.0f)) adal += dz * zv;
+            dz = act_backward(dz, zv, act, alpha);
+        }
+        const float4 xv = __ldg(reinterpret_cast<const float4 *>(x + m * ldx) + cg);
+        aw[0] = fmaf(dz, xv.x, aw[0]); aw[1] = fmaf(dz, xv.y, aw[1]);
+        aw[2] = fmaf(dz, xv.z, aw[2]); aw[3] = fmaf(dz, xv.w, aw[3]);
+        if (cg == 0) adb += dz;
+        if (dx) reinterpret_cast<float4 *>(dx + m * lddx)[cg] = make_float4(dz * w.x, dz * w.y, dz * w.z, dz * w.w);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sm[threadIdx.x * 5 + j] = aw[j];
+    sm[threadIdx.x * 5 + 4] = adb;
+    __syncthreads();
+    float *dst = part + static_cast<int64_t>(blockIdx.x) * (k + 1);   // [k | db]
+    for (int idx = threadIdx.x; idx < lpr * 5; idx += THREADS) {
+        const int c_g = idx / 5, j = idx % 5;
+        float s = 0.0f;
+        for (int sl = 0; sl < slots_per_cta; ++sl) s += sm[(sl * lpr + c_g) * 5 + j];
+        if (j < 4) dst[c_g * 4 + j] = s;
+        else if (c_g == 0) dst[k] = s;
+    }
+    __syncthreads();
+    const float da = block_sum(adal, red);
+    if (threadIdx.x == 0 && alpha_part) alpha_part[blockIdx.x] = da;
 }
 
 inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -208,7 +298,10 @@ bool bwd_eligible(const float *g, int64_t ldg, const float *z, int64_t ldz, int 
 }
 
 int64_t bwd_workspace_bytes(int n, int k) {
-    return align_up(static_cast<int64_t>(kNumSMs) * 4 * (static_cast<int64_t>(n) * (k + DMAX + 1) + 1) * 4, 256) + 256;
+    const int64_t ctas = static_cast<int64_t>(kNumSMs) * 4;
+    const int64_t thin = ctas * (static_cast<int64_t>(n) * ((k < KMAX ? k : KMAX) + DMAX + 1) + 1) + static_cast<int64_t>(n) * DMAX;
+    const int64_t head = ctas * (k + 2) + 8;
+    return align_up((thin > head ? thin : head) * 4, 256) + 256;
 }
 
 int32_t linear_fwd(int64_t rows, const float *x, int64_t ldx, int k, const float *W, const float *bias, int n, int act,
@@ -230,9 +323,47 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
     const bool want_alpha = dalpha && act == HGIN_ACT_PRELU;
     thin_bwd_kernel<<<ctas, THREADS, 0, s>>>(rows, g, ldg, z, ldz, act, alpha, x, ldx, k, dot_x, ld_dot, d, n, part,
                                              want_alpha ? alpha_part : nullptr);
-    thin_finalize_kernel<<<1, 1024, 0, s>>>(part, ctas, n, k, d, W, c0, dW, db, ddot, want_alpha ? alpha_part : nullptr,
-                                            dalpha);
+    float *tbuf = alpha_part + ctas;
+    const int total = n * (k + d + 1);
+    thin_finalize_kernel<<<static_cast<unsigned>(ceil_div(total, 256)), 256, 0, s>>>(part, ctas, n, k, d, dW, db, tbuf);
+    if (ddot || dalpha)
+        thin_scalars_kernel<<<1, 256, 0, s>>>(tbuf, n, k, d, W, c0, ddot, want_alpha ? alpha_part : nullptr, ctas,
+                                              dalpha);
     HGIN_CHECK_LAUNCH("hgin_linear_bwd(thin)");
+    return HGIN_OK;
+}
+
+bool head_fwd_eligible(const float *x1, int64_t ld1, int k1, int k2, int n) {
+    return n == 1 && k2 == 0 && k1 >= 4 && k1 <= 128 && k1 % 4 == 0 && pow2(k1 >> 2) && ld1 % 4 == 0 && aligned16(x1);
+}
+
+bool head_bwd_eligible(const float *x1, int64_t ld1, int k1, int k2, int n, int c0, int c1, const float *dx,
+                       int64_t lddx, const float *dot_x, const float *W) {
+    return head_fwd_eligible(x1, ld1, k1, k2, n) && dot_x == nullptr && aligned16(W) &&
+           (dx == nullptr || (c0 == 0 && c1 == k1 && lddx % 4 == 0 && aligned16(dx))) && (c1 == c0 || dx != nullptr);
+}
+
+int32_t head_fwd(int64_t rows, const float *x, int64_t ldx, int k, const float *W, const float *bias, int act,
+                 const float *alpha, float *z, int64_t ldz, float *out, int64_t ldo, int accumulate_out, cudaStream_t s) {
+    head_fwd_kernel<<<thin_ctas(rows, k), THREADS, 0, s>>>(rows, x, ldx, k, W, bias, act, alpha, z, ldz, out, ldo,
+                                                          accumulate_out);
+    HGIN_CHECK_LAUNCH("hgin_linear_fwd(head)");
+    return HGIN_OK;
+}
+
+int32_t head_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, int64_t ldz, int act, const float *alpha,
+                 const float *x, int64_t ldx, int k, const float *W, float *dx, int64_t lddx, float *dW, float *db,
+                 float *dalpha, void *workspace, cudaStream_t s) {
+    const int ctas = thin_ctas(rows, k);
+    float *part = static_cast<float *>(workspace);
+    float *alpha_part = part + static_cast<int64_t>(ctas) * (k + 1);
+    float *tbuf = alpha_part + ctas;
+    const bool want_alpha = dalpha && act == HGIN_ACT_PRELU;
+    head_bwd_kernel<<<ctas, THREADS, 0, s>>>(rows, g, ldg, z, ldz, act, alpha, x, ldx, k, W, dx, lddx, part,
+                                             want_alpha ? alpha_part : nullptr);
+    thin_finalize_kernel<<<static_cast<unsigned>(ceil_div(k + 1, 256)), 256, 0, s>>>(part, ctas, 1, k, 0, dW, db, tbuf);
+    if (dalpha) thin_scalars_kernel<<<1, 256, 0, s>>>(tbuf, 1, k, 0, W, 0, nullptr, want_alpha ? alpha_part : nullptr, ctas, dalpha);
+    HGIN_CHECK_LAUNCH("hgin_linear_bwd(head)");
     return HGIN_OK;
 }
 

@@ -18,5 +18,15 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
                    const float *x, int64_t ldx, int k, const float *W, int n, int c0, int c1, const float *dot_x,
                    int64_t ld_dot, float *ddot, float *dW, float *db, float *dalpha, void *workspace, cudaStream_t s);
 
+// n = 1 head (Linear(k, 1), models.py:328)
+bool head_fwd_eligible(const float *x1, int64_t ld1, int k1, int k2, int n);
+bool head_bwd_eligible(const float *x1, int64_t ld1, int k1, int k2, int n, int c0, int c1, const float *dx,
+                       int64_t lddx, const float *dot_x, const float *W);
+int32_t head_fwd(int64_t rows, const float *x, int64_t ldx, int k, const float *W, const float *bias, int act,
+                 const float *alpha, float *z, int64_t ldz, float *out, int64_t ldo, int accumulate_out, cudaStream_t s);
+int32_t head_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, int64_t ldz, int act, const float *alpha,
+                 const float *x, int64_t ldx, int k, const float *W, float *dx, int64_t lddx, float *dW, float *db,
+                 float *dalpha, void *workspace, cudaStream_t s);
+
 }  // namespace thin
 }  // namespace hgin

@@ -178,3 +178,49 @@ class DataLoader:
             batch = Batch.from_data_list([self.dataset[i] for i in order[lo:lo + self.batch_size]],
                                          index_dtype=self.index_dtype, edge_types=self.edge_types)
             yield batch.pin_memory() if self.pin_memory else batch
+
+
+class DevicePrefetcher:
+    """Iterates device-resident batches while the NEXT batch's host->device copy runs on a side
+    stream, hidden behind the current step (what `DataLoader(pin_memory=True)` + `non_blocking`
+    buys a PyTorch training loop; the reference copies synchronously with `sample.cuda()`,
+    train.py:28).  Source batches should be pinned (`DataLoader(..., pin_memory=True)`).
+
+        for batch in DevicePrefetcher(loader):        # batch tensors already live on the GPU
+            loss = step(batch)
+    """
+
+    def __init__(self, batches, device=None):
+        self.source = batches
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+
+    def _stage(self, host):
+        if host is None:
+            return None
+        dev = Batch()
+        with torch.cuda.stream(self.stream):
+            for nt in host.node_types:
+                for k, v in host[nt].items():
+                    dev[nt][k] = v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) else v
+            for et in host.edge_types:
+                for k, v in host[et].items():
+                    dev[et][k] = v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) else v
+            ready = torch.cuda.Event()
+            ready.record(self.stream)
+        dev.__dict__["num_graphs"] = getattr(host, "num_graphs", None)
+        return dev, ready
+
+    def __iter__(self):
+        it = iter(self.source)
+        staged = self._stage(next(it, None))
+        while staged is not None:
+            dev, ready = staged
+            staged = self._stage(next(it, None))        # next copy overlaps this batch's step
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(ready)
+            for store in list(dev._nodes.values()) + list(dev._edges.values()):
+                for v in store.values():
+                    if isinstance(v, torch.Tensor):
+                        v.record_stream(cur)                # allocator: memory is in use on `cur`
+            yield dev

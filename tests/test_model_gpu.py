@@ -233,3 +233,20 @@ def test_tf32_tensor_core_mode_against_oracle(emb, layers, batch):
             assert abs(float(p.grad) - float(g_ref[k])) <= 1e-2 * scale + 1e-1 * abs(float(g_ref[k])), k
         else:
             close(p.grad, g_ref[k], rtol=1e-2, atol_rel=1e-2)
+
+
+def test_device_prefetcher_yields_identical_batches():
+    from gnn_link_prediction_b200.data import DataLoader, DevicePrefetcher
+    ds = SyntheticDataset(5, num_nodes=9, num_links=12, num_topologies=2)
+    loader = DataLoader(ds, batch_size=2, pin_memory=True, index_dtype=torch.int32, edge_types=CONV_EDGE_TYPES)
+    host = list(loader)
+    got = list(DevicePrefetcher(loader))
+    torch.cuda.synchronize()
+    assert len(got) == len(host) == 3
+    for h, d in zip(host, got):
+        assert d.num_graphs == h.num_graphs
+        for nt in h.node_types:
+            for k, v in h[nt].items():
+                assert d[nt][k].is_cuda and torch.equal(d[nt][k].cpu(), v)
+        for et in h.edge_types:
+            assert torch.equal(d[et].edge_index.cpu(), h[et].edge_index)

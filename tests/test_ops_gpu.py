@@ -334,10 +334,12 @@ def test_thin_layer_forward_backward(rows, k, n, d0, act):
         assert torch.equal(r[key], r2[key]), key
 
 
-def test_head_layer_weight_gradient_swapped_tile():
-    """32 -> 1 readout head: n = 1 sits on the narrow side of the weight-gradient tile."""
+@pytest.mark.parametrize("k", [32, 128, 24])
+def test_head_layer(k):
+    """k -> 1 readout head (models.py:328): streaming head kernels when k/4 is a power of two,
+    otherwise the SIMT engine with n = 1 on the narrow side of the weight-gradient tile."""
     g = torch.Generator().manual_seed(9)
-    rows, k, n = 30000, 32, 1
+    rows, n = 30000, 1
     x = torch.randn(rows, k, generator=g, dtype=torch.float64)
     W = torch.randn(n, k, generator=g, dtype=torch.float64, requires_grad=True)
     b = torch.randn(n, generator=g, dtype=torch.float64, requires_grad=True)
@@ -345,6 +347,8 @@ def test_head_layer_weight_gradient_swapped_tile():
     xr = x.clone().requires_grad_(True)
     (xr @ W.t() + b).backward(gout)
     f32 = lambda t: t.detach().float().cuda()
+    z, o = ops.linear_fwd(f32(x), f32(W), f32(b))
+    torch.testing.assert_close(o.cpu().double(), (x @ W.t() + b).detach(), rtol=RTOL, atol=ATOL)
     r = ops.linear_bwd(f32(gout), None, f32(x), f32(W), act=ops.ACT_NONE)
     torch.testing.assert_close(r["dW"].cpu().double(), W.grad, rtol=RTOL, atol=ATOL * rows ** 0.5)
     torch.testing.assert_close(r["db"].cpu().double(), b.grad, rtol=RTOL, atol=ATOL * rows ** 0.5)
