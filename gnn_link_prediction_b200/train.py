@@ -112,18 +112,24 @@ class TrainStep:
         dev = self.live[0].device
         if dev.type != "cuda":
             raise ops.HginError("TrainStep: move the model to the GPU first (there is no CPU path)")
-        n = sum(p.numel() for p in self.live)
-        self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
+        # every parameter starts on a 256-byte boundary of the bucket (vector loads / TMA need 16 B);
+        # the padding holds zeros with zero gradients, which Adam leaves at zero
+        align = 64
+        offsets, n = [], 0
+        for p in self.live:
+            offsets.append(n)
+            n += (p.numel() + align - 1) // align * align
+        self.flat_p = torch.zeros(n, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
-        off = 0
+        self.grad_views = []
         with torch.no_grad():
-            for p in self.live:                      # parameters become views of the flat bucket
+            for p, off in zip(self.live, offsets):   # parameters become views of the flat bucket
                 self.flat_p[off:off + p.numel()].copy_(p.reshape(-1))
                 p.data = self.flat_p[off:off + p.numel()].view_as(p)
-                off += p.numel()
+                self.grad_views.append(self.flat_g[off:off + p.numel()].view_as(p))
 
     def __call__(self, batch):
         """`batch` already resident on the GPU.  Returns a CUDA tensor [mape, sqrt(mape)] (global)."""
@@ -136,7 +142,7 @@ class TrainStep:
         self.comm.all_reduce_sum_(sums)          # global (S, N): every rank differentiates the same loss
         loss_out, dpred = ops.sqrt_mape_bwd(out.detach(), y, sums)
         out.backward(dpred)
-        torch.cat([p.grad.reshape(-1) for p in self.live], out=self.flat_g)
+        torch._foreach_copy_(self.grad_views, [p.grad for p in self.live])   # gather into the flat bucket
         self.comm.all_reduce_sum_(self.flat_g)   # SUM of partial gradients (no division by world size)
         ops.increment(self.step_count)
         ops.adam_step(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, self.step_count, **self.hyper)
