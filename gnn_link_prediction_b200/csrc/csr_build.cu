@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(256) csr_histogram(const IndexT *__restrict__ 
     for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < num_edges; e += stride) {
         const int64_t k = static_cast<int64_t>(key[e]);
         const int64_t o = static_cast<int64_t>(other[e]);
+        if (k == -1 && o == -1) continue;   // padding slot (static-shape batches), not an error
         if (k < 0 || k >= num_rows || o < 0 || o >= num_cols) {
             bad = true;
         } else {

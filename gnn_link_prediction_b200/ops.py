@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from .profiling import L2_BYTES, combine_bytes
+from .profiling import combine_bytes
 from ._lib import (ACT_NONE, ACT_PRELU, ACT_RELU, MATH_FP32, MATH_TF32, SELF_ADD, SELF_CONCAT,  # noqa: F401
                    SELF_NONE, HginError, check)
 
@@ -130,9 +130,7 @@ def gin_combine(csr, x_src, x_self=None, eps=None, self_mode=SELF_NONE, out=None
         raise HginError(f"gin_combine: out is {tuple(out.shape)}, expected {(csr.num_rows, width)}")
     alg, comp = combine_bytes(csr.num_rows, csr.num_cols, csr.num_edges, f_src,
                               f_self if self_mode != SELF_NONE else 0, width * (2 if accumulate else 1))
-    big = csr.num_cols * f_src * 4 > L2_BYTES
-    with _region("gin_combine", kernels=1, alg_bytes=alg, compulsory_bytes=comp,
-                 roofline_bytes=alg if big else comp):
+    with _region("gin_combine", kernels=1, alg_bytes=alg, compulsory_bytes=comp):
         check(_lib.load().hgin_gin_combine(csr.num_rows, csr.rowptr.data_ptr(), _ptr(csr.col), csr.num_edges, ps, lds, f_src, pf,
                                            ldf, f_self, _scalar(eps, "gin_combine.eps"), self_mode,
                                            1 if accumulate else 0, po, ldo, _stream()), "hgin_gin_combine")

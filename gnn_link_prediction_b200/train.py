@@ -147,3 +147,89 @@ class TrainStep:
         ops.increment(self.step_count)
         ops.adam_step(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, self.step_count, **self.hyper)
         return loss_out
+
+
+class GraphedTrainStep:
+    """`TrainStep` replayed as ONE CUDA graph per batch shape.
+
+    At config.json's sizes (8 topologies, hidden 8, one layer) a step is ~60 kernels of a few
+    microseconds each: launch latency and Python, not the GPU, set the pace.  Capture
+    removes both.  A graph needs static shapes, so the batch is copied into static buffers and each
+    relation's edge list is padded to a bucket with (-1, -1) slots, which hgin_csr_build drops; node
+    counts are part of the cache key (a new shape triggers a new capture, LRU of `max_graphs`).
+    Parameters and optimizer state are snapshotted around the warm-up runs, so capturing does not
+    perturb the training trajectory.
+    """
+
+    def __init__(self, step: TrainStep, edge_bucket=8192, max_graphs=4, warmup=2):
+        if step.comm.world > 1:
+            raise NotImplementedError("GraphedTrainStep: capture of the NCCL all-reduces is not enabled; "
+                                      "use TrainStep for multi-GPU runs")
+        self.step, self.edge_bucket, self.max_graphs, self.warmup = step, edge_bucket, max_graphs, warmup
+        self.cache = {}
+
+    def _signature(self, batch):
+        nodes = tuple((nt, k, tuple(v.shape), v.dtype) for nt in batch.node_types for k, v in batch[nt].items()
+                      if isinstance(v, torch.Tensor))
+        b = self.edge_bucket
+        edges = tuple((et, (batch[et].edge_index.shape[1] + b - 1) // b * b, batch[et].edge_index.dtype)
+                      for et in batch.edge_types)
+        return nodes, edges
+
+    def _capture(self, batch, sig):
+        from .data import Batch
+        dev = self.step.flat_p.device
+        static = Batch()
+        for nt, k, shape, dtype in sig[0]:
+            static[nt][k] = torch.empty(shape, dtype=dtype, device=dev)
+        for et, e_pad, dtype in sig[1]:
+            static[et].edge_index = torch.full((2, e_pad), -1, dtype=dtype, device=dev)
+        static.__dict__["num_graphs"] = getattr(batch, "num_graphs", None)
+        entry = {"static": static, "graph": torch.cuda.CUDAGraph(), "loss": None}
+        self._load(entry, batch)
+        st = self.step
+        snap = [t.clone() for t in (st.flat_p, st.exp_avg, st.exp_avg_sq, st.step_count)]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):
+                st(static)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        from . import ops as _ops
+        timer, _ops.TIMER = _ops.TIMER, None          # timing events cannot be recorded while capturing
+        try:
+            with torch.cuda.graph(entry["graph"]):
+                entry["loss"] = st(static)
+        finally:
+            _ops.TIMER = timer
+        for t, s0 in zip((st.flat_p, st.exp_avg, st.exp_avg_sq, st.step_count), snap):
+            t.copy_(s0)                               # undo the warm-up steps
+        if len(self.cache) >= self.max_graphs:
+            self.cache.pop(next(iter(self.cache)))
+        self.cache[sig] = entry
+        return entry
+
+    @staticmethod
+    def _load(entry, batch):
+        static = entry["static"]
+        for nt in batch.node_types:
+            for k, v in batch[nt].items():
+                if isinstance(v, torch.Tensor):
+                    static[nt][k].copy_(v, non_blocking=True)
+        for et in batch.edge_types:
+            ei = batch[et].edge_index
+            dst = static[et].edge_index
+            dst[:, :ei.shape[1]].copy_(ei, non_blocking=True)
+            if ei.shape[1] < dst.shape[1]:
+                dst[:, ei.shape[1]:].fill_(-1)
+
+    def __call__(self, batch):
+        """`batch` on the GPU or in pinned host memory.  Returns the static [mape, sqrt(mape)] tensor
+        (overwritten by the next call)."""
+        sig = self._signature(batch)
+        entry = self.cache.get(sig)
+        if entry is None:
+            entry = self._capture(batch, sig)
+        self._load(entry, batch)
+        entry["graph"].replay()
+        return entry["loss"]

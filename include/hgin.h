@@ -67,6 +67,8 @@ const char *hgin_last_error(void);
  *   rowptr     : int32 [num_rows + 1];  col : int32 [num_edges];  perm : int32 [num_edges] or NULL.
  *   status     : int32 [1], set to 1 if any index is outside [0,num_rows) x [0,num_cols); such
  *                edges are dropped.  The caller reads it when it chooses to (no sync here).
+ *                An edge (-1, -1) is a PADDING slot: dropped silently, so a batch can be padded
+ *                to a fixed edge count and the whole step replayed as a CUDA graph.
  *   workspace  : hgin_csr_workspace_bytes(num_edges, num_rows) bytes.
  */
 int64_t hgin_csr_workspace_bytes(int64_t num_edges, int64_t num_rows);
