@@ -54,27 +54,30 @@ struct GradZ {  // element (m, nn) of dz = g * act'(z)
     }
 };
 
-struct GradZT {  // element (nn, m) of dz^T, also accumulating dalpha on the side
+// element (nn, m) of dz^T.  Side sums ride on the loads: each thread fetches a FIXED nn (the tile
+// extent divides the thread count), so it can accumulate db[nn] = sum_m dz locally; dalpha likewise.
+struct GradZT {
     GradZ dz;
     float *dalpha_acc;  // thread-local
+    float *db_acc;      // thread-local
     bool want_alpha;
+    bool want_db;
     __device__ __forceinline__ float operator()(int64_t nn, int64_t m) const {
         if (m >= dz.rows || nn >= dz.n) return 0.0f;
-        const float gv = __ldg(dz.g + m * dz.ldg + nn);
-        if (dz.act == HGIN_ACT_NONE) return gv;
-        const float zv = __ldg(dz.z + m * dz.ldz + nn);
-        if (want_alpha && !(zv > 0.0f)) *dalpha_acc += gv * zv;   // at::prelu_backward: x > 0 ? 0 : x*g
-        return act_backward(gv, zv, dz.act, dz.alpha);
+        float v = __ldg(dz.g + m * dz.ldg + nn);
+        if (dz.act != HGIN_ACT_NONE) {
+            const float zv = __ldg(dz.z + m * dz.ldz + nn);
+            if (want_alpha && !(zv > 0.0f)) *dalpha_acc += v * zv;   // at::prelu_backward: x > 0 ? 0 : x*g
+            v = act_backward(v, zv, dz.act, dz.alpha);
+        }
+        if (want_db) *db_acc += v;
+        return v;
     }
 };
 
-struct ConcatColsT {  // element (k, m) of [x1 | x2 | 1]^T — the ones column yields db
+struct ConcatColsT {  // element (k, m) of [x1 | x2]^T
     ConcatRows x;
-    __device__ __forceinline__ float operator()(int64_t k, int64_t m) const {
-        if (m >= x.rows) return 0.0f;
-        if (k == x.k1 + x.k2) return 1.0f;
-        return x(m, k);
-    }
+    __device__ __forceinline__ float operator()(int64_t k, int64_t m) const { return x(m, k); }
 };
 
 // ---- forward ----------------------------------------------------------------------------------
@@ -182,26 +185,27 @@ linear_bwd_dx_kernel(GradZ fa, const float *__restrict__ alpha_ptr, WeightCols f
     }
 }
 
-// ---- weight gradient: partial[cta][n][k] over this CTA's row range; k == K is the bias column --
+// ---- weight gradient: partial[cta][n][k] over this CTA's row range -------------------------------
 // SWAP = false: tile rows index n (dz columns), tile columns index k; SWAP = true: the roles are
-// exchanged so that a tiny n (the 32 -> 1 readout head) sits on the narrow BN side of the tile.
+// exchanged so that a tiny n sits on the narrow BN side of the tile.  db and dalpha are summed on
+// the side by the dz accessor (first tile along the x side only, so every dz element counts once).
 template <class T, bool SWAP>
 __global__ void __launch_bounds__(THREADS)
-linear_bwd_dw_kernel(GradZ dzf, const float *__restrict__ alpha_ptr, ConcatRows xf, int want_alpha,
-                     int64_t rows_per_cta, float *__restrict__ partials /* [gridDim.x][n][kp] */,
-                     float *__restrict__ alpha_partials) {
+linear_bwd_dw_kernel(GradZ dzf, const float *__restrict__ alpha_ptr, ConcatRows xf, int want_alpha, int want_db,
+                     int64_t rows_per_cta, float *__restrict__ partials /* [gridDim.x][n][k] */,
+                     float *__restrict__ db_partials /* [gridDim.x][n] */, float *__restrict__ alpha_partials) {
     __shared__ __align__(16) float smem[T::SMEM_FLOATS];
     __shared__ float red[32];
+    __shared__ float dbs[THREADS];
     dzf.alpha = (dzf.act == HGIN_ACT_PRELU) ? __ldg(alpha_ptr) : 0.0f;
-    const int kp = xf.k1 + xf.k2 + 1;
+    const int k = xf.k1 + xf.k2;
     const int r0 = blockIdx.y * T::BM;   // tile-row offset (n if !SWAP, k if SWAP)
     const int q0 = blockIdx.z * T::BN;   // tile-col offset (k if !SWAP, n if SWAP)
     const int64_t mbeg = static_cast<int64_t>(blockIdx.x) * rows_per_cta;
     const int64_t mend = min(mbeg + rows_per_cta, dzf.rows);
-    float dalpha = 0.0f;
-    // each dz element must feed dalpha exactly once per row range: only the first tile on the x side
-    const bool alpha_here = want_alpha && (SWAP ? blockIdx.y == 0 : blockIdx.z == 0);
-    GradZT fz{dzf, &dalpha, alpha_here};
+    float dalpha = 0.0f, db_local = 0.0f;
+    const bool first_x_tile = SWAP ? blockIdx.y == 0 : blockIdx.z == 0;
+    GradZT fz{dzf, &dalpha, &db_local, want_alpha && first_x_tile, want_db && first_x_tile};
     ConcatColsT fx{xf};
     float acc[T::TM][T::TN];
 #pragma unroll
@@ -215,37 +219,50 @@ linear_bwd_dw_kernel(GradZ dzf, const float *__restrict__ alpha_ptr, ConcatRows 
         else simt::mainloop<T, false, false>(acc, fz, fx, r0, q0, mbeg, mend, smem);
     }
     const int tx = threadIdx.x % T::TX, ty = threadIdx.x / T::TX;
-    float *dst = partials + static_cast<int64_t>(blockIdx.x) * dzf.n * kp;
+    float *dst = partials + static_cast<int64_t>(blockIdx.x) * dzf.n * k;
 #pragma unroll
     for (int i = 0; i < T::TM; ++i) {
 #pragma unroll
         for (int j = 0; j < T::TN; ++j) {
             const int rr = r0 + T::row_of(ty, i), qq = q0 + T::col_of(tx, j);
-            const int n = SWAP ? qq : rr, k = SWAP ? rr : qq;
-            if (n < dzf.n && k < kp) dst[static_cast<int64_t>(n) * kp + k] = acc[i][j];
+            const int n = SWAP ? qq : rr, kk = SWAP ? rr : qq;
+            if (n < dzf.n && kk < k) dst[static_cast<int64_t>(n) * k + kk] = acc[i][j];
         }
     }
-    if (alpha_partials && alpha_here) {
+    if (want_db && first_x_tile) {
+        // threads t, t + EXT, t + 2 EXT, ... fetched the same dz column: add them in a fixed order
+        constexpr int EXT = SWAP ? T::BN : T::BM;
+        dbs[threadIdx.x] = db_local;
+        __syncthreads();
+        if (threadIdx.x < EXT) {
+            float s = 0.0f;
+            for (int t = threadIdx.x; t < THREADS; t += EXT) s += dbs[t];
+            const int n = (SWAP ? q0 : r0) + threadIdx.x;
+            if (n < dzf.n) db_partials[static_cast<int64_t>(blockIdx.x) * dzf.n + n] = s;
+        }
+    }
+    if (alpha_partials && want_alpha && first_x_tile) {
         dalpha = block_sum(dalpha, red);
         if (threadIdx.x == 0) alpha_partials[(SWAP ? blockIdx.z : blockIdx.y) * gridDim.x + blockIdx.x] = dalpha;
     }
 }
 
-// out[i] = sum_p partials[p][i] in fixed order; columns split into dW / db.
+// out[i] = sum_p partials[p][i] for i < count, fixed association (four chains).
 __global__ void __launch_bounds__(256)
-reduce_dw_kernel(const float *__restrict__ partials, int num_partials, int n, int kp, float *__restrict__ dW,
-                 float *__restrict__ db) {
-    const int64_t total = static_cast<int64_t>(n) * kp;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+reduce_partials_simt_kernel(const float *__restrict__ partials, int num_partials, int64_t count,
+                            float *__restrict__ out) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        float s = 0.0f;
-        for (int p = 0; p < num_partials; ++p) s += partials[static_cast<int64_t>(p) * total + i];
-        const int row = static_cast<int>(i / kp), k = static_cast<int>(i % kp);
-        if (k == kp - 1) {
-            if (db) db[row] = s;
-        } else if (dW) {
-            dW[static_cast<int64_t>(row) * (kp - 1) + k] = s;
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+        int p = 0;
+        for (; p + 3 < num_partials; p += 4) {
+            s0 += partials[static_cast<int64_t>(p) * count + i];
+            s1 += partials[static_cast<int64_t>(p + 1) * count + i];
+            s2 += partials[static_cast<int64_t>(p + 2) * count + i];
+            s3 += partials[static_cast<int64_t>(p + 3) * count + i];
         }
+        for (; p < num_partials; ++p) s0 += partials[static_cast<int64_t>(p) * count + i];
+        out[i] = (s0 + s1) + (s2 + s3);
     }
 }
 
@@ -268,7 +285,7 @@ using T8 = simt::Tile<128, 8, 4, 1>;
 constexpr int kDwSplit = kNumSMs * 2;  // row ranges of the weight-gradient pass
 
 inline int64_t dw_splits(int64_t rows) {
-    int64_t s = ceil_div(rows, 512);
+    int64_t s = ceil_div(rows, 128);
     if (s < 1) s = 1;
     return s < kDwSplit ? s : kDwSplit;
 }
@@ -419,19 +436,21 @@ extern "C" int32_t hgin_linear_bwd(int64_t rows, const float *g, int64_t ldg, co
         const int64_t rows_per_cta = align_up(ceil_div(rows, splits), BK);
         const unsigned gx = static_cast<unsigned>(ceil_div(rows, rows_per_cta));
         float *alpha_partials = (dalpha && act == HGIN_ACT_PRELU) ? scal : nullptr;
-        const int kp = k + 1;
-        const bool swap = n <= 16 && kp > n;   // tiny n: put it on the narrow side of the tile
-        const int wide = swap ? kp : n, narrow = swap ? n : kp;
+        float *db_partials = dw_partials + static_cast<int64_t>(gx) * n * k;
+        const bool swap = n <= 16 && k > n;   // tiny n: put it on the narrow side of the tile
+        const int wide = swap ? k : n, narrow = swap ? n : k;
         const unsigned gy = static_cast<unsigned>(ceil_div(wide, 128));
         unsigned gz = 1;
 #define HGIN_DW(T)                                                                                              \
     gz = static_cast<unsigned>(ceil_div(narrow, T::BN));                                                        \
     if (swap)                                                                                                   \
-        linear_bwd_dw_kernel<T, true><<<dim3(gx, gy, gz), THREADS, 0, s>>>(dzf, alpha, xf, alpha_partials != nullptr, \
-                                                                           rows_per_cta, dw_partials, alpha_partials); \
+        linear_bwd_dw_kernel<T, true><<<dim3(gx, gy, gz), THREADS, 0, s>>>(                                     \
+            dzf, alpha, xf, alpha_partials != nullptr, db != nullptr, rows_per_cta, dw_partials, db_partials,   \
+            alpha_partials);                                                                                    \
     else                                                                                                        \
-        linear_bwd_dw_kernel<T, false><<<dim3(gx, gy, gz), THREADS, 0, s>>>(dzf, alpha, xf, alpha_partials != nullptr, \
-                                                                            rows_per_cta, dw_partials, alpha_partials)
+        linear_bwd_dw_kernel<T, false><<<dim3(gx, gy, gz), THREADS, 0, s>>>(                                    \
+            dzf, alpha, xf, alpha_partials != nullptr, db != nullptr, rows_per_cta, dw_partials, db_partials,   \
+            alpha_partials)
         if (narrow > 64) { HGIN_DW(T128); }
         else if (narrow > 32) { HGIN_DW(T64); }
         else if (narrow > 16) { HGIN_DW(T32); }
@@ -439,8 +458,10 @@ extern "C" int32_t hgin_linear_bwd(int64_t rows, const float *g, int64_t ldg, co
         else { HGIN_DW(T8); }
 #undef HGIN_DW
         const unsigned alpha_count = gx * (swap ? gz : gy);
-        reduce_dw_kernel<<<grid_for(static_cast<int64_t>(n) * kp, 256, 4), 256, 0, s>>>(dw_partials, static_cast<int>(gx),
-                                                                                      n, kp, dW, db);
+        if (dW)
+            reduce_partials_simt_kernel<<<grid_for(static_cast<int64_t>(n) * k, 256, 4), 256, 0, s>>>(
+                dw_partials, static_cast<int>(gx), static_cast<int64_t>(n) * k, dW);
+        if (db) reduce_partials_simt_kernel<<<1, 256, 0, s>>>(db_partials, static_cast<int>(gx), n, db);
         if (dalpha) {
             if (alpha_partials) reduce_scalar_kernel<<<1, 1024, 0, s>>>(alpha_partials, alpha_count, dalpha);
             else cudaMemsetAsync(dalpha, 0, sizeof(float), s);

@@ -224,3 +224,57 @@ class DevicePrefetcher:
                     if isinstance(v, torch.Tensor):
                         v.record_stream(cur)                # allocator: memory is in use on `cur`
             yield dev
+
+
+class PackedBatch:
+    """A batch laid out in ONE contiguous byte buffer (every tensor at a 256-byte-aligned offset,
+    edge lists padded to `edge_bucket` with (-1, -1) slots that hgin_csr_build drops), so that a
+    step's whole input crosses PCIe as a single copy and lands in the static buffers of a captured
+    CUDA graph.  `views()` exposes it through the usual Batch API."""
+
+    def __init__(self, buffer, layout, num_graphs):
+        self.buffer, self.layout, self.num_graphs = buffer, layout, num_graphs
+
+    @property
+    def signature(self):
+        return tuple((kind, key, name, dtype, shape) for kind, key, name, dtype, shape, _ in self.layout)
+
+    def views(self, buffer=None):
+        buf = self.buffer if buffer is None else buffer
+        out = Batch()
+        for kind, key, name, dtype, shape, off in self.layout:
+            n = 1
+            for d in shape:
+                n *= d
+            nbytes = n * torch.empty(0, dtype=dtype).element_size()
+            out[key][name] = buf[off:off + nbytes].view(dtype).view(shape)
+        out.__dict__["num_graphs"] = self.num_graphs
+        return out
+
+    def nbytes(self):
+        return self.buffer.numel()
+
+
+def pack_batch(batch, edge_bucket=8192, pin=True):
+    """Batch -> PackedBatch (host side; run it in the loader, next to the collate)."""
+    items = []
+    for nt in batch.node_types:
+        for name, v in batch[nt].items():
+            if isinstance(v, torch.Tensor):
+                items.append(("node", nt, name, v.contiguous()))
+    for et in batch.edge_types:
+        ei = batch[et].edge_index
+        e_pad = (ei.shape[1] + edge_bucket - 1) // edge_bucket * edge_bucket
+        padded = torch.full((2, e_pad), -1, dtype=ei.dtype)
+        padded[:, :ei.shape[1]] = ei
+        items.append(("edge", et, "edge_index", padded))
+    layout, off = [], 0
+    for kind, key, name, v in items:
+        layout.append((kind, key, name, v.dtype, tuple(v.shape), off))
+        off += (v.numel() * v.element_size() + 255) // 256 * 256
+    buf = torch.empty(off, dtype=torch.uint8, pin_memory=pin and torch.cuda.is_available())
+    packed = PackedBatch(buf, layout, getattr(batch, "num_graphs", None))
+    dst = packed.views()
+    for kind, key, name, v in items:
+        dst[key][name].copy_(v)
+    return packed

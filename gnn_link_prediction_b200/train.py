@@ -187,7 +187,18 @@ class GraphedTrainStep:
         static.__dict__["num_graphs"] = getattr(batch, "num_graphs", None)
         entry = {"static": static, "graph": torch.cuda.CUDAGraph(), "loss": None}
         self._load(entry, batch)
+        self._record(entry)
+        if len(self.cache) >= self.max_graphs:
+            self.cache.pop(next(iter(self.cache)))
+        self.cache[sig] = entry
+        return entry
+
+    def _record(self, entry):
+        """Warm up on the static buffers, capture one step, then restore parameters and optimizer
+        state so that capturing leaves the training trajectory untouched."""
         st = self.step
+        dev = st.flat_p.device
+        static = entry["static"]
         snap = [t.clone() for t in (st.flat_p, st.exp_avg, st.exp_avg_sq, st.step_count)]
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -204,10 +215,6 @@ class GraphedTrainStep:
             _ops.TIMER = timer
         for t, s0 in zip((st.flat_p, st.exp_avg, st.exp_avg_sq, st.step_count), snap):
             t.copy_(s0)                               # undo the warm-up steps
-        if len(self.cache) >= self.max_graphs:
-            self.cache.pop(next(iter(self.cache)))
-        self.cache[sig] = entry
-        return entry
 
     @staticmethod
     def _load(entry, batch):
@@ -223,13 +230,32 @@ class GraphedTrainStep:
             if ei.shape[1] < dst.shape[1]:
                 dst[:, ei.shape[1]:].fill_(-1)
 
+    def _capture_packed(self, packed, sig):
+        dev = self.step.flat_p.device
+        buf = torch.empty(packed.buffer.numel(), dtype=torch.uint8, device=dev)
+        buf.copy_(packed.buffer, non_blocking=True)
+        entry = {"buffer": buf, "static": packed.views(buf), "graph": torch.cuda.CUDAGraph(), "loss": None}
+        self._record(entry)
+        if len(self.cache) >= self.max_graphs:
+            self.cache.pop(next(iter(self.cache)))
+        self.cache[sig] = entry
+        return entry
+
     def __call__(self, batch):
-        """`batch` on the GPU or in pinned host memory.  Returns the static [mape, sqrt(mape)] tensor
-        (overwritten by the next call)."""
-        sig = self._signature(batch)
-        entry = self.cache.get(sig)
-        if entry is None:
-            entry = self._capture(batch, sig)
-        self._load(entry, batch)
+        """`batch`: a Batch (GPU or pinned host) or a data.PackedBatch (one copy per step).  Returns
+        the static [mape, sqrt(mape)] tensor (overwritten by the next call)."""
+        from .data import PackedBatch
+        if isinstance(batch, PackedBatch):
+            sig = ("packed", batch.signature)
+            entry = self.cache.get(sig)
+            if entry is None:
+                entry = self._capture_packed(batch, sig)
+            entry["buffer"].copy_(batch.buffer, non_blocking=True)   # the step's whole input: one copy
+        else:
+            sig = self._signature(batch)
+            entry = self.cache.get(sig)
+            if entry is None:
+                entry = self._capture(batch, sig)
+            self._load(entry, batch)
         entry["graph"].replay()
         return entry["loss"]

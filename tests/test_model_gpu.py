@@ -283,3 +283,35 @@ def test_csr_build_skips_padding_edges():
     csr = ops.csr_build(ei, 3, 2).validate()            # padding does not raise
     assert csr.rowptr.cpu().tolist() == [0, 1, 3]
     assert csr.col.cpu().tolist()[:3] == [2, 0, 1]
+
+
+def test_packed_batch_round_trip_and_graph_replay():
+    from gnn_link_prediction_b200.data import pack_batch
+    from gnn_link_prediction_b200.train import GraphedTrainStep
+    ds = SyntheticDataset(6, num_nodes=10, num_links=14, num_topologies=3)
+    host = [Batch.from_data_list([ds[3 * b + i] for i in range(3)], index_dtype=torch.int32,
+                                 edge_types=CONV_EDGE_TYPES) for b in range(2)]
+    packed = [pack_batch(h, edge_bucket=128) for h in host]
+    v = packed[0].views()
+    assert torch.equal(v["path"].x, host[0]["path"].x) and torch.equal(v["path"].y, host[0]["path"].y)
+    for et in CONV_EDGE_TYPES:
+        e = host[0][et].edge_index.shape[1]
+        assert v[et].edge_index.shape[1] % 128 == 0
+        assert torch.equal(v[et].edge_index[:, :e], host[0][et].edge_index)
+        assert bool((v[et].edge_index[:, e:] == -1).all())
+    kw = dict(node_embedding_size=8, message_passing_layers=1, dropout=0.0, concat_path=True, bl_features=False,
+              divided_features=False, global_feats=False, mlp_layers=[16], act="torch.nn.PReLU()",
+              mlp_head_act=None, mlp_bn=False)
+    out = []
+    for use_packed in (False, True):
+        torch.manual_seed(2)
+        step = TrainStep(HetroGIN({"link": 7, "path": 7, "node": 3}, **kw).cuda().train())
+        if use_packed:
+            run = GraphedTrainStep(step)
+            losses = [run(packed[i % 2]).clone() for i in range(5)]
+        else:
+            losses = [step(Batch.from_data_list([ds[3 * (i % 2) + j] for j in range(3)], index_dtype=torch.int32,
+                                                edge_types=CONV_EDGE_TYPES).cuda()).clone() for i in range(5)]
+        torch.cuda.synchronize()
+        out.append(torch.stack(losses).cpu())
+    assert torch.equal(out[0], out[1])
