@@ -24,7 +24,6 @@ import os
 import statistics
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -56,35 +55,40 @@ def measured_peaks():
     return 6650.0, 1590.0, "fallback"
 
 
-class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+class ClockSampler:
+    """`nvidia-smi -lms 100` running beside the timed region: SM clock and throttle reasons."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.index, self.proc = index, None
 
-    def run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+        time.sleep(0.25)   # let the first sample land before the timed region starts
 
     def result(self):
-        self.stop_flag.set()
-        self.join(timeout=6)
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        samples = []
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+                out, _ = self.proc.communicate()
+            samples = [[c.strip() for c in line.split(",")] for line in out.splitlines() if line.count(",") >= 5]
+        sm = [float(s[0]) for s in samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in samples if s[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for s in samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(samples)}
 
 
 def make_host_batches(w, count, rank, pin):
@@ -182,7 +186,7 @@ def timed_steps(step_fn, steps, flush_buf):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfgC", choices=sorted(WORKLOADS) + ["cfgD"])
@@ -238,9 +242,11 @@ def main():
     torch.cuda.synchronize()
     # one instrumented eager step: counts the kernels a step launches (graph replays cannot be
     # instrumented per kernel) and gives the eager per-kernel breakdown
+    eager_step(dev_batches[0])   # un-instrumented first call: lazy init, allocator warm-up
+    torch.cuda.synchronize()
     probe = KernelTimer()
     ops.TIMER = probe
-    eager_step(dev_batches[0])
+    eager_step(dev_batches[1 % n_host])
     ops.TIMER = None
     probe_kernels = probe.summary()
     kernels_per_step = sum(k.get("kernels", k["launches"]) for k in probe_kernels.values())
