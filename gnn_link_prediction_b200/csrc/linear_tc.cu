@@ -1,7 +1,10 @@
 // Host side of the tensor-core dense-layer path (HGIN_MATH_TF32): TMA tensor maps, the small
 // helper kernels (dz = g * act'(z) with fused db / dalpha / tail-dW reductions, weight repacking)
 // and the dispatch used by hgin_linear_fwd / hgin_linear_bwd.  Kernels: linear_tc.cuh.
+#include <stdlib.h>
+
 #include "linear_tc.cuh"
+#include "linear_tc_fused.cuh"
 
 namespace hgin {
 namespace tcgemm {
@@ -209,6 +212,8 @@ static int32_t set_attrs() {
         e = cudaFuncSetAttribute(gemm_nt_kernel<EPI_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, NtSmem::total);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TnSmem::total);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedSmem::total);
     if (e != cudaSuccess) return fail(HGIN_ERR_CUDA, "tensor-core kernels: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     g_attr_set = true;
     return HGIN_OK;
@@ -278,6 +283,51 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
     float *alpha_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(dz_ctas()) * 4));
     float *dw_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(kNumSMs) * n * k1 * 4));
     float *dot_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(kNumSMs) * 4));
+
+    // 0. fused single-pass backward when the shapes allow it (linear_tc_fused.cuh)
+    static const bool fused_enabled = !(getenv("HGIN_FUSED_BWD") && atoi(getenv("HGIN_FUSED_BWD")) == 0);
+    if (fused_enabled && !dbg && dW && n % 32 == 0 && k1 % 16 == 0 && k1 >= 32 && c0 == 0 && c1 == k1 && (dx || ddot)) {
+        const int width = k1;
+        transpose_cols_kernel<<<grid_for(n * width, 256, 1), 256, 0, s>>>(W, n, k, 0, width, Wt);
+        CUtensorMap tm_g, tm_z, tm_wt, tm_h, tm_dx, tm_e;
+        bool ok = make_map(&tm_g, g, n, rows, ldg, 32, BM, CU_TENSOR_MAP_SWIZZLE_128B) &&
+                  make_map(&tm_z, z ? z : g, n, rows, z ? ldz : ldg, 32, BM, CU_TENSOR_MAP_SWIZZLE_128B) &&
+                  make_map(&tm_wt, Wt, n, width, n, 32, width, CU_TENSOR_MAP_SWIZZLE_128B) &&
+                  make_map(&tm_h, x1, k1, rows, ld1, 32, BM, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
+                  make_map(&tm_dx, dx ? dx : dz, dx ? width : n, rows, dx ? lddx : n, 32, BM, CU_TENSOR_MAP_SWIZZLE_128B) &&
+                  make_map(&tm_e, dot_x ? dot_x : dz, dot_x ? width : n, rows, dot_x ? ld_dot : n, 32, BM,
+                           CU_TENSOR_MAP_SWIZZLE_128B);
+        if (!ok) return fail(HGIN_ERR_CUDA, "hgin_linear_bwd(tf32 fused): cuTensorMapEncodeTiled failed");
+        FusedParams p{};
+        p.rows = rows;
+        p.num_tiles = static_cast<int>(ceil_div(rows, BM));
+        p.n = n;
+        p.k1 = k1;
+        p.act = act;
+        p.alpha = alpha;
+        p.x2 = x2;
+        p.ld2 = ld2;
+        p.k2 = k2;
+        p.want_dx = dx != nullptr;
+        p.use_e = ddot != nullptr;
+        p.want_sums = 1;
+        const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+        p.dot_partials = ddot ? dot_part : nullptr;
+        p.dw_partials = dw_part;
+        p.sum_partials = sum_part;
+        p.alpha_partials = alpha_part;
+        bwd_fused_kernel<<<grid, FUSED_THREADS, FusedSmem::total, s>>>(tm_g, tm_z, tm_wt, tm_h, tm_dx, tm_e, p);
+        reduce_partials_kernel<<<grid_for(n * k1, 256, 2), 256, 0, s>>>(dw_part, grid, n, k1, 0, dW, k, 0, nullptr);
+        if (db || k2 > 0)
+            reduce_partials_kernel<<<grid_for(n * (k2 + 1), 256, 1), 256, 0, s>>>(sum_part, grid, n, k2, 1, dW, k, k1, db);
+        if (dalpha) {
+            if (act == HGIN_ACT_PRELU) reduce_scalar_tc_kernel<<<1, 1024, 0, s>>>(alpha_part, grid * 4, dalpha);
+            else cudaMemsetAsync(dalpha, 0, sizeof(float), s);
+        }
+        if (ddot) reduce_scalar_tc_kernel<<<1, 1024, 0, s>>>(dot_part, grid, ddot);
+        HGIN_CHECK_LAUNCH("hgin_linear_bwd(tf32 fused)");
+        return HGIN_OK;
+    }
 
     // 1. dz and the cheap reductions that ride on it
     const int want_sums = (dW || db || dalpha) ? 1 : 0;
