@@ -38,6 +38,7 @@ SIGNATURES = {
     "hgin_sqrt_mape_bwd": (_i32, [_i64, _ptr, _ptr, _ptr, _f32, _ptr, _ptr, _ptr]),
     "hgin_adam_step": (_i32, [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _f64, _f64, _f64, _f64, _f64, _i32, _ptr]),
     "hgin_increment": (_i32, [_ptr, _ptr]),
+    "hgin_set_option": (_i32, [ctypes.c_char_p, _i32]),
     "hgin_debug_gemm_tn": (_i32, [_i64, _ptr, _i32, _ptr, _i32, _ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _ptr]),
 }
 

@@ -5,6 +5,8 @@
 //                                     dalpha = sum g*min(z,0);  d(eps) = sum dx_self * x_dst.
 // All reductions over rows are two-stage and deterministic: every CTA writes its partial to the
 // caller's workspace and a second kernel adds the partials in CTA order.
+#include <string.h>
+
 #include "gemm_simt.cuh"
 #include "linear_tc_api.h"
 #include "linear_thin_api.h"
@@ -485,4 +487,14 @@ extern "C" int32_t hgin_debug_gemm_tn(int64_t rows, const float *a, int32_t n, c
     return tcgemm::linear_bwd(rows, a, n, nullptr, 0, HGIN_ACT_NONE, nullptr, b, k, k, nullptr, 0, 0, out /*W unused*/, n,
                               0, 0, nullptr, 0, nullptr, 0, nullptr, out, nullptr, nullptr, workspace, &d,
                               static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int32_t hgin_set_option(const char *name, int32_t value) {
+    using namespace hgin;
+    HGIN_CHECK_ARG(name != nullptr, "hgin_set_option: null name");
+    if (strcmp(name, "fused_bwd") == 0) {
+        tcgemm::set_fused_bwd(value);
+        return HGIN_OK;
+    }
+    return fail(HGIN_ERR_INVALID_ARGUMENT, "hgin_set_option: unknown option '%s'", name);
 }

@@ -204,6 +204,13 @@ int64_t bwd_workspace_bytes(int64_t rows, int k1, int k2, int n) {
     return b + 1024;
 }
 
+static int g_fused_bwd = -1;
+bool fused_bwd_enabled() {
+    if (g_fused_bwd < 0) g_fused_bwd = (getenv("HGIN_FUSED_BWD") && atoi(getenv("HGIN_FUSED_BWD")) != 0) ? 1 : 0;
+    return g_fused_bwd == 1;
+}
+void set_fused_bwd(int on) { g_fused_bwd = on ? 1 : 0; }
+
 static bool g_attr_set = false;
 static int32_t set_attrs() {
     if (g_attr_set) return HGIN_OK;
@@ -263,7 +270,7 @@ int32_t linear_fwd(int64_t rows, const float *x1, int64_t ld1, int k1, const flo
     p.use_e = (out != nullptr && accumulate_out) ? 1 : 0;
     p.dot_partials = nullptr;
     const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-    gemm_nt_kernel<EPI_FWD><<<grid, THREADS, NtSmem::total, s>>>(tm_a, tm_b, tm_o, tm_z, tm_e, p);
+    gemm_nt_kernel<EPI_FWD><<<grid, NT_THREADS, NtSmem::total, s>>>(tm_a, tm_b, tm_o, tm_z, tm_e, p);
     HGIN_CHECK_LAUNCH("hgin_linear_fwd(tf32)");
     return HGIN_OK;
 }
@@ -285,8 +292,11 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
     float *dot_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(kNumSMs) * 4));
 
     // 0. fused single-pass backward when the shapes allow it (linear_tc_fused.cuh)
-    static const bool fused_enabled = !(getenv("HGIN_FUSED_BWD") && atoi(getenv("HGIN_FUSED_BWD")) == 0);
-    if (fused_enabled && !dbg && dW && n % 32 == 0 && k1 % 16 == 0 && k1 >= 32 && c0 == 0 && c1 == k1 && (dx || ddot)) {
+    // Opt-in (HGIN_FUSED_BWD=1 or hgin_set_option("fused_bwd", 1)): on B200 the fused kernel is bound
+    // by bytes in flight — W (64 KB) + the x tile (64 KB) leave shared memory for a 2-stage ring only,
+    // ~64 KB of DRAM reads outstanding per SM against the ~130 KB that 43 GB/s/SM x ~3 us loaded
+    // latency require — and measures 2.3 ms against 1.5 ms for the three-pass path.
+    if (fused_bwd_enabled() && !dbg && dW && n % 32 == 0 && k1 % 16 == 0 && k1 >= 32 && c0 == 0 && c1 == k1 && (dx || ddot)) {
         const int width = k1;
         transpose_cols_kernel<<<grid_for(n * width, 256, 1), 256, 0, s>>>(W, n, k, 0, width, Wt);
         CUtensorMap tm_g, tm_z, tm_wt, tm_h, tm_dx, tm_e;
@@ -365,7 +375,7 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
         p.use_e = ddot != nullptr;
         p.dot_partials = ddot ? dot_part : nullptr;
         const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-        gemm_nt_kernel<EPI_DX><<<grid, THREADS, NtSmem::total, s>>>(tm_a, tm_b, tm_o, tm_o, tm_e, p);
+        gemm_nt_kernel<EPI_DX><<<grid, NT_THREADS, NtSmem::total, s>>>(tm_a, tm_b, tm_o, tm_o, tm_e, p);
         if (ddot) reduce_scalar_tc_kernel<<<1, 1024, 0, s>>>(dot_part, grid, ddot);
     } else if (ddot) {
         cudaMemsetAsync(ddot, 0, sizeof(float), s);

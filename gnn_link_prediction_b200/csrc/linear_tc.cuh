@@ -7,13 +7,15 @@
 //   gemm_tn_kernel       D[N x K] = A[M x N]^T * B[M x K]     both operands MN-major, split over M
 //        partial dW per CTA, reduced deterministically afterwards                   weight grad (K3)
 //
-// Structure of both (persistent, one CTA per SM, 256 threads):
+// Structure of both (persistent, one CTA per SM):
 //   warp 0  TMA producer: operand tiles -> 128B-swizzled shared-memory ring, mbarrier complete_tx
 //   warp 1  one elected thread issues tcgen05.mma; tcgen05.commit frees ring slots / publishes TMEM
 //   warp 2  TMA producer for the epilogue operand (old `out` when merging, dot_x for d(eps))
 //   warp 3  allocates / frees TMEM
-//   warps 4-7  epilogue: tcgen05.ld (warp q owns TMEM lanes 32q..32q+31, i.e. one row per thread)
-//           -> bias / PReLU / merge in registers -> swizzled staging tile -> TMA store
+//   warps 4-7, 8-11  two epilogue warpgroups on alternating 32-column chunks: tcgen05.ld (warp q of a
+//           group owns TMEM lanes 32q..32q+31, i.e. one row per thread) -> bias / PReLU / merge in
+//           registers -> the group's own swizzled staging tiles -> TMA store by the group's issuer
+//           (the per-tile epilogue, not the MMA, is what competes with HBM time here)
 // Every one of these layers is HBM-bound (32 flop/B against a ridge of ~220), so the design goal
 // is to keep the TMA queues full: MMA time per 128-row tile is ~0.6 us against ~4 us of HBM time.
 #pragma once
@@ -31,11 +33,13 @@ constexpr int BM = 128;               // rows per tile (UMMA M)
 constexpr int KB = 32;                // fp32 per 128-byte swizzle row = one K-block
 constexpr int UMMA_K = 8;             // tf32
 constexpr int TILE_BYTES = BM * 128;  // 16 KB: 128 rows x 128 B
-constexpr int NT_STAGES = 5;          // A ring, K-block granularity
-constexpr int THREADS = 256;
+constexpr int NT_STAGES = 4;          // A ring, K-block granularity
+constexpr int THREADS = 256;          // gemm_tn_kernel
+constexpr int NT_THREADS = 384;       // gemm_nt_kernel: 4 service warps + 2 epilogue warpgroups
 constexpr uint32_t TMEM_COLS = 256;   // two 128-column fp32 accumulators
 constexpr int EPI_FWD = 0, EPI_DX = 1;
-constexpr int EPI_BAR = 1;            // named barrier id of the 128 epilogue threads
+constexpr int EPI_BAR = 1;            // named barrier ids 1, 2: the two epilogue warpgroups (128 threads each)
+constexpr int EPI_ALL_BAR = 3;        // both groups (256 threads)
 
 struct NtParams {
     int64_t rows;
@@ -62,7 +66,7 @@ struct NtParams {
 struct NtSmem {
     static constexpr int kB = 4 * TILE_BYTES;            // W: up to 4 K-blocks of [128 x 128 B]
     static constexpr int kA = NT_STAGES * TILE_BYTES;    // A ring
-    static constexpr int kStage = 2 * TILE_BYTES;        // staging for TMA stores (z / out chunk)
+    static constexpr int kStage = 4 * TILE_BYTES;        // staging for TMA stores: (out, z) chunk per epilogue group
     static constexpr int kE = 2 * TILE_BYTES;            // epilogue-operand ring
     static constexpr int off_b = 0;
     static constexpr int off_a = off_b + kB;
@@ -70,16 +74,19 @@ struct NtSmem {
     static constexpr int off_e = off_stage + kStage;
     static constexpr int off_small = off_e + kE;
     static constexpr int small_bytes = 128 * 4 /*bias*/ + 128 * 4 * 4 /*w_tail*/ + 32 * 8 /*barriers*/ + 64;
-    static constexpr int total = off_small + small_bytes + 1024 /*alignment slack*/;
+    // 224 KB of tiles + 2.8 KB: fits the 227 KB limit only without alignment slack, so the kernel
+    // declares its dynamic shared memory __align__(1024) (no static shared memory precedes it).
+    static constexpr int total = off_small + small_bytes;
+    static_assert(total <= 227 * 1024, "gemm_nt shared memory exceeds the sm_100 per-CTA limit");
 };
 
 template <int EPI>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(NT_THREADS, 1)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                const __grid_constant__ CUtensorMap tm_o0, const __grid_constant__ CUtensorMap tm_o1,
                const __grid_constant__ CUtensorMap tm_e, const NtParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw;   // SWIZZLE_128B tiles need 1024-byte alignment: guaranteed by the declaration
     uint8_t *smem_b = smem + NtSmem::off_b;
     uint8_t *smem_a = smem + NtSmem::off_a;
     uint8_t *smem_stage = smem + NtSmem::off_stage;
@@ -115,7 +122,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         mbar_init(b_full, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 4);   // one arrive per epilogue warp
+            mbar_init(&tmem_empty[i], 8);   // one arrive per epilogue warp (2 groups x 4)
             mbar_init(&e_full[i], 1);
             mbar_init(&e_empty[i], 4);
         }
@@ -176,63 +183,77 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     } else if (warp == 2) {
         // ===== epilogue-operand producer =====
         if (lane == 0 && p.use_e) {
-            int b = 0;
-            uint32_t ph = 0;
+            uint32_t ph[2] = {0, 0};   // chunk c goes to buffer c & 1, consumed by epilogue group c & 1
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 for (int c = 0; c < nchunks; ++c) {
-                    mbar_wait(&e_empty[b], ph ^ 1);
+                    const int b = c & 1;
+                    mbar_wait(&e_empty[b], ph[b] ^ 1);
                     mbar_expect_tx(&e_full[b], TILE_BYTES);
                     tma_load_2d(smem_e + b * TILE_BYTES, &tm_e, &e_full[b], c * 32, tile * BM);
-                    if (++b == 2) { b = 0; ph ^= 1; }
+                    ph[b] ^= 1;
                 }
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue =====
-        const int q = warp - 4;                 // TMEM lane quarter == row block inside the tile
-        const int et = threadIdx.x - 128;       // 0..127
+        // ===== epilogue: group 0 (warps 4-7) takes chunks 0, 2; group 1 (warps 8-11) chunks 1, 3 =====
+        const int grp = (warp - 4) >> 2;
+        const int q = (warp - 4) & 3;           // TMEM lane quarter == row block inside the tile
+        const int gt = threadIdx.x - 128 - grp * 128;   // 0..127 inside the group
+        const int et = threadIdx.x - 128;       // 0..255 over both groups
         const int r = q * 32 + lane;            // row inside the tile owned by this thread
+        const int bar_id = EPI_BAR + grp;
         if (EPI == EPI_FWD) {
-            for (int i = et; i < 128; i += 128) bias_s[i] = (p.bias && i < p.n) ? __ldg(p.bias + i) : 0.0f;
-            for (int i = et; i < 128 * 4; i += 128) {
+            for (int i = et; i < 128; i += 256) bias_s[i] = (p.bias && i < p.n) ? __ldg(p.bias + i) : 0.0f;
+            for (int i = et; i < 128 * 4; i += 256) {
                 const int nn = i >> 2, t = i & 3;
                 wtail_s[i] = (nn < p.n && t < p.k2) ? __ldg(p.w_tail + static_cast<int64_t>(nn) * p.ldw + t) : 0.0f;
             }
-            named_barrier(EPI_BAR, 128);
+            named_barrier(EPI_ALL_BAR, 256);
         }
         const float alpha = (EPI == EPI_FWD && p.act == HGIN_ACT_PRELU) ? __ldg(p.alpha) : 0.0f;
+        // this group's staging tiles (st0: out / dx, st1: z) and epilogue-operand buffer
+        const uint32_t sa0 = smem_u32(smem_stage + grp * 2 * TILE_BYTES);
+        const uint32_t sa1 = sa0 + TILE_BYTES;
+        const uint32_t eb_ptr = smem_u32(smem_e + grp * TILE_BYTES);
+        const int my_chunks = (nchunks - grp + 1) / 2;   // chunks grp, grp + 2, ...
         float dot = 0.0f;
-        int it = 0, eb = 0;
+        int it = 0;
         uint32_t eph = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const int64_t grow = static_cast<int64_t>(tile) * BM + r;
             float x2v[4] = {0.f, 0.f, 0.f, 0.f};
             if (EPI == EPI_FWD && p.k2 > 0 && grow < p.rows) {
-                for (int t = 0; t < p.k2; ++t) x2v[t] = __ldg(p.x2 + grow * p.ld2 + t);
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (t < p.k2) x2v[t] = __ldg(p.x2 + grow * p.ld2 + t);
             }
             mbar_wait(&tmem_full[acc], (it >> 1) & 1);
             tcgen05_fence_after();
-            for (int c = 0; c < nchunks; ++c) {
+            if (my_chunks == 0) {   // nothing to read for this group: release the accumulator at once
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            }
+            for (int c = grp; c < nchunks; c += 2) {
                 float v[32];
                 tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 128 + c * 32, v);
-                if (c == nchunks - 1) {          // accumulator drained: hand it back to the MMA warp
+                if (c + 2 >= nchunks) {          // this group's last chunk: hand the accumulator back
                     tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 }
                 float ev[32];
-                if (p.use_e) {
-                    mbar_wait(&e_full[eb], eph);
-                    const uint8_t *eb_ptr = smem_e + eb * TILE_BYTES;
+                if (p.use_e) {                   // chunk c was loaded into buffer c & 1 == grp
+                    mbar_wait(&e_full[grp], eph);
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
-                        const float4 t = *reinterpret_cast<const float4 *>(eb_ptr + swz128(r, j4 * 4));
+                        const float4 t = lds_v4(eb_ptr + swz128(r, j4 * 4));
                         ev[j4 * 4 + 0] = t.x; ev[j4 * 4 + 1] = t.y; ev[j4 * 4 + 2] = t.z; ev[j4 * 4 + 3] = t.w;
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&e_empty[eb]);
-                    if (++eb == 2) { eb = 0; eph ^= 1; }
+                    if (lane == 0) mbar_arrive(&e_empty[grp]);
+                    eph ^= 1;
                 }
                 float o[32];
                 if (EPI == EPI_FWD) {
@@ -255,43 +276,40 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                         for (int j = 0; j < 32; ++j) dot = fmaf(v[j], ev[j], dot);  // OOB columns of e are zero-filled
                     }
                 }
-                // staging buffers are free once the previous chunk's TMA stores have read them
-                if (et == 0) tma_store_wait_read<0>();
-                named_barrier(EPI_BAR, 128);
-                uint8_t *st0 = smem_stage;                // EPI_FWD: out,  EPI_DX: dx
-                uint8_t *st1 = smem_stage + TILE_BYTES;   // EPI_FWD: z
+                // the group's staging tiles are free once its previous TMA stores have read them
+                if (gt == 0) tma_store_wait_read<0>();
+                named_barrier(bar_id, 128);
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
                     const uint32_t off = swz128(r, j4 * 4);
                     if (EPI == EPI_FWD) {
-                        if (p.want_out)
-                            *reinterpret_cast<float4 *>(st0 + off) = make_float4(o[j4 * 4], o[j4 * 4 + 1], o[j4 * 4 + 2], o[j4 * 4 + 3]);
-                        if (p.want_z)
-                            *reinterpret_cast<float4 *>(st1 + off) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                        if (p.want_out) sts_v4(sa0 + off, o[j4 * 4], o[j4 * 4 + 1], o[j4 * 4 + 2], o[j4 * 4 + 3]);
+                        if (p.want_z) sts_v4(sa1 + off, v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
                     } else {
-                        *reinterpret_cast<float4 *>(st0 + off) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                        sts_v4(sa0 + off, v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
                     }
                 }
                 fence_proxy_async_smem();
-                named_barrier(EPI_BAR, 128);
-                if (et == 0) {
+                named_barrier(bar_id, 128);
+                if (gt == 0) {
                     if (EPI == EPI_FWD) {
-                        if (p.want_out) tma_store_2d(&tm_o0, st0, c * 32, tile * BM);
-                        if (p.want_z) tma_store_2d(&tm_o1, st1, c * 32, tile * BM);
+                        if (p.want_out) tma_store_2d(&tm_o0, smem_stage + grp * 2 * TILE_BYTES, c * 32, tile * BM);
+                        if (p.want_z) tma_store_2d(&tm_o1, smem_stage + grp * 2 * TILE_BYTES + TILE_BYTES, c * 32, tile * BM);
                     } else if (p.want_out) {
-                        tma_store_2d(&tm_o0, st0, c * 32, tile * BM);
+                        tma_store_2d(&tm_o0, smem_stage + grp * 2 * TILE_BYTES, c * 32, tile * BM);
                     }
                     tma_store_commit();
                 }
             }
         }
-        if (et == 0) tma_store_wait<0>();
+        if (gt == 0) tma_store_wait<0>();
         if (EPI == EPI_DX && p.dot_partials) {
             dot = warp_sum(dot);
             float *red = bias_s;  // unused by EPI_DX
-            if (lane == 0) red[q] = dot;
-            named_barrier(EPI_BAR, 128);
-            if (et == 0) p.dot_partials[blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+            if (lane == 0) red[grp * 4 + q] = dot;
+            named_barrier(EPI_ALL_BAR, 256);
+            if (et == 0)
+                p.dot_partials[blockIdx.x] = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
         }
     }
     tcgen05_fence_before();

@@ -216,8 +216,8 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant
             int it = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
                 const int c = it * num_kb + kb;
-                uint8_t *gs = ring + (c % FUSED_STAGES) * FUSED_STAGE_BYTES;
-                const uint8_t *zs = gs + TILE_BYTES;
+                const uint32_t gs = smem_u32(ring + (c % FUSED_STAGES) * FUSED_STAGE_BYTES);
+                const uint32_t zs = gs + TILE_BYTES;
                 mbar_wait(&full[c & 3], (c >> 2) & 1);
                 mbar_wait(a_free, (it & 1) ^ 1);   // previous tile's dW MMAs have consumed the TMEM operand
                 tcgen05_fence_after();
@@ -228,12 +228,12 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const uint32_t off = swz128(m0 + j, lane);
-                        float d = *reinterpret_cast<const float *>(gs + off);
+                        float d = lds_f32(gs + off);
                         if (act_on) {
-                            const float zv = *reinterpret_cast<const float *>(zs + off);
+                            const float zv = lds_f32(zs + off);
                             if (p.act == HGIN_ACT_PRELU && !(zv > 0.0f)) dalpha += d * zv;
                             d = act_backward(d, zv, p.act, alpha);
-                            *reinterpret_cast<float *>(gs + off) = d;
+                            sts_f32(gs + off, d);
                         }
                         v[j] = d;
                     }
@@ -243,7 +243,9 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant
                             db += v[j];
                             if (p.k2 > 0 && row0 + m0 + j < p.rows) {
                                 const float *xr = p.x2 + (row0 + m0 + j) * p.ld2;
-                                for (int t = 0; t < p.k2; ++t) tail[t] = fmaf(v[j], __ldg(xr + t), tail[t]);
+#pragma unroll
+                                for (int t = 0; t < 4; ++t)   // static indices keep tail[] in registers
+                                    if (t < p.k2) tail[t] = fmaf(v[j], __ldg(xr + t), tail[t]);
                             }
                         }
                     }
@@ -257,7 +259,9 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant
             }
             if (p.want_sums && nn < p.n) {
                 float *dst = p.sum_partials + (static_cast<int64_t>(blockIdx.x) * p.n + nn) * (p.k2 + 1);
-                for (int t = 0; t < p.k2; ++t) dst[t] = tail[t];
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (t < p.k2) dst[t] = tail[t];
                 dst[p.k2] = db;
             }
         }
@@ -286,11 +290,11 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant
                 }
                 if (p.use_e) {
                     mbar_wait(&e_full[eb], eph);
-                    const uint8_t *eb_ptr = smem_e + eb * TILE_BYTES;
+                    const uint32_t eb_ptr = smem_u32(smem_e + eb * TILE_BYTES);
                     if (grow < p.rows) {
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 t = *reinterpret_cast<const float4 *>(eb_ptr + swz128(r, j4 * 4));
+                            const float4 t = lds_v4(eb_ptr + swz128(r, j4 * 4));
                             dot = fmaf(v[j4 * 4 + 0], t.x, dot);
                             dot = fmaf(v[j4 * 4 + 1], t.y, dot);
                             dot = fmaf(v[j4 * 4 + 2], t.z, dot);
@@ -306,8 +310,8 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant
                     named_barrier(FUSED_EPI_BAR, 128);
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4)
-                        *reinterpret_cast<float4 *>(smem_stage + swz128(r, j4 * 4)) =
-                            make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                        sts_v4(smem_u32(smem_stage) + swz128(r, j4 * 4), v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2],
+                               v[j4 * 4 + 3]);
                     fence_proxy_async_smem();
                     named_barrier(FUSED_EPI_BAR, 128);
                     if (et == 0) {

@@ -213,6 +213,11 @@ def linear_bwd(g, z, x1, W, x2=None, act=ACT_NONE, alpha=None, dx_cols=None, wan
     return {"dx": dx, "ddot": ddot, "dW": dW, "db": db, "dalpha": dalpha}
 
 
+def set_option(name, value):
+    """Process-wide library option (see include/hgin.h), e.g. set_option("fused_bwd", 1)."""
+    check(_lib.load().hgin_set_option(name.encode(), int(value)), "hgin_set_option")
+
+
 def debug_gemm_tn(a, b, tma_swizzle=-1, lbo=-1, sbo=-1, layout_type=-1, k_step_bytes=-1):
     """Diagnostics: a[rows,n]^T @ b[rows,k] through the tcgen05 MN-major kernel (hgin_debug_gemm_tn)."""
     rows, n = a.shape

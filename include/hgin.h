@@ -164,6 +164,12 @@ int32_t hgin_adam_step(int64_t n, float *param, const float *grad, float *exp_av
                        void *stream);
 int32_t hgin_increment(int32_t *counter, void *stream);
 
+/* ---- runtime options --------------------------------------------------------------------------
+ * "fused_bwd" (0/1, default 0): HGIN_MATH_TF32 backward through the single-pass fused kernel
+ * (csrc/linear_tc_fused.cuh) instead of dz / dx / dW passes.  Process-wide, not thread-safe.
+ */
+int32_t hgin_set_option(const char *name, int32_t value);
+
 /* ---- diagnostics ------------------------------------------------------------------------------
  * out[n,k] = a[rows,n]^T * b[rows,k] through the tcgen05 MN-major weight-gradient kernel with the
  * UMMA shared-memory descriptor fields given explicitly (tests pin the layout with it):

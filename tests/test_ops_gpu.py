@@ -260,9 +260,16 @@ def test_linear_fwd_tf32(rows, k1, k2, n, act):
     _tc_close(acc, prev.double() + o_ref)
 
 
+@pytest.fixture(params=[0, 1], ids=["three-pass", "fused"])
+def fused_bwd(request):
+    ops.set_option("fused_bwd", request.param)
+    yield request.param
+    ops.set_option("fused_bwd", 0)
+
+
 @pytest.mark.parametrize("rows,k1,k2,n", [s for s in TC_SHAPES if s[1] % 16 == 0])
 @pytest.mark.parametrize("act", [ops.ACT_PRELU, ops.ACT_NONE])
-def test_linear_bwd_tf32(rows, k1, k2, n, act):
+def test_linear_bwd_tf32(rows, k1, k2, n, act, fused_bwd):
     g = torch.Generator().manual_seed(rows * 3 + n)
     k = k1 + k2
     x = torch.randn(rows, k, generator=g, dtype=torch.float64, requires_grad=True)
