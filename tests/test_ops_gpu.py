@@ -55,6 +55,20 @@ def test_csr_build_long_rows_and_strided_input():
     assert np.array_equal(csr.rowptr.cpu().numpy(), rowptr) and np.array_equal(csr.col.cpu().numpy(), col)
 
 
+def test_csr_build_sorted_fast_path_with_gaps_and_padding():
+    """Keys already sorted (the reference's by-source order): empty rows at both ends and in the
+    middle, duplicate keys, trailing (-1,-1) padding."""
+    src = torch.tensor([2, 2, 2, 5, 5, 9, 9, 9, 9, -1, -1], dtype=torch.int32)
+    dst = torch.tensor([7, 0, 3, 3, 1, 4, 4, 0, 2, -1, -1], dtype=torch.int32)
+    csr = ops.csr_build(torch.stack([src, dst]).cuda(), 12, 8, by="src", want_perm=True).validate()
+    assert csr.rowptr.cpu().tolist() == [0, 0, 0, 3, 3, 3, 5, 5, 5, 5, 9, 9, 9]
+    assert csr.col.cpu().tolist()[:9] == [7, 0, 3, 3, 1, 4, 4, 0, 2]
+    assert csr.perm.cpu().tolist()[:9] == list(range(9))
+    # all padding
+    pad = torch.full((2, 6), -1, dtype=torch.int64).cuda()
+    assert ops.csr_build(pad, 4, 3).validate().rowptr.cpu().tolist() == [0, 0, 0, 0]
+
+
 def test_csr_build_flags_out_of_range():
     ei = torch.tensor([[0, 5, 1], [0, 1, 9]])
     csr = ops.csr_build(ei.cuda(), 3, 2)
