@@ -315,3 +315,76 @@ def test_packed_batch_round_trip_and_graph_replay():
         torch.cuda.synchronize()
         out.append(torch.stack(losses).cpu())
     assert torch.equal(out[0], out[1])
+
+
+def _tiny_model(emb=8, layers=2):
+    torch.manual_seed(4)
+    kw = dict(node_embedding_size=emb, message_passing_layers=layers, dropout=0.0, concat_path=True,
+              bl_features=False, divided_features=False, global_feats=False, mlp_layers=[16, 8],
+              act="torch.nn.PReLU()", mlp_head_act=None, mlp_bn=False)
+    ref = hgin_oracle.HetroGIN(input_channels={"link": 7, "path": 7, "node": 3}, **kw)
+    m = HetroGIN(input_channels={"link": 7, "path": 7, "node": 3}, **kw)
+    m.load_state_dict(ref.state_dict())
+    return ref, m.cuda().train()
+
+
+def _check_against_oracle(ref, m, x_dict, ei_dict, rtol=1e-4):
+    o_ref = ref({k: v.clone() for k, v in x_dict.items()}, ei_dict, None)
+    o = m({k: v.cuda() for k, v in x_dict.items()}, {k: v.cuda() for k, v in ei_dict.items()}, None)
+    close(o, o_ref, rtol=rtol)
+    o_ref.sum().backward()
+    o.sum().backward()
+    g_ref = {k: p.grad for k, p in ref.named_parameters()}
+    for k, p in m.named_parameters():
+        assert (p.grad is None) == (g_ref[k] is None), k
+        if p.grad is not None:
+            close(p.grad, g_ref[k], rtol=2e-3, atol_rel=2e-5)
+
+
+def test_ragged_graph_with_empty_relation_isolated_nodes_and_duplicate_edges():
+    """Edge cases of the path: a relation with no edges, destination rows with no neighbours,
+    repeated (multi-)edges, unsorted edge order, a single-path / single-link graph."""
+    from gnn_link_prediction_b200.data import EDGE_TYPES
+    g = torch.Generator().manual_seed(1)
+    for n_path, n_link, n_node, e in [(37, 11, 5, 90), (1, 1, 1, 3), (300, 2, 40, 500)]:
+        x = {"path": torch.randn(n_path, 7, generator=g), "link": torch.randn(n_link, 7, generator=g),
+             "node": torch.ones(n_node, 3)}
+        rnd = lambda ns, nd, cnt: torch.stack([torch.randint(0, ns, (cnt,), generator=g),
+                                               torch.randint(0, nd, (cnt,), generator=g)])
+        ei = {EDGE_TYPES[0]: rnd(n_path, n_link, e),                 # unsorted, with duplicates
+              EDGE_TYPES[1]: rnd(n_link, n_path, max(e // 3, 1)),     # leaves most path rows empty
+              EDGE_TYPES[2]: torch.zeros(2, 0, dtype=torch.int64),    # empty relation
+              EDGE_TYPES[3]: rnd(n_node, n_link, 7)}
+        ref, m = _tiny_model()
+        _check_against_oracle(ref, m, x, ei)
+
+
+def test_single_sample_batch_and_int32_indices():
+    ds = SyntheticDataset(1, num_nodes=9, num_links=10)
+    b = Batch.from_data_list([ds[0]])
+    ref, m = _tiny_model(emb=16, layers=3)
+    _check_against_oracle(ref, m, b.x_dict, b.edge_index_dict)
+    m.zero_grad()
+    o64 = m(Batch.from_data_list([ds[0]]).cuda().x_dict, {k: v.cuda() for k, v in b.edge_index_dict.items()}, None)
+    o32 = m(Batch.from_data_list([ds[0]]).cuda().x_dict, {k: v.int().cuda() for k, v in b.edge_index_dict.items()}, None)
+    assert torch.equal(o64, o32)   # int64 (reference dtype) and host-narrowed int32 give identical results
+
+
+def test_bad_inputs_raise():
+    from gnn_link_prediction_b200 import ops
+    _, m = _tiny_model()
+    ds = SyntheticDataset(1, num_nodes=8, num_links=9)
+    b = Batch.from_data_list([ds[0]]).cuda()
+    with pytest.raises(ops.HginError):                       # CPU features: no CPU path
+        m({k: v.cpu() for k, v in b.x_dict.items()}, b.edge_index_dict, None)
+    with pytest.raises(ops.HginError):                       # float64 features
+        m({k: v.double() for k, v in b.x_dict.items()}, b.edge_index_dict, None)
+    bad = dict(b.edge_index_dict)
+    k0 = next(iter(bad))
+    bad[k0] = bad[k0].clone()
+    bad[k0][1, 0] = 10 ** 6                                  # destination id out of range
+    from gnn_link_prediction_b200.functional import GraphCSR
+    graph = GraphCSR(bad, {t: v.shape[0] for t, v in b.x_dict.items()})
+    m(b.x_dict, graph, None)
+    with pytest.raises(IndexError):
+        graph.validate()
