@@ -252,10 +252,17 @@ int32_t csr_build_impl(const IndexT *edge_index, int64_t num_edges, int64_t ld_e
         return HGIN_OK;
     }
     const int edge_grid = grid_for(num_edges, 256 * 4, 8);
-    cudaMemsetAsync(sorted_flag, 0xff, sizeof(int32_t), s);   // non-zero = sorted until a descent is seen
-    csr_check_sorted<IndexT><<<edge_grid, 256, 0, s>>>(key, other, num_edges, num_rows, num_cols, sorted_flag);
-    csr_from_sorted<IndexT><<<edge_grid, 256, 0, s>>>(key, other, num_edges, num_rows, num_cols, rowptr, col, perm,
-                                                       sorted_flag);
+    // The sortedness probe is only worth its pass over the edge list where the reference's edge
+    // order makes it succeed: builds keyed by SOURCE (sort_row == 0).  Destination-keyed builds go
+    // straight to the general path (flag = 0).
+    if (sort_row == 0) {
+        cudaMemsetAsync(sorted_flag, 0xff, sizeof(int32_t), s);   // non-zero = sorted until a descent is seen
+        csr_check_sorted<IndexT><<<edge_grid, 256, 0, s>>>(key, other, num_edges, num_rows, num_cols, sorted_flag);
+        csr_from_sorted<IndexT><<<edge_grid, 256, 0, s>>>(key, other, num_edges, num_rows, num_cols, rowptr, col, perm,
+                                                           sorted_flag);
+    } else {
+        cudaMemsetAsync(sorted_flag, 0, sizeof(int32_t), s);
+    }
     csr_histogram<IndexT><<<edge_grid, 256, 0, s>>>(key, other, num_edges, num_rows, num_cols, cnt, status, sorted_flag);
     if (!exclusive_scan(cnt, rowptr, num_rows + 1, scratch, scratch_elems, sorted_flag, s))
         return fail(HGIN_ERR_WORKSPACE_TOO_SMALL, "hgin_csr_build: scan scratch too small");

@@ -144,25 +144,21 @@ thin_bwd_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, const fl
     if (threadIdx.x == 0 && alpha_part) alpha_part[blockIdx.x] = da;
 }
 
-// Stage 2a (grid): out[i] = sum over CTAs of part[cta][i] (fixed association); columns [0,k) -> dW,
-// [k,k+d) -> tbuf (T = dz^T dot_x), k+d -> db.
+// Stage 2a (grid): out[i] = sum over CTAs of part[cta][i]; columns [0,k) -> dW, [k,k+d) -> tbuf
+// (T = dz^T dot_x), k+d -> db.  One WARP per output element: lane l adds partials l, l+32, ... in
+// order, then a fixed xor tree — deterministic, and 32 loads in flight instead of one chain.
 __global__ void __launch_bounds__(256)
 thin_finalize_kernel(const float *__restrict__ part, int num_part, int n, int k, int d, float *__restrict__ dW,
                      float *__restrict__ db, float *__restrict__ tbuf) {
     const int kp = k + d + 1;
     const int total = n * kp;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (i >= total) return;
-    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;   // four independent chains, fixed association
-    int p = 0;
-    for (; p + 3 < num_part; p += 4) {
-        s0 += part[static_cast<int64_t>(p) * total + i];
-        s1 += part[static_cast<int64_t>(p + 1) * total + i];
-        s2 += part[static_cast<int64_t>(p + 2) * total + i];
-        s3 += part[static_cast<int64_t>(p + 3) * total + i];
-    }
-    for (; p < num_part; ++p) s0 += part[static_cast<int64_t>(p) * total + i];
-    const float s = (s0 + s1) + (s2 + s3);
+    float s = 0.0f;
+    for (int p = lane; p < num_part; p += 32) s += part[static_cast<int64_t>(p) * total + i];
+    s = warp_sum(s);
+    if (lane != 0) return;
     const int nn = i / kp, c = i % kp;
     if (c < k) {
         if (dW) dW[nn * k + c] = s;
@@ -325,7 +321,7 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
                                              want_alpha ? alpha_part : nullptr);
     float *tbuf = alpha_part + ctas;
     const int total = n * (k + d + 1);
-    thin_finalize_kernel<<<static_cast<unsigned>(ceil_div(total, 256)), 256, 0, s>>>(part, ctas, n, k, d, dW, db, tbuf);
+    thin_finalize_kernel<<<static_cast<unsigned>(ceil_div(total, 8)), 256, 0, s>>>(part, ctas, n, k, d, dW, db, tbuf);
     if (ddot || dalpha)
         thin_scalars_kernel<<<1, 256, 0, s>>>(tbuf, n, k, d, W, c0, ddot, want_alpha ? alpha_part : nullptr, ctas,
                                               dalpha);
@@ -361,7 +357,7 @@ int32_t head_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, int6
     const bool want_alpha = dalpha && act == HGIN_ACT_PRELU;
     head_bwd_kernel<<<ctas, THREADS, 0, s>>>(rows, g, ldg, z, ldz, act, alpha, x, ldx, k, W, dx, lddx, part,
                                              want_alpha ? alpha_part : nullptr);
-    thin_finalize_kernel<<<static_cast<unsigned>(ceil_div(k + 1, 256)), 256, 0, s>>>(part, ctas, 1, k, 0, dW, db, tbuf);
+    thin_finalize_kernel<<<static_cast<unsigned>(ceil_div(k + 1, 8)), 256, 0, s>>>(part, ctas, 1, k, 0, dW, db, tbuf);
     if (dalpha) thin_scalars_kernel<<<1, 256, 0, s>>>(tbuf, 1, k, 0, W, 0, nullptr, want_alpha ? alpha_part : nullptr, ctas, dalpha);
     HGIN_CHECK_LAUNCH("hgin_linear_bwd(head)");
     return HGIN_OK;
