@@ -496,5 +496,9 @@ extern "C" int32_t hgin_set_option(const char *name, int32_t value) {
         tcgemm::set_fused_bwd(value);
         return HGIN_OK;
     }
+    if (strcmp(name, "fused_dw") == 0) {
+        tcgemm::set_fused_dw(value);
+        return HGIN_OK;
+    }
     return fail(HGIN_ERR_INVALID_ARGUMENT, "hgin_set_option: unknown option '%s'", name);
 }

@@ -18,6 +18,8 @@ struct TnDebug {   // overrides of the MN-major descriptor fields (hgin_debug_ge
 
 bool fused_bwd_enabled();
 void set_fused_bwd(int on);
+bool fused_dw_enabled();
+void set_fused_dw(int on);
 bool fwd_eligible(int64_t rows, const float *x1, int64_t ld1, int k1, int k2, int n, const float *z, int64_t ldz,
                   const float *out, int64_t ldo);
 bool bwd_eligible(int64_t rows, const float *g, int64_t ldg, const float *z, int64_t ldz, int act, const float *x1,

@@ -166,7 +166,9 @@ int32_t hgin_increment(int32_t *counter, void *stream);
 
 /* ---- runtime options --------------------------------------------------------------------------
  * "fused_bwd" (0/1, default 0): HGIN_MATH_TF32 backward through the single-pass fused kernel
- * (csrc/linear_tc_fused.cuh) instead of dz / dx / dW passes.  Process-wide, not thread-safe.
+ * (csrc/linear_tc_fused.cuh) instead of separate passes.
+ * "fused_dw" (0/1, default 0): dz = g*act'(z) fused into the weight-gradient kernel
+ * (csrc/linear_tc_dw.cuh) instead of dz_prepare + gemm_tn.  Process-wide, not thread-safe.
  */
 int32_t hgin_set_option(const char *name, int32_t value);
 

@@ -274,11 +274,15 @@ def test_linear_fwd_tf32(rows, k1, k2, n, act):
     _tc_close(acc, prev.double() + o_ref)
 
 
-@pytest.fixture(params=[0, 1], ids=["three-pass", "fused"])
+@pytest.fixture(params=["three-pass", "fused-dw", "fused-all"])
 def fused_bwd(request):
-    ops.set_option("fused_bwd", request.param)
+    """The three tensor-core backward variants: dz_prepare + dx + dW passes (default); dz fused
+    into the dW kernel (opt-in); everything in one kernel (opt-in)."""
+    ops.set_option("fused_bwd", 1 if request.param == "fused-all" else 0)
+    ops.set_option("fused_dw", 1 if request.param == "fused-dw" else 0)
     yield request.param
     ops.set_option("fused_bwd", 0)
+    ops.set_option("fused_dw", 0)
 
 
 @pytest.mark.parametrize("rows,k1,k2,n", [s for s in TC_SHAPES if s[1] % 16 == 0])
