@@ -98,7 +98,7 @@ def make_host_batches(w, count, rank, pin):
     batches = []
     for b in range(count):
         samples = [ds[b * w["batch"] + i] for i in range(w["batch"])]
-        batch = Batch.from_data_list(samples, index_dtype=torch.int32, edge_types=CONV_EDGE_TYPES)
+        batch = Batch.from_data_list(samples, index_dtype=torch.int32, edge_types=CONV_EDGE_TYPES, batch_vector=False)
         batches.append(batch.pin_memory() if pin else batch)
     return batches
 

@@ -29,9 +29,19 @@ CONV_EDGE_TYPES = EDGE_TYPES[:4]
 
 
 class Store(dict):
-    """dict with attribute access (`store.x` == `store['x']`), like a PyG storage."""
+    """dict with attribute access (`store.x` == `store['x']`), like a PyG storage.  A batched node
+    store that was collated without its `batch` vector derives it from `ptr` on first access."""
 
     __slots__ = ()
+
+    def __missing__(self, key):
+        if key == "batch" and "ptr" in self:
+            ptr = dict.__getitem__(self, "ptr")
+            counts = ptr[1:] - ptr[:-1]
+            vec = torch.repeat_interleave(torch.arange(counts.numel(), dtype=torch.int64, device=ptr.device), counts)
+            dict.__setitem__(self, "batch", vec)
+            return vec
+        raise KeyError(key)
 
     def __getattr__(self, name):
         try:
@@ -118,11 +128,13 @@ class Batch(HeteroData):
     """Block-diagonal concatenation of samples (PyG `Batch.from_data_list` semantics)."""
 
     @classmethod
-    def from_data_list(cls, samples, index_dtype=None, edge_types=None):
+    def from_data_list(cls, samples, index_dtype=None, edge_types=None, batch_vector=True):
         """`index_dtype=None` keeps the samples' dtype (int64 in the reference,
         generateFiles.py:172-181); `torch.int32` narrows on the host so that only 4-byte
         indices cross PCIe.  `edge_types` restricts the relations that are collated (the
-        reference ships all six, of which HetroGIN reads four)."""
+        reference ships all six, of which HetroGIN reads four).  `batch_vector=False` leaves the
+        per-node graph ids (`store.batch`, int64, only read when GLOBAL_FEATS is on, models.py:347)
+        to be derived from `ptr` on first access instead of shipping them every step."""
         out = cls()
         first = samples[0]
         base = {}
@@ -135,9 +147,10 @@ class Batch(HeteroData):
             store = out[nt]
             for key in first[nt].keys():
                 store[key] = torch.cat([s[nt][key] for s in samples], dim=0)
-            store["batch"] = torch.repeat_interleave(
-                torch.arange(len(samples), dtype=torch.int64), torch.tensor(counts, dtype=torch.int64))
             store["ptr"] = torch.tensor(starts, dtype=torch.int64)
+            if batch_vector:
+                store["batch"] = torch.repeat_interleave(
+                    torch.arange(len(samples), dtype=torch.int64), torch.tensor(counts, dtype=torch.int64))
         for et in (first.edge_types if edge_types is None else edge_types):
             src, _, dst = et
             pieces = []
@@ -159,7 +172,7 @@ class DataLoader:
     partial batch, reshuffles every epoch with `generator`."""
 
     def __init__(self, dataset, batch_size=1, shuffle=False, generator=None, index_dtype=None,
-                 edge_types=None, pin_memory=False):
+                 edge_types=None, pin_memory=False, batch_vector=True):
         self.dataset = dataset
         self.batch_size = int(batch_size)
         self.shuffle = shuffle
@@ -167,6 +180,7 @@ class DataLoader:
         self.index_dtype = index_dtype
         self.edge_types = edge_types
         self.pin_memory = pin_memory
+        self.batch_vector = batch_vector
 
     def __len__(self):
         return (len(self.dataset) + self.batch_size - 1) // self.batch_size
@@ -176,7 +190,8 @@ class DataLoader:
         order = torch.randperm(n, generator=self.generator).tolist() if self.shuffle else list(range(n))
         for lo in range(0, n, self.batch_size):
             batch = Batch.from_data_list([self.dataset[i] for i in order[lo:lo + self.batch_size]],
-                                         index_dtype=self.index_dtype, edge_types=self.edge_types)
+                                         index_dtype=self.index_dtype, edge_types=self.edge_types,
+                                         batch_vector=self.batch_vector)
             yield batch.pin_memory() if self.pin_memory else batch
 
 

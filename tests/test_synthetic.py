@@ -81,3 +81,13 @@ def test_loader_len_iter_and_narrowing():
     for et in CONV_EDGE_TYPES:
         assert batches[0][et].edge_index.dtype == torch.int32
         assert torch.equal(batches[0][et].edge_index.long(), wide[et].edge_index)
+
+
+def test_batch_vector_is_derived_lazily_from_ptr():
+    ds = SyntheticDataset(3, num_nodes=9, num_links=12, num_topologies=3)
+    eager = Batch.from_data_list([ds[i] for i in range(3)])
+    lazy = Batch.from_data_list([ds[i] for i in range(3)], batch_vector=False)
+    assert "batch" not in lazy["path"]                        # nothing shipped ...
+    assert torch.equal(lazy["path"].batch, eager["path"].batch)   # ... derived on first access
+    assert torch.equal(lazy["node"]["batch"], eager["node"]["batch"])
+    assert lazy.nbytes() > 0
