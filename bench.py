@@ -91,21 +91,25 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(samples)}
 
 
-def make_host_batches(w, count, rank, pin):
+def make_host_batches(w, count, rank, pin, collate="csr"):
     from gnn_link_prediction_b200.data import Batch, CONV_EDGE_TYPES
     from gnn_link_prediction_b200.synthetic import SyntheticDataset
     ds = SyntheticDataset(w["batch"] * count, num_topologies=16, seed=1997 + 100003 * rank)
     batches = []
     for b in range(count):
         samples = [ds[b * w["batch"] + i] for i in range(w["batch"])]
-        batch = Batch.from_data_list(samples, index_dtype=torch.int32, edge_types=CONV_EDGE_TYPES, batch_vector=False)
+        # default: per-sample CSRs (built once per sample by K0, cached) are concatenated by the collate, so
+        # the step runs no CSR build; --collate coo ships the COO lists and K0 runs inside every step
+        batch = Batch.from_data_list(samples, index_dtype=torch.int32, edge_types=CONV_EDGE_TYPES, batch_vector=False,
+                                     csr=collate == "csr", keep_coo=collate != "csr")
         batches.append(batch.pin_memory() if pin else batch)
     return batches
 
 
 def batch_counts(batch):
     from gnn_link_prediction_b200.data import CONV_EDGE_TYPES
-    edges = sum(batch[et].edge_index.shape[1] for et in CONV_EDGE_TYPES)
+    edges = sum((batch[et]["csr_dst_col"].shape[0] if "csr_dst_col" in batch[et] else batch[et].edge_index.shape[1])
+                for et in CONV_EDGE_TYPES)
     return batch.num_graphs, edges
 
 
@@ -117,7 +121,8 @@ def copy_batch_to_device(host):
         for k, v in host[nt].items():
             dev[nt][k] = v.cuda(non_blocking=True)
     for et in host.edge_types:
-        dev[et].edge_index = host[et].edge_index.cuda(non_blocking=True)
+        for k, v in host[et].items():
+            dev[et][k] = v.cuda(non_blocking=True)
     dev.__dict__["num_graphs"] = host.num_graphs
     return dev
 
@@ -194,6 +199,9 @@ def main():
                     help="dense-layer arithmetic; default tf32 tensor cores for cfgC (BASELINE configs[2] allows "
                          "reduced-precision MLP GEMMs), fp32 for cfgA")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collate", default="csr", choices=["csr", "coo"],
+                    help="csr: the collate concatenates cached per-sample CSRs (no CSR build in the step); "
+                         "coo: ship COO edge lists, hgin_csr_build runs inside every step")
     ap.add_argument("--graph", dest="graph", action="store_true", default=None,
                     help="replay the step as a CUDA graph (default: on for cfgA at 1 GPU)")
     ap.add_argument("--no-graph", dest="graph", action="store_false")
@@ -223,7 +231,7 @@ def main():
 
     args.warmup = max(args.warmup, 3)
     n_host = 2
-    host = make_host_batches(w, n_host, rank, pin=True)
+    host = make_host_batches(w, n_host, rank, pin=True, collate=args.collate)
     graphs, edges = batch_counts(host[0])
     h2d_bytes = host[0].nbytes()
 
@@ -363,6 +371,7 @@ def main():
         "config": {"workload": args.workload, "desc": w["desc"], "emb": w["emb"], "layers": w["layers"],
                    "graphs_per_gpu_per_step": graphs, "edges_per_gpu_per_step": edges,
                    "l2": "flushed between timed steps" if small else "inputs+activations larger than L2",
+                   "collate": args.collate,
                    "parallelism": f"dp{world} (samples sharded, NCCL sum-allreduce of one flat grad bucket)"},
         "edges_per_s": edges * world * args.steps / (resident_ms * 1e-3),
         "e2e": {"value": graphs * world * args.steps / (e2e_ms * 1e-3), "unit": "graphs/s",

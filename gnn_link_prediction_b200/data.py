@@ -124,11 +124,41 @@ class HeteroData:
         return total
 
 
+CSR_KEYS = ("csr_dst_rowptr", "csr_dst_col", "csr_src_rowptr", "csr_src_col")
+_CSR_CACHE = {}   # id(edge_index tensor) -> (tensor kept alive, per-sample CSR dict): shared topologies build once
+
+
+def attach_csr(sample, edge_types=None):
+    """Per-sample adjacency in kernel layout, built ONCE per sample by K0 on the GPU and kept on the
+    host next to the COO list: for every relation the destination-sorted CSR (forward aggregation)
+    and the source-sorted one (backward gather) as int32 `csr_{dst,src}_{rowptr,col}`.  Batches are
+    block-diagonal with contiguous ids, so the batch CSR is the concatenation of these with offsets
+    (`Batch.from_data_list(csr=True)`) and no CSR has to be built inside the training step."""
+    from . import ops
+    for et in (sample.edge_types if edge_types is None else edge_types):
+        store = sample[et]
+        if all(k in store for k in CSR_KEYS):
+            continue
+        ei = store["edge_index"]
+        hit = _CSR_CACHE.get(id(ei))
+        if hit is None:
+            n_src, n_dst = sample[et[0]]["x"].shape[0], sample[et[2]]["x"].shape[0]
+            dev = ei.cuda()
+            by_dst = ops.csr_build(dev, n_src, n_dst, by="dst").validate()
+            by_src = ops.csr_build(dev, n_src, n_dst, by="src").validate()
+            hit = (ei, {"csr_dst_rowptr": by_dst.rowptr.cpu(), "csr_dst_col": by_dst.col.cpu(),
+                        "csr_src_rowptr": by_src.rowptr.cpu(), "csr_src_col": by_src.col.cpu()})
+            _CSR_CACHE[id(ei)] = hit
+        store.update(hit[1])
+    return sample
+
+
 class Batch(HeteroData):
     """Block-diagonal concatenation of samples (PyG `Batch.from_data_list` semantics)."""
 
     @classmethod
-    def from_data_list(cls, samples, index_dtype=None, edge_types=None, batch_vector=True):
+    def from_data_list(cls, samples, index_dtype=None, edge_types=None, batch_vector=True, csr=False,
+                       keep_coo=True):
         """`index_dtype=None` keeps the samples' dtype (int64 in the reference,
         generateFiles.py:172-181); `torch.int32` narrows on the host so that only 4-byte
         indices cross PCIe.  `edge_types` restricts the relations that are collated (the
@@ -158,12 +188,38 @@ class Batch(HeteroData):
                 ei = s[et]["edge_index"]
                 shift = torch.tensor([[base[src][i]], [base[dst][i]]], dtype=ei.dtype)
                 pieces.append(ei + shift)
-            ei = torch.cat(pieces, dim=1)
-            if index_dtype is not None:
-                ei = ei.to(index_dtype)
-            out[et]["edge_index"] = ei
+            if keep_coo or not csr:
+                ei = torch.cat(pieces, dim=1)
+                if index_dtype is not None:
+                    ei = ei.to(index_dtype)
+                out[et]["edge_index"] = ei
+            if csr:
+                # batch CSR = per-sample CSRs (attach_csr) concatenated with node / edge offsets
+                for s in samples:
+                    attach_csr(s, [et])
+                e_counts = [s[et]["csr_dst_col"].shape[0] for s in samples]
+                e_base = [0]
+                for c in e_counts:
+                    e_base.append(e_base[-1] + c)
+                for side, rows_t, cols_t in (("dst", dst, src), ("src", src, dst)):
+                    rp = [s[et][f"csr_{side}_rowptr"][:-1] + e_base[i] for i, s in enumerate(samples)]
+                    rp.append(torch.tensor([e_base[-1]], dtype=torch.int32))
+                    out[et][f"csr_{side}_rowptr"] = torch.cat(rp).to(torch.int32)
+                    out[et][f"csr_{side}_col"] = torch.cat(
+                        [s[et][f"csr_{side}_col"] + base[cols_t][i] for i, s in enumerate(samples)]).to(torch.int32)
         out.__dict__["num_graphs"] = len(samples)
         return out
+
+    @property
+    def graph(self):
+        """The adjacency the model consumes: a prebuilt `functional.GraphCSR` when the batch was
+        collated with `csr=True`, otherwise the COO `edge_index_dict` (the model then runs K0)."""
+        from .functional import GraphCSR
+        ets = [et for et in self.edge_types if "csr_dst_rowptr" in self[et]]
+        if not ets:
+            return self.edge_index_dict
+        num_nodes = {nt: self[nt]["x"].shape[0] for nt in self.node_types}
+        return GraphCSR.from_prebuilt({et: self[et] for et in ets}, num_nodes)
 
 
 class DataLoader:
@@ -172,7 +228,7 @@ class DataLoader:
     partial batch, reshuffles every epoch with `generator`."""
 
     def __init__(self, dataset, batch_size=1, shuffle=False, generator=None, index_dtype=None,
-                 edge_types=None, pin_memory=False, batch_vector=True):
+                 edge_types=None, pin_memory=False, batch_vector=True, csr=False, keep_coo=True):
         self.dataset = dataset
         self.batch_size = int(batch_size)
         self.shuffle = shuffle
@@ -181,6 +237,7 @@ class DataLoader:
         self.edge_types = edge_types
         self.pin_memory = pin_memory
         self.batch_vector = batch_vector
+        self.csr, self.keep_coo = csr, keep_coo
 
     def __len__(self):
         return (len(self.dataset) + self.batch_size - 1) // self.batch_size
@@ -191,7 +248,7 @@ class DataLoader:
         for lo in range(0, n, self.batch_size):
             batch = Batch.from_data_list([self.dataset[i] for i in order[lo:lo + self.batch_size]],
                                          index_dtype=self.index_dtype, edge_types=self.edge_types,
-                                         batch_vector=self.batch_vector)
+                                         batch_vector=self.batch_vector, csr=self.csr, keep_coo=self.keep_coo)
             yield batch.pin_memory() if self.pin_memory else batch
 
 
@@ -278,11 +335,20 @@ def pack_batch(batch, edge_bucket=8192, pin=True):
             if isinstance(v, torch.Tensor):
                 items.append(("node", nt, name, v.contiguous()))
     for et in batch.edge_types:
-        ei = batch[et].edge_index
-        e_pad = (ei.shape[1] + edge_bucket - 1) // edge_bucket * edge_bucket
-        padded = torch.full((2, e_pad), -1, dtype=ei.dtype)
-        padded[:, :ei.shape[1]] = ei
-        items.append(("edge", et, "edge_index", padded))
+        for name, v in batch[et].items():
+            if not isinstance(v, torch.Tensor):
+                continue
+            if name == "edge_index":          # COO: pad with (-1,-1) slots, which K0 drops
+                e_pad = (v.shape[1] + edge_bucket - 1) // edge_bucket * edge_bucket
+                padded = torch.full((2, e_pad), -1, dtype=v.dtype)
+                padded[:, :v.shape[1]] = v
+                v = padded
+            elif name.endswith("_col"):       # prebuilt CSR columns: rowptr bounds them, the tail is never read
+                e_pad = (v.shape[0] + edge_bucket - 1) // edge_bucket * edge_bucket
+                padded = torch.zeros(e_pad, dtype=v.dtype)
+                padded[:v.shape[0]] = v
+                v = padded
+            items.append(("edge", et, name, v.contiguous()))
     layout, off = [], 0
     for kind, key, name, v in items:
         layout.append((kind, key, name, v.dtype, tuple(v.shape), off))

@@ -31,6 +31,18 @@ class GraphCSR:
         self.num_nodes = dict(num_nodes)
         self._by_dst, self._by_src = {}, {}
 
+    @classmethod
+    def from_prebuilt(cls, stores, num_nodes):
+        """From CSR tensors already on the device (`data.Batch.from_data_list(csr=True)`): stores[et]
+        holds int32 `csr_{dst,src}_{rowptr,col}`; no K0 launch happens for these relations."""
+        g = cls({et: st.get("edge_index") for et, st in stores.items()}, num_nodes)
+        for et, st in stores.items():
+            n_src, n_dst = num_nodes[et[0]], num_nodes[et[2]]
+            e = st["csr_dst_col"].shape[0]
+            g._by_dst[et] = ops.CSR(st["csr_dst_rowptr"], st["csr_dst_col"], None, None, n_dst, n_src, e)
+            g._by_src[et] = ops.CSR(st["csr_src_rowptr"], st["csr_src_col"], None, None, n_src, n_dst, e)
+        return g
+
     # mapping protocol, so a GraphCSR can be passed wherever an edge_index_dict is expected
     def items(self):
         return self.edge_index_dict.items()
@@ -58,7 +70,8 @@ class GraphCSR:
 
     def validate(self):
         for c in list(self._by_dst.values()) + list(self._by_src.values()):
-            c.validate()
+            if c.status is not None:   # prebuilt CSRs were validated when they were built per sample
+                c.validate()
         return self
 
 

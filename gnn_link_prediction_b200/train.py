@@ -137,7 +137,8 @@ class TrainStep:
         for p in self.live:
             p.grad = None
         # the per-node graph ids are only read with GLOBAL_FEATS (unsupported here): do not force them
-        out = model(batch.x_dict, batch.edge_index_dict, dict.get(batch["path"], "batch"))
+        graph = batch.graph if hasattr(batch, "graph") else batch.edge_index_dict   # prebuilt CSR if collated so
+        out = model(batch.x_dict, graph, dict.get(batch["path"], "batch"))
         y = batch["path"].y
         sums = ops.mape_sum(out.detach(), y)
         self.comm.all_reduce_sum_(sums)          # global (S, N): every rank differentiates the same loss
