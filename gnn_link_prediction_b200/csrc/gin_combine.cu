@@ -13,8 +13,6 @@
 // Neighbour indices are fetched LPR at a time with one coalesced load and handed round by
 // shuffle; the gathers of a batch are issued back to back (UNROLL in flight) before the
 // dependent adds.
-#include <stdlib.h>
-
 #include "hgin_common.cuh"
 
 namespace hgin {
@@ -254,7 +252,6 @@ extern "C" int32_t hgin_gin_combine(int64_t num_rows, const int32_t *rowptr, con
     // rows (link->path, ~3 neighbours) the per-row latency chain rowptr -> col -> gather dominates,
     // so several rows share a warp and each lane carries more 128-bit chunks.
     const double avg_len = (num_edges >= 0 && num_rows > 0) ? static_cast<double>(num_edges) / num_rows : 1e9;
-    static const int force_lpr = getenv("HGIN_COMBINE_LPR") ? atoi(getenv("HGIN_COMBINE_LPR")) : 0;
     if (vec4) {
         const int chunks = f_src / 4;
         // Measured on B200 (profiles/): 2.5 M rows x ~3 neighbours, F = 128: warp/row 1.10 ms ->
@@ -262,9 +259,12 @@ extern "C" int32_t hgin_gin_combine(int64_t num_rows, const int32_t *rowptr, con
         int lpr = chunks <= 32 ? chunks : 32;
         const bool short_rows = avg_len <= 8.0;
         if ((chunks == 32 || chunks == 16) && short_rows) lpr = chunks / 2;
-        if (force_lpr > 0 && (chunks == 32 || chunks == 16) && (force_lpr == chunks || force_lpr == chunks / 2)) lpr = force_lpr;
-        if (chunks == 32 && lpr == 16) launch<4, 16, 2, true, 4>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, accumulate, out, ld_out, s);
-        else if (chunks == 16 && lpr == 8) launch<4, 8, 2, true, 4>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, accumulate, out, ld_out, s);
+        if (chunks == 32 && lpr == 16)
+            launch<4, 16, 2, true, 4>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps,
+                                      self_mode, accumulate, out, ld_out, s);
+        else if (chunks == 16 && lpr == 8)
+            launch<4, 8, 2, true, 4>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps,
+                                     self_mode, accumulate, out, ld_out, s);
         else if (chunks <= 1) HGIN_LAUNCH(4, 1, 1);
         else if (chunks <= 2) HGIN_LAUNCH(4, 2, 1);
         else if (chunks <= 4) HGIN_LAUNCH(4, 4, 1);
