@@ -429,3 +429,46 @@ def test_collate_with_cached_per_sample_csr_matches_k0_on_batched_coo():
                                                   csr=True, keep_coo=False, batch_vector=False), edge_bucket=64)
         losses.append(torch.stack([run(arg).clone() for _ in range(3)]).cpu())
     assert torch.equal(losses[0], losses[1]) and torch.equal(losses[0], losses[2])
+
+
+def test_reference_loop_functions_follow_the_oracle_loop():
+    """Drop-in surface of train.py: load_model / load_optmizer / train_one_epoch / test with the
+    reference's config dict drive the same trajectory as the oracle's restatement of the loop."""
+    from gnn_link_prediction_b200.data import DataLoader
+    from gnn_link_prediction_b200.train import load_model, load_optmizer, test as run_test, train_one_epoch
+    config = {"SEED": 1997, "OPTIMIZER": "adam", "LEARNING_RATE": 0.001, "WEIGHT_DECAY": 0, "NODE_EMBEDDING_SIZE": 8,
+              "MP_LAYERS": 2, "DROPOUT": 0.0, "BL_FEATURES": False, "DIVIDED_FEATURES": False, "MODEL": "GIN",
+              "CONCAT_PATH": True, "GLOBAL_FEATS": False, "MLP_LAYERS": [32, 16], "MLP_ACT": "torch.nn.PReLU()",
+              "MLP_BN": False, "MLP_HEAD_ACT": None}
+    ds = SyntheticDataset(6, num_nodes=10, num_links=14, num_topologies=3)
+    torch.manual_seed(config["SEED"])
+    model = load_model(config, {"train": ds})
+    ref = hgin_oracle.HetroGIN(input_channels={"link": 7, "path": 7, "node": 3}, **config_to_kwargs(config))
+    ref.load_state_dict(model.state_dict())
+    model.cuda().train()
+    opt = load_optmizer(config, model)
+    assert isinstance(opt, torch.optim.Adam)
+    loss, weighted = train_one_epoch(0, mape, opt, DataLoader(ds, batch_size=2), model)
+    # oracle: the same three steps on the CPU
+    ref_opt = torch.optim.Adam(ref.parameters(), lr=1e-3, weight_decay=0)
+    ref_losses, num, den = [], 0.0, 0
+    for b in DataLoader(ds, batch_size=2):
+        lv, out = hgin_oracle.train_step(ref, ref_opt, b)
+        ref_losses.append(float(lv))
+        num += float(hgin_oracle.mape(out, b["path"].y.reshape(-1, 1))) * b["path"].x.shape[0]
+        den += b["path"].x.shape[0]
+    assert abs(loss - sum(ref_losses) / 3) <= 1e-4 * abs(loss)
+    assert abs(weighted - num / den) <= 1e-4 * abs(weighted)
+    for (k, p), (_, q) in zip(model.state_dict().items(), ref.state_dict().items()):
+        close(p, q, rtol=1e-3, atol_rel=1e-4)
+    model.eval()
+    val = run_test(0, mape, DataLoader(ds, batch_size=1), model, "Validation")
+    ref.eval()
+    with torch.no_grad():
+        want = sum(float(hgin_oracle.mape(ref(b.x_dict, b.edge_index_dict, None), b["path"].y.reshape(-1, 1)))
+                   for b in DataLoader(ds, batch_size=1)) / 6
+    assert abs(val - want) <= 1e-4 * abs(want)
+    with pytest.raises(NotImplementedError):
+        load_model({**config, "MODEL": "GAT"}, {"train": ds})
+    with pytest.raises(IOError):
+        load_model({**config, "MODEL": "nope"}, {"train": ds})
