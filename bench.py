@@ -202,6 +202,10 @@ def main():
     ap.add_argument("--collate", default="csr", choices=["csr", "coo"],
                     help="csr: the collate concatenates cached per-sample CSRs (no CSR build in the step); "
                          "coo: ship COO edge lists, hgin_csr_build runs inside every step")
+    ap.add_argument("--stage", default="packed", choices=["packed", "tensors"],
+                    help="e2e arm: H2D of one packed pinned buffer per batch (data.pack_batch) or one copy per tensor")
+    ap.add_argument("--readback", default="deferred", choices=["deferred", "sync"],
+                    help="e2e arm: how each step's loss reaches the host (see e2e_run)")
     ap.add_argument("--graph", dest="graph", action="store_true", default=None,
                     help="replay the step as a CUDA graph (default: on for cfgA at 1 GPU)")
     ap.add_argument("--no-graph", dest="graph", action="store_false")
@@ -300,15 +304,41 @@ def main():
     # while step i runs; every step's copy and its loss read-back are inside the timed region (the
     # first copy is exposed, the rest overlap compute).
     from gnn_link_prediction_b200.data import DevicePrefetcher
+    from gnn_link_prediction_b200.train import LossReadback
     losses = []
+    e2e_host = host
+    if not graphed and args.stage == "packed":
+        from gnn_link_prediction_b200.data import pack_batch
+        e2e_host = [pack_batch(h) for h in host]       # loader-side work, like the collate itself
+        h2d_bytes = e2e_host[0].nbytes()
+    prefetcher = DevicePrefetcher(())
+
+    def prefetcher_over(source):      # one prefetcher (one device ring) for the whole run
+        prefetcher.source = source
+        return prefetcher
 
     def e2e_run(n_steps):
+        # every step's loss is read back to the host inside the timed region; with the default
+        # `deferred` read-back (train.LossReadback) the host collects step i's loss after launching
+        # step i+1, `sync` is the reference's blocking `.item()` (train.py:50)
+        reader = LossReadback() if args.readback == "deferred" else None
+
+        def collect(loss):
+            if reader is None:
+                losses.append(loss.cpu())
+            else:
+                done = reader.push(loss)
+                if done is not None:
+                    losses.append(done)
+
         if graphed:   # one H2D copy of the packed pinned batch into the graph's static buffer, replay, D2H
             for i in range(n_steps):
-                losses.append(step(packed_host[i % n_host]).cpu())
-            return
-        for dev in DevicePrefetcher(host[i % n_host] for i in range(n_steps)):
-            losses.append(step(dev).cpu())   # D2H read of [mape, sqrt(mape)] — synchronises the step (a copy)
+                collect(step(packed_host[i % n_host]))
+        else:         # packed pinned batch -> one DMA into the prefetcher's device ring, overlapping the previous step
+            for dev in prefetcher_over(e2e_host[i % n_host] for i in range(n_steps)):
+                collect(step(dev))
+        if reader is not None:
+            losses.append(reader.flush())
 
     e2e_run(2)
     barrier()
@@ -375,7 +405,11 @@ def main():
                    "parallelism": f"dp{world} (samples sharded, NCCL sum-allreduce of one flat grad bucket)"},
         "edges_per_s": edges * world * args.steps / (resident_ms * 1e-3),
         "e2e": {"value": graphs * world * args.steps / (e2e_ms * 1e-3), "unit": "graphs/s",
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8, "ms_per_step": e2e_ms / args.steps},
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8, "ms_per_step": e2e_ms / args.steps,
+                "staging": "one packed pinned buffer per batch -> DevicePrefetcher ring" if (graphed or args.stage == "packed")
+                else "one H2D copy per tensor (DevicePrefetcher)",
+                "readback": "every step, collected one step later (train.LossReadback)" if args.readback == "deferred"
+                else "every step, blocking"},
         "gpu_launches": launches, "kernels_per_step": kernels_per_step,
         "execution": "one CUDA graph replay per step (GraphedTrainStep)" if graphed else "eager launches",
         "wall_s_resident": t_wall,

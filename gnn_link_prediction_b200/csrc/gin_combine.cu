@@ -52,13 +52,25 @@ __device__ __forceinline__ void store_pack(float *p, const Pack<VEC> &r) {
 
 // LPR lanes per row, VEC features per lane per chunk, NC chunks per lane:
 // covers f_src <= LPR * VEC * NC.
-template <int VEC, int LPR, int NC, bool CONTIG, int MINB>
+// POST: the row result is a gradient w.r.t. the OUTPUT of the layer below; the kernel multiplies
+// it by that layer's activation derivative (reading its saved pre-activation `post.z`) and so
+// writes dz directly, plus the per-CTA partial of dalpha = sum grad * min(z, 0) — the separate
+// dz = g * act'(z) pass over the row-sized tensors of the layer below disappears.
+struct PostAct {
+    const float *z;
+    int64_t ldz;
+    int act;
+    const float *alpha;
+    float *dalpha_partials;   // [gridDim.x]
+};
+
+template <int VEC, int LPR, int NC, bool CONTIG, int MINB, bool POST>
 __global__ void __launch_bounds__(256, MINB)
 gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                    const float *__restrict__ x_src, int64_t ld_src, int f_src,
                    const float *__restrict__ x_self, int64_t ld_self, int f_self,
                    const float *__restrict__ eps_ptr, int self_mode, int accumulate,
-                   float *__restrict__ out, int64_t ld_out) {
+                   float *__restrict__ out, int64_t ld_out, const PostAct post) {
     // gathers in flight per lane before the dependent adds; bounded by the batch (LPR) and by
     // the register budget when a lane carries several chunks
     constexpr int UNROLL_MAX = (NC >= 4) ? 2 : ((NC == 2) ? 4 : 8);
@@ -70,6 +82,8 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
     const unsigned full = 0xffffffffu;
     // fl(1 + eps): the reference computes (1 + self.eps) as an fp32 tensor op (models.py:213/215).
     const float ope = __fadd_rn(1.0f, eps_ptr ? __ldg(eps_ptr) : 0.0f);
+    const float post_alpha = (POST && post.act == HGIN_ACT_PRELU) ? __ldg(post.alpha) : 0.0f;
+    float dalpha = 0.0f;
 
     // Row -> warp mapping.
     // CONTIG (short rows): each CTA owns a CONTIGUOUS block of rows, its warps interleaving inside it.
@@ -101,7 +115,7 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
         const int64_t r = r0 + grp;
         b = 0;
         l = 0;
-        if (r < cta_end) {
+        if (r < cta_end && rowptr != nullptr) {   // rowptr == NULL: no edges at all (self term only)
             b = __ldg(rowptr + r);
             l = __ldg(rowptr + r + 1) - b;
         }
@@ -124,6 +138,14 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
             for (int c = 0; c < NC; ++c) {
                 const int f = (c * LPR + sub) * VEC;
                 if (f < f_src) self_v[c] = load_pack<VEC>(x_self + row * ld_self + f);
+            }
+        }
+        Pack<VEC> post_v[NC];
+        if (POST && post.act != HGIN_ACT_NONE && live) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int f = (c * LPR + sub) * VEC;
+                if (f < f_src) post_v[c] = load_pack<VEC>(post.z + row * post.ldz + f);
             }
         }
         // warp-uniform trip count so the shuffles below are always convergent
@@ -191,6 +213,14 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
 #pragma unroll
                     for (int i = 0; i < VEC; ++i) r.v[i] = __fadd_rn(old.v[i], r.v[i]);
                 }
+                if (POST && post.act != HGIN_ACT_NONE) {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        const float zv = post_v[c].v[i];
+                        if (post.act == HGIN_ACT_PRELU && !(zv > 0.f)) dalpha = fmaf(r.v[i], zv, dalpha);
+                        r.v[i] = act_backward(r.v[i], zv, post.act, post_alpha);
+                    }
+                }
                 store_pack<VEC>(orow + f, r);
             }
             if (self_mode == HGIN_SELF_CONCAT) {
@@ -205,49 +235,97 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
         beg = nbeg; len = nlen; mine = nmine;
         nbeg = nnbeg; nlen = nnlen;
     }
+    if (POST && post.dalpha_partials) {   // fixed association: lanes -> warps -> CTA partial
+        __shared__ float red[32];
+        dalpha = block_sum(dalpha, red);
+        if (threadIdx.x == 0) post.dalpha_partials[blockIdx.x] = dalpha;
+    }
 }
 
+__global__ void __launch_bounds__(1024) combine_reduce_scalar_kernel(const float *__restrict__ v, int count,
+                                                                     float *__restrict__ out) {
+    __shared__ float red[32];
+    float s = 0.0f;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) s += v[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+constexpr int kMaxCombineCtas = kNumSMs * 32;
+
 template <int VEC, int LPR, int NC, bool CONTIG = false, int MINB = ((VEC * NC <= 4) ? 4 : 1)>
-void launch(int64_t num_rows, const int32_t *rowptr, const int32_t *col, const float *x_src, int64_t ld_src,
-            int f_src, const float *x_self, int64_t ld_self, int f_self, const float *eps, int self_mode,
-            int accumulate, float *out, int64_t ld_out, cudaStream_t s) {
+int launch(int64_t num_rows, const int32_t *rowptr, const int32_t *col, const float *x_src, int64_t ld_src,
+           int f_src, const float *x_self, int64_t ld_self, int f_self, const float *eps, int self_mode,
+           int accumulate, float *out, int64_t ld_out, const PostAct *post, cudaStream_t s) {
     constexpr int rows_per_cta = (256 / 32) * (32 / LPR);
     // Grid-stride over rows with whole waves of CTAs: enough CTAs (32 per SM) that the hardware
     // scheduler evens out the heavy-tailed row lengths of the path->link relation.
     const int grid = grid_for(num_rows, rows_per_cta, 32);
-    gin_combine_kernel<VEC, LPR, NC, CONTIG, MINB><<<grid, 256, 0, s>>>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self,
-                                                          ld_self, f_self, eps, self_mode, accumulate, out, ld_out);
+    if (post)
+        gin_combine_kernel<VEC, LPR, NC, CONTIG, MINB, true><<<grid, 256, 0, s>>>(
+            num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, accumulate, out, ld_out,
+            *post);
+    else
+        gin_combine_kernel<VEC, LPR, NC, CONTIG, MINB, false><<<grid, 256, 0, s>>>(
+            num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, accumulate, out, ld_out,
+            PostAct{});
+    return grid;
 }
 
 }  // namespace
 }  // namespace hgin
 
-extern "C" int32_t hgin_gin_combine(int64_t num_rows, const int32_t *rowptr, const int32_t *col, int64_t num_edges,
-                                    const float *x_src, int64_t ld_src, int32_t f_src, const float *x_self, int64_t ld_self,
-                                    int32_t f_self, const float *eps, int32_t self_mode, int32_t accumulate,
-                                    float *out, int64_t ld_out, void *stream) {
-    using namespace hgin;
-    HGIN_CHECK_ARG(num_rows >= 0 && num_rows < INT32_MAX, "hgin_gin_combine: bad num_rows %lld", (long long)num_rows);
-    HGIN_CHECK_ARG(f_src > 0 && f_src <= 512, "hgin_gin_combine: f_src must be in [1,512], got %d", f_src);
-    HGIN_CHECK_ARG(self_mode >= HGIN_SELF_NONE && self_mode <= HGIN_SELF_CONCAT, "hgin_gin_combine: bad self_mode %d",
-                   self_mode);
-    HGIN_CHECK_ARG(self_mode == HGIN_SELF_NONE || x_self != nullptr, "hgin_gin_combine: x_self is null");
-    HGIN_CHECK_ARG(self_mode != HGIN_SELF_ADD || f_self == f_src, "hgin_gin_combine: SELF_ADD needs f_self == f_src");
-    HGIN_CHECK_ARG(self_mode != HGIN_SELF_CONCAT || f_self > 0, "hgin_gin_combine: SELF_CONCAT needs f_self > 0");
-    if (num_rows == 0) return HGIN_OK;
-    // `col` may be null for an edgeless relation (every row empty): it is never dereferenced then.
-    HGIN_CHECK_ARG(rowptr && x_src && out, "hgin_gin_combine: null pointer");
-    const int width = f_src + (self_mode == HGIN_SELF_CONCAT ? f_self : 0);
-    HGIN_CHECK_ARG(ld_src >= f_src && ld_out >= width, "hgin_gin_combine: leading dimension too small");
+namespace hgin {
+namespace {
+
+int32_t combine_dispatch(int64_t num_rows, const int32_t *rowptr, const int32_t *col, int64_t num_edges,
+                         const float *x_src, int64_t ld_src, int32_t f_src, const float *x_self, int64_t ld_self,
+                         int32_t f_self, const float *eps, int32_t self_mode, int32_t accumulate, float *out,
+                         int64_t ld_out, const float *post_z, int64_t ld_post, int32_t post_act,
+                         const float *post_alpha, float *post_dalpha, void *workspace, int64_t workspace_bytes,
+                         void *stream, const char *who) {
+    HGIN_CHECK_ARG(num_rows >= 0 && num_rows < INT32_MAX, "%s: bad num_rows %lld", who, (long long)num_rows);
+    HGIN_CHECK_ARG(f_src > 0 && f_src <= 512, "%s: f_src must be in [1,512], got %d", who, f_src);
+    HGIN_CHECK_ARG(self_mode >= HGIN_SELF_NONE && self_mode <= HGIN_SELF_CONCAT, "%s: bad self_mode %d", who, self_mode);
+    HGIN_CHECK_ARG(self_mode == HGIN_SELF_NONE || x_self != nullptr, "%s: x_self is null", who);
+    HGIN_CHECK_ARG(self_mode != HGIN_SELF_ADD || f_self == f_src, "%s: SELF_ADD needs f_self == f_src", who);
+    HGIN_CHECK_ARG(self_mode != HGIN_SELF_CONCAT || f_self > 0, "%s: SELF_CONCAT needs f_self > 0", who);
+    const bool post_on = post_z != nullptr && post_act != HGIN_ACT_NONE;
+    HGIN_CHECK_ARG(post_act >= HGIN_ACT_NONE && post_act <= HGIN_ACT_RELU, "%s: bad post_act %d", who, post_act);
+    HGIN_CHECK_ARG(!post_on || self_mode != HGIN_SELF_CONCAT, "%s: post-activation needs a [rows, f_src] result", who);
+    HGIN_CHECK_ARG(!post_on || post_act != HGIN_ACT_PRELU || post_alpha, "%s: PReLU post-activation needs alpha", who);
+    HGIN_CHECK_ARG(!post_on || ld_post >= f_src, "%s: ld_post too small", who);
+    const bool want_dalpha = post_dalpha != nullptr;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (want_dalpha && !(post_on && post_act == HGIN_ACT_PRELU)) {
+        cudaMemsetAsync(post_dalpha, 0, sizeof(float), s);
+    } else if (want_dalpha) {
+        if (!workspace || workspace_bytes < static_cast<int64_t>(kMaxCombineCtas) * 4)
+            return fail(HGIN_ERR_WORKSPACE_TOO_SMALL, "%s: workspace %lld < %lld bytes", who, (long long)workspace_bytes,
+                        (long long)kMaxCombineCtas * 4);
+        if (num_rows == 0) cudaMemsetAsync(post_dalpha, 0, sizeof(float), s);
+    }
+    if (num_rows == 0) return HGIN_OK;
+    // `rowptr` may be null when the relation has no edges at all (self term only), `col` for an
+    // edgeless relation (every row empty): neither is dereferenced then.
+    HGIN_CHECK_ARG(x_src && out, "%s: null pointer", who);
+    HGIN_CHECK_ARG(rowptr || self_mode != HGIN_SELF_NONE, "%s: no adjacency and no self term", who);
+    const int width = f_src + (self_mode == HGIN_SELF_CONCAT ? f_self : 0);
+    HGIN_CHECK_ARG(ld_src >= f_src && ld_out >= width, "%s: leading dimension too small", who);
+    PostAct post{post_z, ld_post, post_act, post_alpha,
+                 (want_dalpha && post_act == HGIN_ACT_PRELU) ? static_cast<float *>(workspace) : nullptr};
+    const PostAct *pp = post_on ? &post : nullptr;
+    if (!rowptr) num_edges = 0;
 
     // 128-bit lanes need every row start 16-byte aligned.
     bool vec4 = (f_src % 4 == 0) && (ld_src % 4 == 0) && (ld_out % 4 == 0) && aligned16(x_src) && aligned16(out);
     if (self_mode == HGIN_SELF_ADD) vec4 = vec4 && (ld_self % 4 == 0) && aligned16(x_self);
+    if (post_on) vec4 = vec4 && (ld_post % 4 == 0) && aligned16(post_z);
 
+    int grid = 0;
 #define HGIN_LAUNCH(V, L, N)                                                                                    \
-    launch<V, L, N>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode,      \
-                    accumulate, out, ld_out, s)
+    grid = launch<V, L, N>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, \
+                           accumulate, out, ld_out, pp, s)
     // Lanes per row: a full warp per row suits long rows (path->link, ~36 neighbours); for short
     // rows (link->path, ~3 neighbours) the per-row latency chain rowptr -> col -> gather dominates,
     // so several rows share a warp and each lane carries more 128-bit chunks.
@@ -260,11 +338,11 @@ extern "C" int32_t hgin_gin_combine(int64_t num_rows, const int32_t *rowptr, con
         const bool short_rows = avg_len <= 8.0;
         if ((chunks == 32 || chunks == 16) && short_rows) lpr = chunks / 2;
         if (chunks == 32 && lpr == 16)
-            launch<4, 16, 2, true, 4>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps,
-                                      self_mode, accumulate, out, ld_out, s);
+            grid = launch<4, 16, 2, true, 4>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps,
+                                             self_mode, accumulate, out, ld_out, pp, s);
         else if (chunks == 16 && lpr == 8)
-            launch<4, 8, 2, true, 4>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps,
-                                     self_mode, accumulate, out, ld_out, s);
+            grid = launch<4, 8, 2, true, 4>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps,
+                                            self_mode, accumulate, out, ld_out, pp, s);
         else if (chunks <= 1) HGIN_LAUNCH(4, 1, 1);
         else if (chunks <= 2) HGIN_LAUNCH(4, 2, 1);
         else if (chunks <= 4) HGIN_LAUNCH(4, 4, 1);
@@ -286,6 +364,32 @@ extern "C" int32_t hgin_gin_combine(int64_t num_rows, const int32_t *rowptr, con
         else HGIN_LAUNCH(1, 32, 16);
     }
 #undef HGIN_LAUNCH
-    HGIN_CHECK_LAUNCH("hgin_gin_combine");
+    if (post.dalpha_partials && pp) combine_reduce_scalar_kernel<<<1, 1024, 0, s>>>(post.dalpha_partials, grid, post_dalpha);
+    HGIN_CHECK_LAUNCH(who);
     return HGIN_OK;
+}
+
+}  // namespace
+}  // namespace hgin
+
+extern "C" int32_t hgin_gin_combine(int64_t num_rows, const int32_t *rowptr, const int32_t *col, int64_t num_edges,
+                                    const float *x_src, int64_t ld_src, int32_t f_src, const float *x_self, int64_t ld_self,
+                                    int32_t f_self, const float *eps, int32_t self_mode, int32_t accumulate,
+                                    float *out, int64_t ld_out, void *stream) {
+    return hgin::combine_dispatch(num_rows, rowptr, col, num_edges, x_src, ld_src, f_src, x_self, ld_self, f_self, eps,
+                                  self_mode, accumulate, out, ld_out, nullptr, 0, HGIN_ACT_NONE, nullptr, nullptr,
+                                  nullptr, 0, stream, "hgin_gin_combine");
+}
+
+extern "C" int64_t hgin_gin_combine_post_workspace_bytes(void) { return static_cast<int64_t>(hgin::kMaxCombineCtas) * 4; }
+
+extern "C" int32_t hgin_gin_combine_post(int64_t num_rows, const int32_t *rowptr, const int32_t *col, int64_t num_edges,
+                                         const float *x_src, int64_t ld_src, int32_t f_src, const float *x_self,
+                                         int64_t ld_self, int32_t f_self, const float *eps, int32_t self_mode,
+                                         int32_t accumulate, float *out, int64_t ld_out, const float *post_z,
+                                         int64_t ld_post, int32_t post_act, const float *post_alpha, float *post_dalpha,
+                                         void *workspace, int64_t workspace_bytes, void *stream) {
+    return hgin::combine_dispatch(num_rows, rowptr, col, num_edges, x_src, ld_src, f_src, x_self, ld_self, f_self, eps,
+                                  self_mode, accumulate, out, ld_out, post_z, ld_post, post_act, post_alpha, post_dalpha,
+                                  workspace, workspace_bytes, stream, "hgin_gin_combine_post");
 }

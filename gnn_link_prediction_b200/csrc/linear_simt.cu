@@ -360,12 +360,40 @@ extern "C" int64_t hgin_linear_bwd_workspace_bytes(int64_t rows, int32_t k, int3
     return simt > tc ? simt : tc;
 }
 
-extern "C" int32_t hgin_linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, int64_t ldz,
-                                   int32_t act, const float *alpha, const float *x1, int64_t ld1, int32_t k1,
-                                   const float *x2, int64_t ld2, int32_t k2, const float *W, int32_t n, int32_t c0,
-                                   int32_t c1, float *dx, int64_t lddx, const float *dot_x, int64_t ld_dot,
-                                   float *ddot, float *dW, float *db, float *dalpha, void *workspace,
-                                   int64_t workspace_bytes, int32_t math_mode, void *stream) {
+// dx *= act'(post_z) in place, post_dalpha = sum dx * min(post_z, 0): the generic (non-fused) form of
+// the post-activation used when the tensor-core kernel does not take the shape.
+namespace hgin {
+namespace {
+__global__ void __launch_bounds__(256)
+post_apply_kernel(int64_t rows, int width, float *__restrict__ dx, int64_t lddx, const float *__restrict__ z, int64_t ldz,
+                  int act, const float *__restrict__ alpha_ptr, float *__restrict__ partials) {
+    __shared__ float red[32];
+    const float alpha = (act == HGIN_ACT_PRELU) ? __ldg(alpha_ptr) : 0.0f;
+    float dal = 0.0f;
+    const int64_t total = rows * width;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t m = i / width;
+        const int c = static_cast<int>(i % width);
+        const float zv = __ldg(z + m * ldz + c);
+        const float v = dx[m * lddx + c];
+        if (act == HGIN_ACT_PRELU && !(zv > 0.f)) dal = fmaf(v, zv, dal);
+        dx[m * lddx + c] = act_backward(v, zv, act, alpha);
+    }
+    dal = block_sum(dal, red);
+    if (threadIdx.x == 0 && partials) partials[blockIdx.x] = dal;
+}
+constexpr int kPostCtas = kNumSMs * 8;
+}  // namespace
+}  // namespace hgin
+
+static int32_t linear_bwd_impl(int64_t rows, const float *g, int64_t ldg, const float *z, int64_t ldz,
+                               int32_t act, const float *alpha, const float *x1, int64_t ld1, int32_t k1,
+                               const float *x2, int64_t ld2, int32_t k2, const float *W, int32_t n, int32_t c0,
+                               int32_t c1, float *dx, int64_t lddx, const float *dot_x, int64_t ld_dot,
+                               float *ddot, float *dW, float *db, float *dalpha, void *workspace,
+                               int64_t workspace_bytes, int32_t math_mode, void *stream,
+                               const hgin::tcgemm::PostArgs *post) {
     using namespace hgin;
     const int k = k1 + k2;
     HGIN_CHECK_ARG(rows >= 0 && k1 > 0 && k2 >= 0 && n > 0, "hgin_linear_bwd: bad sizes");
@@ -385,16 +413,19 @@ extern "C" int32_t hgin_linear_bwd(int64_t rows, const float *g, int64_t ldg, co
     float *dw_partials = static_cast<float *>(workspace);
     float *scal = reinterpret_cast<float *>(static_cast<char *>(workspace) + align_up(splits * n * (k + 1) * 4, 256));
 
-    if (rows > 0 && thin::head_bwd_eligible(x1, ld1, k1, k2, n, c0, c1, dx, lddx, dot_x, W) && !ddot)
+    const bool tc_ok = math_mode == HGIN_MATH_TF32 && rows > 0 &&
+        tcgemm::bwd_eligible(rows, g, ldg, z, ldz, act, x1, ld1, k1, k2, n, c0, c1, dx, lddx, dot_x, ld_dot) &&
+        (!post || (c1 - c0 >= 16 && post->ldz % 4 == 0 && aligned16(post->z)));
+    if (post && !tc_ok) return HGIN_ERR_UNSUPPORTED;   // hgin_linear_bwd_post then runs the generic form
+    if (!post && rows > 0 && thin::head_bwd_eligible(x1, ld1, k1, k2, n, c0, c1, dx, lddx, dot_x, W) && !ddot)
         return thin::head_bwd(rows, g, ldg, z, ldz, act, alpha, x1, ld1, k1, W, dx, lddx, dW, db, dalpha, workspace,
                               static_cast<cudaStream_t>(stream));
-    if (rows > 0 && thin::bwd_eligible(g, ldg, z, ldz, act, k1, k2, n, c0, c1, dx, dot_x))
+    if (!post && rows > 0 && thin::bwd_eligible(g, ldg, z, ldz, act, k1, k2, n, c0, c1, dx, dot_x))
         return thin::linear_bwd(rows, g, ldg, z, ldz, act, alpha, x1, ld1, k1, W, n, c0, c1, dot_x, ld_dot, ddot, dW, db,
                                 dalpha, workspace, static_cast<cudaStream_t>(stream));
-    if (math_mode == HGIN_MATH_TF32 && rows > 0 &&
-        tcgemm::bwd_eligible(rows, g, ldg, z, ldz, act, x1, ld1, k1, k2, n, c0, c1, dx, lddx, dot_x, ld_dot)) {
+    if (tc_ok) {
         return tcgemm::linear_bwd(rows, g, ldg, z, ldz, act, alpha, x1, ld1, k1, x2, ld2, k2, W, n, c0, c1, dx, lddx,
-                                  dot_x, ld_dot, ddot, dW, db, dalpha, workspace, nullptr,
+                                  dot_x, ld_dot, ddot, dW, db, dalpha, workspace, nullptr, post,
                                   static_cast<cudaStream_t>(stream));
     }
     if (rows == 0) {  // empty batch: all reductions are zero
@@ -473,6 +504,57 @@ extern "C" int32_t hgin_linear_bwd(int64_t rows, const float *g, int64_t ldg, co
     return HGIN_OK;
 }
 
+extern "C" int32_t hgin_linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, int64_t ldz,
+                                   int32_t act, const float *alpha, const float *x1, int64_t ld1, int32_t k1,
+                                   const float *x2, int64_t ld2, int32_t k2, const float *W, int32_t n, int32_t c0,
+                                   int32_t c1, float *dx, int64_t lddx, const float *dot_x, int64_t ld_dot,
+                                   float *ddot, float *dW, float *db, float *dalpha, void *workspace,
+                                   int64_t workspace_bytes, int32_t math_mode, void *stream) {
+    return linear_bwd_impl(rows, g, ldg, z, ldz, act, alpha, x1, ld1, k1, x2, ld2, k2, W, n, c0, c1, dx, lddx, dot_x,
+                           ld_dot, ddot, dW, db, dalpha, workspace, workspace_bytes, math_mode, stream, nullptr);
+}
+
+extern "C" int32_t hgin_linear_bwd_post(int64_t rows, const float *g, int64_t ldg, const float *z, int64_t ldz,
+                                        int32_t act, const float *alpha, const float *x1, int64_t ld1, int32_t k1,
+                                        const float *x2, int64_t ld2, int32_t k2, const float *W, int32_t n, int32_t c0,
+                                        int32_t c1, float *dx, int64_t lddx, float *dW, float *db, float *dalpha,
+                                        const float *post_z, int64_t ld_post, int32_t post_act, const float *post_alpha,
+                                        float *post_dalpha, void *workspace, int64_t workspace_bytes, int32_t math_mode,
+                                        void *stream) {
+    using namespace hgin;
+    HGIN_CHECK_ARG(post_act >= HGIN_ACT_NONE && post_act <= HGIN_ACT_RELU, "hgin_linear_bwd_post: bad post_act %d", post_act);
+    HGIN_CHECK_ARG(post_act == HGIN_ACT_NONE || (post_z && dx && c1 > c0), "hgin_linear_bwd_post: post-activation needs post_z and dx");
+    HGIN_CHECK_ARG(post_act != HGIN_ACT_PRELU || post_alpha, "hgin_linear_bwd_post: PReLU needs post_alpha");
+    HGIN_CHECK_ARG(post_act == HGIN_ACT_NONE || ld_post >= c1 - c0, "hgin_linear_bwd_post: ld_post too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (post_act == HGIN_ACT_NONE) {
+        if (post_dalpha) cudaMemsetAsync(post_dalpha, 0, sizeof(float), s);
+        return linear_bwd_impl(rows, g, ldg, z, ldz, act, alpha, x1, ld1, k1, x2, ld2, k2, W, n, c0, c1, dx, lddx, nullptr,
+                               0, nullptr, dW, db, dalpha, workspace, workspace_bytes, math_mode, stream, nullptr);
+    }
+    tcgemm::PostArgs post{post_z, ld_post, post_act, post_alpha, post_dalpha};
+    int32_t rc = linear_bwd_impl(rows, g, ldg, z, ldz, act, alpha, x1, ld1, k1, x2, ld2, k2, W, n, c0, c1, dx, lddx,
+                                 nullptr, 0, nullptr, dW, db, dalpha, workspace, workspace_bytes, math_mode, stream, &post);
+    if (rc != HGIN_ERR_UNSUPPORTED) return rc;
+    // generic form: plain backward, then one elementwise pass over dx
+    rc = linear_bwd_impl(rows, g, ldg, z, ldz, act, alpha, x1, ld1, k1, x2, ld2, k2, W, n, c0, c1, dx, lddx, nullptr, 0,
+                         nullptr, dW, db, dalpha, workspace, workspace_bytes, math_mode, stream, nullptr);
+    if (rc != HGIN_OK) return rc;
+    if (workspace_bytes < static_cast<int64_t>(kPostCtas) * 4)
+        return fail(HGIN_ERR_WORKSPACE_TOO_SMALL, "hgin_linear_bwd_post: workspace too small");
+    float *partials = static_cast<float *>(workspace);   // the backward's partials are consumed by now (stream order)
+    const bool want = post_dalpha && post_act == HGIN_ACT_PRELU;
+    if (rows > 0) {
+        const int grid = grid_for(rows * (c1 - c0), 256 * 4, 8);
+        post_apply_kernel<<<grid, 256, 0, s>>>(rows, c1 - c0, dx, lddx, post_z, ld_post, post_act, post_alpha,
+                                               want ? partials : nullptr);
+        if (want) reduce_scalar_kernel<<<1, 1024, 0, s>>>(partials, grid, post_dalpha);
+    }
+    if (post_dalpha && (!want || rows == 0)) cudaMemsetAsync(post_dalpha, 0, sizeof(float), s);
+    HGIN_CHECK_LAUNCH("hgin_linear_bwd_post");
+    return HGIN_OK;
+}
+
 extern "C" int32_t hgin_debug_gemm_tn(int64_t rows, const float *a, int32_t n, const float *b, int32_t k, float *out,
                                       void *workspace, int64_t workspace_bytes, int32_t tma_swizzle, int32_t lbo,
                                       int32_t sbo, int32_t layout_type, int32_t k_step_bytes, void *stream) {
@@ -485,7 +567,7 @@ extern "C" int32_t hgin_debug_gemm_tn(int64_t rows, const float *a, int32_t n, c
                       layout_type < 0 ? 1 : layout_type, k_step_bytes < 0 ? 1024 : k_step_bytes};
     // dz = a (no activation), dW = a^T b
     return tcgemm::linear_bwd(rows, a, n, nullptr, 0, HGIN_ACT_NONE, nullptr, b, k, k, nullptr, 0, 0, out /*W unused*/, n,
-                              0, 0, nullptr, 0, nullptr, 0, nullptr, out, nullptr, nullptr, workspace, &d,
+                              0, 0, nullptr, 0, nullptr, 0, nullptr, out, nullptr, nullptr, workspace, &d, nullptr,
                               static_cast<cudaStream_t>(stream));
 }
 

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(DZ_THREADS)
 dz_prepare_kernel(int64_t rows, int n, const float *__restrict__ g, int64_t ldg, const float *__restrict__ z,
                   int64_t ldz, int act, const float *__restrict__ alpha_ptr, const float *__restrict__ x2,
                   int64_t ld2, int k2, float *__restrict__ dz, float *__restrict__ part,
-                  float *__restrict__ alpha_part, int want_sums) {
+                  float *__restrict__ alpha_part, int want_sums, int write_dz) {
     extern __shared__ float sm[];  // [slots][n][5] for the cross-slot combine
     __shared__ float red[32];
     const int tpr = n / 4;                       // threads per row (float4 each)
@@ -98,7 +98,7 @@ dz_prepare_kernel(int64_t rows, int n, const float *__restrict__ g, int64_t ldg,
                     d[i] = act_backward(d[i], zv[i], act, alpha);
                 }
             }
-            reinterpret_cast<float4 *>(dz + m * n)[cg] = make_float4(d[0], d[1], d[2], d[3]);
+            if (write_dz) reinterpret_cast<float4 *>(dz + m * n)[cg] = make_float4(d[0], d[1], d[2], d[3]);
             if (want_sums) {
                 float xv[4] = {0.f, 0.f, 0.f, 0.f};
                 for (int t = 0; t < k2; ++t) xv[t] = __ldg(x2 + m * ld2 + t);
@@ -202,6 +202,7 @@ int64_t bwd_workspace_bytes(int64_t rows, int k1, int k2, int n) {
     b += align_up(static_cast<int64_t>(dz_ctas()) * 4, 1024);              // dalpha partials
     b += align_up(static_cast<int64_t>(kNumSMs) * n * k1 * 4, 1024);       // dW partials
     b += align_up(static_cast<int64_t>(kNumSMs) * 4, 1024);                // dot partials
+    b += align_up(static_cast<int64_t>(kNumSMs) * n * 4, 1024);            // db partials of the weight-gradient kernel
     return b + 1024;
 }
 
@@ -292,9 +293,11 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
                    const float *alpha, const float *x1, int64_t ld1, int k1, const float *x2, int64_t ld2, int k2,
                    const float *W, int n, int c0, int c1, float *dx, int64_t lddx, const float *dot_x,
                    int64_t ld_dot, float *ddot, float *dW, float *db, float *dalpha, void *workspace,
-                   const TnDebug *dbg, cudaStream_t s) {
+                   const TnDebug *dbg, const PostArgs *post, cudaStream_t s) {
     if (int32_t rc = set_attrs()) return rc;
     const int k = k1 + k2;
+    const bool post_on = post && post->z && post->act != HGIN_ACT_NONE;
+    if (post_on && ddot) return fail(HGIN_ERR_UNSUPPORTED, "hgin_linear_bwd(tf32): post-activation and ddot together");
     char *ws = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
     float *dz = reinterpret_cast<float *>(carve(ws, rows * n * 4));
     float *Wt = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(128) * n * 4));
@@ -302,13 +305,14 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
     float *alpha_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(dz_ctas()) * 4));
     float *dw_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(kNumSMs) * n * k1 * 4));
     float *dot_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(kNumSMs) * 4));
+    float *db_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(kNumSMs) * n * 4));
 
     // 0. fused single-pass backward when the shapes allow it (linear_tc_fused.cuh)
     // Opt-in (HGIN_FUSED_BWD=1 or hgin_set_option("fused_bwd", 1)): on B200 the fused kernel is bound
     // by bytes in flight — W (64 KB) + the x tile (64 KB) leave shared memory for a 2-stage ring only,
     // ~64 KB of DRAM reads outstanding per SM against the ~130 KB that 43 GB/s/SM x ~3 us loaded
     // latency require — and measures 2.3 ms against 1.5 ms for the three-pass path.
-    if (fused_bwd_enabled() && !dbg && dW && n % 32 == 0 && k1 % 16 == 0 && k1 >= 32 && c0 == 0 && c1 == k1 && (dx || ddot)) {
+    if (fused_bwd_enabled() && !dbg && !post_on && act != HGIN_ACT_NONE && dW && n % 32 == 0 && k1 % 16 == 0 && k1 >= 32 && c0 == 0 && c1 == k1 && (dx || ddot)) {
         const int width = k1;
         transpose_cols_kernel<<<grid_for(n * width, 256, 1), 256, 0, s>>>(W, n, k, 0, width, Wt);
         CUtensorMap tm_g, tm_z, tm_wt, tm_h, tm_dx, tm_e;
@@ -357,7 +361,7 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
     const float *dz_src = dz;     // what step 2 contracts with W
     int64_t dz_ld = n;
     bool dw_done = false;
-    if (fused_dw_enabled() && !dbg && dW && (n == 32 || n == 64 || n == 128) && k1 % 16 == 0) {
+    if (fused_dw_enabled() && !dbg && act != HGIN_ACT_NONE && dW && (n == 32 || n == 64 || n == 128) && k1 % 16 == 0) {
         CUtensorMap tm_g, tm_z, tm_h, tm_dz;
         const bool act_on = act != HGIN_ACT_NONE;
         bool ok = make_map(&tm_g, g, n, rows, ldg, 32, BM, CU_TENSOR_MAP_SWIZZLE_128B) &&
@@ -394,19 +398,33 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
         }
         dw_done = true;
     }
+    // act == NONE: g already IS dz (the producer of g applied this layer's activation derivative,
+    // hgin_linear_bwd_post / hgin_gin_combine_post) and is consumed in place by both GEMMs; db comes
+    // out of the weight-gradient MMA (ones column), so no pass over g remains unless the rank-k2
+    // tail of dW is wanted.
+    bool db_from_mma = false;
     if (!dw_done) {
-    const int want_sums = (dW || db || dalpha) ? 1 : 0;
-    const bool want_alpha = dalpha && act == HGIN_ACT_PRELU;
-    const int tpr = n / 4, slots = DZ_THREADS / tpr;
-    const int ctas = static_cast<int>(ceil_div(rows, slots) < dz_ctas() ? ceil_div(rows, slots) : dz_ctas());
-    dz_prepare_kernel<<<ctas, DZ_THREADS, static_cast<size_t>(slots) * n * 5 * 4, s>>>(
-        rows, n, g, ldg, z, ldz, act, alpha, x2, ld2, k2, dz, sum_part, want_alpha ? alpha_part : nullptr, want_sums);
-    if (want_sums && (db || (dW && k2 > 0)))
-        reduce_partials_kernel<<<grid_for(n * (k2 + 1), 256, 1), 256, 0, s>>>(sum_part, ctas, n, k2, 1, dW, k, k1, db);
-    if (dalpha) {
-        if (want_alpha) reduce_scalar_tc_kernel<<<1, 1024, 0, s>>>(alpha_part, ctas, dalpha);
-        else cudaMemsetAsync(dalpha, 0, sizeof(float), s);
-    }
+        const bool inplace = act == HGIN_ACT_NONE && !dbg;
+        db_from_mma = inplace && dW && db && k1 % 32 == 0;
+        const bool tail = dW && k2 > 0;
+        const int want_sums = inplace ? ((tail || (db && !db_from_mma)) ? 1 : 0) : ((dW || db || dalpha) ? 1 : 0);
+        const bool want_alpha = dalpha && act == HGIN_ACT_PRELU;
+        if (inplace) {
+            dz_src = g;
+            dz_ld = ldg;
+        }
+        if (!inplace || want_sums) {
+            const int tpr = n / 4, slots = DZ_THREADS / tpr;
+            const int ctas = static_cast<int>(ceil_div(rows, slots) < dz_ctas() ? ceil_div(rows, slots) : dz_ctas());
+            dz_prepare_kernel<<<ctas, DZ_THREADS, static_cast<size_t>(slots) * n * 5 * 4, s>>>(
+                rows, n, g, ldg, z, ldz, act, alpha, x2, ld2, k2, dz, sum_part, want_alpha ? alpha_part : nullptr, want_sums,
+                inplace ? 0 : 1);
+            if (want_sums && ((db && !db_from_mma) || tail))
+                reduce_partials_kernel<<<grid_for(n * (k2 + 1), 256, 1), 256, 0, s>>>(sum_part, ctas, n, k2, 1, dW, k, k1,
+                                                                                     db_from_mma ? nullptr : db);
+            if (want_alpha) reduce_scalar_tc_kernel<<<1, 1024, 0, s>>>(alpha_part, ctas, dalpha);
+        }
+        if (dalpha && !want_alpha) cudaMemsetAsync(dalpha, 0, sizeof(float), s);
     }
 
     // 2. input gradient: dx[:, c0:c1] = dz * W[:, c0:c1]
@@ -418,30 +436,37 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
                   make_map(&tm_b, Wt, n, width, n, KB, width, CU_TENSOR_MAP_SWIZZLE_128B);
         // without a dx destination the store map still needs a valid (never written) target
         ok = ok && make_map(&tm_o, dx ? dx : dz, dx ? width : n, rows, dx ? lddx : n, 32, BM, CU_TENSOR_MAP_SWIZZLE_128B);
-        ok = ok && make_map(&tm_e, dot_x ? dot_x : dz, dot_x ? width : n, rows, dot_x ? ld_dot : n, 32, BM,
-                            CU_TENSOR_MAP_SWIZZLE_128B);
+        const float *e_src = post_on ? post->z : (dot_x ? dot_x : dz);
+        const int64_t e_ld = post_on ? post->ldz : (dot_x ? ld_dot : n);
+        ok = ok && make_map(&tm_e, e_src, (post_on || dot_x) ? width : n, rows, e_ld, 32, BM, CU_TENSOR_MAP_SWIZZLE_128B);
         if (!ok) return fail(HGIN_ERR_CUDA, "hgin_linear_bwd(tf32): cuTensorMapEncodeTiled failed (dx)");
         NtParams p{};
         p.rows = rows;
         p.num_tiles = static_cast<int>(ceil_div(rows, BM));
         p.num_kb = static_cast<int>(ceil_div(n, KB));
         p.n = width;
-        p.act = HGIN_ACT_NONE;
+        p.act = post_on ? post->act : HGIN_ACT_NONE;
+        p.alpha = post_on ? post->alpha : nullptr;
         p.want_out = dx != nullptr;
-        p.use_e = ddot != nullptr;
-        p.dot_partials = ddot ? dot_part : nullptr;
+        p.use_e = post_on ? 2 : (ddot != nullptr ? 1 : 0);
+        const bool post_alpha = post_on && post->dalpha && post->act == HGIN_ACT_PRELU;
+        p.dot_partials = (ddot || post_alpha) ? dot_part : nullptr;
         const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
         gemm_nt_kernel<EPI_DX><<<grid, NT_THREADS, NtSmem::total, s>>>(tm_a, tm_b, tm_o, tm_o, tm_e, p);
         if (ddot) reduce_scalar_tc_kernel<<<1, 1024, 0, s>>>(dot_part, grid, ddot);
-    } else if (ddot) {
-        cudaMemsetAsync(ddot, 0, sizeof(float), s);
+        if (post_alpha) reduce_scalar_tc_kernel<<<1, 1024, 0, s>>>(dot_part, grid, post->dalpha);
+        else if (post && post->dalpha) cudaMemsetAsync(post->dalpha, 0, sizeof(float), s);
+    } else {
+        if (ddot) cudaMemsetAsync(ddot, 0, sizeof(float), s);
+        if (post && post->dalpha) cudaMemsetAsync(post->dalpha, 0, sizeof(float), s);
     }
 
     // 3. weight gradient: dW[:, :k1] = dz^T x1 (unless step 1 already produced it)
     if (dW && !dw_done) {
         const CUtensorMapSwizzle swz = dbg ? static_cast<CUtensorMapSwizzle>(dbg->tma_swizzle) : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
         CUtensorMap tm_a, tm_b;
-        bool ok = make_map(&tm_a, dz, n, rows, n, 32, TN_ROWS, swz) && make_map(&tm_b, x1, k1, rows, ld1, 32, TN_ROWS, swz);
+        bool ok = make_map(&tm_a, dz_src, n, rows, dz_ld, 32, TN_ROWS, swz) &&
+                  make_map(&tm_b, x1, k1, rows, ld1, 32, TN_ROWS, swz);
         if (!ok) return fail(HGIN_ERR_CUDA, "hgin_linear_bwd(tf32): cuTensorMapEncodeTiled failed (dW)");
         TnParams p{};
         p.rows = rows;
@@ -449,6 +474,8 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
         p.n = n;
         p.k = k1;
         p.partials = dw_part;
+        p.ones_col = db_from_mma ? 1 : 0;
+        p.db_partials = db_part;
         p.lbo = dbg ? dbg->lbo : TN_BOX_BYTES;
         p.sbo = dbg ? dbg->sbo : 512;
         p.layout_type = dbg ? dbg->layout_type : 1;
@@ -456,6 +483,7 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
         const int grid = static_cast<int>(ceil_div(rows, p.rows_per_cta));
         gemm_tn_kernel<<<grid, THREADS, TnSmem::total, s>>>(tm_a, tm_b, p);
         reduce_partials_kernel<<<grid_for(n * k1, 256, 2), 256, 0, s>>>(dw_part, grid, n, k1, 0, dW, k, 0, nullptr);
+        if (db_from_mma) reduce_partials_kernel<<<1, 256, 0, s>>>(db_part, grid, n, 0, 1, nullptr, 0, 0, db);
     }
     HGIN_CHECK_LAUNCH("hgin_linear_bwd(tf32)");
     return HGIN_OK;

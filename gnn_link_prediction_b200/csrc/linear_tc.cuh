@@ -57,7 +57,9 @@ struct NtParams {
     int ldw;
     int want_z;
     int want_out;
-    int use_e;        // EPI_FWD: e = previous `out` (HeteroConv sum merge); EPI_DX: e = dot_x
+    int use_e;        // EPI_FWD: e = previous `out` (HeteroConv sum merge); EPI_DX: 1: e = dot_x,
+                      // 2: e = pre-activation z of the layer below -> dx is stored as dx * act'(e)
+                      // (act / alpha describe THAT layer) and dot_partials receive sum dx * min(e, 0)
     // EPI_DX
     float *dot_partials;  // [gridDim.x]
 };
@@ -210,7 +212,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             }
             named_barrier(EPI_ALL_BAR, 256);
         }
-        const float alpha = (EPI == EPI_FWD && p.act == HGIN_ACT_PRELU) ? __ldg(p.alpha) : 0.0f;
+        const float alpha = (p.act == HGIN_ACT_PRELU) ? __ldg(p.alpha) : 0.0f;
         // this group's staging tiles (st0: out / dx, st1: z) and epilogue-operand buffer
         const uint32_t sa0 = smem_u32(smem_stage + grp * 2 * TILE_BYTES);
         const uint32_t sa1 = sa0 + TILE_BYTES;
@@ -270,10 +272,17 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                         if (p.use_e) oo += ev[j];
                         o[j] = oo;
                     }
-                } else {
-                    if (p.use_e && grow < p.rows) {
+                } else if (p.use_e == 1) {
+                    if (grow < p.rows) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) dot = fmaf(v[j], ev[j], dot);  // OOB columns of e are zero-filled
+                    }
+                } else if (p.use_e == 2) {
+                    // rows past the end and OOB columns: v == 0 or e == 0, so they add nothing to dot
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (p.act == HGIN_ACT_PRELU && !(ev[j] > 0.f)) dot = fmaf(v[j], ev[j], dot);
+                        v[j] = act_backward(v[j], ev[j], p.act, alpha);
                     }
                 }
                 // the group's staging tiles are free once its previous TMA stores have read them
@@ -332,6 +341,10 @@ struct TnParams {
     int n;                  // columns of A = output rows   (<= 128, multiple of 16)
     int k;                  // columns of B = output cols   (<= 128, multiple of 16)
     float *partials;        // [gridDim.x][n][k]
+    // db = sum_m dz[m][:] through the tensor core: one extra [32 x 32] box of ones behind B's last
+    // box widens the MMA to N = k + 16, so D[:, k] = A^T 1.  Needs k % 32 == 0.
+    int ones_col;
+    float *db_partials;     // [gridDim.x][n]
     // MN-major operand descriptor fields (defaults in linear_tc.cu; overridable by hgin_debug_gemm_tn)
     int lbo;                // bytes between 32-column boxes of one operand
     int sbo;                // bytes between swizzle atoms along the contraction rows
@@ -340,7 +353,7 @@ struct TnParams {
 };
 
 struct TnSmem {
-    static constexpr int stage_bytes = 2 * TN_OPERAND_BYTES;    // A then B
+    static constexpr int stage_bytes = 2 * TN_OPERAND_BYTES + TN_BOX_BYTES;    // A, B, the ones box
     static constexpr int off_ring = 0;
     static constexpr int off_small = TN_STAGES * stage_bytes;
     static constexpr int total = off_small + 32 * 8 + 64 + 1024;
@@ -376,7 +389,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         mbar_init(done, 1);
         fence_barrier_init();
     }
-    if (warp == 3) tmem_alloc<128>(tmem_ptr);
+    if (warp == 3) tmem_alloc<256>(tmem_ptr);
+    if (p.ones_col) {   // TMA never writes this box: fill it once per stage
+        for (int i = threadIdx.x; i < TN_STAGES * (TN_BOX_BYTES / 4); i += THREADS) {
+            const int st = i / (TN_BOX_BYTES / 4), w = i % (TN_BOX_BYTES / 4);
+            reinterpret_cast<float *>(ring + st * TnSmem::stage_bytes + TN_OPERAND_BYTES + b_boxes * TN_BOX_BYTES)[w] = 1.0f;
+        }
+        fence_proxy_async_smem();
+    }
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -401,7 +421,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(128, p.k, 1, 1);
+            const uint32_t idesc = make_idesc_tf32(128, p.k + (p.ones_col ? 16 : 0), 1, 1);
             int s = 0;
             uint32_t ph = 0;
             for (int i = 0; i < steps; ++i) {
@@ -436,15 +456,21 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                         if (c * 32 + j < p.k) dst[c * 32 + j] = v[j];
                 }
             }
+            if (p.ones_col) {
+                float v[32];
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b_boxes * 32, v);
+                if (nn < p.n) p.db_partials[static_cast<int64_t>(blockIdx.x) * p.n + nn] = v[0];
+            }
         } else if (nn < p.n) {
             for (int j = 0; j < p.k; ++j) dst[j] = 0.0f;
+            if (p.ones_col) p.db_partials[static_cast<int64_t>(blockIdx.x) * p.n + nn] = 0.0f;
         }
     }
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 3) {
         tcgen05_fence_after();
-        tmem_dealloc<128>(tmem_base);
+        tmem_dealloc<256>(tmem_base);
     }
 }
 

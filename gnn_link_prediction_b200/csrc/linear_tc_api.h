@@ -16,6 +16,14 @@ struct TnDebug {   // overrides of the MN-major descriptor fields (hgin_debug_ge
     int k_step_bytes;
 };
 
+struct PostArgs {  // activation derivative of the layer BELOW, applied to dx on its way out
+    const float *z;
+    int64_t ldz;
+    int act;
+    const float *alpha;
+    float *dalpha;  // [1] out: sum dx * min(z, 0), or NULL
+};
+
 bool fused_bwd_enabled();
 void set_fused_bwd(int on);
 bool fused_dw_enabled();
@@ -34,7 +42,7 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
                    const float *alpha, const float *x1, int64_t ld1, int k1, const float *x2, int64_t ld2, int k2,
                    const float *W, int n, int c0, int c1, float *dx, int64_t lddx, const float *dot_x,
                    int64_t ld_dot, float *ddot, float *dW, float *db, float *dalpha, void *workspace,
-                   const TnDebug *dbg, cudaStream_t s);
+                   const TnDebug *dbg, const PostArgs *post, cudaStream_t s);
 
 }  // namespace tcgemm
 }  // namespace hgin

@@ -260,16 +260,39 @@ class DevicePrefetcher:
 
         for batch in DevicePrefetcher(loader):        # batch tensors already live on the GPU
             loss = step(batch)
-    """
 
-    def __init__(self, batches, device=None):
+    A source of `PackedBatch`es (`pack_batch` in the loader) is staged through a ring of `depth`
+    preallocated device buffers: ONE DMA per batch and no allocator traffic in the loop.  A slot is
+    overwritten only after the step that read it has finished (event recorded on the compute stream
+    when the consumer asks for the next batch)."""
+
+    def __init__(self, batches, device=None, depth=3):
         self.source = batches
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.stream = torch.cuda.Stream(device=self.device)
+        self.depth = depth
+        self._ring, self._free, self._n = [None] * depth, [None] * depth, 0
+
+    def _stage_packed(self, host):
+        slot = self._n % self.depth
+        self._n += 1
+        nbytes = host.buffer.numel()
+        if self._ring[slot] is None or self._ring[slot].numel() < nbytes:
+            self._ring[slot] = torch.empty(nbytes + nbytes // 8, dtype=torch.uint8, device=self.device)
+        dst = self._ring[slot][:nbytes]
+        with torch.cuda.stream(self.stream):
+            if self._free[slot] is not None:
+                self.stream.wait_event(self._free[slot])     # the step that last read this slot is done
+            dst.copy_(host.buffer, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self.stream)
+        return host.views(dst), ready, slot
 
     def _stage(self, host):
         if host is None:
             return None
+        if isinstance(host, PackedBatch):
+            return self._stage_packed(host)
         dev = Batch()
         with torch.cuda.stream(self.stream):
             for nt in host.node_types:
@@ -281,21 +304,26 @@ class DevicePrefetcher:
             ready = torch.cuda.Event()
             ready.record(self.stream)
         dev.__dict__["num_graphs"] = getattr(host, "num_graphs", None)
-        return dev, ready
+        return dev, ready, None
 
     def __iter__(self):
         it = iter(self.source)
         staged = self._stage(next(it, None))
         while staged is not None:
-            dev, ready = staged
+            dev, ready, slot = staged
             staged = self._stage(next(it, None))        # next copy overlaps this batch's step
             cur = torch.cuda.current_stream(self.device)
             cur.wait_event(ready)
-            for store in list(dev._nodes.values()) + list(dev._edges.values()):
-                for v in store.values():
-                    if isinstance(v, torch.Tensor):
-                        v.record_stream(cur)                # allocator: memory is in use on `cur`
+            if slot is None:
+                for store in list(dev._nodes.values()) + list(dev._edges.values()):
+                    for v in store.values():
+                        if isinstance(v, torch.Tensor):
+                            v.record_stream(cur)                # allocator: memory is in use on `cur`
             yield dev
+            if slot is not None:                                # the consumer has launched its step on `cur`
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.device))
+                self._free[slot] = ev
 
 
 class PackedBatch:

@@ -85,12 +85,25 @@ class RelationSpec:
         self.concat, self.act = bool(concat), act
 
 
+def _fold_eligible(rows, k, n, math_mode):
+    """Shapes for which the tensor-core backward consumes dz in place (csrc/linear_tc.cu): only
+    there does moving act'(z) into the producer of the gradient remove a pass over the rows."""
+    return (math_mode == ops.MATH_TF32 and rows >= 128 and 16 <= k <= 128 and k % 16 == 0
+            and 16 <= n <= 128 and n % 16 == 0)
+
+
 class HeteroConvFn(torch.autograd.Function):
-    """args: specs, graph, types, math_mode, x[types...], then (W, b, alpha, eps) per spec.
-    returns one tensor per destination type, in order of first appearance."""
+    """args: specs, graph, types, math_mode, links_in, links_out, x[types...], then (W, b, alpha, eps)
+    per spec.  returns one tensor per destination type, in order of first appearance.
+
+    links_in / links_out (dicts node type -> ops.PostAct, or None) chain consecutive layers INSIDE
+    HetroGIN.forward, where every intermediate activation has exactly one consumer: links_out is
+    filled with (z, act, alpha) of each output produced by a single relation; the next node receives
+    it as links_in and, in its backward, lets the kernel that produces the gradient for that input
+    apply act'(z) on the way out (hgin_gin_combine_post), so this node's backward starts from dz."""
 
     @staticmethod
-    def forward(ctx, specs, graph, types, math_mode, *tensors):
+    def forward(ctx, specs, graph, types, math_mode, links_in, links_out, *tensors):
         nt = len(types)
         xs = dict(zip(types, tensors[:nt]))
         params = tensors[nt:]
@@ -104,8 +117,13 @@ class HeteroConvFn(torch.autograd.Function):
                                   out=outs.get(sp.dst), accumulate_out=sp.dst in outs, math_mode=math_mode)
             outs[sp.dst] = o
             saved += [h if training else None, z]
-            if training and ctx.needs_input_grad[4 + types.index(sp.src)]:
+            if training and ctx.needs_input_grad[6 + types.index(sp.src)]:
                 graph.bwd(sp.et)  # build the transposed CSR alongside the forward work
+            if (training and links_out is not None and z is not None and sum(1 for q in specs if q.dst == sp.dst) == 1
+                    and _fold_eligible(h.shape[0], h.shape[1], W.shape[0], math_mode)):
+                links_out[sp.dst] = ops.PostAct(z, sp.act, alpha)
+        ctx.links_in = dict(links_in) if links_in else {}
+        ctx.links_out = dict(links_out) if links_out else {}
         ctx.specs, ctx.graph, ctx.types, ctx.math_mode = specs, graph, types, math_mode
         ctx.out_types = list(outs)
         ctx.set_materialize_grads(False)
@@ -120,7 +138,7 @@ class HeteroConvFn(torch.autograd.Function):
         xs = dict(zip(types, tensors[:nt]))
         params = tensors[nt:nt + 4 * ns]
         saved = tensors[nt + 4 * ns:]
-        need = ctx.needs_input_grad[4:]
+        need = ctx.needs_input_grad[6:]
         need_x = dict(zip(types, need[:nt]))
         g_out = dict(zip(ctx.out_types, gouts))
         grads_p = [None] * (4 * ns)
@@ -141,9 +159,16 @@ class HeteroConvFn(torch.autograd.Function):
             k = h.shape[1]
             want_agg, want_self = need_x[sp.src], need_x[sp.dst]
             common = dict(act=sp.act, alpha=alpha, math_mode=ctx.math_mode)
+            done = ctx.links_out.get(sp.dst)
+            done = done if (done is not None and done.applied) else None
+            if done is not None:      # g already is dz: the consumer of our output applied act'(z)
+                common.update(act=ACT_NONE, alpha=None)
+                z, nalpha_here = None, False
+            else:
+                nalpha_here = bool(nalpha)
             if sp.concat:
                 r = ops.linear_bwd(g, z, h, W, dx_cols=(fs, k), want_dx=want_self, dot_x=x_dst if neps else None,
-                                   want_dw=nW, want_db=bool(nb), want_dalpha=bool(nalpha), **common)
+                                   want_dw=nW, want_db=bool(nb), want_dalpha=nalpha_here, **common)
                 dh_self = r["dx"]
                 dh_agg = None
                 if want_agg:
@@ -152,8 +177,10 @@ class HeteroConvFn(torch.autograd.Function):
             else:
                 r = ops.linear_bwd(g, z, h, W, dx_cols=(0, k), want_dx=want_agg or want_self,
                                    dot_x=x_dst if neps else None, want_dw=nW, want_db=bool(nb),
-                                   want_dalpha=bool(nalpha), **common)
+                                   want_dalpha=nalpha_here, **common)
                 dh_agg = dh_self = r["dx"]
+            if done is not None and nalpha:
+                r["dalpha"] = done.dalpha
             grads_p[4 * i:4 * i + 4] = [r["dW"], r["db"],
                                         None if r["dalpha"] is None else r["dalpha"].view_as(alpha),
                                         None if r["ddot"] is None else r["ddot"].view_as(eps)]
@@ -164,30 +191,38 @@ class HeteroConvFn(torch.autograd.Function):
 
         grads_x = []
         for t in types:
-            dx = None
             selfs = self_terms[t]
+            passes = []                      # (transposed csr | None, gathered rows, self rows, eps)
             for csr_t, dh in gather_terms[t]:
-                if selfs:  # fold one (1+eps)*dh self branch into this gather pass
-                    s_dh, s_eps = selfs.pop(0)
-                    dx = ops.gin_combine(csr_t, dh, s_dh, s_eps, SELF_ADD, out=dx, accumulate=dx is not None)
-                else:
-                    dx = ops.gin_combine(csr_t, dh, None, None, SELF_NONE, out=dx, accumulate=dx is not None)
-            for s_dh, s_eps in selfs:  # self branches with no gather to ride on
-                term = s_dh * (1 + s_eps) if s_eps is not None else s_dh
-                dx = term if dx is None else dx.add_(term)
+                s_dh, s_eps = selfs.pop(0) if selfs else (None, None)   # one (1+eps)*dh branch rides on each gather
+                passes.append((csr_t, dh, s_dh, s_eps))
+            for s_dh, s_eps in selfs:        # self branches with no gather to ride on: edgeless pass
+                passes.append((None, s_dh, s_dh, s_eps))
+            post = ctx.links_in.get(t)
+            dx = None
+            for j, (csr_t, dh, s_dh, s_eps) in enumerate(passes):
+                dx = ops.gin_combine(csr_t, dh, s_dh, s_eps, SELF_ADD if s_dh is not None else SELF_NONE, out=dx,
+                                     accumulate=dx is not None, post=post if j == len(passes) - 1 else None)
             grads_x.append(dx)
-        return (None, None, None, None, *grads_x, *grads_p)
+        return (None, None, None, None, None, None, *grads_x, *grads_p)
 
 
 class LinearActFn(torch.autograd.Function):
     """out = act([x1 | x2] W^T + b)."""
 
     @staticmethod
-    def forward(ctx, x1, x2, W, b, alpha, act, math_mode):
+    def forward(ctx, x1, x2, W, b, alpha, act, math_mode, link_in=None, link_out=None):
+        """link_in: ops.PostAct of the layer that produced x1 (or None); link_out: a list that receives
+        this layer's own PostAct for the next layer in the chain (see HeteroConvFn)."""
         training = any(ctx.needs_input_grad)
         z, out = ops.linear_fwd(x1, W, b, x2=x2, act=act, alpha=alpha, want_z=training and act != ACT_NONE,
                                 math_mode=math_mode)
         ctx.act, ctx.math_mode = act, math_mode
+        ctx.link_in, ctx.link_self = link_in, None
+        if (training and link_out is not None and z is not None
+                and _fold_eligible(x1.shape[0], x1.shape[1], W.shape[0], math_mode)):
+            ctx.link_self = ops.PostAct(z, act, alpha)
+            link_out.append(ctx.link_self)
         ctx.save_for_backward(x1, x2, W, alpha, z)
         return out
 
@@ -200,13 +235,21 @@ class LinearActFn(torch.autograd.Function):
         k1 = x1.shape[1]
         k = W.shape[1]
         c0, c1 = (0 if n1 else k1), (k if n2 else k1)
-        r = ops.linear_bwd(g, z, x1, W, x2=x2, act=ctx.act, alpha=alpha, dx_cols=(c0, c1), want_dx=n1 or n2,
-                           want_dw=nW, want_db=bool(nb), want_dalpha=bool(nalpha), math_mode=ctx.math_mode)
+        act = ctx.act
+        done = ctx.link_self if (ctx.link_self is not None and ctx.link_self.applied) else None
+        if done is not None:          # g already is dz
+            act, z = ACT_NONE, None
+        post = ctx.link_in if (n1 and not n2) else None     # dx must be exactly the gradient of x1
+        r = ops.linear_bwd(g, z, x1, W, x2=x2, act=act, alpha=alpha if done is None else None, dx_cols=(c0, c1),
+                           want_dx=n1 or n2, want_dw=nW, want_db=bool(nb), want_dalpha=bool(nalpha) and done is None,
+                           math_mode=ctx.math_mode, post=post)
+        if done is not None and nalpha:
+            r["dalpha"] = done.dalpha
         dx = r["dx"]
         dx1 = dx[:, :k1 - c0] if n1 else None
         dx2 = dx[:, k1 - c0:] if n2 else None
         dalpha = None if r["dalpha"] is None else r["dalpha"].view_as(alpha)
-        return dx1, dx2, r["dW"], r["db"], dalpha, None, None
+        return dx1, dx2, r["dW"], r["db"], dalpha, None, None, None, None
 
 
 def activation_of(module):

@@ -78,8 +78,8 @@ class GINConv(torch.nn.Module):
             raise ValueError(f"size {size} does not match the feature matrices {num}")
         graph = edge_index if isinstance(edge_index, GraphCSR) else GraphCSR({et: edge_index}, num)
         W, b, alpha, eps, act = self.kernel_args()
-        (out,) = HeteroConvFn.apply([RelationSpec(et, self.concat, act)], graph, types, self.math_mode, *xs,
-                                    W, b, alpha, eps)
+        (out,) = HeteroConvFn.apply([RelationSpec(et, self.concat, act)], graph, types, self.math_mode, None, None,
+                                    *xs, W, b, alpha, eps)
         return out
 
     def __repr__(self):
@@ -119,8 +119,11 @@ class HeteroConv(torch.nn.Module):
         for conv in self.convs.values():
             conv.reset_parameters()
 
-    def forward(self, x_dict, edge_index_dict, only=None):
-        """`only`: optional collection of edge types to evaluate (dead-branch pruning by HetroGIN)."""
+    def forward(self, x_dict, edge_index_dict, only=None, chain=None):
+        """`only`: optional collection of edge types to evaluate (dead-branch pruning by HetroGIN).
+        `chain`: dict node type -> ops.PostAct describing how `x_dict`'s tensors were produced, passed
+        by HetroGIN.forward between consecutive layers (every intermediate has one consumer there);
+        updated in place to describe this layer's outputs.  See functional.HeteroConvFn."""
         graph = edge_index_dict if isinstance(edge_index_dict, GraphCSR) else GraphCSR(
             edge_index_dict, {t: v.shape[0] for t, v in x_dict.items()})
         specs, params = [], []
@@ -136,7 +139,12 @@ class HeteroConv(torch.nn.Module):
         if not specs:
             return {}
         types = tuple(dict.fromkeys(t for sp in specs for t in (sp.src, sp.dst)))
-        outs = HeteroConvFn.apply(specs, graph, types, self.math_mode, *[x_dict[t] for t in types], *params)
+        links_out = {} if chain is not None else None
+        outs = HeteroConvFn.apply(specs, graph, types, self.math_mode, dict(chain) if chain else None, links_out,
+                                  *[x_dict[t] for t in types], *params)
+        if chain is not None:
+            chain.clear()
+            chain.update(links_out)
         out_types = list(dict.fromkeys(sp.dst for sp in specs))
         return dict(zip(out_types, outs))
 
@@ -163,6 +171,7 @@ class HetroGIN(torch.nn.Module):
         self.dropout = dropout
         self.global_feats = global_feats
         self.math_mode = MATH_FP32
+        self.fold_activation_grad = True   # see forward(); only takes effect for tensor-core-sized layers
 
         # channel arithmetic, in place on the caller's dict exactly as models.py:260-269 does
         if not self.divided_features:
@@ -237,13 +246,19 @@ class HetroGIN(torch.nn.Module):
         graph = edge_index_dict if isinstance(edge_index_dict, GraphCSR) else GraphCSR(
             edge_index_dict, {t: v.shape[0] for t, v in x_dict.items()})
         live = self.live_relations(graph.keys())
+        # Inside this function every intermediate activation has exactly one consumer, so a layer's
+        # backward may hand the layer below its dz instead of g (functional.HeteroConvFn).
+        chain = {} if (self.fold_activation_grad and torch.is_grad_enabled()) else None
         for i in range(self.num_layers):
-            x_dict = self.convs[i](x_dict, graph, only=live[i])
+            x_dict = self.convs[i](x_dict, graph, only=live[i], chain=chain)
             # dropout(p=0) / eval mode is the identity (models.py:358-359)
 
         x1 = x_dict["path"]
         x2 = origin_path if self.concat_path else None
+        link = chain.get("path") if chain is not None else None
         for i, layer in enumerate(self.readout):
             W, b, act, alpha = F_.linear_act_of(layer)
-            x1 = LinearActFn.apply(x1, x2 if i == 0 else None, W, b, alpha, act, self.math_mode)
+            nxt = [] if chain is not None else None
+            x1 = LinearActFn.apply(x1, x2 if i == 0 else None, W, b, alpha, act, self.math_mode, link, nxt)
+            link = nxt[0] if nxt else None
         return x1

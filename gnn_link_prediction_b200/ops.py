@@ -110,8 +110,32 @@ def csr_build(edge_index, num_src, num_dst, by="dst", want_perm=False):
     return CSR(rowptr, col, perm, status, rows, cols, E)
 
 
-def gin_combine(csr, x_src, x_self=None, eps=None, self_mode=SELF_NONE, out=None, accumulate=False):
-    """K1/K4.  out[r] (+)= sum_{e in row r} x_src[col[e]]  {+ | concat}  (1+eps) * x_self[r]."""
+class PostAct:
+    """Activation derivative of the layer BELOW, applied by whichever kernel produces the gradient
+    w.r.t. that layer's output (hgin_gin_combine_post / hgin_linear_bwd_post): the producer stores
+    dz = grad * act'(z) and fills `dalpha` = sum grad * min(z, 0); the layer below then runs its
+    backward with ACT_NONE on dz.  `applied` tells that layer this has happened."""
+
+    __slots__ = ("z", "act", "alpha", "dalpha", "applied")
+
+    def __init__(self, z, act, alpha):
+        self.z, self.act, self.alpha = z, act, alpha
+        self.dalpha, self.applied = None, False
+
+
+class _NoEdges:
+    """Stand-in adjacency for a self-term-only pass (rowptr = NULL at the ABI)."""
+
+    def __init__(self, num_rows):
+        self.num_rows, self.num_cols, self.num_edges, self.rowptr, self.col = num_rows, num_rows, 0, None, None
+
+
+def gin_combine(csr, x_src, x_self=None, eps=None, self_mode=SELF_NONE, out=None, accumulate=False, post=None):
+    """K1/K4.  out[r] (+)= sum_{e in row r} x_src[col[e]]  {+ | concat}  (1+eps) * x_self[r].
+    csr=None: no edges (self term only; x_src is then only a shape donor).
+    post: a PostAct — the stored result is multiplied by act'(post.z) and post.dalpha is filled."""
+    if csr is None:
+        csr = _NoEdges(x_self.shape[0])
     ps, lds = _f32_matrix(x_src, "gin_combine.x_src")
     pf, ldf = _f32_matrix(x_self, "gin_combine.x_self")
     if x_src.shape[0] != csr.num_cols:
@@ -130,8 +154,26 @@ def gin_combine(csr, x_src, x_self=None, eps=None, self_mode=SELF_NONE, out=None
         raise HginError(f"gin_combine: out is {tuple(out.shape)}, expected {(csr.num_rows, width)}")
     alg, comp = combine_bytes(csr.num_rows, csr.num_cols, csr.num_edges, f_src,
                               f_self if self_mode != SELF_NONE else 0, width * (2 if accumulate else 1))
+    if post is not None and post.act != ACT_NONE:
+        pz, ldz = _f32_matrix(post.z, "gin_combine.post.z")
+        if tuple(post.z.shape) != (csr.num_rows, f_src) or self_mode == SELF_CONCAT:
+            raise HginError(f"gin_combine: post.z is {tuple(post.z.shape)}, expected {(csr.num_rows, f_src)}")
+        lib = _lib.load()
+        want = post.act == ACT_PRELU
+        post.dalpha = torch.empty(1, dtype=torch.float32, device=out.device) if want else None
+        ws_bytes = lib.hgin_gin_combine_post_workspace_bytes()
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=out.device)
+        extra = 4 * csr.num_rows * f_src     # the pre-activation rows read on top of the plain pass
+        with _region("gin_combine", kernels=2 if want else 1, alg_bytes=alg + extra, compulsory_bytes=comp + extra):
+            check(lib.hgin_gin_combine_post(csr.num_rows, _ptr(csr.rowptr), _ptr(csr.col), csr.num_edges, ps, lds, f_src,
+                                            pf, ldf, f_self, _scalar(eps, "gin_combine.eps"), self_mode,
+                                            1 if accumulate else 0, po, ldo, pz, ldz, post.act,
+                                            _scalar(post.alpha, "gin_combine.post.alpha"), _ptr(post.dalpha),
+                                            ws.data_ptr(), ws_bytes, _stream()), "hgin_gin_combine_post")
+        post.applied = True
+        return out
     with _region("gin_combine", kernels=1, alg_bytes=alg, compulsory_bytes=comp):
-        check(_lib.load().hgin_gin_combine(csr.num_rows, csr.rowptr.data_ptr(), _ptr(csr.col), csr.num_edges, ps, lds, f_src, pf,
+        check(_lib.load().hgin_gin_combine(csr.num_rows, _ptr(csr.rowptr), _ptr(csr.col), csr.num_edges, ps, lds, f_src, pf,
                                            ldf, f_self, _scalar(eps, "gin_combine.eps"), self_mode,
                                            1 if accumulate else 0, po, ldo, _stream()), "hgin_gin_combine")
     return out
@@ -171,9 +213,11 @@ def linear_fwd(x1, W, bias=None, x2=None, act=ACT_NONE, alpha=None, want_z=True,
 
 
 def linear_bwd(g, z, x1, W, x2=None, act=ACT_NONE, alpha=None, dx_cols=None, want_dx=True, dot_x=None,
-               want_dw=True, want_db=True, want_dalpha=False, math_mode=MATH_FP32):
+               want_dw=True, want_db=True, want_dalpha=False, math_mode=MATH_FP32, post=None):
     """K3.  Returns dict(dx, ddot, dW, db, dalpha) with None for what was not requested.
-    dx_cols=(c0,c1) restricts the input gradient to those columns of [x1|x2]."""
+    dx_cols=(c0,c1) restricts the input gradient to those columns of [x1|x2].
+    act=ACT_NONE: g is dz itself (z may be None).  post: a PostAct for the layer that produced the
+    dx columns — dx leaves as that layer's dz and post.dalpha is filled (no dot_x then)."""
     pg, ldg = _f32_matrix(g, "linear_bwd.g")
     pz, ldz = _f32_matrix(z, "linear_bwd.z")
     p1, ld1 = _f32_matrix(x1, "linear_bwd.x1")
@@ -204,6 +248,22 @@ def linear_bwd(g, z, x1, W, x2=None, act=ACT_NONE, alpha=None, dx_cols=None, wan
     reduces = want_dw or want_db or want_dalpha
     n_kernels = ((1 + (1 if ddot is not None else 0)) if c1 > c0 else 0) + \
         ((2 + (1 if (want_dalpha and act == ACT_PRELU) else 0)) if reduces else 0)
+    if post is not None and post.act != ACT_NONE and dx is not None:
+        if dot_x is not None:
+            raise HginError("linear_bwd: post-activation and dot_x cannot be combined")
+        ppz, ldpz = _f32_matrix(post.z, "linear_bwd.post.z")
+        if tuple(post.z.shape) != (rows, c1 - c0):
+            raise HginError(f"linear_bwd: post.z is {tuple(post.z.shape)}, expected {(rows, c1 - c0)}")
+        post.dalpha = torch.empty(1, dtype=torch.float32, device=dev) if post.act == ACT_PRELU else None
+        with _region("linear_bwd", kernels=n_kernels + 1, flops=flops,
+                     bytes=4 * rows * (n * (1 if act == ACT_NONE else 4) + k + 2 * (c1 - c0))):
+            check(lib.hgin_linear_bwd_post(rows, pg, ldg, pz, ldz, act, _scalar(alpha, "linear_bwd.alpha"), p1, ld1, k1,
+                                           p2, ld2, k2, W.data_ptr(), n, c0, c1, pdx, lddx, _ptr(dW), _ptr(db),
+                                           _ptr(dalpha), ppz, ldpz, post.act, _scalar(post.alpha, "linear_bwd.post.alpha"),
+                                           _ptr(post.dalpha), ws.data_ptr(), ws_bytes, math_mode, _stream()),
+                  "hgin_linear_bwd_post")
+        post.applied = True
+        return {"dx": dx, "ddot": None, "dW": dW, "db": db, "dalpha": dalpha}
     with _region("linear_bwd", kernels=n_kernels, flops=flops,
                  bytes=4 * rows * (2 * n * (2 if c1 > c0 else 1) + k + (c1 - c0))):
         check(lib.hgin_linear_bwd(rows, pg, ldg, pz, ldz, act, _scalar(alpha, "linear_bwd.alpha"), p1, ld1, k1, p2,

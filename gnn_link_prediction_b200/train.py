@@ -151,6 +151,44 @@ class TrainStep:
         return loss_out
 
 
+class LossReadback:
+    """Device->host read of every step's loss WITHOUT stalling the launch queue: `push(loss)`
+    enqueues an asynchronous copy of this step's `[mape, sqrt(mape)]` into pinned memory and returns
+    the PREVIOUS step's values (already complete by then, or waited for), so the host is never more
+    than one step behind and the GPU never idles between steps.  The reference reads
+    `loss_value.item()` synchronously every step (train.py:50); `flush()` yields the last one.
+
+        reader = LossReadback()
+        for batch in DevicePrefetcher(loader):
+            done = reader.push(step(batch))        # None on the first step
+        last = reader.flush()
+    """
+
+    def __init__(self, numel=2, depth=2):
+        self.bufs = [torch.empty(numel, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.events = [torch.cuda.Event() for _ in range(depth)]
+        self.i, self.pending = 0, None
+
+    def _wait(self):
+        if self.pending is None:
+            return None
+        j, self.pending = self.pending, None
+        self.events[j].synchronize()
+        return self.bufs[j].clone()
+
+    def push(self, loss):
+        j = self.i % len(self.bufs)
+        self.i += 1
+        prev = self._wait() if self.pending is not None else None
+        self.bufs[j].copy_(loss.detach().reshape(-1), non_blocking=True)
+        self.events[j].record()
+        self.pending = j
+        return prev
+
+    def flush(self):
+        return self._wait()
+
+
 class GraphedTrainStep:
     """`TrainStep` replayed as ONE CUDA graph per batch shape.
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HGIN_VERSION 100 /* major*100 + minor */
+#define HGIN_VERSION 101 /* major*100 + minor */
 
 typedef enum hgin_status {
     HGIN_OK = 0,
@@ -99,6 +99,27 @@ int32_t hgin_gin_combine(int64_t num_rows, const int32_t *rowptr, const int32_t 
                          const float *eps, int32_t self_mode, int32_t accumulate,
                          float *out, int64_t ld_out, void *stream);
 
+/* ---- K4 with the activation derivative of the layer below ("post-activation") ---------------
+ * Replaces: the first op of the NEXT autograd node on the way down, PReLU.backward of the layer
+ * whose output this gradient is for (models.py:238 -> at::prelu_backward).  The row result r of
+ * hgin_gin_combine is a gradient w.r.t. that layer's output; with post_z (its saved
+ * pre-activation, [num_rows, f_src]) the kernel stores  r * act'(post_z)  — i.e. that layer's dz —
+ * and reduces  post_dalpha[0] = sum r * min(post_z, 0)  (two-stage, deterministic; NULL to skip).
+ * The layer below is then called with HGIN_ACT_NONE (hgin_linear_bwd consumes dz in place).
+ * post_act == HGIN_ACT_NONE or post_z == NULL: identical to hgin_gin_combine.
+ * rowptr == NULL: the relation has no edges; the call reduces to the self term (used for
+ * `(1+eps) * dh` when no gather shares the pass).  Not with HGIN_SELF_CONCAT.
+ * workspace: hgin_gin_combine_post_workspace_bytes() bytes (per-CTA partials of post_dalpha).
+ */
+int64_t hgin_gin_combine_post_workspace_bytes(void);
+int32_t hgin_gin_combine_post(int64_t num_rows, const int32_t *rowptr, const int32_t *col,
+                              int64_t num_edges, const float *x_src, int64_t ld_src, int32_t f_src,
+                              const float *x_self, int64_t ld_self, int32_t f_self,
+                              const float *eps, int32_t self_mode, int32_t accumulate,
+                              float *out, int64_t ld_out, const float *post_z, int64_t ld_post,
+                              int32_t post_act, const float *post_alpha, float *post_dalpha,
+                              void *workspace, int64_t workspace_bytes, void *stream);
+
 /* ---- K2: dense layer forward  z = [x1 | x2] W^T + b,  out (+)= act(z) ------------------------
  * Replaces: GINLayer.mlp = Linear + PReLU (models.py:236-239, applied at models.py:217), the
  * HeteroConv 'sum' merge over relations with the same destination type (models.py:286-298 ->
@@ -139,6 +160,25 @@ int32_t hgin_linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *
                         int32_t c0, int32_t c1, float *dx, int64_t lddx, const float *dot_x,
                         int64_t ld_dot, float *ddot, float *dW, float *db, float *dalpha,
                         void *workspace, int64_t workspace_bytes, int32_t math_mode, void *stream);
+
+/* hgin_linear_bwd with act == HGIN_ACT_NONE takes g as dz itself; in HGIN_MATH_TF32 both GEMMs then
+ * read it in place and db is produced inside the weight-gradient MMA (a column of ones), so no
+ * separate pass over g remains.
+ *
+ * hgin_linear_bwd_post: the same backward whose input gradient leaves as
+ *     dx[:, c0:c1] = (dz W)[:, c0:c1] * act'(post_z),   post_dalpha[0] = sum (dz W) * min(post_z, 0)
+ * with post_z [rows, c1-c0] the saved pre-activation of the layer that produced x (see
+ * hgin_gin_combine_post).  Fused into the epilogue of the tcgen05 input-gradient kernel when the
+ * shapes qualify, one extra elementwise pass otherwise.  No dot_x / ddot on this entry point.
+ */
+int32_t hgin_linear_bwd_post(int64_t rows, const float *g, int64_t ldg, const float *z, int64_t ldz,
+                             int32_t act, const float *alpha, const float *x1, int64_t ld1,
+                             int32_t k1, const float *x2, int64_t ld2, int32_t k2, const float *W,
+                             int32_t n, int32_t c0, int32_t c1, float *dx, int64_t lddx, float *dW,
+                             float *db, float *dalpha, const float *post_z, int64_t ld_post,
+                             int32_t post_act, const float *post_alpha, float *post_dalpha,
+                             void *workspace, int64_t workspace_bytes, int32_t math_mode,
+                             void *stream);
 
 /* ---- loss: sqrt(MAPE) (train.py:12-13, 40-42) -----------------------------------------------
  * hgin_mape_sum:       sums[0] = sum_i |(pred_i - y_i) / y_i|,  sums[1] = n  (fp32, two-stage,

@@ -197,8 +197,9 @@ def test_unsupported_configurations_fail_loudly():
         m(dev.x_dict, dev.edge_index_dict, None)
 
 
+@pytest.mark.parametrize("fold", [True, False])
 @pytest.mark.parametrize("emb,layers,batch", [(128, 4, 4), (64, 2, 3)])
-def test_tf32_tensor_core_mode_against_oracle(emb, layers, batch):
+def test_tf32_tensor_core_mode_against_oracle(emb, layers, batch, fold):
     """HGIN_MATH_TF32 (tcgen05 kind::tf32 GEMMs, fp32 aggregation): the north star's reduced-precision
     bar, rel 1e-2, on scores and gradients."""
     from gnn_link_prediction_b200.models import MATH_TF32
@@ -213,6 +214,7 @@ def test_tf32_tensor_core_mode_against_oracle(emb, layers, batch):
     m = HetroGIN(input_channels={"link": 7, "path": 7, "node": 3}, **kw)
     m.load_state_dict(ref.state_dict())
     m.cuda().train().set_math_mode(MATH_TF32)
+    m.fold_activation_grad = fold      # producers of a gradient apply the act'(z) of the layer below (default)
     y = cpu_batch["path"].y.reshape(-1, 1)
     o_ref = ref(cpu_batch.x_dict, cpu_batch.edge_index_dict, None)
     torch.sqrt(hgin_oracle.mape(o_ref, y)).backward()
