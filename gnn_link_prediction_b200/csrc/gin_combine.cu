@@ -62,6 +62,10 @@ struct PostAct {
     int act;
     const float *alpha;
     float *dalpha_partials;   // [gridDim.x]
+    // d(eps) of the relation whose self branch rides on this pass: sum x_self * act(z) — the rows of
+    // x_self are dh_self and act(z) IS x_dst (the output of the layer below), so the input-gradient
+    // GEMM above no longer has to read x_dst for it.
+    float *ddot_partials;     // [gridDim.x] or NULL
 };
 
 template <int VEC, int LPR, int NC, bool CONTIG, int MINB, bool POST>
@@ -83,7 +87,7 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
     // fl(1 + eps): the reference computes (1 + self.eps) as an fp32 tensor op (models.py:213/215).
     const float ope = __fadd_rn(1.0f, eps_ptr ? __ldg(eps_ptr) : 0.0f);
     const float post_alpha = (POST && post.act == HGIN_ACT_PRELU) ? __ldg(post.alpha) : 0.0f;
-    float dalpha = 0.0f;
+    float dalpha = 0.0f, ddot = 0.0f;
 
     // Row -> warp mapping.
     // CONTIG (short rows): each CTA owns a CONTIGUOUS block of rows, its warps interleaving inside it.
@@ -214,6 +218,11 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
                     for (int i = 0; i < VEC; ++i) r.v[i] = __fadd_rn(old.v[i], r.v[i]);
                 }
                 if (POST && post.act != HGIN_ACT_NONE) {
+                    if (post.ddot_partials && self_mode == HGIN_SELF_ADD) {
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i)
+                            ddot = fmaf(self_v[c].v[i], act_forward(post_v[c].v[i], post.act, post_alpha), ddot);
+                    }
 #pragma unroll
                     for (int i = 0; i < VEC; ++i) {
                         const float zv = post_v[c].v[i];
@@ -235,10 +244,16 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
         beg = nbeg; len = nlen; mine = nmine;
         nbeg = nnbeg; nlen = nnlen;
     }
-    if (POST && post.dalpha_partials) {   // fixed association: lanes -> warps -> CTA partial
+    if (POST && (post.dalpha_partials || post.ddot_partials)) {   // fixed association: lanes -> warps -> CTA partial
         __shared__ float red[32];
-        dalpha = block_sum(dalpha, red);
-        if (threadIdx.x == 0) post.dalpha_partials[blockIdx.x] = dalpha;
+        if (post.dalpha_partials) {
+            dalpha = block_sum(dalpha, red);
+            if (threadIdx.x == 0) post.dalpha_partials[blockIdx.x] = dalpha;
+        }
+        if (post.ddot_partials) {
+            ddot = block_sum(ddot, red);
+            if (threadIdx.x == 0) post.ddot_partials[blockIdx.x] = ddot;
+        }
     }
 }
 
@@ -282,8 +297,8 @@ int32_t combine_dispatch(int64_t num_rows, const int32_t *rowptr, const int32_t 
                          const float *x_src, int64_t ld_src, int32_t f_src, const float *x_self, int64_t ld_self,
                          int32_t f_self, const float *eps, int32_t self_mode, int32_t accumulate, float *out,
                          int64_t ld_out, const float *post_z, int64_t ld_post, int32_t post_act,
-                         const float *post_alpha, float *post_dalpha, void *workspace, int64_t workspace_bytes,
-                         void *stream, const char *who) {
+                         const float *post_alpha, float *post_dalpha, float *post_ddot, void *workspace,
+                         int64_t workspace_bytes, void *stream, const char *who) {
     HGIN_CHECK_ARG(num_rows >= 0 && num_rows < INT32_MAX, "%s: bad num_rows %lld", who, (long long)num_rows);
     HGIN_CHECK_ARG(f_src > 0 && f_src <= 512, "%s: f_src must be in [1,512], got %d", who, f_src);
     HGIN_CHECK_ARG(self_mode >= HGIN_SELF_NONE && self_mode <= HGIN_SELF_CONCAT, "%s: bad self_mode %d", who, self_mode);
@@ -296,15 +311,15 @@ int32_t combine_dispatch(int64_t num_rows, const int32_t *rowptr, const int32_t 
     HGIN_CHECK_ARG(!post_on || post_act != HGIN_ACT_PRELU || post_alpha, "%s: PReLU post-activation needs alpha", who);
     HGIN_CHECK_ARG(!post_on || ld_post >= f_src, "%s: ld_post too small", who);
     const bool want_dalpha = post_dalpha != nullptr;
+    HGIN_CHECK_ARG(!post_ddot || (post_on && self_mode == HGIN_SELF_ADD), "%s: post_ddot needs a post-activation and SELF_ADD", who);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (want_dalpha && !(post_on && post_act == HGIN_ACT_PRELU)) {
-        cudaMemsetAsync(post_dalpha, 0, sizeof(float), s);
-    } else if (want_dalpha) {
-        if (!workspace || workspace_bytes < static_cast<int64_t>(kMaxCombineCtas) * 4)
+    if ((want_dalpha && post_on && post_act == HGIN_ACT_PRELU) || post_ddot) {
+        if (!workspace || workspace_bytes < static_cast<int64_t>(kMaxCombineCtas) * 8)
             return fail(HGIN_ERR_WORKSPACE_TOO_SMALL, "%s: workspace %lld < %lld bytes", who, (long long)workspace_bytes,
-                        (long long)kMaxCombineCtas * 4);
-        if (num_rows == 0) cudaMemsetAsync(post_dalpha, 0, sizeof(float), s);
+                        (long long)kMaxCombineCtas * 8);
     }
+    if (want_dalpha && (num_rows == 0 || !(post_on && post_act == HGIN_ACT_PRELU))) cudaMemsetAsync(post_dalpha, 0, sizeof(float), s);
+    if (post_ddot && num_rows == 0) cudaMemsetAsync(post_ddot, 0, sizeof(float), s);
     if (num_rows == 0) return HGIN_OK;
     // `rowptr` may be null when the relation has no edges at all (self term only), `col` for an
     // edgeless relation (every row empty): neither is dereferenced then.
@@ -313,7 +328,8 @@ int32_t combine_dispatch(int64_t num_rows, const int32_t *rowptr, const int32_t 
     const int width = f_src + (self_mode == HGIN_SELF_CONCAT ? f_self : 0);
     HGIN_CHECK_ARG(ld_src >= f_src && ld_out >= width, "%s: leading dimension too small", who);
     PostAct post{post_z, ld_post, post_act, post_alpha,
-                 (want_dalpha && post_act == HGIN_ACT_PRELU) ? static_cast<float *>(workspace) : nullptr};
+                 (want_dalpha && post_act == HGIN_ACT_PRELU) ? static_cast<float *>(workspace) : nullptr,
+                 post_ddot ? static_cast<float *>(workspace) + kMaxCombineCtas : nullptr};
     const PostAct *pp = post_on ? &post : nullptr;
     if (!rowptr) num_edges = 0;
 
@@ -365,6 +381,7 @@ int32_t combine_dispatch(int64_t num_rows, const int32_t *rowptr, const int32_t 
     }
 #undef HGIN_LAUNCH
     if (post.dalpha_partials && pp) combine_reduce_scalar_kernel<<<1, 1024, 0, s>>>(post.dalpha_partials, grid, post_dalpha);
+    if (post.ddot_partials && pp) combine_reduce_scalar_kernel<<<1, 1024, 0, s>>>(post.ddot_partials, grid, post_ddot);
     HGIN_CHECK_LAUNCH(who);
     return HGIN_OK;
 }
@@ -377,19 +394,19 @@ extern "C" int32_t hgin_gin_combine(int64_t num_rows, const int32_t *rowptr, con
                                     int32_t f_self, const float *eps, int32_t self_mode, int32_t accumulate,
                                     float *out, int64_t ld_out, void *stream) {
     return hgin::combine_dispatch(num_rows, rowptr, col, num_edges, x_src, ld_src, f_src, x_self, ld_self, f_self, eps,
-                                  self_mode, accumulate, out, ld_out, nullptr, 0, HGIN_ACT_NONE, nullptr, nullptr,
+                                  self_mode, accumulate, out, ld_out, nullptr, 0, HGIN_ACT_NONE, nullptr, nullptr, nullptr,
                                   nullptr, 0, stream, "hgin_gin_combine");
 }
 
-extern "C" int64_t hgin_gin_combine_post_workspace_bytes(void) { return static_cast<int64_t>(hgin::kMaxCombineCtas) * 4; }
+extern "C" int64_t hgin_gin_combine_post_workspace_bytes(void) { return static_cast<int64_t>(hgin::kMaxCombineCtas) * 8; }
 
 extern "C" int32_t hgin_gin_combine_post(int64_t num_rows, const int32_t *rowptr, const int32_t *col, int64_t num_edges,
                                          const float *x_src, int64_t ld_src, int32_t f_src, const float *x_self,
                                          int64_t ld_self, int32_t f_self, const float *eps, int32_t self_mode,
                                          int32_t accumulate, float *out, int64_t ld_out, const float *post_z,
                                          int64_t ld_post, int32_t post_act, const float *post_alpha, float *post_dalpha,
-                                         void *workspace, int64_t workspace_bytes, void *stream) {
+                                         float *post_ddot, void *workspace, int64_t workspace_bytes, void *stream) {
     return hgin::combine_dispatch(num_rows, rowptr, col, num_edges, x_src, ld_src, f_src, x_self, ld_self, f_self, eps,
                                   self_mode, accumulate, out, ld_out, post_z, ld_post, post_act, post_alpha, post_dalpha,
-                                  workspace, workspace_bytes, stream, "hgin_gin_combine_post");
+                                  post_ddot, workspace, workspace_bytes, stream, "hgin_gin_combine_post");
 }

@@ -416,10 +416,13 @@ static int32_t linear_bwd_impl(int64_t rows, const float *g, int64_t ldg, const 
     const bool tc_ok = math_mode == HGIN_MATH_TF32 && rows > 0 &&
         tcgemm::bwd_eligible(rows, g, ldg, z, ldz, act, x1, ld1, k1, k2, n, c0, c1, dx, lddx, dot_x, ld_dot) &&
         (!post || (c1 - c0 >= 16 && post->ldz % 4 == 0 && aligned16(post->z)));
-    if (post && !tc_ok) return HGIN_ERR_UNSUPPORTED;   // hgin_linear_bwd_post then runs the generic form
-    if (!post && rows > 0 && thin::head_bwd_eligible(x1, ld1, k1, k2, n, c0, c1, dx, lddx, dot_x, W) && !ddot)
+    if (rows > 0 && thin::head_bwd_eligible(x1, ld1, k1, k2, n, c0, c1, dx, lddx, dot_x, W) && !ddot &&
+        (!post || (post->ldz % 4 == 0 && aligned16(post->z))))
         return thin::head_bwd(rows, g, ldg, z, ldz, act, alpha, x1, ld1, k1, W, dx, lddx, dW, db, dalpha, workspace,
+                              post ? post->z : nullptr, post ? post->ldz : 0, post ? post->act : HGIN_ACT_NONE,
+                              post ? post->alpha : nullptr, post ? post->dalpha : nullptr,
                               static_cast<cudaStream_t>(stream));
+    if (post && !tc_ok) return HGIN_ERR_UNSUPPORTED;   // hgin_linear_bwd_post then runs the generic form
     if (!post && rows > 0 && thin::bwd_eligible(g, ldg, z, ldz, act, k1, k2, n, c0, c1, dx, dot_x))
         return thin::linear_bwd(rows, g, ldg, z, ldz, act, alpha, x1, ld1, k1, W, n, c0, c1, dot_x, ld_dot, ddot, dW, db,
                                 dalpha, workspace, static_cast<cudaStream_t>(stream));

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) transpose_cols_kernel(const float *__rest
 // Partial layout: part[cta][nn][k2 + 1] with the LAST column = db (same convention as the SIMT
 // weight-gradient partials), alpha_part[cta].
 constexpr int DZ_THREADS = 256;
-__global__ void __launch_bounds__(DZ_THREADS)
+__global__ void __launch_bounds__(DZ_THREADS, 3)
 dz_prepare_kernel(int64_t rows, int n, const float *__restrict__ g, int64_t ldg, const float *__restrict__ z,
                   int64_t ldz, int act, const float *__restrict__ alpha_ptr, const float *__restrict__ x2,
                   int64_t ld2, int k2, float *__restrict__ dz, float *__restrict__ part,
@@ -85,28 +85,45 @@ dz_prepare_kernel(int64_t rows, int n, const float *__restrict__ g, int64_t ldg,
         for (int t = 0; t < 4; ++t) tail[i][t] = 0.f;
     float dalpha = 0.f;
     if (active) {
-        for (int64_t m = static_cast<int64_t>(blockIdx.x) * slots + slot; m < rows;
-             m += static_cast<int64_t>(gridDim.x) * slots) {
-            const float4 gv = __ldg(reinterpret_cast<const float4 *>(g + m * ldg) + cg);
-            float d[4] = {gv.x, gv.y, gv.z, gv.w};
-            if (act != HGIN_ACT_NONE) {
-                const float4 zv4 = __ldg(reinterpret_cast<const float4 *>(z + m * ldz) + cg);
-                const float zv[4] = {zv4.x, zv4.y, zv4.z, zv4.w};
+        // RIF rows per thread and iteration with every g / z vector requested before the first use
+        // (one row per thread kept ~16 KB of reads in flight per SM; same per-thread row order)
+        constexpr int RIF = 4;
+        const int64_t stride = static_cast<int64_t>(gridDim.x) * slots;
+        for (int64_t m0 = static_cast<int64_t>(blockIdx.x) * slots + slot; m0 < rows; m0 += stride * RIF) {
+            float4 gq[RIF], zq[RIF];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (act == HGIN_ACT_PRELU && !(zv[i] > 0.f)) dalpha += d[i] * zv[i];
-                    d[i] = act_backward(d[i], zv[i], act, alpha);
+            for (int u = 0; u < RIF; ++u) {
+                const int64_t m = m0 + u * stride;
+                gq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                zq[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (m < rows) {
+                    gq[u] = __ldg(reinterpret_cast<const float4 *>(g + m * ldg) + cg);
+                    if (act != HGIN_ACT_NONE) zq[u] = __ldg(reinterpret_cast<const float4 *>(z + m * ldz) + cg);
                 }
             }
-            if (write_dz) reinterpret_cast<float4 *>(dz + m * n)[cg] = make_float4(d[0], d[1], d[2], d[3]);
-            if (want_sums) {
-                float xv[4] = {0.f, 0.f, 0.f, 0.f};
-                for (int t = 0; t < k2; ++t) xv[t] = __ldg(x2 + m * ld2 + t);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    db[i] += d[i];
+            for (int u = 0; u < RIF; ++u) {
+                const int64_t m = m0 + u * stride;
+                if (m >= rows) break;
+                float d[4] = {gq[u].x, gq[u].y, gq[u].z, gq[u].w};
+                if (act != HGIN_ACT_NONE) {
+                    const float zv[4] = {zq[u].x, zq[u].y, zq[u].z, zq[u].w};
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) tail[i][t] = fmaf(d[i], xv[t], tail[i][t]);
+                    for (int i = 0; i < 4; ++i) {
+                        if (act == HGIN_ACT_PRELU && !(zv[i] > 0.f)) dalpha += d[i] * zv[i];
+                        d[i] = act_backward(d[i], zv[i], act, alpha);
+                    }
+                }
+                if (write_dz) reinterpret_cast<float4 *>(dz + m * n)[cg] = make_float4(d[0], d[1], d[2], d[3]);
+                if (want_sums) {
+                    float xv[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int t = 0; t < k2; ++t) xv[t] = __ldg(x2 + m * ld2 + t);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        db[i] += d[i];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) tail[i][t] = fmaf(d[i], xv[t], tail[i][t]);
+                    }
                 }
             }
         }
@@ -190,7 +207,7 @@ bool bwd_eligible(int64_t rows, const float *g, int64_t ldg, const float *z, int
            encode_fn() != nullptr;
 }
 
-static int dz_ctas() { return kNumSMs * 4; }
+static int dz_ctas() { return kNumSMs * 3; }   // 80 registers/thread: three resident CTAs per SM
 
 int64_t fwd_workspace_bytes(int k1, int n) { return align_up(static_cast<int64_t>(n) * k1 * 4, 1024) + 1024; }
 
@@ -199,7 +216,7 @@ int64_t bwd_workspace_bytes(int64_t rows, int k1, int k2, int n) {
     b += align_up(rows * n * 4, 1024);                                     // dz
     b += align_up(static_cast<int64_t>(128) * n * 4, 1024);                // W^T slice
     b += align_up(static_cast<int64_t>(dz_ctas()) * n * (k2 + 1) * 4, 1024);  // db / tail partials
-    b += align_up(static_cast<int64_t>(dz_ctas()) * 4, 1024);              // dalpha partials
+    b += align_up(static_cast<int64_t>(kNumSMs) * 4 * 4, 1024);            // dalpha partials (<= 4 per CTA of the fused kernels)
     b += align_up(static_cast<int64_t>(kNumSMs) * n * k1 * 4, 1024);       // dW partials
     b += align_up(static_cast<int64_t>(kNumSMs) * 4, 1024);                // dot partials
     b += align_up(static_cast<int64_t>(kNumSMs) * n * 4, 1024);            // db partials of the weight-gradient kernel
@@ -302,7 +319,7 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
     float *dz = reinterpret_cast<float *>(carve(ws, rows * n * 4));
     float *Wt = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(128) * n * 4));
     float *sum_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(dz_ctas()) * n * (k2 + 1) * 4));
-    float *alpha_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(dz_ctas()) * 4));
+    float *alpha_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(kNumSMs) * 4 * 4));
     float *dw_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(kNumSMs) * n * k1 * 4));
     float *dot_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(kNumSMs) * 4));
     float *db_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(kNumSMs) * n * 4));

@@ -66,7 +66,7 @@ thin_fwd_kernel(int64_t rows, const float *__restrict__ x, int64_t ldx, int k, c
 }
 
 // part[cta][n][kp], kp = k + d + 1: columns [0,k) = dW, [k, k+d) = T, k+d = db;  alpha_part[cta].
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 2)
 thin_bwd_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, const float *__restrict__ z, int64_t ldz,
                 int act, const float *__restrict__ alpha_ptr, const float *__restrict__ x, int64_t ldx, int k,
                 const float *__restrict__ dot_x, int64_t ld_dot, int d, int n, float *__restrict__ part,
@@ -84,30 +84,48 @@ thin_bwd_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, const fl
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.0f;
     // acc layout: [i*KMAX + kk] dW, [32 + i*DMAX + c] T, [48 + i] db, [52] dalpha
-    for (int64_t m = slot; m < rows; m += num_slots) {
-        const float4 gv = __ldg(reinterpret_cast<const float4 *>(g + m * ldg) + cg);
-        float dz[4] = {gv.x, gv.y, gv.z, gv.w};
-        if (act != HGIN_ACT_NONE) {
-            const float4 zv4 = __ldg(reinterpret_cast<const float4 *>(z + m * ldz) + cg);
-            const float zv[4] = {zv4.x, zv4.y, zv4.z, zv4.w};
+    // ROWS_IN_FLIGHT rows per thread and iteration, all their g / z vectors requested before the
+    // first use: with 94+ registers only two CTAs fit an SM, and one row per thread left ~16 KB of
+    // DRAM reads outstanding per SM (2.2 TB/s measured); the per-thread row order is unchanged.
+    constexpr int RIF = 4;
+    for (int64_t m0 = slot; m0 < rows; m0 += num_slots * RIF) {
+        float4 gq[RIF], zq[RIF];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (act == HGIN_ACT_PRELU && !(zv[i] > 0.0f)) acc[52] += dz[i] * zv[i];
-                dz[i] = act_backward(dz[i], zv[i], act, alpha);
+        for (int u = 0; u < RIF; ++u) {
+            const int64_t m = m0 + u * num_slots;
+            gq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            zq[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (m < rows) {
+                gq[u] = __ldg(reinterpret_cast<const float4 *>(g + m * ldg) + cg);
+                if (act != HGIN_ACT_NONE) zq[u] = __ldg(reinterpret_cast<const float4 *>(z + m * ldz) + cg);
             }
         }
-        float xv[KMAX], dv[DMAX];
 #pragma unroll
-        for (int kk = 0; kk < KMAX; ++kk) xv[kk] = kk < k ? __ldg(x + m * ldx + kk) : 0.0f;
+        for (int u = 0; u < RIF; ++u) {
+            const int64_t m = m0 + u * num_slots;
+            if (m >= rows) break;
+            float dz[4] = {gq[u].x, gq[u].y, gq[u].z, gq[u].w};
+            if (act != HGIN_ACT_NONE) {
+                const float zv[4] = {zq[u].x, zq[u].y, zq[u].z, zq[u].w};
 #pragma unroll
-        for (int c = 0; c < DMAX; ++c) dv[c] = c < d ? __ldg(dot_x + m * ld_dot + c) : 0.0f;
+                for (int i = 0; i < 4; ++i) {
+                    if (act == HGIN_ACT_PRELU && !(zv[i] > 0.0f)) acc[52] += dz[i] * zv[i];
+                    dz[i] = act_backward(dz[i], zv[i], act, alpha);
+                }
+            }
+            float xv[KMAX], dv[DMAX];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+            for (int kk = 0; kk < KMAX; ++kk) xv[kk] = kk < k ? __ldg(x + m * ldx + kk) : 0.0f;
 #pragma unroll
-            for (int kk = 0; kk < KMAX; ++kk) acc[i * KMAX + kk] = fmaf(dz[i], xv[kk], acc[i * KMAX + kk]);
+            for (int c = 0; c < DMAX; ++c) dv[c] = c < d ? __ldg(dot_x + m * ld_dot + c) : 0.0f;
 #pragma unroll
-            for (int c = 0; c < DMAX; ++c) acc[32 + i * DMAX + c] = fmaf(dz[i], dv[c], acc[32 + i * DMAX + c]);
-            acc[48 + i] += dz[i];
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int kk = 0; kk < KMAX; ++kk) acc[i * KMAX + kk] = fmaf(dz[i], xv[kk], acc[i * KMAX + kk]);
+#pragma unroll
+                for (int c = 0; c < DMAX; ++c) acc[32 + i * DMAX + c] = fmaf(dz[i], dv[c], acc[32 + i * DMAX + c]);
+                acc[48 + i] += dz[i];
+            }
         }
     }
     // CTA combine, 8 accumulators at a time: sm[thread][8] -> sum over row slots in slot order
@@ -229,7 +247,10 @@ __global__ void __launch_bounds__(THREADS)
 head_bwd_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, const float *__restrict__ z, int64_t ldz,
                 int act, const float *__restrict__ alpha_ptr, const float *__restrict__ x, int64_t ldx, int k,
                 const float *__restrict__ W, float *__restrict__ dx, int64_t lddx, float *__restrict__ part,
-                float *__restrict__ alpha_part) {
+                float *__restrict__ alpha_part, const float *__restrict__ pz, int64_t ldpz, int pact,
+                const float *__restrict__ palpha_ptr, float *__restrict__ palpha_part) {
+    // pz != NULL: dx leaves as dx * act'(pz) (the dz of the layer that produced x) and
+    // palpha_part[cta] = sum dx * min(pz, 0) — see hgin_linear_bwd_post.
     __shared__ float sm[THREADS * 5];
     __shared__ float red[32];
     const int lpr = k >> 2;
@@ -239,7 +260,8 @@ head_bwd_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, const fl
     const int64_t slots = static_cast<int64_t>(gridDim.x) * slots_per_cta;
     const float4 w = __ldg(reinterpret_cast<const float4 *>(W) + cg);
     const float alpha = act == HGIN_ACT_PRELU ? __ldg(alpha_ptr) : 0.0f;
-    float aw[4] = {0.f, 0.f, 0.f, 0.f}, adb = 0.0f, adal = 0.0f;
+    const float palpha = (pz && pact == HGIN_ACT_PRELU) ? __ldg(palpha_ptr) : 0.0f;
+    float aw[4] = {0.f, 0.f, 0.f, 0.f}, adb = 0.0f, adal = 0.0f, apal = 0.0f;
     for (int64_t m = static_cast<int64_t>(blockIdx.x) * slots_per_cta + grp; m < rows; m += slots) {
         float dz = __ldg(g + m * ldg);
         if (act != HGIN_ACT_NONE) {
@@ -251,7 +273,19 @@ head_bwd_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, const fl
         aw[0] = fmaf(dz, xv.x, aw[0]); aw[1] = fmaf(dz, xv.y, aw[1]);
         aw[2] = fmaf(dz, xv.z, aw[2]); aw[3] = fmaf(dz, xv.w, aw[3]);
         if (cg == 0) adb += dz;
-        if (dx) reinterpret_cast<float4 *>(dx + m * lddx)[cg] = make_float4(dz * w.x, dz * w.y, dz * w.z, dz * w.w);
+        if (dx) {
+            float o[4] = {dz * w.x, dz * w.y, dz * w.z, dz * w.w};
+            if (pz) {
+                const float4 p4 = __ldg(reinterpret_cast<const float4 *>(pz + m * ldpz) + cg);
+                const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (pact == HGIN_ACT_PRELU && !(pv[i] > 0.0f)) apal = fmaf(o[i], pv[i], apal);
+                    o[i] = act_backward(o[i], pv[i], pact, palpha);
+                }
+            }
+            reinterpret_cast<float4 *>(dx + m * lddx)[cg] = make_float4(o[0], o[1], o[2], o[3]);
+        }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) sm[threadIdx.x * 5 + j] = aw[j];
@@ -268,13 +302,17 @@ head_bwd_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, const fl
     __syncthreads();
     const float da = block_sum(adal, red);
     if (threadIdx.x == 0 && alpha_part) alpha_part[blockIdx.x] = da;
+    if (palpha_part) {
+        const float dp = block_sum(apal, red);
+        if (threadIdx.x == 0) palpha_part[blockIdx.x] = dp;
+    }
 }
 
 inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
-inline int thin_ctas(int64_t rows, int n) {
+inline int thin_ctas(int64_t rows, int n, int per_sm = 4) {
     const int slots = THREADS / (n >> 2);
     const int64_t want = ceil_div(rows, static_cast<int64_t>(slots) * 4);
-    const int64_t cap = static_cast<int64_t>(kNumSMs) * 4;
+    const int64_t cap = static_cast<int64_t>(kNumSMs) * per_sm;
     return static_cast<int>(want < 1 ? 1 : (want < cap ? want : cap));
 }
 
@@ -296,7 +334,7 @@ bool bwd_eligible(const float *g, int64_t ldg, const float *z, int64_t ldz, int 
 int64_t bwd_workspace_bytes(int n, int k) {
     const int64_t ctas = static_cast<int64_t>(kNumSMs) * 4;
     const int64_t thin = ctas * (static_cast<int64_t>(n) * ((k < KMAX ? k : KMAX) + DMAX + 1) + 1) + static_cast<int64_t>(n) * DMAX;
-    const int64_t head = ctas * (k + 2) + 8;
+    const int64_t head = ctas * (k + 3) + 8;
     return align_up((thin > head ? thin : head) * 4, 256) + 256;
 }
 
@@ -313,7 +351,7 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
                    const float *x, int64_t ldx, int k, const float *W, int n, int c0, int c1, const float *dot_x,
                    int64_t ld_dot, float *ddot, float *dW, float *db, float *dalpha, void *workspace, cudaStream_t s) {
     const int d = dot_x ? c1 - c0 : 0;
-    const int ctas = thin_ctas(rows, n);
+    const int ctas = thin_ctas(rows, n, 2);   // 128 registers/thread: two resident CTAs per SM, one wave
     float *part = static_cast<float *>(workspace);
     float *alpha_part = part + static_cast<int64_t>(ctas) * n * (k + d + 1);
     const bool want_alpha = dalpha && act == HGIN_ACT_PRELU;
@@ -349,16 +387,24 @@ int32_t head_fwd(int64_t rows, const float *x, int64_t ldx, int k, const float *
 
 int32_t head_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, int64_t ldz, int act, const float *alpha,
                  const float *x, int64_t ldx, int k, const float *W, float *dx, int64_t lddx, float *dW, float *db,
-                 float *dalpha, void *workspace, cudaStream_t s) {
+                 float *dalpha, void *workspace, const float *post_z, int64_t ld_post, int post_act,
+                 const float *post_alpha, float *post_dalpha, cudaStream_t s) {
     const int ctas = thin_ctas(rows, k);
     float *part = static_cast<float *>(workspace);
     float *alpha_part = part + static_cast<int64_t>(ctas) * (k + 1);
-    float *tbuf = alpha_part + ctas;
+    float *palpha_part = alpha_part + ctas;
+    float *tbuf = palpha_part + ctas;
     const bool want_alpha = dalpha && act == HGIN_ACT_PRELU;
+    const bool post_on = post_z && dx && post_act != HGIN_ACT_NONE;
+    const bool want_palpha = post_on && post_dalpha && post_act == HGIN_ACT_PRELU;
     head_bwd_kernel<<<ctas, THREADS, 0, s>>>(rows, g, ldg, z, ldz, act, alpha, x, ldx, k, W, dx, lddx, part,
-                                             want_alpha ? alpha_part : nullptr);
+                                             want_alpha ? alpha_part : nullptr, post_on ? post_z : nullptr, ld_post,
+                                             post_act, post_alpha, want_palpha ? palpha_part : nullptr);
     thin_finalize_kernel<<<static_cast<unsigned>(ceil_div(k + 1, 8)), 256, 0, s>>>(part, ctas, 1, k, 0, dW, db, tbuf);
     if (dalpha) thin_scalars_kernel<<<1, 256, 0, s>>>(tbuf, 1, k, 0, W, 0, nullptr, want_alpha ? alpha_part : nullptr, ctas, dalpha);
+    if (post_dalpha)
+        thin_scalars_kernel<<<1, 256, 0, s>>>(tbuf, 1, k, 0, W, 0, nullptr, want_palpha ? palpha_part : nullptr, ctas,
+                                              post_dalpha);
     HGIN_CHECK_LAUNCH("hgin_linear_bwd(head)");
     return HGIN_OK;
 }

@@ -26,7 +26,8 @@ int32_t head_fwd(int64_t rows, const float *x, int64_t ldx, int k, const float *
                  const float *alpha, float *z, int64_t ldz, float *out, int64_t ldo, int accumulate_out, cudaStream_t s);
 int32_t head_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, int64_t ldz, int act, const float *alpha,
                  const float *x, int64_t ldx, int k, const float *W, float *dx, int64_t lddx, float *dW, float *db,
-                 float *dalpha, void *workspace, cudaStream_t s);
+                 float *dalpha, void *workspace, const float *post_z, int64_t ld_post, int post_act,
+                 const float *post_alpha, float *post_dalpha, cudaStream_t s);
 
 }  // namespace thin
 }  // namespace hgin

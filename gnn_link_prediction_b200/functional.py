@@ -86,10 +86,14 @@ class RelationSpec:
 
 
 def _fold_eligible(rows, k, n, math_mode):
-    """Shapes for which the tensor-core backward consumes dz in place (csrc/linear_tc.cu): only
-    there does moving act'(z) into the producer of the gradient remove a pass over the rows."""
-    return (math_mode == ops.MATH_TF32 and rows >= 128 and 16 <= k <= 128 and k % 16 == 0
-            and 16 <= n <= 128 and n % 16 == 0)
+    """Shapes for which the backward consumes dz in place (csrc/linear_tc.cu, linear_thin.cu): only
+    there does moving act'(z) into the producer of the gradient remove a pass over the rows (and
+    lets d(eps) of the layer above come out of the same pass)."""
+    if math_mode != ops.MATH_TF32:
+        return False
+    tensor_core = rows >= 128 and 16 <= k <= 128 and k % 16 == 0 and 16 <= n <= 128 and n % 16 == 0
+    thin = k <= 8 and 4 <= n <= 128 and (n & (n - 1)) == 0      # csrc/linear_thin.cu: reads g only with ACT_NONE
+    return tensor_core or thin
 
 
 class HeteroConvFn(torch.autograd.Function):
@@ -142,13 +146,31 @@ class HeteroConvFn(torch.autograd.Function):
         need_x = dict(zip(types, need[:nt]))
         g_out = dict(zip(ctx.out_types, gouts))
         grads_p = [None] * (4 * ns)
-        gather_terms = {t: [] for t in types}   # (transposed csr, dh_agg)
-        self_terms = {t: [] for t in types}     # (dh_self, eps)
 
-        for i, sp in enumerate(specs):
-            g = g_out.get(sp.dst)
-            if g is None:
-                continue
+        # Plan of the per-node-type gather passes (K4), fixed before any kernel runs: every live
+        # relation contributes a gather (to its source type) and a (1+eps)*dh self branch (to its
+        # destination type); one self branch rides on each gather pass, the rest get an edgeless pass.
+        live = [i for i, sp in enumerate(specs) if g_out.get(sp.dst) is not None]
+        plan = {}
+        for t in types:
+            gathers = [i for i in live if specs[i].src == t and need_x[t]]
+            selfs = [i for i in live if specs[i].dst == t and need_x[t]]
+            passes = [(gi, selfs.pop(0) if selfs else None) for gi in gathers] + [(None, si) for si in selfs]
+            plan[t] = passes
+        # d(eps) of the relation whose self branch rides on the LAST pass of a type comes out of that
+        # pass when it applies the post-activation (x_dst = act(z) of the layer below is in registers)
+        eps_from_pass = {}
+        for t in types:
+            post = ctx.links_in.get(t)
+            if post is not None and post.usable() and plan[t] and plan[t][-1][1] is not None:
+                si = plan[t][-1][1]
+                if need[nt + 4 * si + 3] and not specs[si].concat:
+                    eps_from_pass[si] = t
+
+        dh_agg_of, dh_self_of = {}, {}
+        for i in live:
+            sp = specs[i]
+            g = g_out[sp.dst]
             if g.stride(-1) != 1:
                 g = g.contiguous()
             W, b, alpha, eps = params[4 * i:4 * i + 4]
@@ -166,8 +188,9 @@ class HeteroConvFn(torch.autograd.Function):
                 z, nalpha_here = None, False
             else:
                 nalpha_here = bool(nalpha)
+            dot_x = x_dst if (neps and i not in eps_from_pass) else None
             if sp.concat:
-                r = ops.linear_bwd(g, z, h, W, dx_cols=(fs, k), want_dx=want_self, dot_x=x_dst if neps else None,
+                r = ops.linear_bwd(g, z, h, W, dx_cols=(fs, k), want_dx=want_self, dot_x=dot_x,
                                    want_dw=nW, want_db=bool(nb), want_dalpha=nalpha_here, **common)
                 dh_self = r["dx"]
                 dh_agg = None
@@ -175,34 +198,34 @@ class HeteroConvFn(torch.autograd.Function):
                     dh_agg = ops.linear_bwd(g, z, h, W, dx_cols=(0, fs), want_dx=True, want_dw=False, want_db=False,
                                             **common)["dx"]
             else:
-                r = ops.linear_bwd(g, z, h, W, dx_cols=(0, k), want_dx=want_agg or want_self,
-                                   dot_x=x_dst if neps else None, want_dw=nW, want_db=bool(nb),
-                                   want_dalpha=nalpha_here, **common)
+                r = ops.linear_bwd(g, z, h, W, dx_cols=(0, k), want_dx=want_agg or want_self, dot_x=dot_x,
+                                   want_dw=nW, want_db=bool(nb), want_dalpha=nalpha_here, **common)
                 dh_agg = dh_self = r["dx"]
             if done is not None and nalpha:
                 r["dalpha"] = done.dalpha
             grads_p[4 * i:4 * i + 4] = [r["dW"], r["db"],
                                         None if r["dalpha"] is None else r["dalpha"].view_as(alpha),
                                         None if r["ddot"] is None else r["ddot"].view_as(eps)]
-            if want_agg:
-                gather_terms[sp.src].append((graph.bwd(sp.et), dh_agg))
-            if want_self:
-                self_terms[sp.dst].append((dh_self, eps))
+            dh_agg_of[i], dh_self_of[i] = dh_agg, dh_self
 
         grads_x = []
         for t in types:
-            selfs = self_terms[t]
-            passes = []                      # (transposed csr | None, gathered rows, self rows, eps)
-            for csr_t, dh in gather_terms[t]:
-                s_dh, s_eps = selfs.pop(0) if selfs else (None, None)   # one (1+eps)*dh branch rides on each gather
-                passes.append((csr_t, dh, s_dh, s_eps))
-            for s_dh, s_eps in selfs:        # self branches with no gather to ride on: edgeless pass
-                passes.append((None, s_dh, s_dh, s_eps))
             post = ctx.links_in.get(t)
             dx = None
-            for j, (csr_t, dh, s_dh, s_eps) in enumerate(passes):
-                dx = ops.gin_combine(csr_t, dh, s_dh, s_eps, SELF_ADD if s_dh is not None else SELF_NONE, out=dx,
-                                     accumulate=dx is not None, post=post if j == len(passes) - 1 else None)
+            for j, (gi, si) in enumerate(plan[t]):
+                last = j == len(plan[t]) - 1
+                s_dh = dh_self_of[si] if si is not None else None
+                s_eps = params[4 * si + 3] if si is not None else None
+                csr_t = graph.bwd(specs[gi].et) if gi is not None else None
+                src_rows = dh_agg_of[gi] if gi is not None else s_dh
+                want_ddot = last and si is not None and eps_from_pass.get(si) == t
+                res = ops.gin_combine(csr_t, src_rows, s_dh, s_eps, SELF_ADD if si is not None else SELF_NONE, out=dx,
+                                      accumulate=dx is not None, post=post if last else None, want_ddot=want_ddot)
+                if want_ddot:
+                    dx, ddot = res
+                    grads_p[4 * si + 3] = ddot.view_as(s_eps)
+                else:
+                    dx = res
             grads_x.append(dx)
         return (None, None, None, None, None, None, *grads_x, *grads_p)
 

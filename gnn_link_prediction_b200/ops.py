@@ -122,6 +122,9 @@ class PostAct:
         self.z, self.act, self.alpha = z, act, alpha
         self.dalpha, self.applied = None, False
 
+    def usable(self):
+        return self.z is not None and self.act != ACT_NONE
+
 
 class _NoEdges:
     """Stand-in adjacency for a self-term-only pass (rowptr = NULL at the ABI)."""
@@ -130,10 +133,12 @@ class _NoEdges:
         self.num_rows, self.num_cols, self.num_edges, self.rowptr, self.col = num_rows, num_rows, 0, None, None
 
 
-def gin_combine(csr, x_src, x_self=None, eps=None, self_mode=SELF_NONE, out=None, accumulate=False, post=None):
+def gin_combine(csr, x_src, x_self=None, eps=None, self_mode=SELF_NONE, out=None, accumulate=False, post=None,
+                want_ddot=False):
     """K1/K4.  out[r] (+)= sum_{e in row r} x_src[col[e]]  {+ | concat}  (1+eps) * x_self[r].
     csr=None: no edges (self term only; x_src is then only a shape donor).
-    post: a PostAct — the stored result is multiplied by act'(post.z) and post.dalpha is filled."""
+    post: a PostAct — the stored result is multiplied by act'(post.z) and post.dalpha is filled.
+    want_ddot (with post, SELF_ADD): returns (out, ddot) with ddot = sum x_self * act(post.z)."""
     if csr is None:
         csr = _NoEdges(x_self.shape[0])
     ps, lds = _f32_matrix(x_src, "gin_combine.x_src")
@@ -161,17 +166,21 @@ def gin_combine(csr, x_src, x_self=None, eps=None, self_mode=SELF_NONE, out=None
         lib = _lib.load()
         want = post.act == ACT_PRELU
         post.dalpha = torch.empty(1, dtype=torch.float32, device=out.device) if want else None
+        ddot = torch.empty(1, dtype=torch.float32, device=out.device) if want_ddot else None
         ws_bytes = lib.hgin_gin_combine_post_workspace_bytes()
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=out.device)
         extra = 4 * csr.num_rows * f_src     # the pre-activation rows read on top of the plain pass
-        with _region("gin_combine", kernels=2 if want else 1, alg_bytes=alg + extra, compulsory_bytes=comp + extra):
+        with _region("gin_combine", kernels=1 + int(want) + int(want_ddot), alg_bytes=alg + extra,
+                     compulsory_bytes=comp + extra):
             check(lib.hgin_gin_combine_post(csr.num_rows, _ptr(csr.rowptr), _ptr(csr.col), csr.num_edges, ps, lds, f_src,
                                             pf, ldf, f_self, _scalar(eps, "gin_combine.eps"), self_mode,
                                             1 if accumulate else 0, po, ldo, pz, ldz, post.act,
-                                            _scalar(post.alpha, "gin_combine.post.alpha"), _ptr(post.dalpha),
+                                            _scalar(post.alpha, "gin_combine.post.alpha"), _ptr(post.dalpha), _ptr(ddot),
                                             ws.data_ptr(), ws_bytes, _stream()), "hgin_gin_combine_post")
         post.applied = True
-        return out
+        return (out, ddot) if want_ddot else out
+    if want_ddot:
+        raise HginError("gin_combine: want_ddot needs a post-activation")
     with _region("gin_combine", kernels=1, alg_bytes=alg, compulsory_bytes=comp):
         check(_lib.load().hgin_gin_combine(csr.num_rows, _ptr(csr.rowptr), _ptr(csr.col), csr.num_edges, ps, lds, f_src, pf,
                                            ldf, f_self, _scalar(eps, "gin_combine.eps"), self_mode,

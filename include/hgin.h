@@ -105,6 +105,9 @@ int32_t hgin_gin_combine(int64_t num_rows, const int32_t *rowptr, const int32_t 
  * hgin_gin_combine is a gradient w.r.t. that layer's output; with post_z (its saved
  * pre-activation, [num_rows, f_src]) the kernel stores  r * act'(post_z)  — i.e. that layer's dz —
  * and reduces  post_dalpha[0] = sum r * min(post_z, 0)  (two-stage, deterministic; NULL to skip).
+ * post_ddot (NULL to skip; HGIN_SELF_ADD only):  sum x_self * act(post_z).  In the backward pass the
+ * rows of x_self are dh_self and act(post_z) is x_dst, so this is d(eps) = sum dh_self * x_dst of the
+ * relation whose self branch rides on the pass (models.py:213/215) without reading x_dst again.
  * The layer below is then called with HGIN_ACT_NONE (hgin_linear_bwd consumes dz in place).
  * post_act == HGIN_ACT_NONE or post_z == NULL: identical to hgin_gin_combine.
  * rowptr == NULL: the relation has no edges; the call reduces to the self term (used for
@@ -118,7 +121,7 @@ int32_t hgin_gin_combine_post(int64_t num_rows, const int32_t *rowptr, const int
                               const float *eps, int32_t self_mode, int32_t accumulate,
                               float *out, int64_t ld_out, const float *post_z, int64_t ld_post,
                               int32_t post_act, const float *post_alpha, float *post_dalpha,
-                              void *workspace, int64_t workspace_bytes, void *stream);
+                              float *post_ddot, void *workspace, int64_t workspace_bytes, void *stream);
 
 /* ---- K2: dense layer forward  z = [x1 | x2] W^T + b,  out (+)= act(z) ------------------------
  * Replaces: GINLayer.mlp = Linear + PReLU (models.py:236-239, applied at models.py:217), the

@@ -382,7 +382,14 @@ def test_gin_combine_post_activation(ns, nd, e, f, act):
                                 out=prev.clone() if acc else None, accumulate=acc)
         post = ops.PostAct(z, act, alpha)
         got = ops.gin_combine(csr_arg, xs, x_self if mode != ops.SELF_NONE else None, eps, mode,
-                              out=prev.clone() if acc else None, accumulate=acc, post=post)
+                              out=prev.clone() if acc else None, accumulate=acc, post=post,
+                              want_ddot=mode == ops.SELF_ADD)
+        if mode == ops.SELF_ADD:   # d(eps) = sum x_self * act(z), with act(z) the x_dst of the layer above
+            got, ddot = got
+            zd = z.double()
+            xd = torch.where(zd > 0, zd, 0.2 * zd if act == ops.ACT_PRELU else torch.zeros_like(zd))
+            ref_dot = (x_self.double() * xd)
+            assert abs(float(ddot) - float(ref_dot.sum())) <= 1e-5 * float(ref_dot.abs().sum()) + 1e-6
         want = torch.where(z > 0, plain, (alpha * plain) if act == ops.ACT_PRELU else torch.zeros_like(plain))
         assert post.applied and torch.equal(got, want)
         if csr_arg is None and not acc:
