@@ -91,6 +91,9 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(samples)}
 
 
+ALL_SAMPLES = []   # the samples behind the host batches (the device-resident dataset arm reuses them)
+
+
 def make_host_batches(w, count, rank, pin, collate="csr"):
     from gnn_link_prediction_b200.data import Batch, CONV_EDGE_TYPES
     from gnn_link_prediction_b200.synthetic import SyntheticDataset
@@ -98,6 +101,7 @@ def make_host_batches(w, count, rank, pin, collate="csr"):
     batches = []
     for b in range(count):
         samples = [ds[b * w["batch"] + i] for i in range(w["batch"])]
+        ALL_SAMPLES.extend(samples)
         # default: per-sample CSRs (built once per sample by K0, cached) are concatenated by the collate, so
         # the step runs no CSR build; --collate coo ships the COO lists and K0 runs inside every step
         batch = Batch.from_data_list(samples, index_dtype=torch.int32, edge_types=CONV_EDGE_TYPES, batch_vector=False,
@@ -351,10 +355,42 @@ def main():
     barrier()
     e2e_ms = ea.elapsed_time(eb)
 
+    # ---- device-resident dataset arm: the samples live in HBM (arena.DeviceDataset), every step assembles a
+    # FRESH random batch on the GPU from its sample ids (H2D = the id list), then runs the same step.
+    dd_ms, dd_collate_ms, dd_bytes = 0.0, 0.0, 0
+    if not graphed and args.collate == "csr":
+        from gnn_link_prediction_b200.arena import DeviceDataset, SampleArena
+        dds = DeviceDataset(SampleArena.from_samples(ALL_SAMPLES, keep_coo=False))
+        gen = torch.Generator().manual_seed(1997 + rank)
+        id_lists = [torch.randint(0, len(dds), (graphs,), generator=gen).numpy() for _ in range(args.steps + 2)]
+        dd_bytes = dds.h2d_bytes(graphs)
+
+        def dd_run(lists):
+            reader = LossReadback()
+            for ids in lists:
+                reader.push(step(dds.collate(ids)))
+            reader.flush()
+
+        dd_run(id_lists[:2])
+        barrier()
+        da, db_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        da.record()
+        dd_run(id_lists[2:])
+        db_.record()
+        barrier()
+        dd_ms = da.elapsed_time(db_)
+        ca, cb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ca.record()
+        for ids in id_lists[2:]:
+            dds.collate(ids)
+        cb.record()
+        torch.cuda.synchronize()
+        dd_collate_ms = ca.elapsed_time(cb) / args.steps
+
     # max over ranks (device time)
-    t = torch.tensor([resident_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([resident_ms, e2e_ms, dd_ms], dtype=torch.float64, device="cuda")
     comm.all_reduce_max_(t)
-    resident_ms, e2e_ms = (float(v) for v in t.tolist())
+    resident_ms, e2e_ms, dd_ms = (float(v) for v in t.tolist())
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
@@ -410,6 +446,11 @@ def main():
                 else "one H2D copy per tensor (DevicePrefetcher)",
                 "readback": "every step, collected one step later (train.LossReadback)" if args.readback == "deferred"
                 else "every step, blocking"},
+        "e2e_device_dataset": None if dd_ms == 0.0 else {
+            "value": graphs * world * args.steps / (dd_ms * 1e-3), "unit": "graphs/s", "ms_per_step": dd_ms / args.steps,
+            "h2d_bytes_per_step": dd_bytes, "d2h_bytes_per_step": 8, "collate_ms_per_step": dd_collate_ms,
+            "what": "dataset resident in HBM (arena.DeviceDataset); every step: H2D of the sample ids, on-GPU collate "
+                    "of a fresh random batch, train step, loss read-back"},
         "gpu_launches": launches, "kernels_per_step": kernels_per_step,
         "execution": "one CUDA graph replay per step (GraphedTrainStep)" if graphed else "eager launches",
         "wall_s_resident": t_wall,

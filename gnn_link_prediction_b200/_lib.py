@@ -18,6 +18,12 @@ MATH_FP32, MATH_TF32 = 0, 1
 
 _i32, _i64, _f32, _f64, _ptr = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_void_p
 
+class CollateField(ctypes.Structure):
+    """hgin_collate_field (include/hgin.h)."""
+    _fields_ = [("src", ctypes.c_void_p), ("dst", ctypes.c_void_p), ("ptr", ctypes.c_void_p), ("width", ctypes.c_int32),
+                ("size_class", ctypes.c_int32), ("add_class", ctypes.c_int32), ("closing_row", ctypes.c_int32)]
+
+
 # name -> (restype, argtypes); must list every function include/hgin.h declares
 # (tests/test_abi.py parses the header and checks both directions).
 SIGNATURES = {
@@ -44,6 +50,8 @@ SIGNATURES = {
     "hgin_sqrt_mape_bwd": (_i32, [_i64, _ptr, _ptr, _ptr, _f32, _ptr, _ptr, _ptr]),
     "hgin_adam_step": (_i32, [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _f64, _f64, _f64, _f64, _f64, _i32, _ptr]),
     "hgin_increment": (_i32, [_ptr, _ptr]),
+    "hgin_collate_offsets": (_i32, [_i32, _ptr, _i32, _ptr, _i64, _ptr, _ptr, _ptr]),
+    "hgin_collate_gather": (_i32, [_i32, _ptr, _i64, _i32, ctypes.POINTER(CollateField), _i32, _ptr, _i64, _ptr]),
     "hgin_set_option": (_i32, [ctypes.c_char_p, _i32]),
     "hgin_debug_gemm_tn": (_i32, [_i64, _ptr, _i32, _ptr, _i32, _ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _ptr]),
 }

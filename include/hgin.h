@@ -207,6 +207,45 @@ int32_t hgin_adam_step(int64_t n, float *param, const float *grad, float *exp_av
                        void *stream);
 int32_t hgin_increment(int32_t *counter, void *stream);
 
+/* ---- device-side batch assembly (collate) ------------------------------------------------------
+ * Replaces: PyG's collate — `Batch.from_data_list`, reached through
+ * torch_geometric.loader.DataLoader (dataset.py:242-244) — and the per-step `sample.cuda()`
+ * (train.py:28).  The dataset is resident in HBM as flat ARENAS, one per field (path.x, path.y,
+ * link.x, node.x and, per relation, the per-sample CSR row pointers / columns in LOCAL ids), each
+ * with an int64 table ptr[num_samples + 1] of first rows; a batch is assembled on the GPU from the
+ * sample ids alone, so a step's host->device traffic is the id list.
+ *
+ * hgin_collate_offsets: offsets[c][b] (int64 [num_classes][batch + 1]) = exclusive prefix sum over
+ *   the batch of (class_ptr[c][ids[b] + 1] - class_ptr[c][ids[b]]), class_ptr being int64
+ *   [num_classes][num_samples + 1]; offsets[c][batch] is the batch total.  These are the per-type
+ *   node offsets and per-relation edge offsets PyG adds when it concatenates `edge_index`.
+ *   status: int32 [1], set to 1 when an id is outside [0, num_samples) (that sample is skipped).
+ * hgin_collate_gather: for every field f and batch slot b, rows [ptr[id], ptr[id+1]) of f.src
+ *   (width 4-byte elements per row) are copied to f.dst at row offsets[f.size_class][b]; with
+ *   f.add_class >= 0 the elements are int32 and offsets[f.add_class][b] is added (CSR columns get
+ *   the node offset of the type they index, row pointers the edge offset of their relation);
+ *   f.closing_row = 1: every sample's block ends with a closing row (the n+1-th entry of a local
+ *   row-pointer array) that is dropped for all but the LAST batch slot.  Integer-exact with the host collate.  `fields_host` is a HOST array (read during the
+ *   call); max_words_per_sample sizes the grid (largest rows*width of one sample over the fields).
+ */
+typedef struct hgin_collate_field {
+    const void *src;      /* device: arena of this field */
+    void *dst;            /* device: start of this field in the batch */
+    const int64_t *ptr;   /* device: int64 [num_samples + 1], first row of every sample in src */
+    int32_t width;        /* 4-byte elements per row */
+    int32_t size_class;   /* row of `offsets` holding this field's batch row offsets */
+    int32_t add_class;    /* >= 0: row of `offsets` added to every (int32) element; -1: plain copy */
+    int32_t closing_row;  /* 1: blocks end with a closing row kept only for the last batch slot */
+} hgin_collate_field;
+
+int32_t hgin_collate_offsets(int32_t batch, const int32_t *ids, int32_t num_classes,
+                             const int64_t *class_ptr, int64_t num_samples, int64_t *offsets,
+                             int32_t *status, void *stream);
+int32_t hgin_collate_gather(int32_t batch, const int32_t *ids, int64_t num_samples,
+                            int32_t num_fields, const hgin_collate_field *fields_host,
+                            int32_t num_classes, const int64_t *offsets,
+                            int64_t max_words_per_sample, void *stream);
+
 /* ---- runtime options --------------------------------------------------------------------------
  * "fused_bwd" (0/1, default 0): HGIN_MATH_TF32 backward through the single-pass fused kernel
  * (csrc/linear_tc_fused.cuh) instead of separate passes.
