@@ -52,6 +52,9 @@ SIGNATURES = {
     "hgin_increment": (_i32, [_ptr, _ptr]),
     "hgin_collate_offsets": (_i32, [_i32, _ptr, _i32, _ptr, _i64, _ptr, _ptr, _ptr]),
     "hgin_collate_gather": (_i32, [_i32, _ptr, _i64, _i32, ctypes.POINTER(CollateField), _i32, _ptr, _i64, _ptr]),
+    "hgin_qt_baseline_workspace_bytes": (_i64, [_i64, _i64]),
+    "hgin_qt_baseline": (_i32, [_i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _ptr, _ptr, _ptr,
+                                _i64, _ptr]),
     "hgin_set_option": (_i32, [ctypes.c_char_p, _i32]),
     "hgin_debug_gemm_tn": (_i32, [_i64, _ptr, _i32, _ptr, _i32, _ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _ptr]),
 }

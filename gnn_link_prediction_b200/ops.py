@@ -282,6 +282,32 @@ def linear_bwd(g, z, x1, W, x2=None, act=ACT_NONE, alpha=None, dx_cols=None, wan
     return {"dx": dx, "ddot": ddot, "dW": dW, "db": db, "dalpha": dalpha}
 
 
+def qt_baseline(p_l, avg_bw, capacity, num_paths, num_links, num_iterations=3):
+    """Queueing-theory baseline on a (batched) path->link relation.  p_l: CUDA int64/int32 [2,E],
+    every path's edges in route order; avg_bw f32 [num_paths]; capacity f32 [num_links] (raw).
+    Returns (path_delay f32 [num_paths], link_out f32 [num_links,3] = occupancy, rho, pi_0)."""
+    for t, n, name in ((avg_bw, num_paths, "avg_bw"), (capacity, num_links, "capacity")):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n):
+            raise HginError(f"qt_baseline: {name} must be a contiguous CUDA float32 vector of {n} elements")
+    by_path = csr_build(p_l, num_paths, num_links, by="src", want_perm=True)
+    by_link = csr_build(p_l, num_paths, num_links, by="dst", want_perm=True)
+    cap_scaled = capacity / 1000                       # models.py:73-74, the same fp32 division
+    dev = avg_bw.device
+    path_delay = torch.empty(num_paths, dtype=torch.float32, device=dev)
+    link_out = torch.empty(num_links, 3, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    e = by_path.num_edges
+    ws_bytes = lib.hgin_qt_baseline_workspace_bytes(num_links, e)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with _region("qt_baseline", kernels=2 + 2 * num_iterations):
+        check(lib.hgin_qt_baseline(num_paths, num_links, e, by_path.rowptr.data_ptr(), _ptr(by_path.col),
+                                   _ptr(by_path.perm), by_link.rowptr.data_ptr(), _ptr(by_link.perm), avg_bw.data_ptr(),
+                                   cap_scaled.data_ptr(), capacity.data_ptr(), num_iterations, path_delay.data_ptr(),
+                                   link_out.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "hgin_qt_baseline")
+    by_path.validate()
+    return path_delay, link_out
+
+
 def set_option(name, value):
     """Process-wide library option (see include/hgin.h), e.g. set_option("fused_bwd", 1)."""
     check(_lib.load().hgin_set_option(name.encode(), int(value)), "hgin_set_option")

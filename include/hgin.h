@@ -246,6 +246,31 @@ int32_t hgin_collate_gather(int32_t batch, const int32_t *ids, int64_t num_sampl
                             int32_t num_classes, const int64_t *offsets,
                             int64_t max_words_per_sample, void *stream);
 
+/* ---- queueing-theory baseline (pre-processing features) -----------------------------------------
+ * Replaces: QTBaseline.forward + separate_edge_timesteps (models.py:15-158), called once per
+ * sample by GNN21Dataset.preprocess (dataset.py:86); its outputs are the `bl_features` columns of
+ * link.x and path.x (dataset.py:105-106).  The reference runs it on the CPU as a Python loop over
+ * hop positions; here one call handles a whole block-diagonal batch of samples.
+ *   path->link relation as two CSRs over the SAME edge list (hgin_csr_build with perm):
+ *     rowptr_src/col_src/perm_src : rows = paths, each row the path's links in ROUTE order
+ *                                   (perm_src may be NULL when the edge list is already grouped by
+ *                                   path, as the reference ships it: edge id == CSR position);
+ *     rowptr_dst/perm_dst         : rows = links, perm_dst = edge ids of the incoming edges.
+ *   avg_bw          [num_paths]  P[:,1], the traffic a path offers (models.py:94)
+ *   capacity_scaled [num_links]  L / 1000 (models.py:73-74);  capacity_raw [num_links]  L
+ *   num_iterations  fixed-point iterations (3 in the reference, models.py:43)
+ *   path_delay [num_paths]       sum over the path's links of occupancy * 32000 / capacity_raw
+ *   link_out   [num_links, 3]    occupancy, rho, pi_0 (as the reference returns them)
+ * fp32 like the reference; agrees to rounding (powf), including the NaN pattern on overflow.
+ */
+int64_t hgin_qt_baseline_workspace_bytes(int64_t num_links, int64_t num_edges);
+int32_t hgin_qt_baseline(int64_t num_paths, int64_t num_links, int64_t num_edges,
+                         const int32_t *rowptr_src, const int32_t *col_src, const int32_t *perm_src,
+                         const int32_t *rowptr_dst, const int32_t *perm_dst, const float *avg_bw,
+                         const float *capacity_scaled, const float *capacity_raw,
+                         int32_t num_iterations, float *path_delay, float *link_out,
+                         void *workspace, int64_t workspace_bytes, void *stream);
+
 /* ---- runtime options --------------------------------------------------------------------------
  * "fused_bwd" (0/1, default 0): HGIN_MATH_TF32 backward through the single-pass fused kernel
  * (csrc/linear_tc_fused.cuh) instead of separate passes.
