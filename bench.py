@@ -198,11 +198,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfgC", choices=sorted(WORKLOADS) + ["cfgD"])
+    ap.add_argument("--workload", default="cfgC", choices=sorted(WORKLOADS) + ["cfgD", "qt"])
     ap.add_argument("--math", default=None, choices=["fp32", "tf32"],
                     help="dense-layer arithmetic; default tf32 tensor cores for cfgC (BASELINE configs[2] allows "
                          "reduced-precision MLP GEMMs), fp32 for cfgA")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the cfgA line reported beside the default cfgC run")
     ap.add_argument("--collate", default="csr", choices=["csr", "coo"],
                     help="csr: the collate concatenates cached per-sample CSRs (no CSR build in the step); "
                          "coo: ship COO edge lists, hgin_csr_build runs inside every step")
@@ -221,6 +222,9 @@ def main():
     if args.workload == "cfgD":
         import bench_conv
         return bench_conv.main(args)
+    if args.workload == "qt":
+        import bench_qt
+        return bench_qt.main(args)
     w = WORKLOADS[args.workload]
     if args.math is None:
         args.math = "tf32" if args.workload == "cfgC" else "fp32"
@@ -442,8 +446,9 @@ def main():
         "edges_per_s": edges * world * args.steps / (resident_ms * 1e-3),
         "e2e": {"value": graphs * world * args.steps / (e2e_ms * 1e-3), "unit": "graphs/s",
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8, "ms_per_step": e2e_ms / args.steps,
-                "staging": "one packed pinned buffer per batch -> DevicePrefetcher ring" if (graphed or args.stage == "packed")
-                else "one H2D copy per tensor (DevicePrefetcher)",
+                "staging": "one packed pinned buffer per batch -> the CUDA graph's static buffer" if graphed
+                else ("one packed pinned buffer per batch -> DevicePrefetcher ring" if args.stage == "packed"
+                      else "one H2D copy per tensor (DevicePrefetcher)"),
                 "readback": "every step, collected one step later (train.LossReadback)" if args.readback == "deferred"
                 else "every step, blocking"},
         "e2e_device_dataset": None if dd_ms == 0.0 else {
@@ -457,6 +462,20 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "kernels": breakdown,
         "loss_first_last": [float(losses[0][0]), float(losses[-1][0])],
     }
+    if args.workload == "cfgC" and world == 1 and not args.no_extra:
+        # BASELINE configs[1] (config.json defaults, launch-bound) beside the default workload: same script, own process
+        import subprocess
+        try:
+            torch.cuda.empty_cache()
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", "cfgA", "--no-cpu-baseline",
+                                "--no-extra", "--steps", str(max(args.steps, 20)), "--warmup", str(args.warmup)],
+                               capture_output=True, text=True, timeout=300)
+            a = json.loads(r.stdout.strip().splitlines()[-1])
+            line["other_workloads"] = {"cfgA": {"desc": a["config"]["desc"], "value": a["value"], "unit": a["unit"],
+                                                "ms_per_step": a["ms_per_step"], "e2e": a["e2e"], "execution": a["execution"],
+                                                "kernels_per_step": a["kernels_per_step"], "dtype": a["dtype"]}}
+        except Exception as exc:   # the default line must not depend on the extra run
+            line["other_workloads"] = {"cfgA": {"error": repr(exc)[:200]}}
     print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -6,7 +6,7 @@
 # Usage: tools/capture_profiles.sh <tag>
 set -u
 TAG=${1:-r01}
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra"
 $CMD > gpurun_out/${TAG}_plain.json 2> gpurun_out/${TAG}_plain.err || { tail -5 gpurun_out/${TAG}_plain.err; exit 1; }
 # launch list (cold-cache, serialised): ~2 steps after the warm-up steps
 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 700 -c 300 --csv \
