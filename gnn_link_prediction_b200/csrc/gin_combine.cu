@@ -41,6 +41,33 @@ __device__ __forceinline__ Pack<VEC> load_pack(const float *p) {
     return r;
 }
 
+// Streaming variants for rows that are touched exactly once (self rows, post-activation rows, the
+// output): they must not displace the gathered source rows, which ARE reused (each link row ~35
+// times per topology), from L1.
+template <int VEC>
+__device__ __forceinline__ Pack<VEC> load_pack_stream(const float *p) {
+    Pack<VEC> r;
+    if constexpr (VEC == 4) {
+        asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+            : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3])
+            : "l"(p));
+    } else {
+        r.v[0] = __ldg(p);
+    }
+    return r;
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_pack_stream(float *p, const Pack<VEC> &r) {
+    if constexpr (VEC == 4) {
+        asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]),
+                     "f"(r.v[2]), "f"(r.v[3])
+                     : "memory");
+    } else {
+        p[0] = r.v[0];
+    }
+}
+
 template <int VEC>
 __device__ __forceinline__ void store_pack(float *p, const Pack<VEC> &r) {
     if constexpr (VEC == 4) {
@@ -141,7 +168,8 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 const int f = (c * LPR + sub) * VEC;
-                if (f < f_src) self_v[c] = load_pack<VEC>(x_self + row * ld_self + f);
+                if (f < f_src)
+                    self_v[c] = CONTIG ? load_pack_stream<VEC>(x_self + row * ld_self + f) : load_pack<VEC>(x_self + row * ld_self + f);
             }
         }
         Pack<VEC> post_v[NC];
@@ -149,7 +177,8 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 const int f = (c * LPR + sub) * VEC;
-                if (f < f_src) post_v[c] = load_pack<VEC>(post.z + row * post.ldz + f);
+                if (f < f_src)
+                    post_v[c] = CONTIG ? load_pack_stream<VEC>(post.z + row * post.ldz + f) : load_pack<VEC>(post.z + row * post.ldz + f);
             }
         }
         // warp-uniform trip count so the shuffles below are always convergent
@@ -230,7 +259,8 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
                         r.v[i] = act_backward(r.v[i], zv, post.act, post_alpha);
                     }
                 }
-                store_pack<VEC>(orow + f, r);
+                if constexpr (CONTIG) store_pack_stream<VEC>(orow + f, r);
+                else store_pack<VEC>(orow + f, r);
             }
             if (self_mode == HGIN_SELF_CONCAT) {
                 // [agg | (1+eps) x_self]: the self block starts at column f_src (rarely 16B aligned) -> scalar
@@ -272,16 +302,17 @@ template <int VEC, int LPR, int NC, bool CONTIG = false, int MINB = ((VEC * NC <
 int launch(int64_t num_rows, const int32_t *rowptr, const int32_t *col, const float *x_src, int64_t ld_src,
            int f_src, const float *x_self, int64_t ld_self, int f_self, const float *eps, int self_mode,
            int accumulate, float *out, int64_t ld_out, const PostAct *post, cudaStream_t s) {
-    constexpr int rows_per_cta = (256 / 32) * (32 / LPR);
+    constexpr int threads = 256;
+    constexpr int rows_per_cta = (threads / 32) * (32 / LPR);
     // Grid-stride over rows with whole waves of CTAs: enough CTAs (32 per SM) that the hardware
     // scheduler evens out the heavy-tailed row lengths of the path->link relation.
     const int grid = grid_for(num_rows, rows_per_cta, 32);
     if (post)
-        gin_combine_kernel<VEC, LPR, NC, CONTIG, MINB, true><<<grid, 256, 0, s>>>(
+        gin_combine_kernel<VEC, LPR, NC, CONTIG, MINB, true><<<grid, threads, 0, s>>>(
             num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, accumulate, out, ld_out,
             *post);
     else
-        gin_combine_kernel<VEC, LPR, NC, CONTIG, MINB, false><<<grid, 256, 0, s>>>(
+        gin_combine_kernel<VEC, LPR, NC, CONTIG, MINB, false><<<grid, threads, 0, s>>>(
             num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, accumulate, out, ld_out,
             PostAct{});
     return grid;

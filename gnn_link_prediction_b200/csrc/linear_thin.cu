@@ -66,6 +66,7 @@ thin_fwd_kernel(int64_t rows, const float *__restrict__ x, int64_t ldx, int k, c
 }
 
 // part[cta][n][kp], kp = k + d + 1: columns [0,k) = dW, [k, k+d) = T, k+d = db;  alpha_part[cta].
+template <bool HAS_ACT>
 __global__ void __launch_bounds__(THREADS, 2)
 thin_bwd_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, const float *__restrict__ z, int64_t ldz,
                 int act, const float *__restrict__ alpha_ptr, const float *__restrict__ x, int64_t ldx, int k,
@@ -87,17 +88,18 @@ thin_bwd_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, const fl
     // ROWS_IN_FLIGHT rows per thread and iteration, all their g / z vectors requested before the
     // first use: with 94+ registers only two CTAs fit an SM, and one row per thread left ~16 KB of
     // DRAM reads outstanding per SM (2.2 TB/s measured); the per-thread row order is unchanged.
-    constexpr int RIF = 4;
+    // (with ACT_NONE — g already is dz — only g is read, so twice as many rows fit the same registers)
+    constexpr int RIF = HAS_ACT ? 4 : 8;
     for (int64_t m0 = slot; m0 < rows; m0 += num_slots * RIF) {
-        float4 gq[RIF], zq[RIF];
+        float4 gq[RIF], zq[HAS_ACT ? RIF : 1];
 #pragma unroll
         for (int u = 0; u < RIF; ++u) {
             const int64_t m = m0 + u * num_slots;
             gq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            zq[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (HAS_ACT) zq[u] = make_float4(1.f, 1.f, 1.f, 1.f);
             if (m < rows) {
                 gq[u] = __ldg(reinterpret_cast<const float4 *>(g + m * ldg) + cg);
-                if (act != HGIN_ACT_NONE) zq[u] = __ldg(reinterpret_cast<const float4 *>(z + m * ldz) + cg);
+                if (HAS_ACT) zq[u] = __ldg(reinterpret_cast<const float4 *>(z + m * ldz) + cg);
             }
         }
 #pragma unroll
@@ -105,7 +107,7 @@ thin_bwd_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, const fl
             const int64_t m = m0 + u * num_slots;
             if (m >= rows) break;
             float dz[4] = {gq[u].x, gq[u].y, gq[u].z, gq[u].w};
-            if (act != HGIN_ACT_NONE) {
+            if (HAS_ACT) {
                 const float zv[4] = {zq[u].x, zq[u].y, zq[u].z, zq[u].w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -355,8 +357,12 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
     float *part = static_cast<float *>(workspace);
     float *alpha_part = part + static_cast<int64_t>(ctas) * n * (k + d + 1);
     const bool want_alpha = dalpha && act == HGIN_ACT_PRELU;
-    thin_bwd_kernel<<<ctas, THREADS, 0, s>>>(rows, g, ldg, z, ldz, act, alpha, x, ldx, k, dot_x, ld_dot, d, n, part,
-                                             want_alpha ? alpha_part : nullptr);
+    if (act != HGIN_ACT_NONE)
+        thin_bwd_kernel<true><<<ctas, THREADS, 0, s>>>(rows, g, ldg, z, ldz, act, alpha, x, ldx, k, dot_x, ld_dot, d, n, part,
+                                                       want_alpha ? alpha_part : nullptr);
+    else
+        thin_bwd_kernel<false><<<ctas, THREADS, 0, s>>>(rows, g, ldg, z, ldz, act, alpha, x, ldx, k, dot_x, ld_dot, d, n, part,
+                                                        nullptr);
     float *tbuf = alpha_part + ctas;
     const int total = n * (k + d + 1);
     thin_finalize_kernel<<<static_cast<unsigned>(ceil_div(total, 8)), 256, 0, s>>>(part, ctas, n, k, d, dW, db, tbuf);

@@ -254,6 +254,38 @@ def test_device_prefetcher_yields_identical_batches():
             assert torch.equal(d[et].edge_index.cpu(), h[et].edge_index)
 
 
+def test_packed_prefetcher_ring_and_deferred_loss_readback():
+    """PackedBatch source: one DMA per batch into a ring of device buffers that is reused only after
+    the consuming step has finished; LossReadback hands every step's loss to the host one step later."""
+    from gnn_link_prediction_b200.data import DataLoader, DevicePrefetcher, pack_batch
+    from gnn_link_prediction_b200.train import LossReadback
+    ds = SyntheticDataset(14, num_nodes=9, num_links=12, num_topologies=3)
+    loader = DataLoader(ds, batch_size=2, pin_memory=True, index_dtype=torch.int32, edge_types=CONV_EDGE_TYPES, csr=True,
+                        keep_coo=False, batch_vector=False)
+    host = list(loader)
+    packed = [pack_batch(h) for h in host]
+    pre = DevicePrefetcher(packed, depth=2)          # 7 batches through 2 slots: every slot is reused
+    reader, seen, sums = LossReadback(numel=2), [], []
+    for h, d in zip(host, pre):
+        # consume the batch on the compute stream (a stand-in for the step), then check it later
+        sums.append(torch.stack([d["path"]["x"].sum(), d["link"]["x"].sum()]))
+        done = reader.push(sums[-1])
+        if done is not None:
+            seen.append(done)
+        assert d.num_graphs == h.num_graphs
+        for et in CONV_EDGE_TYPES:
+            rows = h[et]["csr_dst_col"].shape[0]
+            assert torch.equal(d[et]["csr_dst_col"][:rows].cpu(), h[et]["csr_dst_col"])
+            assert torch.equal(d[et]["csr_dst_rowptr"].cpu(), h[et]["csr_dst_rowptr"])
+        assert torch.equal(d["path"]["x"].cpu(), h["path"]["x"])
+    seen.append(reader.flush())
+    assert len(seen) == len(host) and reader.flush() is None
+    for h, got in zip(host, seen):
+        want = torch.stack([h["path"]["x"].sum(), h["link"]["x"].sum()])
+        torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-4)
+    assert sum(r is not None for r in pre._ring) == 2
+
+
 def test_graphed_train_step_matches_eager_trajectory():
     """CUDA-graph replay of the whole step (static buffers, (-1,-1)-padded edges) follows the
     eager TrainStep bit for bit over several different batches of the same shape bucket."""
