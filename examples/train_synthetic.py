@@ -4,7 +4,8 @@ with this package swapped in for `models` / the PyG loader.  Two equivalent ways
 
     --mode dropin   train.py's own step body: model(...); sqrt(mape).backward(); torch.optim step
     --mode fused    gnn_link_prediction_b200.train.TrainStep (fused loss, flat bucket, hgin Adam);
-                    add --graph to replay every step as one CUDA graph
+                    add --graph to replay every step as one CUDA graph, or --device-dataset to keep
+                    the samples in HBM and assemble every batch on the GPU (arena.DeviceDataset)
 
     python examples/train_synthetic.py --epochs 3 --samples 64
     torchrun --nproc-per-node 2 examples/train_synthetic.py --mode fused      # sample-sharded
@@ -49,6 +50,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mode", default="dropin", choices=["dropin", "fused"])
     ap.add_argument("--graph", action="store_true")
+    ap.add_argument("--device-dataset", action="store_true")
     ap.add_argument("--epochs", type=int, default=3)
     ap.add_argument("--samples", type=int, default=64)
     ap.add_argument("--config", default=None, help="a config.json in the reference's format")
@@ -81,12 +83,25 @@ def main():
         step = TrainStep(model.train(), lr=config["LEARNING_RATE"], weight_decay=config["WEIGHT_DECAY"],
                          optimizer=config["OPTIMIZER"], communicator=comm)
         run = GraphedTrainStep(step) if args.graph else step
+        if args.device_dataset:
+            from gnn_link_prediction_b200.arena import DeviceDataset, DeviceLoader, SampleArena
+            n_train = int(args.samples * 0.75)
+            dev_ds = DeviceDataset(SampleArena.from_samples([full[i] for i in range(n_train)], keep_coo=False))
+            loader = DeviceLoader(dev_ds, batch_size=config["TRAIN_BATCH_SIZE"], shuffle=True, rank=comm.rank,
+                                  world=comm.world)
+        from gnn_link_prediction_b200.train import LossReadback
         for epoch in range(args.epochs):
             total, n = 0.0, 0
-            batches = (pack_batch(b) for b in loader) if args.graph else DevicePrefetcher(loader)
+            if args.device_dataset:
+                batches = loader
+            else:
+                batches = (pack_batch(b) for b in loader) if args.graph else DevicePrefetcher(loader)
+            reader = LossReadback()
             for batch in batches:
-                total += float(run(batch)[0])
+                done = reader.push(run(batch))      # the previous step's loss: no stall in the launch queue
+                total += float(done[0]) if done is not None else 0.0
                 n += 1
+            total += float(reader.flush()[0])
             if comm.rank == 0:
                 print(f"Epoch {epoch + 1} | Train Loss {total / max(n, 1):.4f} ({n} steps, {comm.world} rank(s))")
 

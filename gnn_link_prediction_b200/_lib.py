@@ -35,6 +35,8 @@ SIGNATURES = {
     "hgin_gin_combine_post_workspace_bytes": (_i64, []),
     "hgin_gin_combine_post": (_i32, [_i64, _ptr, _ptr, _i64, _ptr, _i64, _i32, _ptr, _i64, _i32, _ptr, _i32, _i32, _ptr, _i64,
                                      _ptr, _i64, _i32, _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
+    "hgin_gin_combine_pre": (_i32, [_i64, _ptr, _ptr, _i64, _ptr, _i64, _i32, _ptr, _i64, _i32, _ptr, _i32, _i32, _ptr, _i64,
+                                    _i32, _ptr, _i32, _ptr, _ptr]),
     "hgin_linear_fwd_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32]),
     "hgin_linear_fwd": (_i32, [_i64, _ptr, _i64, _i32, _ptr, _i64, _i32, _ptr, _ptr, _i32, _i32, _ptr, _ptr, _i64,
                                _ptr, _i64, _i32, _ptr, _i64, _i32, _ptr]),

@@ -93,9 +93,16 @@ struct PostAct {
     // x_self are dh_self and act(z) IS x_dst (the output of the layer below), so the input-gradient
     // GEMM above no longer has to read x_dst for it.
     float *ddot_partials;     // [gridDim.x] or NULL
+    // MODE 2 (forward, "pre-activation inputs"): x_src / x_self hold the PRE-activations z of the layer
+    // below and act(z) is applied to every element as it is loaded, so that layer never has to write
+    // its activated output (hgin_gin_combine_pre).
+    int src_act;
+    const float *src_alpha;
+    int self_act;
+    const float *self_alpha;
 };
 
-template <int VEC, int LPR, int NC, bool CONTIG, int MINB, bool POST>
+template <int VEC, int LPR, int NC, bool CONTIG, int MINB, int MODE>
 __global__ void __launch_bounds__(256, MINB)
 gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                    const float *__restrict__ x_src, int64_t ld_src, int f_src,
@@ -104,7 +111,8 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
                    float *__restrict__ out, int64_t ld_out, const PostAct post) {
     // gathers in flight per lane before the dependent adds; bounded by the batch (LPR) and by
     // the register budget when a lane carries several chunks
-    constexpr int UNROLL_MAX = (NC >= 4) ? 2 : ((NC == 2) ? 4 : 8);
+    // (pre-activation sources need a few registers for the on-the-fly act: two gathers fewer in flight)
+    constexpr int UNROLL_MAX = (NC >= 4) ? 2 : ((NC == 2) ? 4 : ((MODE == 2 || MODE == 4) ? 6 : 8));
     constexpr int UNROLL = (LPR < UNROLL_MAX) ? LPR : UNROLL_MAX;
     constexpr int ROWS_PER_WARP = 32 / LPR;
     const int lane = threadIdx.x & 31;
@@ -113,7 +121,13 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
     const unsigned full = 0xffffffffu;
     // fl(1 + eps): the reference computes (1 + self.eps) as an fp32 tensor op (models.py:213/215).
     const float ope = __fadd_rn(1.0f, eps_ptr ? __ldg(eps_ptr) : 0.0f);
+    constexpr bool POST = MODE == 1;
+    constexpr bool PRE_SRC = MODE == 2 || MODE == 4;    // x_src holds pre-activations
+    constexpr bool PRE_SELF = MODE == 3 || MODE == 4;   // x_self holds pre-activations
     const float post_alpha = (POST && post.act == HGIN_ACT_PRELU) ? __ldg(post.alpha) : 0.0f;
+    // pre-activation inputs: x = z > 0 ? z : a * z with a = slope (PReLU) or 0 (ReLU)
+    const float src_alpha = !PRE_SRC ? 1.0f : (post.src_act == HGIN_ACT_PRELU ? __ldg(post.src_alpha) : 0.0f);
+    const float self_alpha = !PRE_SELF ? 1.0f : (post.self_act == HGIN_ACT_PRELU ? __ldg(post.self_alpha) : 0.0f);
     float dalpha = 0.0f, ddot = 0.0f;
 
     // Row -> warp mapping.
@@ -224,7 +238,11 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
 #pragma unroll
                         for (int c = 0; c < NC; ++c)
 #pragma unroll
-                            for (int i = 0; i < VEC; ++i) acc[c].v[i] = __fadd_rn(acc[c].v[i], v[u][c].v[i]);
+                            for (int i = 0; i < VEC; ++i) {
+                                float t = v[u][c].v[i];
+                                if (PRE_SRC) t = t > 0.f ? t : src_alpha * t;   // x = act(z), on the fly
+                                acc[c].v[i] = __fadd_rn(acc[c].v[i], t);
+                            }
                     }
                 }
             }
@@ -239,7 +257,11 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
                 Pack<VEC> r = acc[c];
                 if (self_mode == HGIN_SELF_ADD) {
 #pragma unroll
-                    for (int i = 0; i < VEC; ++i) r.v[i] = __fadd_rn(r.v[i], __fmul_rn(ope, self_v[c].v[i]));
+                    for (int i = 0; i < VEC; ++i) {
+                        float xs = self_v[c].v[i];
+                        if (PRE_SELF) xs = xs > 0.f ? xs : self_alpha * xs;
+                        r.v[i] = __fadd_rn(r.v[i], __fmul_rn(ope, xs));
+                    }
                 }
                 if (accumulate) {
                     const Pack<VEC> old = load_pack<VEC>(orow + f);
@@ -265,7 +287,9 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
             if (self_mode == HGIN_SELF_CONCAT) {
                 // [agg | (1+eps) x_self]: the self block starts at column f_src (rarely 16B aligned) -> scalar
                 for (int f = sub; f < f_self; f += LPR) {
-                    float t = __fmul_rn(ope, __ldg(x_self + row * ld_self + f));
+                    float xs = __ldg(x_self + row * ld_self + f);
+                    if (PRE_SELF) xs = xs > 0.f ? xs : self_alpha * xs;
+                    float t = __fmul_rn(ope, xs);
                     if (accumulate) t = __fadd_rn(orow[f_src + f], t);
                     orow[f_src + f] = t;
                 }
@@ -307,12 +331,24 @@ int launch(int64_t num_rows, const int32_t *rowptr, const int32_t *col, const fl
     // Grid-stride over rows with whole waves of CTAs: enough CTAs (32 per SM) that the hardware
     // scheduler evens out the heavy-tailed row lengths of the path->link relation.
     const int grid = grid_for(num_rows, rows_per_cta, 32);
-    if (post)
-        gin_combine_kernel<VEC, LPR, NC, CONTIG, MINB, true><<<grid, threads, 0, s>>>(
+    if (post && post->z)
+        gin_combine_kernel<VEC, LPR, NC, CONTIG, MINB, 1><<<grid, threads, 0, s>>>(
+            num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, accumulate, out, ld_out,
+            *post);
+    else if (post && post->src_act != HGIN_ACT_NONE && post->self_act != HGIN_ACT_NONE)
+        gin_combine_kernel<VEC, LPR, NC, CONTIG, MINB, 4><<<grid, threads, 0, s>>>(
+            num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, accumulate, out, ld_out,
+            *post);
+    else if (post && post->src_act != HGIN_ACT_NONE)
+        gin_combine_kernel<VEC, LPR, NC, CONTIG, MINB, 2><<<grid, threads, 0, s>>>(
+            num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, accumulate, out, ld_out,
+            *post);
+    else if (post)
+        gin_combine_kernel<VEC, LPR, NC, CONTIG, MINB, 3><<<grid, threads, 0, s>>>(
             num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, accumulate, out, ld_out,
             *post);
     else
-        gin_combine_kernel<VEC, LPR, NC, CONTIG, MINB, false><<<grid, threads, 0, s>>>(
+        gin_combine_kernel<VEC, LPR, NC, CONTIG, MINB, 0><<<grid, threads, 0, s>>>(
             num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, accumulate, out, ld_out,
             PostAct{});
     return grid;
@@ -329,7 +365,9 @@ int32_t combine_dispatch(int64_t num_rows, const int32_t *rowptr, const int32_t 
                          int32_t f_self, const float *eps, int32_t self_mode, int32_t accumulate, float *out,
                          int64_t ld_out, const float *post_z, int64_t ld_post, int32_t post_act,
                          const float *post_alpha, float *post_dalpha, float *post_ddot, void *workspace,
-                         int64_t workspace_bytes, void *stream, const char *who) {
+                         int64_t workspace_bytes, void *stream, const char *who, int32_t src_act = HGIN_ACT_NONE,
+                         const float *src_alpha = nullptr, int32_t self_act = HGIN_ACT_NONE,
+                         const float *self_alpha = nullptr) {
     HGIN_CHECK_ARG(num_rows >= 0 && num_rows < INT32_MAX, "%s: bad num_rows %lld", who, (long long)num_rows);
     HGIN_CHECK_ARG(f_src > 0 && f_src <= 512, "%s: f_src must be in [1,512], got %d", who, f_src);
     HGIN_CHECK_ARG(self_mode >= HGIN_SELF_NONE && self_mode <= HGIN_SELF_CONCAT, "%s: bad self_mode %d", who, self_mode);
@@ -337,6 +375,12 @@ int32_t combine_dispatch(int64_t num_rows, const int32_t *rowptr, const int32_t 
     HGIN_CHECK_ARG(self_mode != HGIN_SELF_ADD || f_self == f_src, "%s: SELF_ADD needs f_self == f_src", who);
     HGIN_CHECK_ARG(self_mode != HGIN_SELF_CONCAT || f_self > 0, "%s: SELF_CONCAT needs f_self > 0", who);
     const bool post_on = post_z != nullptr && post_act != HGIN_ACT_NONE;
+    const bool pre_on = src_act != HGIN_ACT_NONE || self_act != HGIN_ACT_NONE;
+    HGIN_CHECK_ARG(src_act >= HGIN_ACT_NONE && src_act <= HGIN_ACT_RELU && self_act >= HGIN_ACT_NONE && self_act <= HGIN_ACT_RELU,
+                   "%s: bad input activation", who);
+    HGIN_CHECK_ARG((src_act != HGIN_ACT_PRELU || src_alpha) && (self_act != HGIN_ACT_PRELU || self_alpha),
+                   "%s: PReLU input activation needs its slope", who);
+    HGIN_CHECK_ARG(!(post_on && pre_on), "%s: input activations and a post-activation cannot be combined", who);
     HGIN_CHECK_ARG(post_act >= HGIN_ACT_NONE && post_act <= HGIN_ACT_RELU, "%s: bad post_act %d", who, post_act);
     HGIN_CHECK_ARG(!post_on || self_mode != HGIN_SELF_CONCAT, "%s: post-activation needs a [rows, f_src] result", who);
     HGIN_CHECK_ARG(!post_on || post_act != HGIN_ACT_PRELU || post_alpha, "%s: PReLU post-activation needs alpha", who);
@@ -360,8 +404,10 @@ int32_t combine_dispatch(int64_t num_rows, const int32_t *rowptr, const int32_t 
     HGIN_CHECK_ARG(ld_src >= f_src && ld_out >= width, "%s: leading dimension too small", who);
     PostAct post{post_z, ld_post, post_act, post_alpha,
                  (want_dalpha && post_act == HGIN_ACT_PRELU) ? static_cast<float *>(workspace) : nullptr,
-                 post_ddot ? static_cast<float *>(workspace) + kMaxCombineCtas : nullptr};
-    const PostAct *pp = post_on ? &post : nullptr;
+                 post_ddot ? static_cast<float *>(workspace) + kMaxCombineCtas : nullptr,
+                 src_act, src_alpha, self_act, self_alpha};
+    if (pre_on) post.z = nullptr;            // MODE 2 is selected by a PostAct without z
+    const PostAct *pp = (post_on || pre_on) ? &post : nullptr;
     if (!rowptr) num_edges = 0;
 
     // 128-bit lanes need every row start 16-byte aligned.
@@ -411,8 +457,8 @@ int32_t combine_dispatch(int64_t num_rows, const int32_t *rowptr, const int32_t 
         else HGIN_LAUNCH(1, 32, 16);
     }
 #undef HGIN_LAUNCH
-    if (post.dalpha_partials && pp) combine_reduce_scalar_kernel<<<1, 1024, 0, s>>>(post.dalpha_partials, grid, post_dalpha);
-    if (post.ddot_partials && pp) combine_reduce_scalar_kernel<<<1, 1024, 0, s>>>(post.ddot_partials, grid, post_ddot);
+    if (post.dalpha_partials && post_on) combine_reduce_scalar_kernel<<<1, 1024, 0, s>>>(post.dalpha_partials, grid, post_dalpha);
+    if (post.ddot_partials && post_on) combine_reduce_scalar_kernel<<<1, 1024, 0, s>>>(post.ddot_partials, grid, post_ddot);
     HGIN_CHECK_LAUNCH(who);
     return HGIN_OK;
 }
@@ -440,4 +486,14 @@ extern "C" int32_t hgin_gin_combine_post(int64_t num_rows, const int32_t *rowptr
     return hgin::combine_dispatch(num_rows, rowptr, col, num_edges, x_src, ld_src, f_src, x_self, ld_self, f_self, eps,
                                   self_mode, accumulate, out, ld_out, post_z, ld_post, post_act, post_alpha, post_dalpha,
                                   post_ddot, workspace, workspace_bytes, stream, "hgin_gin_combine_post");
+}
+
+extern "C" int32_t hgin_gin_combine_pre(int64_t num_rows, const int32_t *rowptr, const int32_t *col, int64_t num_edges,
+                                        const float *x_src, int64_t ld_src, int32_t f_src, const float *x_self,
+                                        int64_t ld_self, int32_t f_self, const float *eps, int32_t self_mode,
+                                        int32_t accumulate, float *out, int64_t ld_out, int32_t src_act,
+                                        const float *src_alpha, int32_t self_act, const float *self_alpha, void *stream) {
+    return hgin::combine_dispatch(num_rows, rowptr, col, num_edges, x_src, ld_src, f_src, x_self, ld_self, f_self, eps,
+                                  self_mode, accumulate, out, ld_out, nullptr, 0, HGIN_ACT_NONE, nullptr, nullptr, nullptr,
+                                  nullptr, 0, stream, "hgin_gin_combine_pre", src_act, src_alpha, self_act, self_alpha);
 }

@@ -107,7 +107,10 @@ class HeteroConvFn(torch.autograd.Function):
     apply act'(z) on the way out (hgin_gin_combine_post), so this node's backward starts from dz."""
 
     @staticmethod
-    def forward(ctx, specs, graph, types, math_mode, links_in, links_out, *tensors):
+    def forward(ctx, specs, graph, types, math_mode, links_in, links_out, allow_lazy, *tensors):
+        """allow_lazy: the consumer of this node's outputs is another HeteroConvFn of the chain, which can
+        read PRE-activations (hgin_gin_combine_pre): an output produced by a single relation is then
+        returned as z, its activated copy is never written, and the link says so (`lazy`)."""
         nt = len(types)
         xs = dict(zip(types, tensors[:nt]))
         params = tensors[nt:]
@@ -116,16 +119,28 @@ class HeteroConvFn(torch.autograd.Function):
         for i, sp in enumerate(specs):
             W, b, alpha, eps = params[4 * i:4 * i + 4]
             x_src, x_dst = xs[sp.src], xs[sp.dst]
-            h = ops.gin_combine(graph.fwd(sp.et), x_src, x_dst, eps, SELF_CONCAT if sp.concat else SELF_ADD)
+            lz_src, lz_dst = (links_in or {}).get(sp.src), (links_in or {}).get(sp.dst)
+            pre = {}
+            if lz_src is not None and lz_src.lazy:       # x_src is the pre-activation of the layer below
+                pre["src_act"] = (lz_src.act, lz_src.alpha)
+            if lz_dst is not None and lz_dst.lazy:
+                pre["self_act"] = (lz_dst.act, lz_dst.alpha)
+            h = ops.gin_combine(graph.fwd(sp.et), x_src, x_dst, eps, SELF_CONCAT if sp.concat else SELF_ADD, **pre)
+            link_ok = (training and links_out is not None and sp.act != ACT_NONE
+                       and sum(1 for q in specs if q.dst == sp.dst) == 1
+                       and _fold_eligible(h.shape[0], h.shape[1], W.shape[0], math_mode))
+            lazy = bool(link_ok and allow_lazy and ctx.needs_input_grad[7 + nt + 4 * i])
             z, o = ops.linear_fwd(h, W, b, act=sp.act, alpha=alpha, want_z=training and sp.act != ACT_NONE,
-                                  out=outs.get(sp.dst), accumulate_out=sp.dst in outs, math_mode=math_mode)
-            outs[sp.dst] = o
+                                  out=outs.get(sp.dst), accumulate_out=sp.dst in outs, math_mode=math_mode,
+                                  want_out=not lazy)
+            outs[sp.dst] = z if lazy else o
             saved += [h if training else None, z]
-            if training and ctx.needs_input_grad[6 + types.index(sp.src)]:
+            if training and ctx.needs_input_grad[7 + types.index(sp.src)]:
                 graph.bwd(sp.et)  # build the transposed CSR alongside the forward work
-            if (training and links_out is not None and z is not None and sum(1 for q in specs if q.dst == sp.dst) == 1
-                    and _fold_eligible(h.shape[0], h.shape[1], W.shape[0], math_mode)):
-                links_out[sp.dst] = ops.PostAct(z, sp.act, alpha)
+            if link_ok:
+                # (a lazy z is also this node's OUTPUT: the link keeps a detached alias, or output -> grad_fn ->
+                # ctx.links_out -> output would be a reference cycle that pins the step's activations until gc runs)
+                links_out[sp.dst] = ops.PostAct(z.detach() if lazy else z, sp.act, alpha, lazy=lazy)
         ctx.links_in = dict(links_in) if links_in else {}
         ctx.links_out = dict(links_out) if links_out else {}
         ctx.specs, ctx.graph, ctx.types, ctx.math_mode = specs, graph, types, math_mode
@@ -142,7 +157,7 @@ class HeteroConvFn(torch.autograd.Function):
         xs = dict(zip(types, tensors[:nt]))
         params = tensors[nt:nt + 4 * ns]
         saved = tensors[nt + 4 * ns:]
-        need = ctx.needs_input_grad[6:]
+        need = ctx.needs_input_grad[7:]
         need_x = dict(zip(types, need[:nt]))
         g_out = dict(zip(ctx.out_types, gouts))
         grads_p = [None] * (4 * ns)
@@ -188,7 +203,16 @@ class HeteroConvFn(torch.autograd.Function):
                 z, nalpha_here = None, False
             else:
                 nalpha_here = bool(nalpha)
+                lz = ctx.links_out.get(sp.dst)
+                if lz is not None and lz.lazy:
+                    raise HginError("a lazily activated output received a gradient that its consumer did not "
+                                    "pass through the activation derivative (chain protocol broken)")
             dot_x = x_dst if (neps and i not in eps_from_pass) else None
+            lz_dst = ctx.links_in.get(sp.dst)
+            if dot_x is not None and lz_dst is not None and lz_dst.lazy:
+                # x_dst was handed over as a pre-activation: materialise act(z) for the d(eps) dot product
+                dot_x = torch.where(x_dst > 0, x_dst, (lz_dst.alpha * x_dst) if lz_dst.act == ops.ACT_PRELU
+                                    else torch.zeros_like(x_dst))
             if sp.concat:
                 r = ops.linear_bwd(g, z, h, W, dx_cols=(fs, k), want_dx=want_self, dot_x=dot_x,
                                    want_dw=nW, want_db=bool(nb), want_dalpha=nalpha_here, **common)
@@ -227,7 +251,7 @@ class HeteroConvFn(torch.autograd.Function):
                 else:
                     dx = res
             grads_x.append(dx)
-        return (None, None, None, None, None, None, *grads_x, *grads_p)
+        return (None, None, None, None, None, None, None, *grads_x, *grads_p)
 
 
 class LinearActFn(torch.autograd.Function):

@@ -79,7 +79,7 @@ class GINConv(torch.nn.Module):
         graph = edge_index if isinstance(edge_index, GraphCSR) else GraphCSR({et: edge_index}, num)
         W, b, alpha, eps, act = self.kernel_args()
         (out,) = HeteroConvFn.apply([RelationSpec(et, self.concat, act)], graph, types, self.math_mode, None, None,
-                                    *xs, W, b, alpha, eps)
+                                    False, *xs, W, b, alpha, eps)
         return out
 
     def __repr__(self):
@@ -119,11 +119,13 @@ class HeteroConv(torch.nn.Module):
         for conv in self.convs.values():
             conv.reset_parameters()
 
-    def forward(self, x_dict, edge_index_dict, only=None, chain=None):
+    def forward(self, x_dict, edge_index_dict, only=None, chain=None, lazy=False):
         """`only`: optional collection of edge types to evaluate (dead-branch pruning by HetroGIN).
         `chain`: dict node type -> ops.PostAct describing how `x_dict`'s tensors were produced, passed
         by HetroGIN.forward between consecutive layers (every intermediate has one consumer there);
-        updated in place to describe this layer's outputs.  See functional.HeteroConvFn."""
+        updated in place to describe this layer's outputs.  `lazy`: the next consumer is another layer of
+        the chain, so single-relation outputs may be handed over as pre-activations.  See
+        functional.HeteroConvFn."""
         graph = edge_index_dict if isinstance(edge_index_dict, GraphCSR) else GraphCSR(
             edge_index_dict, {t: v.shape[0] for t, v in x_dict.items()})
         specs, params = [], []
@@ -141,7 +143,7 @@ class HeteroConv(torch.nn.Module):
         types = tuple(dict.fromkeys(t for sp in specs for t in (sp.src, sp.dst)))
         links_out = {} if chain is not None else None
         outs = HeteroConvFn.apply(specs, graph, types, self.math_mode, dict(chain) if chain else None, links_out,
-                                  *[x_dict[t] for t in types], *params)
+                                  bool(lazy and chain is not None), *[x_dict[t] for t in types], *params)
         if chain is not None:
             chain.clear()
             chain.update(links_out)
@@ -250,7 +252,7 @@ class HetroGIN(torch.nn.Module):
         # backward may hand the layer below its dz instead of g (functional.HeteroConvFn).
         chain = {} if (self.fold_activation_grad and torch.is_grad_enabled()) else None
         for i in range(self.num_layers):
-            x_dict = self.convs[i](x_dict, graph, only=live[i], chain=chain)
+            x_dict = self.convs[i](x_dict, graph, only=live[i], chain=chain, lazy=i < self.num_layers - 1)
             # dropout(p=0) / eval mode is the identity (models.py:358-359)
 
         x1 = x_dict["path"]

@@ -116,11 +116,14 @@ class PostAct:
     dz = grad * act'(z) and fills `dalpha` = sum grad * min(z, 0); the layer below then runs its
     backward with ACT_NONE on dz.  `applied` tells that layer this has happened."""
 
-    __slots__ = ("z", "act", "alpha", "dalpha", "applied")
+    __slots__ = ("z", "act", "alpha", "dalpha", "applied", "lazy")
 
-    def __init__(self, z, act, alpha):
+    def __init__(self, z, act, alpha, lazy=False):
         self.z, self.act, self.alpha = z, act, alpha
         self.dalpha, self.applied = None, False
+        # lazy: the layer did NOT write its activated output; the tensor handed downstream is z itself and
+        # every consumer applies act on load (hgin_gin_combine_pre) — and MUST apply the post-activation
+        self.lazy = lazy
 
     def usable(self):
         return self.z is not None and self.act != ACT_NONE
@@ -134,11 +137,12 @@ class _NoEdges:
 
 
 def gin_combine(csr, x_src, x_self=None, eps=None, self_mode=SELF_NONE, out=None, accumulate=False, post=None,
-                want_ddot=False):
+                want_ddot=False, src_act=None, self_act=None):
     """K1/K4.  out[r] (+)= sum_{e in row r} x_src[col[e]]  {+ | concat}  (1+eps) * x_self[r].
     csr=None: no edges (self term only; x_src is then only a shape donor).
     post: a PostAct — the stored result is multiplied by act'(post.z) and post.dalpha is filled.
-    want_ddot (with post, SELF_ADD): returns (out, ddot) with ddot = sum x_self * act(post.z)."""
+    want_ddot (with post, SELF_ADD): returns (out, ddot) with ddot = sum x_self * act(post.z).
+    src_act / self_act: (act, alpha) when x_src / x_self hold PRE-activations (hgin_gin_combine_pre)."""
     if csr is None:
         csr = _NoEdges(x_self.shape[0])
     ps, lds = _f32_matrix(x_src, "gin_combine.x_src")
@@ -181,6 +185,16 @@ def gin_combine(csr, x_src, x_self=None, eps=None, self_mode=SELF_NONE, out=None
         return (out, ddot) if want_ddot else out
     if want_ddot:
         raise HginError("gin_combine: want_ddot needs a post-activation")
+    if src_act is not None or self_act is not None:
+        sa, sal = src_act if src_act is not None else (ACT_NONE, None)
+        fa, fal = self_act if (self_act is not None and x_self is not None) else (ACT_NONE, None)
+        with _region("gin_combine", kernels=1, alg_bytes=alg, compulsory_bytes=comp):
+            check(_lib.load().hgin_gin_combine_pre(csr.num_rows, _ptr(csr.rowptr), _ptr(csr.col), csr.num_edges, ps, lds,
+                                                   f_src, pf, ldf, f_self, _scalar(eps, "gin_combine.eps"), self_mode,
+                                                   1 if accumulate else 0, po, ldo, sa, _scalar(sal, "gin_combine.src_alpha"),
+                                                   fa, _scalar(fal, "gin_combine.self_alpha"), _stream()),
+                  "hgin_gin_combine_pre")
+        return out
     with _region("gin_combine", kernels=1, alg_bytes=alg, compulsory_bytes=comp):
         check(_lib.load().hgin_gin_combine(csr.num_rows, _ptr(csr.rowptr), _ptr(csr.col), csr.num_edges, ps, lds, f_src, pf,
                                            ldf, f_self, _scalar(eps, "gin_combine.eps"), self_mode,
@@ -189,8 +203,9 @@ def gin_combine(csr, x_src, x_self=None, eps=None, self_mode=SELF_NONE, out=None
 
 
 def linear_fwd(x1, W, bias=None, x2=None, act=ACT_NONE, alpha=None, want_z=True, out=None, accumulate_out=False,
-               math_mode=MATH_FP32):
-    """K2.  z = [x1|x2] W^T + b;  out (+)= act(z).  Returns (z or None, out)."""
+               math_mode=MATH_FP32, want_out=True):
+    """K2.  z = [x1|x2] W^T + b;  out (+)= act(z).  Returns (z or None, out or None).
+    want_out=False: only z is written (the consumers apply act on load, see gin_combine src_act)."""
     p1, ld1 = _f32_matrix(x1, "linear_fwd.x1")
     p2, ld2 = _f32_matrix(x2, "linear_fwd.x2")
     rows, k1 = x1.shape
@@ -202,19 +217,22 @@ def linear_fwd(x1, W, bias=None, x2=None, act=ACT_NONE, alpha=None, want_z=True,
         raise HginError("linear_fwd: x1 and x2 row counts differ")
     dev = x1.device
     z = torch.empty(rows, n, dtype=torch.float32, device=dev) if want_z else None
-    if out is None:
+    if not want_out:
+        if out is not None or accumulate_out or not want_z:
+            raise HginError("linear_fwd: want_out=False needs want_z and no `out`")
+    elif out is None:
         if accumulate_out:
             raise HginError("linear_fwd: accumulate_out needs an existing `out`")
         out = torch.empty(rows, n, dtype=torch.float32, device=dev)
     pz, ldz = _f32_matrix(z, "linear_fwd.z")
     po, ldo = _f32_matrix(out, "linear_fwd.out")
-    if tuple(out.shape) != (rows, n):
+    if out is not None and tuple(out.shape) != (rows, n):
         raise HginError(f"linear_fwd: out is {tuple(out.shape)}, expected {(rows, n)}")
     lib = _lib.load()
     ws_bytes = lib.hgin_linear_fwd_workspace_bytes(rows, k1 + k2, n, math_mode)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes > 0 else None
     with _region("linear_fwd", kernels=1 + (1 if ws_bytes else 0), flops=2 * rows * (k1 + k2) * n,
-                 bytes=4 * rows * (k1 + k2 + n * ((1 if want_z else 0) + (2 if accumulate_out else 1)))):
+                 bytes=4 * rows * (k1 + k2 + n * ((1 if want_z else 0) + (2 if accumulate_out else (1 if want_out else 0))))):
         check(lib.hgin_linear_fwd(rows, p1, ld1, k1, p2, ld2, k2, W.data_ptr(), _ptr(bias), n, act,
                                   _scalar(alpha, "linear_fwd.alpha"), pz, ldz, po, ldo, 1 if accumulate_out else 0,
                                   _ptr(ws), ws_bytes, math_mode, _stream()), "hgin_linear_fwd")

@@ -123,6 +123,20 @@ int32_t hgin_gin_combine_post(int64_t num_rows, const int32_t *rowptr, const int
                               int32_t post_act, const float *post_alpha, float *post_dalpha,
                               float *post_ddot, void *workspace, int64_t workspace_bytes, void *stream);
 
+/* ---- K1 on pre-activation inputs ---------------------------------------------------------------
+ * hgin_gin_combine whose x_src and/or x_self hold the PRE-activation z of the layer that produced
+ * them: act(z) (models.py:238, PReLU / ReLU) is applied to every element as it is loaded, bit for
+ * bit what that layer's `out` would have held, so the layer below never writes its activated
+ * output — one row-sized store less per layer.  src_act / self_act = HGIN_ACT_NONE leaves that
+ * input as it is.  Forward twin of hgin_gin_combine_post.
+ */
+int32_t hgin_gin_combine_pre(int64_t num_rows, const int32_t *rowptr, const int32_t *col,
+                             int64_t num_edges, const float *x_src, int64_t ld_src, int32_t f_src,
+                             const float *x_self, int64_t ld_self, int32_t f_self,
+                             const float *eps, int32_t self_mode, int32_t accumulate,
+                             float *out, int64_t ld_out, int32_t src_act, const float *src_alpha,
+                             int32_t self_act, const float *self_alpha, void *stream);
+
 /* ---- K2: dense layer forward  z = [x1 | x2] W^T + b,  out (+)= act(z) ------------------------
  * Replaces: GINLayer.mlp = Linear + PReLU (models.py:236-239, applied at models.py:217), the
  * HeteroConv 'sum' merge over relations with the same destination type (models.py:286-298 ->
