@@ -263,14 +263,18 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                     for (int j = 0; j < 32; ++j) {
                         const int nn = c * 32 + j;
                         float zz = v[j] + bias_s[nn];
-                        zz = fmaf(x2v[0], wtail_s[nn * 4 + 0], zz);
-                        zz = fmaf(x2v[1], wtail_s[nn * 4 + 1], zz);
-                        zz = fmaf(x2v[2], wtail_s[nn * 4 + 2], zz);
-                        zz = fmaf(x2v[3], wtail_s[nn * 4 + 3], zz);
+                        if (p.k2 > 0) {      // rank-k2 update from the extra input columns (readout layer 1 only)
+                            zz = fmaf(x2v[0], wtail_s[nn * 4 + 0], zz);
+                            zz = fmaf(x2v[1], wtail_s[nn * 4 + 1], zz);
+                            zz = fmaf(x2v[2], wtail_s[nn * 4 + 2], zz);
+                            zz = fmaf(x2v[3], wtail_s[nn * 4 + 3], zz);
+                        }
                         v[j] = zz;
-                        float oo = act_forward(zz, p.act, alpha);
-                        if (p.use_e) oo += ev[j];
-                        o[j] = oo;
+                        if (p.want_out) {    // (a lazily activated layer stores z only)
+                            float oo = act_forward(zz, p.act, alpha);
+                            if (p.use_e) oo += ev[j];
+                            o[j] = oo;
+                        }
                     }
                 } else if (p.use_e == 1) {
                     if (grow < p.rows) {

@@ -38,29 +38,41 @@ thin_fwd_kernel(int64_t rows, const float *__restrict__ x, int64_t ldx, int k, c
         for (int kk = 0; kk < KMAX; ++kk) w[i][kk] = kk < k ? __ldg(W + static_cast<int64_t>(cg * 4 + i) * k + kk) : 0.0f;
     }
     const float alpha = act == HGIN_ACT_PRELU ? __ldg(alpha_ptr) : 0.0f;
-    for (int64_t m = slot; m < rows; m += num_slots) {
-        float xv[KMAX];
+    // ROWS rows per thread and iteration, their inputs requested before the first use: one row per
+    // iteration leaves a write-mostly kernel waiting on its 24-byte input rows (3.2 TB/s measured)
+    constexpr int ROWS = 4;
+    for (int64_t m0 = slot; m0 < rows; m0 += num_slots * ROWS) {
+        float xv[ROWS][KMAX];
 #pragma unroll
-        for (int kk = 0; kk < KMAX; ++kk) xv[kk] = kk < k ? __ldg(x + m * ldx + kk) : 0.0f;
-        float zz[4];
+        for (int u = 0; u < ROWS; ++u) {
+            const int64_t m = m0 + u * num_slots;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float s = 0.0f;
-#pragma unroll
-            for (int kk = 0; kk < KMAX; ++kk) s = fmaf(xv[kk], w[i][kk], s);
-            zz[i] = s + b[i];
+            for (int kk = 0; kk < KMAX; ++kk) xv[u][kk] = (kk < k && m < rows) ? __ldg(x + m * ldx + kk) : 0.0f;
         }
-        if (z) *reinterpret_cast<float4 *>(z + m * ldz + cg * 4) = make_float4(zz[0], zz[1], zz[2], zz[3]);
-        if (out) {
-            float o[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) o[i] = act_forward(zz[i], act, alpha);
-            float4 *po = reinterpret_cast<float4 *>(out + m * ldo + cg * 4);
-            if (accumulate_out) {
-                const float4 old = *po;
-                o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w;
+        for (int u = 0; u < ROWS; ++u) {
+            const int64_t m = m0 + u * num_slots;
+            if (m >= rows) break;
+            float zz[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float s = 0.0f;
+#pragma unroll
+                for (int kk = 0; kk < KMAX; ++kk) s = fmaf(xv[u][kk], w[i][kk], s);
+                zz[i] = s + b[i];
             }
-            *po = make_float4(o[0], o[1], o[2], o[3]);
+            if (z) *reinterpret_cast<float4 *>(z + m * ldz + cg * 4) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+            if (out) {
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[i] = act_forward(zz[i], act, alpha);
+                float4 *po = reinterpret_cast<float4 *>(out + m * ldo + cg * 4);
+                if (accumulate_out) {
+                    const float4 old = *po;
+                    o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w;
+                }
+                *po = make_float4(o[0], o[1], o[2], o[3]);
+            }
         }
     }
 }
@@ -78,34 +90,49 @@ thin_bwd_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, const fl
     const int cg = threadIdx.x % lpr;
     const int grp = threadIdx.x / lpr;             // row slot inside the CTA
     const int slots_per_cta = THREADS / lpr;
-    const int64_t slot = static_cast<int64_t>(blockIdx.x) * slots_per_cta + grp;
-    const int64_t num_slots = static_cast<int64_t>(gridDim.x) * slots_per_cta;
     const float alpha = act == HGIN_ACT_PRELU ? __ldg(alpha_ptr) : 0.0f;
     float acc[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.0f;
     // acc layout: [i*KMAX + kk] dW, [32 + i*DMAX + c] T, [48 + i] db, [52] dalpha
-    // ROWS_IN_FLIGHT rows per thread and iteration, all their g / z vectors requested before the
-    // first use: with 94+ registers only two CTAs fit an SM, and one row per thread left ~16 KB of
-    // DRAM reads outstanding per SM (2.2 TB/s measured); the per-thread row order is unchanged.
+    // Each CTA iteration takes a CONTIGUOUS block of slots_per_cta * RIF rows: every thread requests the
+    // g / z vectors of its RIF rows up front (with 128 registers only two CTAs fit an SM, and one row per
+    // thread left ~16 KB of reads outstanding per SM), and the block's narrow x / dot_x rows (24 + 12
+    // bytes per row, streamed from DRAM) are staged through shared memory with one coalesced load
+    // instead of 12 latency-exposed scalar loads per row and thread.
     // (with ACT_NONE — g already is dz — only g is read, so twice as many rows fit the same registers)
     constexpr int RIF = HAS_ACT ? 4 : 8;
-    for (int64_t m0 = slot; m0 < rows; m0 += num_slots * RIF) {
+    constexpr int XP = KMAX + 1, DP = DMAX + 1;          // padded pitches: row slots fall on distinct banks
+    __shared__ float xs[64 * 8 * XP];                    // up to 64 slots (n = 16) x 8 rows
+    __shared__ float ds[64 * 8 * DP];
+    const int rif = RIF < 512 / slots_per_cta ? RIF : 512 / slots_per_cta;   // tiny n: many slots, fewer rows each
+    const int blk = slots_per_cta * rif;
+    for (int64_t base = static_cast<int64_t>(blockIdx.x) * blk; base < rows; base += static_cast<int64_t>(gridDim.x) * blk) {
         float4 gq[RIF], zq[HAS_ACT ? RIF : 1];
 #pragma unroll
         for (int u = 0; u < RIF; ++u) {
-            const int64_t m = m0 + u * num_slots;
+            const int64_t m = base + u * slots_per_cta + grp;
             gq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (HAS_ACT) zq[u] = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (m < rows) {
+            if (u < rif && m < rows) {
                 gq[u] = __ldg(reinterpret_cast<const float4 *>(g + m * ldg) + cg);
                 if (HAS_ACT) zq[u] = __ldg(reinterpret_cast<const float4 *>(z + m * ldz) + cg);
             }
         }
+        __syncthreads();                                 // the previous block's tiles have been consumed
+        for (int idx = threadIdx.x; idx < blk * k; idx += THREADS) {
+            const int r = idx / k, kk = idx % k;
+            xs[r * XP + kk] = (base + r < rows) ? __ldg(x + (base + r) * ldx + kk) : 0.0f;
+        }
+        for (int idx = threadIdx.x; idx < blk * d; idx += THREADS) {
+            const int r = idx / d, c = idx % d;
+            ds[r * DP + c] = (base + r < rows) ? __ldg(dot_x + (base + r) * ld_dot + c) : 0.0f;
+        }
+        __syncthreads();
 #pragma unroll
         for (int u = 0; u < RIF; ++u) {
-            const int64_t m = m0 + u * num_slots;
-            if (m >= rows) break;
+            const int r = u * slots_per_cta + grp;
+            if (u >= rif || base + r >= rows) break;
             float dz[4] = {gq[u].x, gq[u].y, gq[u].z, gq[u].w};
             if (HAS_ACT) {
                 const float zv[4] = {zq[u].x, zq[u].y, zq[u].z, zq[u].w};
@@ -117,9 +144,9 @@ thin_bwd_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, const fl
             }
             float xv[KMAX], dv[DMAX];
 #pragma unroll
-            for (int kk = 0; kk < KMAX; ++kk) xv[kk] = kk < k ? __ldg(x + m * ldx + kk) : 0.0f;
+            for (int kk = 0; kk < KMAX; ++kk) xv[kk] = kk < k ? xs[r * XP + kk] : 0.0f;
 #pragma unroll
-            for (int c = 0; c < DMAX; ++c) dv[c] = c < d ? __ldg(dot_x + m * ld_dot + c) : 0.0f;
+            for (int c = 0; c < DMAX; ++c) dv[c] = c < d ? ds[r * DP + c] : 0.0f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
 #pragma unroll

@@ -402,6 +402,29 @@ def test_gin_combine_post_activation(ns, nd, e, f, act):
             assert post.dalpha is None
 
 
+@pytest.mark.parametrize("ns,nd,e,f", [(3000, 5000, 15000, 128), (5000, 300, 40000, 128), (900, 1200, 0, 64), (50, 64, 300, 8),
+                                        (40, 33, 100, 5)])
+@pytest.mark.parametrize("which", ["src", "self", "both"])
+@pytest.mark.parametrize("act", [ops.ACT_PRELU, ops.ACT_RELU])
+def test_gin_combine_on_pre_activation_inputs(ns, nd, e, f, which, act):
+    """hgin_gin_combine_pre(z) == hgin_gin_combine(act(z)) bit for bit (short and long rows, both self modes)."""
+    g = torch.Generator().manual_seed(ns + e + f)
+    csr = ops.csr_build(_rand_edges(ns, nd, e, seed=e + 2).cuda(), ns, nd, by="dst")
+    z_src, z_self = torch.randn(ns, f, generator=g).cuda(), torch.randn(nd, f, generator=g).cuda()
+    eps, alpha = torch.tensor([0.3]).cuda(), torch.tensor([0.25]).cuda()
+    activate = lambda z: torch.where(z > 0, z, alpha * z if act == ops.ACT_PRELU else torch.zeros_like(z))
+    for mode in (ops.SELF_ADD, ops.SELF_CONCAT):
+        kw = {}
+        if which in ("src", "both"):
+            kw["src_act"] = (act, alpha if act == ops.ACT_PRELU else None)
+        if which in ("self", "both"):
+            kw["self_act"] = (act, alpha if act == ops.ACT_PRELU else None)
+        got = ops.gin_combine(csr, z_src, z_self, eps, mode, **kw)
+        want = ops.gin_combine(csr, activate(z_src) if "src_act" in kw else z_src,
+                               activate(z_self) if "self_act" in kw else z_self, eps, mode)
+        assert torch.equal(got, want)
+
+
 def test_tn_descriptor_default_is_exact_layout():
     """The MN-major descriptor defaults must reproduce a^T b (tools/sweep_tn_descriptor.py finds them)."""
     g = torch.Generator().manual_seed(1)
