@@ -83,18 +83,34 @@ collate_gather_kernel(const __grid_constant__ FieldTable table, int batch, const
     const int64_t words = rows * fd.width;
     const uint32_t *src = static_cast<const uint32_t *>(fd.src) + src_row * fd.width;
     uint32_t *dst = static_cast<uint32_t *>(fd.dst) + off[b] * fd.width;
+    const int32_t add = fd.add_class >= 0
+        ? static_cast<int32_t>(offsets[static_cast<int64_t>(fd.add_class) * (batch + 1) + b]) : 0;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (fd.add_class >= 0) {
-        const int32_t add = static_cast<int32_t>(offsets[static_cast<int64_t>(fd.add_class) * (batch + 1) + b]);
-        for (; i < words; i += stride) dst[i] = static_cast<uint32_t>(static_cast<int32_t>(__ldg(src + i)) + add);
-    } else {
-        for (; i + 3 * stride < words; i += 4 * stride) {     // four independent loads in flight
-            const uint32_t a0 = __ldg(src + i), a1 = __ldg(src + i + stride), a2 = __ldg(src + i + 2 * stride),
-                           a3 = __ldg(src + i + 3 * stride);
-            dst[i] = a0; dst[i + stride] = a1; dst[i + 2 * stride] = a2; dst[i + 3 * stride] = a3;
+    const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    // widest vector both sides are aligned for (sample starts are only word-aligned in general)
+    const uintptr_t mis = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst);
+    if ((mis & 15u) == 0) {
+        const int64_t nv = words >> 2;
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+        for (int64_t i = t0; i < nv; i += stride) {
+            uint4 v = __ldg(s4 + i);
+            v.x += add; v.y += add; v.z += add; v.w += add;
+            d4[i] = v;
         }
-        for (; i < words; i += stride) dst[i] = __ldg(src + i);
+        for (int64_t i = (nv << 2) + t0; i < words; i += stride) dst[i] = __ldg(src + i) + add;
+    } else if ((mis & 7u) == 0) {
+        const int64_t nv = words >> 1;
+        const uint2 *s2 = reinterpret_cast<const uint2 *>(src);
+        uint2 *d2 = reinterpret_cast<uint2 *>(dst);
+        for (int64_t i = t0; i < nv; i += stride) {
+            uint2 v = __ldg(s2 + i);
+            v.x += add; v.y += add;
+            d2[i] = v;
+        }
+        for (int64_t i = (nv << 1) + t0; i < words; i += stride) dst[i] = __ldg(src + i) + add;
+    } else {
+        for (int64_t i = t0; i < words; i += stride) dst[i] = __ldg(src + i) + add;
     }
 }
 
