@@ -21,6 +21,7 @@ constexpr int THREADS = 256;
 constexpr int KMAX = 8;
 constexpr int DMAX = 4;                      // max dot_x columns
 constexpr int NACC = 4 * KMAX + 4 * DMAX + 4 + 1;  // per-thread accumulators: dW, T, db, dalpha = 53
+constexpr int FWD_BLK = 256;                       // rows per CTA iteration of thin_fwd (>= the most row slots a CTA has)
 
 __global__ void __launch_bounds__(THREADS)
 thin_fwd_kernel(int64_t rows, const float *__restrict__ x, int64_t ldx, int k, const float *__restrict__ W,
@@ -28,8 +29,8 @@ thin_fwd_kernel(int64_t rows, const float *__restrict__ x, int64_t ldx, int k, c
                 float *__restrict__ z, int64_t ldz, float *__restrict__ out, int64_t ldo, int accumulate_out) {
     const int lpr = n >> 2;                        // lanes per row
     const int cg = threadIdx.x % lpr;              // column group: columns 4cg .. 4cg+3
-    const int64_t slot = (static_cast<int64_t>(blockIdx.x) * THREADS + threadIdx.x) / lpr;
-    const int64_t num_slots = (static_cast<int64_t>(gridDim.x) * THREADS) / lpr;
+    const int grp = threadIdx.x / lpr;             // row slot inside the CTA
+    const int slots_per_cta = THREADS / lpr;
     float w[4][KMAX], b[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -38,27 +39,52 @@ thin_fwd_kernel(int64_t rows, const float *__restrict__ x, int64_t ldx, int k, c
         for (int kk = 0; kk < KMAX; ++kk) w[i][kk] = kk < k ? __ldg(W + static_cast<int64_t>(cg * 4 + i) * k + kk) : 0.0f;
     }
     const float alpha = act == HGIN_ACT_PRELU ? __ldg(alpha_ptr) : 0.0f;
-    // ROWS rows per thread and iteration, their inputs requested before the first use: one row per
-    // iteration leaves a write-mostly kernel waiting on its 24-byte input rows (3.2 TB/s measured)
-    constexpr int ROWS = 4;
-    for (int64_t m0 = slot; m0 < rows; m0 += num_slots * ROWS) {
-        float xv[ROWS][KMAX];
-#pragma unroll
-        for (int u = 0; u < ROWS; ++u) {
-            const int64_t m = m0 + u * num_slots;
-#pragma unroll
-            for (int kk = 0; kk < KMAX; ++kk) xv[u][kk] = (kk < k && m < rows) ? __ldg(x + m * ldx + kk) : 0.0f;
+    // A write-mostly kernel whose only reads are the narrow input rows (24-32 bytes each, streamed from
+    // DRAM): with the rows loaded by the threads that use them, every row costs a DRAM latency and the
+    // stores trickle (3.2 TB/s measured).  Each CTA therefore walks contiguous blocks of FWD_BLK rows whose
+    // inputs are staged into shared memory with cp.async one block AHEAD (double buffer, no registers),
+    // so the compute loop only reads shared memory and issues stores.
+    constexpr int XP = KMAX + 1;                       // padded pitch: row slots fall on distinct banks
+    __shared__ float xs[2][FWD_BLK * XP];
+    const int rpt = FWD_BLK / slots_per_cta;           // rows per thread and block (slots_per_cta <= 256 divides FWD_BLK)
+    auto stage = [&](int buf, int64_t base) {
+        for (int idx = threadIdx.x; idx < FWD_BLK * k; idx += THREADS) {
+            const int r = idx / k, kk = idx % k;
+            float *dst = &xs[buf][r * XP + kk];
+            if (base + r < rows) {
+                const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(x + (base + r) * ldx + kk) : "memory");
+            } else {
+                *dst = 0.0f;
+            }
         }
-#pragma unroll
-        for (int u = 0; u < ROWS; ++u) {
-            const int64_t m = m0 + u * num_slots;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int64_t step = static_cast<int64_t>(gridDim.x) * FWD_BLK;
+    int64_t base = static_cast<int64_t>(blockIdx.x) * FWD_BLK;
+    int buf = 0;
+    if (base < rows) stage(0, base);
+    for (; base < rows; base += step, buf ^= 1) {
+        if (base + step < rows) {
+            stage(buf ^ 1, base + step);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        for (int u = 0; u < rpt; ++u) {
+            const int r = u * slots_per_cta + grp;
+            const int64_t m = base + r;
             if (m >= rows) break;
+            float xv[KMAX];
+#pragma unroll
+            for (int kk = 0; kk < KMAX; ++kk) xv[kk] = kk < k ? xs[buf][r * XP + kk] : 0.0f;
             float zz[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 float s = 0.0f;
 #pragma unroll
-                for (int kk = 0; kk < KMAX; ++kk) s = fmaf(xv[u][kk], w[i][kk], s);
+                for (int kk = 0; kk < KMAX; ++kk) s = fmaf(xv[kk], w[i][kk], s);
                 zz[i] = s + b[i];
             }
             if (z) *reinterpret_cast<float4 *>(z + m * ldz + cg * 4) = make_float4(zz[0], zz[1], zz[2], zz[3]);
@@ -74,6 +100,7 @@ thin_fwd_kernel(int64_t rows, const float *__restrict__ x, int64_t ldx, int k, c
                 *po = make_float4(o[0], o[1], o[2], o[3]);
             }
         }
+        __syncthreads();     // everyone is done with xs[buf] before the next iteration stages into it
     }
 }
 

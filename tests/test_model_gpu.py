@@ -254,6 +254,30 @@ def test_device_prefetcher_yields_identical_batches():
             assert torch.equal(d[et].edge_index.cpu(), h[et].edge_index)
 
 
+def test_lazy_activation_chain_protocol_fails_loudly_when_broken():
+    """Inside HetroGIN.forward a single-relation output may travel as its pre-activation (the consumer
+    applies act on load and act' in its backward).  Anyone else differentiating such a tensor must get
+    an error, not silently wrong gradients; outside a chain nothing is lazy."""
+    from gnn_link_prediction_b200.models import MATH_TF32
+    from gnn_link_prediction_b200.ops import HginError
+    ds = SyntheticDataset(3, num_topologies=2)
+    dev = Batch.from_data_list([ds[i] for i in range(3)], index_dtype=torch.int32, edge_types=CONV_EDGE_TYPES).cuda()
+    kw = dict(node_embedding_size=64, message_passing_layers=2, dropout=0.0, concat_path=True, bl_features=False,
+              divided_features=False, global_feats=False, mlp_layers=[32, 16], act="torch.nn.PReLU()", mlp_head_act=None,
+              mlp_bn=False)
+    m = HetroGIN(input_channels={"link": 7, "path": 7, "node": 3}, **kw).cuda().train().set_math_mode(MATH_TF32)
+    x = {k: v[:, :3].contiguous() for k, v in dev.x_dict.items()}
+    chain = {}
+    out = m.convs[0](dict(x), dev.edge_index_dict, chain=chain, lazy=True)
+    assert chain["path"].lazy and chain["path"].z.data_ptr() == out["path"].data_ptr()   # the output IS z
+    with pytest.raises(HginError, match="chain protocol"):
+        out["path"].sum().backward()
+    plain = m.convs[0](dict(x), dev.edge_index_dict)             # no chain: a fully activated output
+    act = torch.where(out["path"] > 0, out["path"], m.convs[0].convs["link__includes__path"].mlp[1].weight * out["path"])
+    assert torch.equal(plain["path"], act.detach())
+    plain["path"].sum().backward()                               # and ordinary autograd semantics
+
+
 def test_packed_prefetcher_ring_and_deferred_loss_readback():
     """PackedBatch source: one DMA per batch into a ring of device buffers that is reused only after
     the consuming step has finished; LossReadback hands every step's loss to the host one step later."""
