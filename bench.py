@@ -269,7 +269,18 @@ def main():
     eager_step(dev_batches[1 % n_host])
     ops.TIMER = None
     probe_kernels = probe.summary()
-    kernels_per_step = sum(k.get("kernels", k["launches"]) for k in probe_kernels.values())
+    kernels_per_step = sum(k.get("kernels", k["launches"]) for k in probe_kernels.values())   # wrapper-side estimate
+    # exact count: one eager step under the CUPTI-based profiler, kernels of libhgin only (namespace hgin::)
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            eager_step(dev_batches[0])
+            torch.cuda.synchronize()
+        counted = sum(1 for e in prof.events() if "hgin::" in e.name)
+        if counted > 0:
+            kernels_per_step = counted
+    except Exception:
+        pass
 
     small = args.workload == "cfgA"   # working set << L2: flush between timed steps
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda") if small else None
