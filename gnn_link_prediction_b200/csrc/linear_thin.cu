@@ -104,6 +104,44 @@ thin_fwd_kernel(int64_t rows, const float *__restrict__ x, int64_t ldx, int k, c
     }
 }
 
+// CTA combine of the per-thread accumulators, 8 at a time: sm[thread][8] -> sum over row slots in slot
+// order -> part[cta][n][kp]; dalpha -> alpha_part[cta].
+__device__ __forceinline__ void thin_bwd_combine(const float (&acc)[NACC], float *sm, float *red, int lpr,
+                                                 int slots_per_cta, int k, int d, int n, float *__restrict__ part,
+                                                 float *__restrict__ alpha_part) {
+    const int kp = k + d + 1;
+    float *dst = part + static_cast<int64_t>(blockIdx.x) * n * kp;
+#pragma unroll
+    for (int round = 0; round < 7; ++round) {   // rounds 0-3: dW of column i; 4-5: T; 6: db (+ dalpha)
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int a = round * 8 + j;
+            sm[threadIdx.x * 8 + j] = a < NACC - 1 ? acc[a] : 0.0f;
+        }
+        __syncthreads();
+        // one thread per (column group, j): sums the row slots
+        for (int idx = threadIdx.x; idx < lpr * 8; idx += THREADS) {
+            const int c_g = idx / 8, j = idx % 8;
+            float s = 0.0f;
+            for (int sl = 0; sl < slots_per_cta; ++sl) s += sm[(sl * lpr + c_g) * 8 + j];
+            const int a = round * 8 + j;
+            if (a < 32) {                       // dW: i = a / 8, kk = a % 8
+                const int i = a >> 3, kk = a & 7;
+                if (kk < k) dst[static_cast<int64_t>(c_g * 4 + i) * kp + kk] = s;
+            } else if (a < 48) {                // T: i = (a-32)/4, c = (a-32)%4
+                const int i = (a - 32) >> 2, c = (a - 32) & 3;
+                if (c < d) dst[static_cast<int64_t>(c_g * 4 + i) * kp + k + c] = s;
+            } else if (a < 52) {                // db
+                dst[static_cast<int64_t>(c_g * 4 + (a - 48)) * kp + k + d] = s;
+            }
+        }
+    }
+    __syncthreads();
+    const float da = block_sum(acc[52], red);
+    if (threadIdx.x == 0 && alpha_part) alpha_part[blockIdx.x] = da;
+}
+
 // part[cta][n][kp], kp = k + d + 1: columns [0,k) = dW, [k, k+d) = T, k+d = db;  alpha_part[cta].
 template <bool HAS_ACT>
 __global__ void __launch_bounds__(THREADS, 2)
@@ -184,38 +222,101 @@ thin_bwd_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, const fl
             }
         }
     }
-    // CTA combine, 8 accumulators at a time: sm[thread][8] -> sum over row slots in slot order
-    const int kp = k + d + 1;
-    float *dst = part + static_cast<int64_t>(blockIdx.x) * n * kp;
+    thin_bwd_combine(acc, sm, red, lpr, slots_per_cta, k, d, n, part, alpha_part);
+}
+
+// thin_bwd for ACT_NONE (g already is dz): every warp runs its own cp.async pipeline — each thread
+// copies exactly the 16-byte pieces of g it will consume itself and the lanes of a row group copy that
+// row's x / dot_x entries — one block AHEAD into a double buffer, so no load latency sits between the
+// row blocks and no CTA barrier is needed (a row group never spans warps: n <= 128).  Dynamic shared
+// memory: 2 x blk x (n + XP + DP) floats.
+constexpr int BWD_RIF = 8;
+inline int thin_bwd_rif(int n) {
+    const int slots = THREADS / (n >> 2);
+    return BWD_RIF < 256 / slots ? BWD_RIF : 256 / slots;   // blocks of at most 256 rows: <= 94 KB of buffers
+}
+inline size_t thin_bwd_async_smem(int n) {
+    const int blk = (THREADS / (n >> 2)) * thin_bwd_rif(n);
+    return static_cast<size_t>(2) * blk * (n + (KMAX + 1) + (DMAX + 1)) * sizeof(float);
+}
+
+__device__ __forceinline__ void cp_async16(float *dst, const float *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async4(float *dst, const float *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 2)
+thin_bwd_async_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, const float *__restrict__ x, int64_t ldx,
+                      int k, const float *__restrict__ dot_x, int64_t ld_dot, int d, int n, int rif,
+                      float *__restrict__ part) {
+    extern __shared__ __align__(16) float dyn[];
+    __shared__ float sm[THREADS * 8];
+    __shared__ float red[32];
+    constexpr int XP = KMAX + 1, DP = DMAX + 1;
+    const int lpr = n >> 2;
+    const int cg = threadIdx.x % lpr;
+    const int grp = threadIdx.x / lpr;
+    const int slots_per_cta = THREADS / lpr;
+    const int blk = slots_per_cta * rif;
+    float *gs = dyn;                                   // [2][blk][n]
+    float *xs = gs + static_cast<size_t>(2) * blk * n; // [2][blk][XP]
+    float *ds = xs + static_cast<size_t>(2) * blk * XP;   // [2][blk][DP]
+    float acc[NACC];
 #pragma unroll
-    for (int round = 0; round < 7; ++round) {   // rounds 0-3: dW of column i; 4-5: T; 6: db (+ dalpha)
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int a = round * 8 + j;
-            sm[threadIdx.x * 8 + j] = a < NACC - 1 ? acc[a] : 0.0f;
-        }
-        __syncthreads();
-        // one thread per (column group, j): sums the row slots
-        for (int idx = threadIdx.x; idx < lpr * 8; idx += THREADS) {
-            const int c_g = idx / 8, j = idx % 8;
-            float s = 0.0f;
-            for (int sl = 0; sl < slots_per_cta; ++sl) s += sm[(sl * lpr + c_g) * 8 + j];
-            const int a = round * 8 + j;
-            if (a < 32) {                       // dW: i = a / 8, kk = a % 8
-                const int i = a >> 3, kk = a & 7;
-                if (kk < k) dst[static_cast<int64_t>(c_g * 4 + i) * kp + kk] = s;
-            } else if (a < 48) {                // T: i = (a-32)/4, c = (a-32)%4
-                const int i = (a - 32) >> 2, c = (a - 32) & 3;
-                if (c < d) dst[static_cast<int64_t>(c_g * 4 + i) * kp + k + c] = s;
-            } else if (a < 52) {                // db
-                dst[static_cast<int64_t>(c_g * 4 + (a - 48)) * kp + k + d] = s;
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.0f;
+
+    auto stage = [&](int buf, int64_t base) {
+        for (int u = 0; u < rif; ++u) {
+            const int r = u * slots_per_cta + grp;
+            const int64_t m = base + r;
+            if (m < rows) {
+                cp_async16(gs + (static_cast<size_t>(buf) * blk + r) * n + cg * 4, g + m * ldg + cg * 4);
+                for (int kk = cg; kk < k; kk += lpr) cp_async4(xs + (static_cast<size_t>(buf) * blk + r) * XP + kk, x + m * ldx + kk);
+                for (int c = cg; c < d; c += lpr) cp_async4(ds + (static_cast<size_t>(buf) * blk + r) * DP + c, dot_x + m * ld_dot + c);
             }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int64_t step = static_cast<int64_t>(gridDim.x) * blk;
+    int64_t base = static_cast<int64_t>(blockIdx.x) * blk;
+    int buf = 0;
+    if (base < rows) stage(0, base);
+    for (; base < rows; base += step, buf ^= 1) {
+        if (base + step < rows) {
+            stage(buf ^ 1, base + step);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();                                  // the x / dot_x entries were copied by other lanes of the row group
+        for (int u = 0; u < rif; ++u) {
+            const int r = u * slots_per_cta + grp;
+            if (base + r >= rows) break;
+            const float4 gv = *reinterpret_cast<const float4 *>(gs + (static_cast<size_t>(buf) * blk + r) * n + cg * 4);
+            const float dz[4] = {gv.x, gv.y, gv.z, gv.w};
+            const float *xr = xs + (static_cast<size_t>(buf) * blk + r) * XP;
+            const float *dr = ds + (static_cast<size_t>(buf) * blk + r) * DP;
+            float xv[KMAX], dv[DMAX];
+#pragma unroll
+            for (int kk = 0; kk < KMAX; ++kk) xv[kk] = kk < k ? xr[kk] : 0.0f;
+#pragma unroll
+            for (int c = 0; c < DMAX; ++c) dv[c] = c < d ? dr[c] : 0.0f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int kk = 0; kk < KMAX; ++kk) acc[i * KMAX + kk] = fmaf(dz[i], xv[kk], acc[i * KMAX + kk]);
+#pragma unroll
+                for (int c = 0; c < DMAX; ++c) acc[32 + i * DMAX + c] = fmaf(dz[i], dv[c], acc[32 + i * DMAX + c]);
+                acc[48 + i] += dz[i];
+            }
+        }
+        __syncwarp();                                  // done with buf before the next iteration stages into it
     }
-    __syncthreads();
-    const float da = block_sum(acc[52], red);
-    if (threadIdx.x == 0 && alpha_part) alpha_part[blockIdx.x] = da;
+    thin_bwd_combine(acc, sm, red, lpr, slots_per_cta, k, d, n, part, nullptr);
 }
 
 // Stage 2a (grid): out[i] = sum over CTAs of part[cta][i]; columns [0,k) -> dW, [k,k+d) -> tbuf
@@ -414,9 +515,15 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
     if (act != HGIN_ACT_NONE)
         thin_bwd_kernel<true><<<ctas, THREADS, 0, s>>>(rows, g, ldg, z, ldz, act, alpha, x, ldx, k, dot_x, ld_dot, d, n, part,
                                                        want_alpha ? alpha_part : nullptr);
-    else
-        thin_bwd_kernel<false><<<ctas, THREADS, 0, s>>>(rows, g, ldg, z, ldz, act, alpha, x, ldx, k, dot_x, ld_dot, d, n, part,
-                                                        nullptr);
+    else {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(thin_bwd_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            attr_set = true;
+        }
+        thin_bwd_async_kernel<<<ctas, THREADS, thin_bwd_async_smem(n), s>>>(rows, g, ldg, x, ldx, k, dot_x, ld_dot, d, n,
+                                                                             thin_bwd_rif(n), part);
+    }
     float *tbuf = alpha_part + ctas;
     const int total = n * (k + d + 1);
     thin_finalize_kernel<<<static_cast<unsigned>(ceil_div(total, 8)), 256, 0, s>>>(part, ctas, n, k, d, dW, db, tbuf);
