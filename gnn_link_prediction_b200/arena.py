@@ -24,7 +24,6 @@ tests compare the two.
 """
 from __future__ import annotations
 
-import ctypes
 import json
 import os
 
@@ -52,8 +51,10 @@ def _as_tensor(a):
 
 
 class SampleArena:
-    """Host-side flat container.  `arrays[name]` is a contiguous numpy array, `ptr[cls]` an int64
-    [S+1] table; `fields` lists (name, dtype, width, size class)."""
+    """Host-side flat container.  `arrays[name]` is a contiguous numpy array ("path.x", "path.y",
+    "link.x", "node.x", "<src>__<rel>__<dst>.csr_{dst,src}_{rowptr,col}" and optionally
+    "....edge_index"), `ptr[cls]` an int64 [S+1] table of first rows per size class ("path", "link",
+    "node", "E:<src>__<rel>__<dst>")."""
 
     def __init__(self, num_samples, edge_types, arrays, ptr, has_coo):
         self.num_samples = int(num_samples)
@@ -224,7 +225,6 @@ class DeviceDataset:
         widths = np.array([f[4] for f in self.fields], dtype=np.int64)
         per_sample = np.stack([self.class_sizes[f[5]] for f in self.fields]) * widths[:, None]
         self.max_words = int(per_sample.max()) + 1 if per_sample.size else 1
-        self._status = []
 
     def _up(self, arr):
         return _as_tensor(arr).to(self.device)

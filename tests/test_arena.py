@@ -94,6 +94,42 @@ def test_device_dataset_needs_a_gpu():
         DeviceDataset(arena)
 
 
+def test_device_loader_shards_every_global_batch_across_ranks():
+    """Host logic of DeviceLoader (no GPU): rank r takes positions r, r+W, ... of every global batch, all
+    ranks walk the same shuffled order, the last partial batch is kept, nothing is seen twice."""
+
+    class Stub:                      # what DeviceLoader needs from a dataset: len() and collate(ids)
+        def __init__(self, n):
+            self.n = n
+
+        def __len__(self):
+            return self.n
+
+        def collate(self, ids):
+            return list(int(i) for i in ids)
+
+    for n, bs, world in [(37, 4, 3), (64, 8, 2), (5, 8, 4), (16, 4, 1)]:
+        per_rank = []
+        for rank in range(world):
+            loader = DeviceLoader(Stub(n), batch_size=bs, shuffle=True, generator=torch.Generator().manual_seed(9),
+                                  rank=rank, world=world)
+            batches = list(loader)
+            assert len(batches) <= len(loader) and all(1 <= len(b) <= bs for b in batches)
+            per_rank.append(batches)
+        seen = sorted(i for batches in per_rank for b in batches for i in b)
+        assert seen == list(range(n))                                    # one epoch, every sample exactly once
+        order = torch.randperm(n, generator=torch.Generator().manual_seed(9)).tolist()
+        step = bs * world
+        for g, lo in enumerate(range(0, n, step)):                       # global batch g, split round-robin
+            chunk = order[lo:lo + step]
+            for rank in range(world):
+                want = chunk[rank::world]
+                if want:
+                    assert per_rank[rank][g] == want
+    plain = list(DeviceLoader(Stub(10), batch_size=4))
+    assert plain == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]]                  # shuffle=False keeps dataset order
+
+
 # ---- on-GPU collate -----------------------------------------------------------------------------
 def _host_batch(samples, ids):
     return Batch.from_data_list([samples[i] for i in ids], index_dtype=torch.int32, edge_types=CONV_EDGE_TYPES,
