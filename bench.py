@@ -457,7 +457,7 @@ def main():
         "edges_per_s": edges * world * args.steps / (resident_ms * 1e-3),
         "e2e": {"value": graphs * world * args.steps / (e2e_ms * 1e-3), "unit": "graphs/s",
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8, "ms_per_step": e2e_ms / args.steps,
-                "staging": "one packed pinned buffer per batch -> the CUDA graph's static buffer" if graphed
+                "staging": "one packed pinned buffer per batch -> ping-pong static buffers of two CUDA graphs, copied on a copy stream" if graphed
                 else ("one packed pinned buffer per batch -> DevicePrefetcher ring" if args.stage == "packed"
                       else "one H2D copy per tensor (DevicePrefetcher)"),
                 "readback": "every step, collected one step later (train.LossReadback)" if args.readback == "deferred"

@@ -207,6 +207,7 @@ class GraphedTrainStep:
                                       "use TrainStep for multi-GPU runs")
         self.step, self.edge_bucket, self.max_graphs, self.warmup = step, edge_bucket, max_graphs, warmup
         self.cache = {}
+        self._copy_stream = None
 
     def _signature(self, batch):
         nodes = tuple((nt, k, tuple(v.shape), v.dtype) for nt in batch.node_types for k, v in batch[nt].items()
@@ -271,15 +272,21 @@ class GraphedTrainStep:
                 dst[:, ei.shape[1]:].fill_(-1)
 
     def _capture_packed(self, packed, sig):
+        """Two graphs per shape, each with its own static input buffer: while one replays, the next
+        batch's single H2D copy lands in the other on a copy stream (ping-pong)."""
         dev = self.step.flat_p.device
-        buf = torch.empty(packed.buffer.numel(), dtype=torch.uint8, device=dev)
-        buf.copy_(packed.buffer, non_blocking=True)
-        entry = {"buffer": buf, "static": packed.views(buf), "graph": torch.cuda.CUDAGraph(), "loss": None}
-        self._record(entry)
+        entries = []
+        for _ in range(2):
+            buf = torch.empty(packed.buffer.numel(), dtype=torch.uint8, device=dev)
+            buf.copy_(packed.buffer, non_blocking=True)
+            entry = {"buffer": buf, "static": packed.views(buf), "graph": torch.cuda.CUDAGraph(), "loss": None,
+                     "done": None}
+            self._record(entry)
+            entries.append(entry)
         if len(self.cache) >= self.max_graphs:
             self.cache.pop(next(iter(self.cache)))
-        self.cache[sig] = entry
-        return entry
+        self.cache[sig] = {"entries": entries, "turn": 0}
+        return self.cache[sig]
 
     def __call__(self, batch):
         """`batch`: a Batch (GPU or pinned host) or a data.PackedBatch (one copy per step).  Returns
@@ -287,10 +294,32 @@ class GraphedTrainStep:
         from .data import PackedBatch
         if isinstance(batch, PackedBatch):
             sig = ("packed", batch.signature)
-            entry = self.cache.get(sig)
-            if entry is None:
-                entry = self._capture_packed(batch, sig)
-            entry["buffer"].copy_(batch.buffer, non_blocking=True)   # the step's whole input: one copy
+            slot = self.cache.get(sig)
+            if slot is None:
+                slot = self._capture_packed(batch, sig)
+            entry = slot["entries"][slot["turn"] % 2]
+            slot["turn"] += 1
+            dev = entry["buffer"].device
+            cur = torch.cuda.current_stream(dev)
+            if batch.buffer.is_cuda:
+                entry["buffer"].copy_(batch.buffer, non_blocking=True)
+            else:
+                # the step's whole input: ONE copy, on the copy stream, into the buffer the previous-but-one
+                # replay used — it overlaps the replay that is still running on the other buffer
+                if self._copy_stream is None:
+                    self._copy_stream = torch.cuda.Stream(device=dev)
+                side = self._copy_stream
+                if entry["done"] is not None:
+                    side.wait_event(entry["done"])
+                with torch.cuda.stream(side):
+                    entry["buffer"].copy_(batch.buffer, non_blocking=True)
+                    ready = torch.cuda.Event()
+                    ready.record(side)
+                cur.wait_event(ready)
+            entry["graph"].replay()
+            entry["done"] = torch.cuda.Event()
+            entry["done"].record(cur)
+            return entry["loss"]
         else:
             sig = self._signature(batch)
             entry = self.cache.get(sig)
