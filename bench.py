@@ -469,7 +469,7 @@ def main():
                     "of a fresh random batch, train step, loss read-back"},
         "gpu_launches": launches, "kernels_per_step": kernels_per_step,
         "execution": "one CUDA graph replay per step (GraphedTrainStep)" if graphed else "eager launches",
-        "wall_s_resident": t_wall,
+        "wall_s_resident": t_wall, "peak_hbm_gb": torch.cuda.max_memory_allocated() / 1e9,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "kernels": breakdown,
         "loss_first_last": [float(losses[0][0]), float(losses[-1][0])],
     }
