@@ -57,6 +57,7 @@ SIGNATURES = {
     "hgin_qt_baseline_workspace_bytes": (_i64, [_i64, _i64]),
     "hgin_qt_baseline": (_i32, [_i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _ptr, _ptr, _ptr,
                                 _i64, _ptr]),
+    "hgin_host_collate": (_i32, [_i32, _ptr, _i64, _i32, ctypes.POINTER(CollateField), _i32, _ptr, _ptr, _i32]),
     "hgin_set_option": (_i32, [ctypes.c_char_p, _i32]),
     "hgin_debug_gemm_tn": (_i32, [_i64, _ptr, _i32, _ptr, _i32, _ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _ptr]),
 }

@@ -134,6 +134,96 @@ class SampleArena:
     def nbytes(self):
         return sum(a.nbytes for a in self.arrays.values()) + sum(p.nbytes for p in self.ptr.values())
 
+    # ---- collate description (shared by the device and the host collate) ---------------------------
+    @property
+    def classes(self):
+        """Size classes: node types, then edges per relation."""
+        return list(NODE_TYPES) + ["E:" + _rel_name(et) for et in self.edge_types]
+
+    def field_specs(self):
+        """[(store key, field name, array name, ptr kind, width, size class, add class, closing row, dtype)]:
+        how every array is laid out per sample and what offset its int32 entries receive in a batch
+        (see hgin_collate_field in include/hgin.h).  ptr kind: a size-class name, or ("rowptr", node type)
+        for local row-pointer blocks (n + 1 entries per sample)."""
+        cidx = {c: i for i, c in enumerate(self.classes)}
+        specs = []
+        for nt in NODE_TYPES:
+            specs.append((nt, "x", f"{nt}.x", nt, int(self.arrays[f"{nt}.x"].shape[1]), cidx[nt], -1, 0, torch.float32))
+        specs.append(("path", "y", "path.y", "path", 1, cidx["path"], -1, 0, torch.float32))
+        for et in self.edge_types:
+            name = _rel_name(et)
+            ec = cidx["E:" + name]
+            for side, rows_t, cols_t in (("dst", et[2], et[0]), ("src", et[0], et[2])):
+                specs.append((et, f"csr_{side}_rowptr", f"{name}.csr_{side}_rowptr", ("rowptr", rows_t), 1, cidx[rows_t], ec,
+                              1, torch.int32))
+                specs.append((et, f"csr_{side}_col", f"{name}.csr_{side}_col", "E:" + name, 1, ec, cidx[cols_t], 0,
+                              torch.int32))
+        return specs
+
+    def _host_tables(self):
+        """Contiguous host copies of the ptr tables the C collate reads (built once)."""
+        t = self.__dict__.get("_tables")
+        if t is None:
+            classes = self.classes
+            t = {"class_ptr": np.ascontiguousarray(np.stack([np.asarray(self.ptr[c], dtype=np.int64) for c in classes])),
+                 "class_sizes": np.stack([self.sizes(c) for c in classes]),
+                 "rowptr": {nt: np.ascontiguousarray(self.rowptr_ptr(nt)) for nt in NODE_TYPES}}
+            self.__dict__["_tables"] = t
+        return t
+
+    def collate_packed(self, ids, pin=True, edge_bucket=None, num_threads=0, out=None):
+        """Host collate of samples `ids` straight into ONE packed (optionally pinned) buffer: a
+        `data.PackedBatch` whose views equal `Batch.from_data_list([self[i] for i in ids], int32, csr=True,
+        keep_coo=False)` plus the `ptr` tables.  Native, multi-threaded (hgin_host_collate); feed it to
+        `data.DevicePrefetcher` or `train.GraphedTrainStep`.  `edge_bucket` pads the CSR column arrays to a
+        multiple (static shapes for CUDA-graph replay); the tail is never read (row pointers bound it).
+        `out`: a uint8 (pinned) tensor to assemble into — reuse a small ring of them in a loader, a fresh
+        230 MB allocation costs more than the collate itself."""
+        from .data import PackedBatch
+        ids_np = np.ascontiguousarray(np.asarray(ids, dtype=np.int32).reshape(-1))
+        B = int(ids_np.shape[0])
+        if B == 0:
+            raise ValueError("SampleArena.collate_packed: empty id list")
+        if ids_np.min() < 0 or ids_np.max() >= self.num_samples:
+            raise IndexError(f"sample ids must be in [0, {self.num_samples})")
+        tables = self._host_tables()
+        classes = self.classes
+        C = len(classes)
+        totals = tables["class_sizes"][:, ids_np].sum(axis=1)
+        specs = self.field_specs()
+        layout, off = [], (C * (B + 1) * 8 + 255) // 256 * 256
+        places = []
+        for key, name, arr_name, ptr_kind, width, sc, ac, closing, dtype in specs:
+            rows = int(totals[sc]) + (1 if closing else 0)
+            alloc_rows = rows
+            if edge_bucket and name.endswith("_col"):
+                alloc_rows = (rows + edge_bucket - 1) // edge_bucket * edge_bucket
+            shape = (alloc_rows, width) if name == "x" else (alloc_rows,)
+            layout.append(("node" if isinstance(key, str) else "edge", key, name, dtype, shape, off))
+            places.append((off, rows, alloc_rows))
+            off += (alloc_rows * width * 4 + 255) // 256 * 256
+        for ci, nt in enumerate(NODE_TYPES):                      # the offsets table doubles as the `ptr` vectors
+            layout.append(("node", nt, "ptr", torch.int64, (B + 1,), ci * (B + 1) * 8))
+        if out is not None:
+            if out.dtype != torch.uint8 or out.is_cuda or out.numel() < off:
+                raise ValueError(f"collate_packed: `out` must be a host uint8 tensor of at least {off} bytes")
+            buf = out[:off]
+        else:
+            buf = torch.empty(off, dtype=torch.uint8, pin_memory=bool(pin and torch.cuda.is_available()))
+        base = buf.data_ptr()
+        table = (_lib.CollateField * len(specs))()
+        for i, ((key, name, arr_name, ptr_kind, width, sc, ac, closing, dtype), (o, rows, alloc_rows)) in enumerate(
+                zip(specs, places)):
+            arr = self.arrays[arr_name]
+            ptr = tables["rowptr"][ptr_kind[1]] if isinstance(ptr_kind, tuple) else tables["class_ptr"][classes.index(ptr_kind)]
+            table[i] = _lib.CollateField(arr.ctypes.data if arr.size else None, base + o, ptr.ctypes.data, width, sc, ac, closing)
+            if alloc_rows > rows:
+                buf[o + rows * width * 4:o + alloc_rows * width * 4].zero_()
+        _lib.check(_lib.load().hgin_host_collate(B, ids_np.ctypes.data, self.num_samples, len(specs), table, C,
+                                                 tables["class_ptr"].ctypes.data, base, int(num_threads)),
+                   "hgin_host_collate")
+        return PackedBatch(buf, layout, B)
+
     # ---- on-disk format ---------------------------------------------------------------------------
     def save(self, path):
         """MAGIC | u32 version | u32 header bytes | JSON header | arrays (64-byte aligned)."""
@@ -199,29 +289,16 @@ class DeviceDataset:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.num_samples = arena.num_samples
         self.edge_types = arena.edge_types
-        # size classes: node types, then edges per relation
-        self.classes = list(NODE_TYPES) + ["E:" + _rel_name(et) for et in self.edge_types]
+        self.classes = arena.classes
         cidx = {c: i for i, c in enumerate(self.classes)}
         self.class_sizes = np.stack([arena.sizes(c) for c in self.classes])            # host: batch totals
         self.class_ptr = self._up(np.stack([np.asarray(arena.ptr[c]) for c in self.classes]))
-        up = lambda name: self._up(np.asarray(arena.arrays[name]))
-        # field table: (store key, field name, device array, ptr table, width, size class, add class, closing row)
-        self.fields = []
-        node_ptr = {nt: self.class_ptr[cidx[nt]] for nt in NODE_TYPES}
         rp_ptr = {nt: self._up(arena.rowptr_ptr(nt)) for nt in NODE_TYPES}
-        for nt in NODE_TYPES:
-            a = up(f"{nt}.x")
-            self.fields.append((nt, "x", a, node_ptr[nt], a.shape[1], cidx[nt], -1, 0, torch.float32))
-        self.fields.append(("path", "y", up("path.y"), node_ptr["path"], 1, cidx["path"], -1, 0, torch.float32))
-        for et in self.edge_types:
-            name = _rel_name(et)
-            ec = cidx["E:" + name]
-            e_ptr = self.class_ptr[ec]
-            for side, rows_t, cols_t in (("dst", et[2], et[0]), ("src", et[0], et[2])):
-                self.fields.append((et, f"csr_{side}_rowptr", up(f"{name}.csr_{side}_rowptr"), rp_ptr[rows_t], 1,
-                                    cidx[rows_t], ec, 1, torch.int32))
-                self.fields.append((et, f"csr_{side}_col", up(f"{name}.csr_{side}_col"), e_ptr, 1, ec, cidx[cols_t], 0,
-                                    torch.int32))
+        # field table: (store key, field name, device array, ptr table, width, size class, add class, closing row, dtype)
+        self.fields = []
+        for key, name, arr_name, ptr_kind, width, sc, ac, closing, dtype in arena.field_specs():
+            ptr = rp_ptr[ptr_kind[1]] if isinstance(ptr_kind, tuple) else self.class_ptr[cidx[ptr_kind]]
+            self.fields.append((key, name, self._up(np.asarray(arena.arrays[arr_name])), ptr, width, sc, ac, closing, dtype))
         widths = np.array([f[4] for f in self.fields], dtype=np.int64)
         per_sample = np.stack([self.class_sizes[f[5]] for f in self.fields]) * widths[:, None]
         self.max_words = int(per_sample.max()) + 1 if per_sample.size else 1
@@ -304,3 +381,101 @@ class DeviceLoader:
             ids = order[lo:lo + step][self.rank::self.world]
             if len(ids):
                 yield self.dataset.collate(ids)
+
+
+class HostLoader:
+    """`DataLoader(dataset, batch_size, shuffle)` (dataset.py:242-244) for a dataset that stays in HOST
+    memory (e.g. a memory-mapped `SampleArena` larger than HBM): a background thread assembles packed
+    batches with the native collate (`SampleArena.collate_packed`) into a ring of pinned buffers while
+    the GPU works; iterate it through `data.DevicePrefetcher` (one DMA per batch):
+
+        for batch in DevicePrefetcher(HostLoader(arena, batch_size=1024, shuffle=True)):
+            loss = step(batch)
+
+    A ring slot is reused only after the H2D copy of the batch it held has completed (the prefetcher
+    leaves its copy event on the PackedBatch).  `rank` / `world` shard like `DeviceLoader`."""
+
+    def __init__(self, arena: SampleArena, batch_size=1, shuffle=False, generator=None, rank=0, world=1, ring=4,
+                 num_threads=0, edge_bucket=None, pin=True, epochs=1):
+        if ring < 3:
+            raise ValueError("HostLoader: ring must be >= 3 (one batch being filled, one queued, one being copied)")
+        self.arena, self.batch_size, self.shuffle, self.generator = arena, int(batch_size), shuffle, generator
+        self.rank, self.world, self.ring, self.num_threads = rank, world, ring, num_threads
+        self.edge_bucket, self.pin, self.epochs = edge_bucket, pin, epochs
+        self._bufs, self._last = [None] * ring, [None] * ring
+
+    def __len__(self):
+        return self.epochs * ((len(self.arena) + self.batch_size * self.world - 1) // (self.batch_size * self.world))
+
+    def _id_batches(self):
+        n = len(self.arena)
+        step = self.batch_size * self.world
+        for _ in range(self.epochs):           # `epochs` > 1: one uninterrupted stream, reshuffled per epoch
+            order = torch.randperm(n, generator=self.generator).numpy() if self.shuffle else np.arange(n)
+            for lo in range(0, n, step):
+                ids = order[lo:lo + step][self.rank::self.world]
+                if len(ids):
+                    yield ids
+
+    def __iter__(self):
+        import queue
+        import threading
+        q = queue.Queue(maxsize=self.ring - 2)
+        stop = threading.Event()
+
+        def produce():
+            try:
+                for k, ids in enumerate(self._id_batches()):
+                    if stop.is_set():
+                        return
+                    slot = k % self.ring
+                    batch = self._produce(slot, ids)
+                    while not stop.is_set():
+                        try:
+                            q.put(batch, timeout=0.1)
+                            break
+                        except queue.Full:
+                            continue
+                q.put(None)
+            except BaseException as exc:      # surface loader errors in the consumer
+                q.put(exc)
+
+        t = threading.Thread(target=produce, daemon=True)
+        t.start()
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    return
+                if isinstance(item, BaseException):
+                    raise item
+                yield item
+        finally:
+            stop.set()
+            for b in self._last:
+                if b is not None:
+                    b.abandoned = True
+
+    def _produce(self, slot, ids):
+        prev = self._last[slot]
+        if prev is not None and torch.cuda.is_available():
+            import time
+            while prev.copied is None and not prev.abandoned:      # taken from the queue but not staged yet (rare)
+                time.sleep(0.0002)
+            if prev.copied is not None:
+                prev.copied.synchronize()                          # its H2D copy has left this buffer
+        buf = self._bufs[slot]
+        if buf is not None:
+            try:
+                batch = self.arena.collate_packed(ids, edge_bucket=self.edge_bucket, num_threads=self.num_threads, out=buf)
+            except ValueError:                                     # this batch is larger than the slot: grow it
+                buf = None
+        if buf is None:
+            batch = self.arena.collate_packed(ids, pin=self.pin, edge_bucket=self.edge_bucket, num_threads=self.num_threads)
+            grown = torch.empty(int(batch.buffer.numel() * 1.125) + 4096, dtype=torch.uint8,
+                                pin_memory=bool(self.pin and torch.cuda.is_available()))
+            grown[:batch.buffer.numel()].copy_(batch.buffer)
+            self._bufs[slot] = grown
+            batch.buffer = grown[:batch.buffer.numel()]
+        self._last[slot] = batch
+        return batch

@@ -286,6 +286,7 @@ class DevicePrefetcher:
             dst.copy_(host.buffer, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(self.stream)
+        host.copied = ready          # a loader that recycles pinned buffers waits on this before refilling
         return host.views(dst), ready, slot
 
     def _stage(self, host):
@@ -334,6 +335,8 @@ class PackedBatch:
 
     def __init__(self, buffer, layout, num_graphs):
         self.buffer, self.layout, self.num_graphs = buffer, layout, num_graphs
+        self.copied = None        # CUDA event of the H2D copy out of `buffer` (set by DevicePrefetcher)
+        self.abandoned = False    # the consumer went away without copying it
 
     @property
     def signature(self):

@@ -260,6 +260,16 @@ int32_t hgin_collate_gather(int32_t batch, const int32_t *ids, int64_t num_sampl
                             int32_t num_classes, const int64_t *offsets,
                             int64_t max_words_per_sample, void *stream);
 
+/* Host twin of the two calls above for datasets that stay in HOST memory: every pointer (ids,
+ * class_ptr, the fields' src / dst / ptr, offsets) is a host pointer; `dst` normally points into one
+ * pinned, packed batch buffer that then crosses PCIe as a single copy.  Runs on `num_threads` host
+ * threads (0 = all); no CUDA call, usable without a GPU.  Ids outside [0, num_samples) are an error.
+ */
+int32_t hgin_host_collate(int32_t batch, const int32_t *ids_host, int64_t num_samples,
+                          int32_t num_fields, const hgin_collate_field *fields_host,
+                          int32_t num_classes, const int64_t *class_ptr_host,
+                          int64_t *offsets_host, int32_t num_threads);
+
 /* ---- queueing-theory baseline (pre-processing features) -----------------------------------------
  * Replaces: QTBaseline.forward + separate_edge_timesteps (models.py:15-158), called once per
  * sample by GNN21Dataset.preprocess (dataset.py:86); its outputs are the `bl_features` columns of

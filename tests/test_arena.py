@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import c_oracle
-from gnn_link_prediction_b200.arena import DeviceDataset, DeviceLoader, SampleArena
+from gnn_link_prediction_b200.arena import DeviceDataset, DeviceLoader, HostLoader, SampleArena
 from gnn_link_prediction_b200.data import CONV_EDGE_TYPES, CSR_KEYS, Batch
 from gnn_link_prediction_b200.synthetic import SyntheticDataset
 
@@ -130,6 +130,57 @@ def test_device_loader_shards_every_global_batch_across_ranks():
     assert plain == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]]                  # shuffle=False keeps dataset order
 
 
+def _assert_views_equal_host_batch(views, want, num_graphs):
+    assert views.num_graphs == num_graphs
+    for nt in ("path", "link", "node"):
+        assert torch.equal(views[nt]["x"].cpu(), want[nt]["x"])
+        assert torch.equal(views[nt]["ptr"].cpu(), want[nt]["ptr"])
+    assert torch.equal(views["path"]["y"].cpu(), want["path"]["y"].reshape(-1))
+    for et in CONV_EDGE_TYPES:
+        for k in CSR_KEYS:
+            w = want[et][k]
+            assert views[et][k].dtype == torch.int32
+            assert torch.equal(views[et][k][:w.shape[0]].cpu(), w), (et, k)     # the tail of a padded col array is never read
+
+
+@pytest.mark.parametrize("ids", [[0, 1, 2, 3, 4, 5, 6, 7, 8], [8, 3, 3, 0, 7], [5], list(range(9)) * 5])
+@pytest.mark.parametrize("edge_bucket", [None, 64])
+def test_native_host_collate_equals_python_collate(ids, edge_bucket):
+    """hgin_host_collate (C++, threads) into one packed buffer == Batch.from_data_list(csr=True), no GPU needed."""
+    samples = _ragged_samples(with_csr=True)
+    arena = SampleArena.from_samples(samples, keep_coo=False)
+    for threads in (1, 3):
+        packed = arena.collate_packed(ids, pin=False, edge_bucket=edge_bucket, num_threads=threads)
+        _assert_views_equal_host_batch(packed.views(), _host_batch(samples, ids), len(ids))
+    out = torch.empty(packed.nbytes() + 1000, dtype=torch.uint8)
+    again = arena.collate_packed(ids, edge_bucket=edge_bucket, out=out)
+    assert again.buffer.data_ptr() == out.data_ptr()              # assembled in place (the gaps between fields are padding)
+    _assert_views_equal_host_batch(again.views(), _host_batch(samples, ids), len(ids))
+    with pytest.raises(ValueError):
+        arena.collate_packed(ids, out=torch.empty(16, dtype=torch.uint8))
+    with pytest.raises(IndexError):
+        arena.collate_packed([0, 99])
+
+
+def test_host_loader_streams_an_epoch_through_a_buffer_ring():
+    samples = _ragged_samples(with_csr=True)
+    arena = SampleArena.from_samples(samples, keep_coo=False)
+    for epoch in range(2):                                   # the ring is reused across epochs
+        loader = HostLoader(arena, batch_size=2, shuffle=False, ring=3, pin=False)
+        seen = 0
+        for k, packed in enumerate(loader):                  # 5 batches through 3 slots
+            ids = list(range(2 * k, min(2 * k + 2, 9)))
+            _assert_views_equal_host_batch(packed.views(), _host_batch(samples, ids), len(ids))
+            seen += packed.num_graphs
+        assert seen == 9 and len(loader) == 5
+    per_rank = [sum(p.num_graphs for p in HostLoader(arena, batch_size=2, shuffle=True, pin=False,
+                                                      generator=torch.Generator().manual_seed(1), rank=r, world=2))
+                for r in range(2)]
+    assert sum(per_rank) == 9
+    with pytest.raises(ValueError):
+        HostLoader(arena, ring=2)
+
+
 # ---- on-GPU collate -----------------------------------------------------------------------------
 def _host_batch(samples, ids):
     return Batch.from_data_list([samples[i] for i in ids], index_dtype=torch.int32, edge_types=CONV_EDGE_TYPES,
@@ -178,6 +229,28 @@ def test_device_collate_large_batch_and_loader_sharding():
         assert len(loader) == 4
         seen.append(sum(b.num_graphs for b in loader))
     assert sum(seen) == 64 and seen[0] == seen[1]
+
+
+@pytest.mark.gpu
+def test_host_loader_through_device_prefetcher_matches_device_collate():
+    from gnn_link_prediction_b200.data import DevicePrefetcher
+    ds0 = SyntheticDataset(22, num_nodes=12, num_links=20, num_topologies=3, seed=8)
+    samples = [ds0[i] for i in range(22)]
+    arena = SampleArena.from_samples(samples, keep_coo=False)
+    dev = DeviceDataset(arena)
+    loader = HostLoader(arena, batch_size=3, shuffle=True, generator=torch.Generator().manual_seed(4), ring=3)
+    order = torch.randperm(22, generator=torch.Generator().manual_seed(4)).tolist()
+    n = 0
+    for k, batch in enumerate(DevicePrefetcher(loader, depth=2)):      # 8 batches: pinned ring and device ring both wrap
+        ids = order[3 * k:3 * k + 3]
+        want = dev.collate(ids)
+        for nt in ("path", "link", "node"):
+            assert torch.equal(batch[nt]["x"], want[nt]["x"]) and torch.equal(batch[nt]["ptr"], want[nt]["ptr"])
+        for et in CONV_EDGE_TYPES:
+            for key in CSR_KEYS:
+                assert torch.equal(batch[et][key][:want[et][key].shape[0]], want[et][key]), (et, key)
+        n += batch.num_graphs
+    assert n == 22
 
 
 @pytest.mark.gpu
