@@ -162,8 +162,10 @@ def cpu_reference_run(w, sample_graphs, steps, warmup, threads=None):
 def run_reference(args, w, rank):
     if rank != 0:
         return
-    sample = 8 if args.workload == "cfgA" else 16
-    steps = max(1, min(args.steps, 5))
+    # a bounded sample of the workload: cfgA is the reference's own batch of 8; cfgC runs 128 of the 1024
+    # topologies per step (~1 s per step on 16 host threads), so a few steps give a stable number
+    sample = 8 if args.workload == "cfgA" else 128
+    steps = max(1, min(args.steps, 40 if args.workload == "cfgA" else 6))
     r = cpu_reference_run(w, sample, steps, min(args.warmup, 1))
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "graphs/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
@@ -466,8 +468,8 @@ def main():
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        sample = 8 if small else 16
-        r = cpu_reference_run(w, sample, 3, 1)
+        sample = 8 if small else 128
+        r = cpu_reference_run(w, sample, 40 if small else 6, 1)
         cpu_baseline = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     launches = kernels_per_step * args.steps
