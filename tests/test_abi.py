@@ -37,6 +37,47 @@ def test_argument_errors_do_not_need_a_gpu(built):
         _lib.check(rc, "hgin_gin_combine")
 
 
+def test_argument_errors_of_the_newer_entry_points(built):
+    """Validation happens before any CUDA call: status < 0 and a message, never an abort."""
+    err = lambda: built.hgin_last_error().decode()
+    rc = built.hgin_gin_combine_post(4, None, None, 0, None, 4, 4, None, 4, 4, None, 2, 0, None, 4, None, 4, 1, None, None, None, None, 0, None)
+    assert rc == -1                                           # null x_self with SELF_CONCAT / post on a concat result
+    rc = built.hgin_gin_combine_pre(4, None, None, 0, None, 4, 4, None, 4, 4, None, 0, 0, None, 4, 1, None, 0, None, None)
+    assert rc == -1 and "slope" in err()                      # PReLU input activation without its slope
+    rc = built.hgin_gin_combine_pre(4, None, None, 0, None, 4, 4, None, 4, 4, None, 0, 0, None, 4, 7, None, 0, None, None)
+    assert rc == -1 and "input activation" in err()
+    assert built.hgin_qt_baseline_workspace_bytes(-1, 0) == -1
+    rc = built.hgin_qt_baseline(10, 4, 20, None, None, None, None, None, None, None, None, 0, None, None, None, 0, None)
+    assert rc == -1 and "num_iterations" in err()
+    rc = built.hgin_qt_baseline(10, 4, 20, None, None, None, None, None, None, None, None, 3, None, None, None, 0, None)
+    assert rc == -1 and "null pointer" in err()
+    rc = built.hgin_collate_offsets(4, None, 99, None, 10, None, None, None)
+    assert rc == -1 and "bad sizes" in err()
+    rc = built.hgin_collate_gather(70000, None, 10, 1, None, 1, None, 1, None)
+    assert rc == -1 and "65535" in err()
+    rc = built.hgin_linear_bwd_post(8, None, 4, None, 4, 0, None, None, 4, 4, None, 0, 0, None, 4, 0, 4, None, 4, None, None, None,
+                                    None, 4, 9, None, None, None, 0, 0, None)
+    assert rc == -1 and "post_act" in err()
+
+
+def test_host_collate_runs_without_a_gpu_and_validates_ids(built):
+    import ctypes as C
+    import numpy as np
+    ptr = np.array([0, 2, 5], dtype=np.int64)                 # two samples: 2 and 3 rows of width 2
+    src = np.arange(10, dtype=np.int32)
+    dst = np.zeros(10, dtype=np.int32)
+    offsets = np.zeros(3, dtype=np.int64)
+    field = (_lib.CollateField * 1)(_lib.CollateField(src.ctypes.data, dst.ctypes.data, ptr.ctypes.data, 2, 0, 0, 0))
+    ids = np.array([1, 0], dtype=np.int32)
+    rc = built.hgin_host_collate(2, ids.ctypes.data, 2, 1, field, 1, ptr.ctypes.data, offsets.ctypes.data, 2)
+    assert rc == 0 and offsets.tolist() == [0, 3, 5]
+    # sample 1 (rows 2..4) first, +0; then sample 0 (rows 0..1) with its row offset 3 added to every int32 entry
+    assert dst.tolist() == [4, 5, 6, 7, 8, 9, 3, 4, 5, 6]
+    bad = np.array([0, 2], dtype=np.int32)
+    rc = built.hgin_host_collate(2, bad.ctypes.data, 2, 1, field, 1, ptr.ctypes.data, offsets.ctypes.data, 1)
+    assert rc == -1 and b"outside" in built.hgin_last_error()
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libhgin.so")
