@@ -275,6 +275,12 @@ def linear_bwd(g, z, x1, W, x2=None, act=ACT_NONE, alpha=None, dx_cols=None, wan
     reduces = want_dw or want_db or want_dalpha
     n_kernels = ((1 + (1 if ddot is not None else 0)) if c1 > c0 else 0) + \
         ((2 + (1 if (want_dalpha and act == ACT_PRELU) else 0)) if reduces else 0)
+    # bytes the passes of this call move (dz pass only with an activation; dx GEMM: dz in, dx out, plus the
+    # epilogue operand; dW GEMM: dz and x in; a sums-only pass over dz when the rank-k2 tail of dW is wanted)
+    width = c1 - c0
+    has_e = dot_x is not None or (post is not None and post.act != ACT_NONE)
+    moved = (3 * n if act != ACT_NONE else 0) + ((n + width * (2 if has_e else 1)) if (width > 0 and dx is not None) else 0) \
+        + ((n + k) if want_dw else 0) + (n if (act == ACT_NONE and want_dw and k2 > 0) else 0)
     if post is not None and post.act != ACT_NONE and dx is not None:
         if dot_x is not None:
             raise HginError("linear_bwd: post-activation and dot_x cannot be combined")
@@ -282,8 +288,7 @@ def linear_bwd(g, z, x1, W, x2=None, act=ACT_NONE, alpha=None, dx_cols=None, wan
         if tuple(post.z.shape) != (rows, c1 - c0):
             raise HginError(f"linear_bwd: post.z is {tuple(post.z.shape)}, expected {(rows, c1 - c0)}")
         post.dalpha = torch.empty(1, dtype=torch.float32, device=dev) if post.act == ACT_PRELU else None
-        with _region("linear_bwd", kernels=n_kernels + 1, flops=flops,
-                     bytes=4 * rows * (n * (1 if act == ACT_NONE else 4) + k + 2 * (c1 - c0))):
+        with _region("linear_bwd", kernels=n_kernels + 1, flops=flops, bytes=4 * rows * moved):
             check(lib.hgin_linear_bwd_post(rows, pg, ldg, pz, ldz, act, _scalar(alpha, "linear_bwd.alpha"), p1, ld1, k1,
                                            p2, ld2, k2, W.data_ptr(), n, c0, c1, pdx, lddx, _ptr(dW), _ptr(db),
                                            _ptr(dalpha), ppz, ldpz, post.act, _scalar(post.alpha, "linear_bwd.post.alpha"),
@@ -291,8 +296,7 @@ def linear_bwd(g, z, x1, W, x2=None, act=ACT_NONE, alpha=None, dx_cols=None, wan
                   "hgin_linear_bwd_post")
         post.applied = True
         return {"dx": dx, "ddot": None, "dW": dW, "db": db, "dalpha": dalpha}
-    with _region("linear_bwd", kernels=n_kernels, flops=flops,
-                 bytes=4 * rows * (2 * n * (2 if c1 > c0 else 1) + k + (c1 - c0))):
+    with _region("linear_bwd", kernels=n_kernels, flops=flops, bytes=4 * rows * moved):
         check(lib.hgin_linear_bwd(rows, pg, ldg, pz, ldz, act, _scalar(alpha, "linear_bwd.alpha"), p1, ld1, k1, p2,
                                   ld2, k2, W.data_ptr(), n, c0, c1, pdx, lddx, pd, ldd, _ptr(ddot), _ptr(dW),
                                   _ptr(db), _ptr(dalpha), ws.data_ptr(), ws_bytes, math_mode, _stream()),
