@@ -19,6 +19,18 @@ def test_header_and_binding_agree():
     assert sorted(_lib.SIGNATURES) == _lib.header_functions()
 
 
+def test_header_is_plain_c(tmp_path):
+    """include/hgin.h is the C ABI: it must compile as C99 on its own (no C++ / CUDA / torch types)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "hgin.h"\nint main(void) { hgin_collate_field f; (void)f; return hgin_version() > 0 ? 0 : 1; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.dirname(_lib.HEADER_PATH),
+                           "-fsyntax-only", str(src)])
+
+
 def test_every_declared_symbol_is_exported(built):
     raw = ctypes.CDLL(_lib.LIB_PATH)
     for name in _lib.header_functions():
