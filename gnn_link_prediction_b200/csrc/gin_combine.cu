@@ -102,13 +102,17 @@ struct PostAct {
     const float *self_alpha;
 };
 
-template <int VEC, int LPR, int NC, bool CONTIG, int MINB, int MODE>
+// Row indices and leading dimensions are 32-bit inside the kernel (the dispatch checks the ranges), so that
+// every row address is ONE widening multiply-add (IMAD.WIDE) instead of a 64 x 64-bit product — the
+// short-row launches issue ~60 % of their scheduler slots, and integer address math was most of it.
+// FULL: f_src == LPR * VEC * NC, the feature-range predicates fold away.
+template <int VEC, int LPR, int NC, bool CONTIG, int MINB, int MODE, bool FULL>
 __global__ void __launch_bounds__(256, MINB)
-gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                   const float *__restrict__ x_src, int64_t ld_src, int f_src,
-                   const float *__restrict__ x_self, int64_t ld_self, int f_self,
+gin_combine_kernel(int num_rows, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                   const float *__restrict__ x_src, int ld_src, int f_src,
+                   const float *__restrict__ x_self, int ld_self, int f_self,
                    const float *__restrict__ eps_ptr, int self_mode, int accumulate,
-                   float *__restrict__ out, int64_t ld_out, const PostAct post) {
+                   float *__restrict__ out, int ld_out, const PostAct post) {
     // gathers in flight per lane before the dependent adds; bounded by the batch (LPR) and by
     // the register budget when a lane carries several chunks
     // (pre-activation sources need a few registers for the on-the-fly act: two gathers fewer in flight)
@@ -129,6 +133,8 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
     const float src_alpha = !PRE_SRC ? 1.0f : (post.src_act == HGIN_ACT_PRELU ? __ldg(post.src_alpha) : 0.0f);
     const float self_alpha = !PRE_SELF ? 1.0f : (post.self_act == HGIN_ACT_PRELU ? __ldg(post.self_alpha) : 0.0f);
     float dalpha = 0.0f, ddot = 0.0f;
+    const int post_ld = static_cast<int>(post.ldz);
+    auto at = [](const float *base, int row, int ld) { return base + static_cast<int64_t>(row) * ld; };   // IMAD.WIDE
 
     // Row -> warp mapping.
     // CONTIG (short rows): each CTA owns a CONTIGUOUS block of rows, its warps interleaving inside it.
@@ -138,26 +144,27 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
     // otherwise (long, heavy-tailed rows): rows are dealt round-robin over all warps of the grid so
     //   that the tail is spread evenly.
     const int warps_per_cta = blockDim.x >> 5;
-    int64_t cta_beg, cta_end, stride;
+    int cta_beg, cta_end, stride;
     if (CONTIG) {
-        const int64_t unit = static_cast<int64_t>(warps_per_cta) * ROWS_PER_WARP;
-        const int64_t rows_per_cta = ((num_rows + gridDim.x - 1) / gridDim.x + unit - 1) / unit * unit;
-        cta_beg = static_cast<int64_t>(blockIdx.x) * rows_per_cta;
-        cta_end = min(cta_beg + rows_per_cta, num_rows);
+        const int unit = warps_per_cta * ROWS_PER_WARP;
+        const int rows_per_cta = ((num_rows + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) + unit - 1) / unit * unit;
+        const int64_t b64 = static_cast<int64_t>(blockIdx.x) * rows_per_cta;
+        cta_beg = b64 < num_rows ? static_cast<int>(b64) : num_rows;
+        cta_end = min(b64 + rows_per_cta, static_cast<int64_t>(num_rows));
         stride = unit;
     } else {
-        cta_beg = static_cast<int64_t>(blockIdx.x) * warps_per_cta * ROWS_PER_WARP;
+        cta_beg = static_cast<int>(blockIdx.x) * warps_per_cta * ROWS_PER_WARP;
         cta_end = num_rows;
-        stride = static_cast<int64_t>(gridDim.x) * warps_per_cta * ROWS_PER_WARP;
+        stride = static_cast<int>(gridDim.x) * warps_per_cta * ROWS_PER_WARP;
     }
 
     // Software pipeline over this warp's rows.  The dependent chain rowptr -> col -> x_src[col] costs
     // three memory latencies; with ~3 neighbours per row (link->path) that chain, not bandwidth,
     // bounds the kernel.  So the row bounds are fetched two iterations ahead and the first batch of
     // neighbour indices one iteration ahead, leaving only the gather itself exposed.
-    int64_t row0 = cta_beg + static_cast<int64_t>(threadIdx.x >> 5) * ROWS_PER_WARP;
-    auto load_bounds = [&](int64_t r0, int32_t &b, int32_t &l) {
-        const int64_t r = r0 + grp;
+    int row0 = cta_beg + static_cast<int>(threadIdx.x >> 5) * ROWS_PER_WARP;
+    auto load_bounds = [&](int r0, int32_t &b, int32_t &l) {
+        const int r = r0 + grp;
         b = 0;
         l = 0;
         if (r < cta_end && rowptr != nullptr) {   // rowptr == NULL: no edges at all (self term only)
@@ -171,7 +178,7 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
     int32_t mine = (sub < len) ? __ldg(col + beg + sub) : -1;
 
     for (; row0 < cta_end; row0 += stride) {
-        const int64_t row = row0 + grp;
+        const int row = row0 + grp;
         const bool live = row < cta_end;
         // issue the prefetches for the following rows before touching this row's data
         const int32_t nmine = (sub < nlen) ? __ldg(col + nbeg + sub) : -1;
@@ -182,8 +189,8 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 const int f = (c * LPR + sub) * VEC;
-                if (f < f_src)
-                    self_v[c] = CONTIG ? load_pack_stream<VEC>(x_self + row * ld_self + f) : load_pack<VEC>(x_self + row * ld_self + f);
+                if (FULL || f < f_src)
+                    self_v[c] = CONTIG ? load_pack_stream<VEC>(at(x_self, row, ld_self) + f) : load_pack<VEC>(at(x_self, row, ld_self) + f);
             }
         }
         Pack<VEC> post_v[NC];
@@ -191,8 +198,8 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 const int f = (c * LPR + sub) * VEC;
-                if (f < f_src)
-                    post_v[c] = CONTIG ? load_pack_stream<VEC>(post.z + row * post.ldz + f) : load_pack<VEC>(post.z + row * post.ldz + f);
+                if (FULL || f < f_src)
+                    post_v[c] = CONTIG ? load_pack_stream<VEC>(at(post.z, row, post_ld) + f) : load_pack<VEC>(at(post.z, row, post_ld) + f);
             }
         }
         // warp-uniform trip count so the shuffles below are always convergent
@@ -224,8 +231,8 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
                         const int f = (c * LPR + sub) * VEC;
-                        if (nb[u] >= 0 && f < f_src) {
-                            v[u][c] = load_pack<VEC>(x_src + static_cast<int64_t>(nb[u]) * ld_src + f);
+                        if (nb[u] >= 0 && (FULL || f < f_src)) {
+                            v[u][c] = load_pack<VEC>(at(x_src, nb[u], ld_src) + f);
                         } else {
 #pragma unroll
                             for (int i = 0; i < VEC; ++i) v[u][c].v[i] = 0.0f;
@@ -249,11 +256,11 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
         }
 
         if (live) {
-            float *orow = out + row * ld_out;
+            float *orow = out + static_cast<int64_t>(row) * ld_out;
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 const int f = (c * LPR + sub) * VEC;
-                if (f >= f_src) continue;
+                if (!FULL && f >= f_src) continue;
                 Pack<VEC> r = acc[c];
                 if (self_mode == HGIN_SELF_ADD) {
 #pragma unroll
@@ -287,7 +294,7 @@ gin_combine_kernel(int64_t num_rows, const int32_t *__restrict__ rowptr, const i
             if (self_mode == HGIN_SELF_CONCAT) {
                 // [agg | (1+eps) x_self]: the self block starts at column f_src (rarely 16B aligned) -> scalar
                 for (int f = sub; f < f_self; f += LPR) {
-                    float xs = __ldg(x_self + row * ld_self + f);
+                    float xs = __ldg(at(x_self, row, ld_self) + f);
                     if (PRE_SELF) xs = xs > 0.f ? xs : self_alpha * xs;
                     float t = __fmul_rn(ope, xs);
                     if (accumulate) t = __fadd_rn(orow[f_src + f], t);
@@ -323,34 +330,37 @@ __global__ void __launch_bounds__(1024) combine_reduce_scalar_kernel(const float
 constexpr int kMaxCombineCtas = kNumSMs * 32;
 
 template <int VEC, int LPR, int NC, bool CONTIG = false, int MINB = ((VEC * NC <= 4) ? 4 : 1)>
-int launch(int64_t num_rows, const int32_t *rowptr, const int32_t *col, const float *x_src, int64_t ld_src,
-           int f_src, const float *x_self, int64_t ld_self, int f_self, const float *eps, int self_mode,
-           int accumulate, float *out, int64_t ld_out, const PostAct *post, cudaStream_t s) {
+int launch(int64_t num_rows64, const int32_t *rowptr, const int32_t *col, const float *x_src, int64_t ld_src64,
+           int f_src, const float *x_self, int64_t ld_self64, int f_self, const float *eps, int self_mode,
+           int accumulate, float *out, int64_t ld_out64, const PostAct *post, cudaStream_t s) {
+    const int num_rows = static_cast<int>(num_rows64), ld_src = static_cast<int>(ld_src64);
+    const int ld_self = static_cast<int>(ld_self64), ld_out = static_cast<int>(ld_out64);
     constexpr int threads = 256;
     constexpr int rows_per_cta = (threads / 32) * (32 / LPR);
     // Grid-stride over rows with whole waves of CTAs: enough CTAs (32 per SM) that the hardware
     // scheduler evens out the heavy-tailed row lengths of the path->link relation.
     const int grid = grid_for(num_rows, rows_per_cta, 32);
-    if (post && post->z)
-        gin_combine_kernel<VEC, LPR, NC, CONTIG, MINB, 1><<<grid, threads, 0, s>>>(
-            num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, accumulate, out, ld_out,
-            *post);
-    else if (post && post->src_act != HGIN_ACT_NONE && post->self_act != HGIN_ACT_NONE)
-        gin_combine_kernel<VEC, LPR, NC, CONTIG, MINB, 4><<<grid, threads, 0, s>>>(
-            num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, accumulate, out, ld_out,
-            *post);
-    else if (post && post->src_act != HGIN_ACT_NONE)
-        gin_combine_kernel<VEC, LPR, NC, CONTIG, MINB, 2><<<grid, threads, 0, s>>>(
-            num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, accumulate, out, ld_out,
-            *post);
-    else if (post)
-        gin_combine_kernel<VEC, LPR, NC, CONTIG, MINB, 3><<<grid, threads, 0, s>>>(
-            num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, accumulate, out, ld_out,
-            *post);
-    else
-        gin_combine_kernel<VEC, LPR, NC, CONTIG, MINB, 0><<<grid, threads, 0, s>>>(
-            num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, accumulate, out, ld_out,
-            PostAct{});
+    const PostAct pa = post ? *post : PostAct{};
+    const int mode = !post ? 0 : (post->z ? 1 : ((post->src_act != HGIN_ACT_NONE && post->self_act != HGIN_ACT_NONE) ? 4
+                                                 : (post->src_act != HGIN_ACT_NONE ? 2 : 3)));
+    const bool full = f_src == LPR * VEC * NC;
+#define HGIN_GO(M, F)                                                                                              \
+    gin_combine_kernel<VEC, LPR, NC, CONTIG, MINB, M, F><<<grid, threads, 0, s>>>(                                  \
+        num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, accumulate, out, ld_out, pa)
+#define HGIN_GO_MODE(M)          \
+    do {                         \
+        if (full) HGIN_GO(M, true); \
+        else HGIN_GO(M, false);  \
+    } while (0)
+    switch (mode) {
+        case 0: HGIN_GO_MODE(0); break;
+        case 1: HGIN_GO_MODE(1); break;
+        case 2: HGIN_GO_MODE(2); break;
+        case 3: HGIN_GO_MODE(3); break;
+        default: HGIN_GO_MODE(4); break;
+    }
+#undef HGIN_GO_MODE
+#undef HGIN_GO
     return grid;
 }
 
@@ -368,7 +378,9 @@ int32_t combine_dispatch(int64_t num_rows, const int32_t *rowptr, const int32_t 
                          int64_t workspace_bytes, void *stream, const char *who, int32_t src_act = HGIN_ACT_NONE,
                          const float *src_alpha = nullptr, int32_t self_act = HGIN_ACT_NONE,
                          const float *self_alpha = nullptr) {
-    HGIN_CHECK_ARG(num_rows >= 0 && num_rows < INT32_MAX, "%s: bad num_rows %lld", who, (long long)num_rows);
+    HGIN_CHECK_ARG(num_rows >= 0 && num_rows < INT32_MAX - (1 << 22), "%s: bad num_rows %lld", who, (long long)num_rows);
+    HGIN_CHECK_ARG(ld_src < INT32_MAX && ld_self < INT32_MAX && ld_out < INT32_MAX && ld_post < INT32_MAX,
+                   "%s: leading dimensions must fit 32 bits", who);
     HGIN_CHECK_ARG(f_src > 0 && f_src <= 512, "%s: f_src must be in [1,512], got %d", who, f_src);
     HGIN_CHECK_ARG(self_mode >= HGIN_SELF_NONE && self_mode <= HGIN_SELF_CONCAT, "%s: bad self_mode %d", who, self_mode);
     HGIN_CHECK_ARG(self_mode == HGIN_SELF_NONE || x_self != nullptr, "%s: x_self is null", who);
