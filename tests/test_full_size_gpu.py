@@ -1,5 +1,7 @@
-"""Parity at BASELINE.json's FULL sizes through size-independent properties (the oracle cannot run
-these sizes in seconds): Cfg-C = 1024 topologies per step, hidden 128, 4 GIN layers, tf32 GEMMs;
+"""Parity at BASELINE.json's FULL sizes: (1) the CPU oracle itself, run ONCE on the whole Cfg-C batch
+(loss and every gradient of the fused train step, ~10-20 s of host time) and on the Cfg-D graph with
+real-valued features (plain-C oracle, bit for bit, forward and transposed); (2) size-independent
+properties: Cfg-C = 1024 topologies per step, hidden 128, 4 GIN layers, tf32 GEMMs;
 Cfg-D = 1 M nodes / 20 M edges.  Integer work is checked exactly (sortedness, transposition,
 agreement of the two CSR constructions); the fp32 aggregation through inputs on which fp32
 addition is exact (small integers), so any summation order must give the same bits as a float64
@@ -149,3 +151,114 @@ def test_cfgd_sweep_graph_aggregation_exact_and_transposed():
     assert torch.equal(got_t, want_t)
     # <A x, g> == <x, A^T g> exactly on integers (adjoint identity of forward and backward gathers)
     assert float((got.double() * gl.double()).sum()) == float((x.double() * got_t.double()).sum())
+
+
+# ---- the CPU oracle at full size --------------------------------------------------------------------------------
+
+def _oracle_topologies():
+    """The oracle port materialises x_j = x_src[edge_index[0]] per relation and keeps autograd's saved
+    tensors: ~24 MB of host memory per 50-node topology at hidden 128 / 4 layers (measured).  Take the whole
+    Cfg-C batch when the box has the memory, the largest power-of-two share otherwise."""
+    import psutil
+    avail = psutil.virtual_memory().available
+    for n in (1024, 512, 256):
+        if avail > n * 40 * 2 ** 20:
+            return n
+    pytest.skip(f"only {avail / 2 ** 30:.0f} GiB of host memory available for the CPU oracle")
+
+
+@pytest.fixture(scope="module")
+def cfgc_oracle():
+    """ONE run of the oracle port (the ATen CPU ops the reference executes, train.py:31-43) on the whole
+    Cfg-C batch: scores, loss and every parameter gradient.  ~20-40 s on the GPU box's host cores."""
+    import os
+    from oracle import hgin_oracle
+    from gnn_link_prediction_b200.data import Batch
+    n = _oracle_topologies()
+    ds = SyntheticDataset(n, num_topologies=16, seed=1997)
+    samples = [ds[i] for i in range(n)]
+    host = Batch.from_data_list(samples)
+    torch.manual_seed(1997)
+    ref = hgin_oracle.HetroGIN(input_channels={"link": 7, "path": 7, "node": 3}, **KW)
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    y = host["path"].y.reshape(-1, 1)
+    out_ref = ref(host.x_dict, host.edge_index_dict, None)
+    loss_ref = hgin_oracle.mape(out_ref, y)
+    torch.sqrt(loss_ref).backward()
+    grads = {k: (None if p.grad is None else p.grad.clone()) for k, p in ref.named_parameters()}
+    res = dict(n=n, samples=samples, state_dict={k: v.clone() for k, v in ref.state_dict().items()},
+               out=out_ref.detach().clone(), loss=float(loss_ref), grads=grads)
+    del out_ref, loss_ref, ref, host
+    return res
+
+
+@pytest.mark.parametrize("math", ["tf32", "bf16"])
+def test_cfgc_full_batch_loss_and_every_gradient_against_the_oracle(cfgc_oracle, math):
+    """`TrainStep` in the bench's arithmetic on the whole Cfg-C batch against the oracle.  Bar: the north star's
+    reduced-precision bound, rel 1e-2 of the largest entry per tensor; one-element gradients (eps, PReLU slope:
+    sums of ~1e8 signed products that largely cancel) against the typical size of such gradients."""
+    from gnn_link_prediction_b200 import ops as _ops
+    from gnn_link_prediction_b200.models import HetroGIN
+    from gnn_link_prediction_b200.train import TrainStep
+    mode = getattr(_ops, "MATH_" + math.upper(), None)
+    if mode is None:
+        pytest.skip(f"math mode {math} is not built")
+    o = cfgc_oracle
+    model = HetroGIN(input_channels={"link": 7, "path": 7, "node": 3}, **KW)
+    model.load_state_dict(o["state_dict"])
+    model.cuda().train().set_math_mode(mode)
+    dev = DeviceDataset(SampleArena.from_samples(o["samples"], keep_coo=False))
+    batch = dev.collate(list(range(o["n"])))
+    with torch.no_grad():
+        out = model.eval()(batch.x_dict, batch.graph, None)
+    model.train()
+    torch.testing.assert_close(out.cpu(), o["out"], rtol=1e-2, atol=1e-2 * float(o["out"].abs().max()))
+    del out
+    step = TrainStep(model, lr=1e-3)
+    loss = step(batch)
+    torch.cuda.synchronize()
+    assert abs(float(loss[0]) - o["loss"]) <= 1e-2 * abs(o["loss"])
+    g_ref = o["grads"]
+    scale1 = max(float(g.abs().max()) for g in g_ref.values() if g is not None and g.numel() == 1)
+    for k, p in model.named_parameters():
+        assert (p.grad is None) == (g_ref[k] is None), k
+        if p.grad is None:
+            continue
+        got, want = p.grad.detach().cpu(), g_ref[k]
+        if p.numel() == 1:
+            assert abs(float(got) - float(want)) <= 1e-2 * scale1 + 1e-1 * abs(float(want)), (k, float(got), float(want))
+        else:
+            torch.testing.assert_close(got, want, rtol=1e-2, atol=1e-2 * float(want.abs().max()),
+                                       msg=lambda m, k=k: f"{k}: {m}")
+
+
+def test_cfgd_real_valued_aggregation_bit_exact_against_the_c_oracle():
+    """Cfg-D (900 k path / 80 k link nodes, 9.96 M uniform random edges, F = 128) with REAL-valued features:
+    stable CSR, forward segmented sum with the GIN self term and the transposed gather, all compared with
+    oracle/hgin_oracle.c (sequential fp32 adds in edge order = what the CPU reference's scatter_add_ /
+    index_add_ do, models.py:208-215) bit for bit."""
+    import numpy as np
+    from oracle import c_oracle
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n_path, n_link, e, f = 900_000, 80_000, 9_960_000, 128
+    ei = torch.stack([torch.randint(0, n_path, (e,), generator=g, device="cuda"),
+                      torch.randint(0, n_link, (e,), generator=g, device="cuda")])
+    x = torch.randn(n_path, f, generator=g, device="cuda")
+    x_link = torch.randn(n_link, f, generator=g, device="cuda")
+    eps = torch.tensor([0.3], device="cuda")
+    fwd = ops.csr_build(ei, n_path, n_link, by="dst").validate()
+    bwd = ops.csr_build(ei, n_path, n_link, by="src").validate()
+    ei_h = ei.cpu().numpy()
+    rp, col, _ = c_oracle.csr_build(ei_h, n_path, n_link)
+    assert np.array_equal(rp, fwd.rowptr.cpu().numpy()) and np.array_equal(col, fwd.col.cpu().numpy())
+    rp_t, col_t, _ = c_oracle.csr_build(ei_h[::-1], n_link, n_path)
+    assert np.array_equal(rp_t, bwd.rowptr.cpu().numpy()) and np.array_equal(col_t, bwd.col.cpu().numpy())
+    # forward: link rows gather ~124 path rows each (table 461 MB >> L2), self term added
+    got = ops.gin_combine(fwd, x, x_link, eps, ops.SELF_ADD).cpu().numpy()
+    want = c_oracle.gin_combine(rp, col, x.cpu().numpy(), x_link.cpu().numpy(), 0.3, False)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # transposed (backward of index_select): path rows gather ~11 link rows each
+    gl = torch.randn(n_link, f, generator=g, device="cuda")
+    got_t = ops.gin_combine(bwd, gl).cpu().numpy()
+    want_t = c_oracle.gather_t(rp_t, col_t, gl.cpu().numpy())
+    assert np.array_equal(got_t.view(np.uint32), want_t.view(np.uint32))

@@ -1,0 +1,32 @@
+"""the module mirror consumes the global RNG in the reference's order (relations
+uses, includes, connects, has per layer, every Linear initialised at construction and again by
+`reset()`, models.py:195-199, 286-330), so constructing it under the reference's seed gives the
+reference's `state_dict` bit for bit.  The fixtures were recorded by oracle/make_golden.py from the
+UNMODIFIED reference (`train.load_model` after `torch.manual_seed(config["SEED"])`)."""
+import pytest
+import torch
+
+from conftest import MODEL_CASES, config_to_kwargs, load_golden
+from gnn_link_prediction_b200.models import HetroGIN
+from gnn_link_prediction_b200.synthetic import Topology, make_sample
+from gnn_link_prediction_b200.train import load_model
+
+
+@pytest.mark.parametrize("case", MODEL_CASES)
+def test_seed_for_seed_state_dict_equals_reference(case):
+    fx = load_golden(f"model_{case}.pt")
+    cfg = fx["config"]
+    torch.manual_seed(cfg["SEED"])
+    # the generator of the fixture built its samples between seeding and model construction
+    samples = [make_sample(Topology(*spec), seed=cfg["SEED"] + i) for i, spec in enumerate(fx["topologies"])]
+    model = HetroGIN(input_channels={"link": 7, "path": 7, "node": 3}, **config_to_kwargs(cfg))
+    sd = model.state_dict()
+    assert list(sd) == list(fx["state_dict"])
+    for k, v in sd.items():
+        assert torch.equal(v, fx["state_dict"][k]), k
+    # the same through the reference's own entry point, train.py:116-137
+    torch.manual_seed(cfg["SEED"])
+    samples = [make_sample(Topology(*spec), seed=cfg["SEED"] + i) for i, spec in enumerate(fx["topologies"])]
+    via_loader = load_model(cfg, {"train": [samples[0]]}).state_dict()
+    for k, v in via_loader.items():
+        assert torch.equal(v, fx["state_dict"][k]), k
