@@ -360,27 +360,46 @@ class DeviceDataset:
         return 4 * batch_size
 
 
+def global_steps(num_samples, batch_size, world):
+    """Steps per epoch that EVERY rank takes: global chunks of batch_size * world samples; the last partial
+    chunk counts only if it gives every rank at least one sample."""
+    step = batch_size * world
+    full, tail = divmod(num_samples, step)
+    return full + (1 if tail >= world else 0)
+
+
+def shard_id_batches(order, batch_size, rank, world):
+    """Rank `rank`'s id list for every global chunk of `order` (positions rank, rank+world, ...).  A final
+    chunk with fewer than `world` samples is dropped on all ranks: a rank with an empty shard would skip
+    the step and leave the others waiting in the all-reduce."""
+    step = batch_size * world
+    for lo in range(0, len(order), step):
+        chunk = order[lo:lo + step]
+        if len(chunk) < world:
+            return
+        yield chunk[rank::world]
+
+
 class DeviceLoader:
     """`DataLoader(dataset, batch_size, shuffle)` (dataset.py:242-244) over a `DeviceDataset`:
     yields batches assembled on the GPU; reshuffles every epoch with `generator`; `rank`/`world`
     shard the ids (rank r takes positions r, r+world, ... of every global batch), keeping the last
-    partial batch like the reference's loader."""
+    partial batch like the reference's loader.  Under data parallelism every rank must enter the two
+    all-reduces of a step, so a final chunk with fewer samples than ranks (some shards would be empty)
+    is dropped on ALL ranks; `len()` counts the steps every rank takes."""
 
     def __init__(self, dataset: DeviceDataset, batch_size=1, shuffle=False, generator=None, rank=0, world=1):
         self.dataset, self.batch_size, self.shuffle, self.generator = dataset, int(batch_size), shuffle, generator
         self.rank, self.world = rank, world
 
     def __len__(self):
-        return (len(self.dataset) + self.batch_size * self.world - 1) // (self.batch_size * self.world)
+        return global_steps(len(self.dataset), self.batch_size, self.world)
 
     def __iter__(self):
         n = len(self.dataset)
         order = torch.randperm(n, generator=self.generator).numpy() if self.shuffle else np.arange(n)
-        step = self.batch_size * self.world
-        for lo in range(0, n, step):
-            ids = order[lo:lo + step][self.rank::self.world]
-            if len(ids):
-                yield self.dataset.collate(ids)
+        for ids in shard_id_batches(order, self.batch_size, self.rank, self.world):
+            yield self.dataset.collate(ids)
 
 
 class HostLoader:
@@ -405,17 +424,13 @@ class HostLoader:
         self._bufs, self._last = [None] * ring, [None] * ring
 
     def __len__(self):
-        return self.epochs * ((len(self.arena) + self.batch_size * self.world - 1) // (self.batch_size * self.world))
+        return self.epochs * global_steps(len(self.arena), self.batch_size, self.world)
 
     def _id_batches(self):
         n = len(self.arena)
-        step = self.batch_size * self.world
         for _ in range(self.epochs):           # `epochs` > 1: one uninterrupted stream, reshuffled per epoch
             order = torch.randperm(n, generator=self.generator).numpy() if self.shuffle else np.arange(n)
-            for lo in range(0, n, step):
-                ids = order[lo:lo + step][self.rank::self.world]
-                if len(ids):
-                    yield ids
+            yield from shard_id_batches(order, self.batch_size, self.rank, self.world)
 
     def __iter__(self):
         import queue
@@ -450,6 +465,10 @@ class HostLoader:
                 if isinstance(item, BaseException):
                     raise item
                 yield item
+                # control returns here when the consumer asks for the NEXT batch.  A consumer that stages
+                # through DevicePrefetcher / GraphedTrainStep has left its copy event on the batch by then; one
+                # that read the host buffer itself (CPU use, its own synchronous copy) is simply done with it.
+                item.released = True
         finally:
             stop.set()
             for b in self._last:
@@ -460,7 +479,8 @@ class HostLoader:
         prev = self._last[slot]
         if prev is not None and torch.cuda.is_available():
             import time
-            while prev.copied is None and not prev.abandoned:      # taken from the queue but not staged yet (rare)
+            # still queued, or taken from the queue but not staged yet (rare): wait for the hand-off
+            while prev.copied is None and not prev.abandoned and not getattr(prev, "released", False):
                 time.sleep(0.0002)
             if prev.copied is not None:
                 prev.copied.synchronize()                          # its H2D copy has left this buffer

@@ -13,6 +13,8 @@ Host-side only: no arithmetic on features happens here.
 """
 from __future__ import annotations
 
+import collections
+
 import torch
 
 # Relation order of the reference's HeteroData (dataset.py:112-117).
@@ -125,7 +127,12 @@ class HeteroData:
 
 
 CSR_KEYS = ("csr_dst_rowptr", "csr_dst_col", "csr_src_rowptr", "csr_src_col")
-_CSR_CACHE = {}   # id(edge_index tensor) -> (tensor kept alive, per-sample CSR dict): shared topologies build once
+# id(edge_index tensor) -> (tensor kept alive, per-sample CSR dict): samples that SHARE one edge_index object (the
+# synthetic generator reuses a topology's tensors) build their CSRs once.  Bounded LRU: a dataset that loads a fresh
+# tensor per __getitem__ (the reference's torch.load per access, dataset.py:160-163) never hits it, and must not
+# grow it without limit — keep the CSRs on the samples / in a SampleArena instead (attach_csr stores them there).
+_CSR_CACHE = collections.OrderedDict()
+_CSR_CACHE_MAX = 256
 
 
 def attach_csr(sample, edge_types=None):
@@ -141,6 +148,10 @@ def attach_csr(sample, edge_types=None):
             continue
         ei = store["edge_index"]
         hit = _CSR_CACHE.get(id(ei))
+        if hit is not None and hit[0] is not ei:      # id() of a dead tensor reused by a new one
+            hit = None
+        if hit is not None:
+            _CSR_CACHE.move_to_end(id(ei))
         if hit is None:
             n_src, n_dst = sample[et[0]]["x"].shape[0], sample[et[2]]["x"].shape[0]
             dev = ei.cuda()
@@ -149,6 +160,8 @@ def attach_csr(sample, edge_types=None):
             hit = (ei, {"csr_dst_rowptr": by_dst.rowptr.cpu(), "csr_dst_col": by_dst.col.cpu(),
                         "csr_src_rowptr": by_src.rowptr.cpu(), "csr_src_col": by_src.col.cpu()})
             _CSR_CACHE[id(ei)] = hit
+            while len(_CSR_CACHE) > _CSR_CACHE_MAX:
+                _CSR_CACHE.popitem(last=False)
         store.update(hit[1])
     return sample
 
@@ -337,6 +350,7 @@ class PackedBatch:
         self.buffer, self.layout, self.num_graphs = buffer, layout, num_graphs
         self.copied = None        # CUDA event of the H2D copy out of `buffer` (set by DevicePrefetcher)
         self.abandoned = False    # the consumer went away without copying it
+        self.released = False     # the consumer asked its loader for the next batch (it is done with this one)
 
     @property
     def signature(self):

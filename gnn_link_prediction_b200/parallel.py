@@ -23,7 +23,12 @@ import torch.distributed as dist
 
 
 def shard_samples(num_samples: int, rank: int, world: int):
-    """Rank r of W takes samples r, r+W, ... of the global batch."""
+    """Rank r of W takes samples r, r+W, ... of the global batch.  Every rank must hold at least one
+    sample (all ranks enter both all-reduces of the step): fewer samples than ranks is an error here;
+    the loaders (arena.shard_id_batches) drop such a tail on all ranks instead."""
+    if num_samples < world:
+        raise ValueError(f"shard_samples: {num_samples} samples cannot be sharded over {world} ranks "
+                         "(a rank with an empty shard would skip the step's all-reduces)")
     return list(range(rank, num_samples, world))
 
 

@@ -316,6 +316,8 @@ class GraphedTrainStep:
                     ready = torch.cuda.Event()
                     ready.record(side)
                 cur.wait_event(ready)
+                if hasattr(batch, "copied"):
+                    batch.copied = ready           # arena.HostLoader reuses the pinned slot after this event
             entry["graph"].replay()
             entry["done"] = torch.cuda.Event()
             entry["done"].record(cur)

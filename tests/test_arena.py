@@ -108,24 +108,26 @@ def test_device_loader_shards_every_global_batch_across_ranks():
         def collate(self, ids):
             return list(int(i) for i in ids)
 
-    for n, bs, world in [(37, 4, 3), (64, 8, 2), (5, 8, 4), (16, 4, 1)]:
+    # (37, 4, 3): tail of 1 < 3 ranks; (33, 4, 4): tail of 1 < 4 ranks; (5, 8, 4): one chunk of 5 >= 4 ranks is kept
+    for n, bs, world in [(37, 4, 3), (64, 8, 2), (5, 8, 4), (16, 4, 1), (33, 4, 4), (3, 8, 4)]:
         per_rank = []
         for rank in range(world):
             loader = DeviceLoader(Stub(n), batch_size=bs, shuffle=True, generator=torch.Generator().manual_seed(9),
                                   rank=rank, world=world)
             batches = list(loader)
-            assert len(batches) <= len(loader) and all(1 <= len(b) <= bs for b in batches)
+            # EVERY rank takes exactly len(loader) steps with a non-empty shard (both all-reduces of a step are
+            # entered by all ranks): a final chunk with fewer samples than ranks is dropped everywhere
+            assert len(batches) == len(loader) and all(1 <= len(b) <= bs for b in batches)
             per_rank.append(batches)
-        seen = sorted(i for batches in per_rank for b in batches for i in b)
-        assert seen == list(range(n))                                    # one epoch, every sample exactly once
-        order = torch.randperm(n, generator=torch.Generator().manual_seed(9)).tolist()
         step = bs * world
-        for g, lo in enumerate(range(0, n, step)):                       # global batch g, split round-robin
+        kept = n - (n % step if n % step < world else 0)
+        order = torch.randperm(n, generator=torch.Generator().manual_seed(9)).tolist()
+        seen = sorted(i for batches in per_rank for b in batches for i in b)
+        assert seen == sorted(order[:kept])                               # every kept sample exactly once
+        for g, lo in enumerate(range(0, kept, step)):                    # global batch g, split round-robin
             chunk = order[lo:lo + step]
             for rank in range(world):
-                want = chunk[rank::world]
-                if want:
-                    assert per_rank[rank][g] == want
+                assert per_rank[rank][g] == chunk[rank::world]
     plain = list(DeviceLoader(Stub(10), batch_size=4))
     assert plain == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]]                  # shuffle=False keeps dataset order
 
@@ -173,12 +175,29 @@ def test_host_loader_streams_an_epoch_through_a_buffer_ring():
             _assert_views_equal_host_batch(packed.views(), _host_batch(samples, ids), len(ids))
             seen += packed.num_graphs
         assert seen == 9 and len(loader) == 5
-    per_rank = [sum(p.num_graphs for p in HostLoader(arena, batch_size=2, shuffle=True, pin=False,
-                                                      generator=torch.Generator().manual_seed(1), rank=r, world=2))
+    per_rank = [[p.num_graphs for p in HostLoader(arena, batch_size=2, shuffle=True, pin=False,
+                                                   generator=torch.Generator().manual_seed(1), rank=r, world=2)]
                 for r in range(2)]
-    assert sum(per_rank) == 9
+    # 9 samples, global chunks of 4: two full chunks, then a tail of 1 < 2 ranks that every rank drops
+    assert per_rank == [[2, 2], [2, 2]]
     with pytest.raises(ValueError):
         HostLoader(arena, ring=2)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(120)
+def test_host_loader_iterated_directly_on_a_gpu_box_does_not_wait_for_a_staging_event():
+    """A consumer that reads the pinned batches itself (no DevicePrefetcher, so nobody sets `copied`) must not
+    stall the producer when the ring wraps: asking for the next batch releases the previous one."""
+    samples = _ragged_samples(with_csr=True)
+    arena = SampleArena.from_samples(samples, keep_coo=False)
+    loader = HostLoader(arena, batch_size=1, shuffle=False, ring=3, pin=True)
+    seen = []
+    for k, packed in enumerate(loader):                      # 9 batches through 3 pinned slots
+        dev = packed.views(packed.buffer.cuda())             # the consumer's own synchronous copy
+        _assert_views_equal_host_batch(dev, _host_batch(samples, [k]), 1)
+        seen.append(packed.num_graphs)
+    assert seen == [1] * 9
 
 
 # ---- on-GPU collate -----------------------------------------------------------------------------

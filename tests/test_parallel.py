@@ -73,9 +73,48 @@ def test_two_rank_gloo_equals_single_process(tmp_path, num_samples):
 
 
 def test_shard_samples_partitions_the_batch():
-    for n, w in [(8, 2), (5, 2), (1024, 8), (3, 4)]:
+    for n, w in [(8, 2), (5, 2), (1024, 8), (4, 4)]:
         parts = [shard_samples(n, r, w) for r in range(w)]
-        assert sorted(i for p in parts for i in p) == list(range(n))
+        assert sorted(i for p in parts for i in p) == list(range(n)) and all(parts)
+    with pytest.raises(ValueError):          # a rank with no samples would skip the step's all-reduces
+        shard_samples(3, 0, 4)
+
+
+def _loader_worker(rank, world, port, n, bs, out_dir):
+    """Every rank iterates its shard of the loader and enters one all-reduce per step: with a ragged tail
+    (n % (bs * world) == 1) a loader that yields on some ranks only would hang here."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import datetime
+    import torch.distributed as dist
+    from gnn_link_prediction_b200.arena import DeviceLoader
+    dist.init_process_group("gloo", timeout=datetime.timedelta(seconds=30))
+
+    class Stub:
+        def __len__(self):
+            return n
+
+        def collate(self, ids):
+            return [int(i) for i in ids]
+
+    loader = DeviceLoader(Stub(), batch_size=bs, shuffle=True, generator=torch.Generator().manual_seed(2), rank=rank,
+                          world=world)
+    steps, total = 0, torch.zeros(1)
+    for ids in loader:
+        t = torch.tensor([float(len(ids))])
+        dist.all_reduce(t)
+        total += t
+        steps += 1
+    assert steps == len(loader)
+    if rank == 0:
+        torch.save({"steps": steps, "total": float(total)}, os.path.join(out_dir, "loader.pt"))
+    dist.destroy_process_group()
+
+
+def test_two_rank_loader_with_ragged_tail_keeps_ranks_in_step(tmp_path):
+    n, bs, world = 9, 2, 2                   # 9 % (2 * 2) == 1: the last chunk has one sample for two ranks
+    mp.spawn(_loader_worker, args=(world, _free_port(), n, bs, str(tmp_path)), nprocs=world, join=True)
+    got = torch.load(tmp_path / "loader.pt")
+    assert got == {"steps": 2, "total": 8.0}
 
 
 def _gpu_worker(rank, world, port, num_samples, out_dir):
