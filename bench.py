@@ -131,13 +131,24 @@ def copy_batch_to_device(host):
     return dev
 
 
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+CPU_SAMPLE = {"cfgA": (8, 40), "cfgC": (256, 4)}     # (topologies per step, timed steps) of the CPU arms
+
+
 def cpu_reference_run(w, sample_graphs, steps, warmup, threads=None):
     """The reference's CPU path (oracle port) on a bounded sample: `sample_graphs` topologies per step."""
     from oracle import hgin_oracle
     from gnn_link_prediction_b200.data import Batch
     from gnn_link_prediction_b200.synthetic import SyntheticDataset
-    if threads:
-        torch.set_num_threads(threads)
+    # all host cores this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    # silently time the CPU arm on ONE thread
+    torch.set_num_threads(threads or host_cores())
     cores = torch.get_num_threads()
     ds = SyntheticDataset(sample_graphs, num_topologies=min(16, sample_graphs))
     batch = Batch.from_data_list([ds[i] for i in range(sample_graphs)])
@@ -162,11 +173,12 @@ def cpu_reference_run(w, sample_graphs, steps, warmup, threads=None):
 def run_reference(args, w, rank):
     if rank != 0:
         return
-    # a bounded sample of the workload: cfgA is the reference's own batch of 8; cfgC runs 128 of the 1024
-    # topologies per step (~1 s per step on 16 host threads), so a few steps give a stable number
-    sample = 8 if args.workload == "cfgA" else 128
-    steps = max(1, min(args.steps, 40 if args.workload == "cfgA" else 6))
-    r = cpu_reference_run(w, sample, steps, min(args.warmup, 1))
+    # a bounded sample of the workload: cfgA is the reference's own batch of 8; cfgC runs 256 of the 1024
+    # topologies per step (~2 s per step on 16 host threads; graphs/s is flat in the batch size from 128 up,
+    # DESIGN.md), so a few steps give a stable number.  ALL host cores, also under torchrun.
+    sample, max_steps = CPU_SAMPLE[args.workload]
+    steps = max(1, min(args.steps, max_steps))
+    r = cpu_reference_run(w, sample, steps, min(args.warmup, 1), threads=host_cores())
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "graphs/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -431,10 +443,26 @@ def main():
         barrier()
         hs_ms = ha.elapsed_time(hb)
 
+    # ---- strong-scaling arm: the SAME global batch (w["batch"] topologies) split over the
+    # ranks, batch resident in HBM; reported beside the weak-scaling `value`.
+    strong_ms, strong_graphs = 0.0, 0
+    if world > 1 and not graphed and w["batch"] % world == 0:
+        from gnn_link_prediction_b200.data import Batch, CONV_EDGE_TYPES
+        share = w["batch"] // world
+        strong_graphs = share * world
+        sb = copy_batch_to_device(Batch.from_data_list(ALL_SAMPLES[:share], index_dtype=torch.int32,
+                                                       edge_types=CONV_EDGE_TYPES, batch_vector=False, csr=True,
+                                                       keep_coo=False))
+        for _ in range(args.warmup):
+            step(sb)
+        barrier()
+        strong_ms = sum(timed_steps(lambda i: step(sb), args.steps, flush))
+        barrier()
+
     # max over ranks (device time)
-    t = torch.tensor([resident_ms, e2e_ms, dd_ms, hs_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([resident_ms, e2e_ms, dd_ms, hs_ms, strong_ms], dtype=torch.float64, device="cuda")
     comm.all_reduce_max_(t)
-    resident_ms, e2e_ms, dd_ms, hs_ms = (float(v) for v in t.tolist())
+    resident_ms, e2e_ms, dd_ms, hs_ms, strong_ms = (float(v) for v in t.tolist())
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
@@ -468,12 +496,29 @@ def main():
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        sample = 8 if small else 128
-        r = cpu_reference_run(w, sample, 40 if small else 6, 1)
+        sample, cpu_steps = CPU_SAMPLE[args.workload]
+        r = cpu_reference_run(w, sample, cpu_steps, 1, threads=host_cores())
         cpu_baseline = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     launches = kernels_per_step * args.steps
     value = graphs * world * args.steps / (resident_ms * 1e-3)
+    e2e_pre = {"value": graphs * world * args.steps / (e2e_ms * 1e-3), "unit": "graphs/s",
+               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8, "ms_per_step": e2e_ms / args.steps,
+               "collate": "outside the timed region (two pre-collated, pre-packed pinned batches cycled)",
+               "staging": "one packed pinned buffer per batch -> ping-pong static buffers of two CUDA graphs, copied on a copy stream" if graphed
+               else ("one packed pinned buffer per batch -> DevicePrefetcher ring" if args.stage == "packed"
+                     else "one H2D copy per tensor (DevicePrefetcher)"),
+               "readback": "every step, collected one step later (train.LossReadback)" if args.readback == "deferred"
+               else "every step, blocking"}
+    # the parsed end-to-end number: a FRESH shuffled batch is collated from host-resident samples INSIDE the timed
+    # region every step (native host collate on a background thread into a pinned ring), copied with one DMA,
+    # trained on, and its loss read back.  (cfgA under a CUDA graph has no streaming loader arm: pre-collated.)
+    e2e_main = e2e_pre if hs_steps == 0 else {
+        "value": graphs * world * hs_steps / (hs_ms * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": h2d_bytes,
+        "d2h_bytes_per_step": 8, "ms_per_step": hs_ms / hs_steps,
+        "collate": "inside the timed region (arena.HostLoader: native host collate of a fresh shuffled batch per step)",
+        "staging": "one packed pinned buffer per batch -> DevicePrefetcher ring (one DMA per step)",
+        "readback": "every step, collected one step later (train.LossReadback)"}
     line = {
         "metric": METRIC, "value": value, "unit": "graphs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": resident_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -484,23 +529,18 @@ def main():
                    "collate": args.collate,
                    "parallelism": f"dp{world} (samples sharded, NCCL sum-allreduce of one flat grad bucket)"},
         "edges_per_s": edges * world * args.steps / (resident_ms * 1e-3),
-        "e2e": {"value": graphs * world * args.steps / (e2e_ms * 1e-3), "unit": "graphs/s",
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8, "ms_per_step": e2e_ms / args.steps,
-                "staging": "one packed pinned buffer per batch -> ping-pong static buffers of two CUDA graphs, copied on a copy stream" if graphed
-                else ("one packed pinned buffer per batch -> DevicePrefetcher ring" if args.stage == "packed"
-                      else "one H2D copy per tensor (DevicePrefetcher)"),
-                "readback": "every step, collected one step later (train.LossReadback)" if args.readback == "deferred"
-                else "every step, blocking"},
+        "e2e": e2e_main,
+        "e2e_precollated": e2e_pre if e2e_main is not e2e_pre else None,
         "e2e_device_dataset": None if dd_ms == 0.0 else {
             "value": graphs * world * args.steps / (dd_ms * 1e-3), "unit": "graphs/s", "ms_per_step": dd_ms / args.steps,
             "h2d_bytes_per_step": dd_bytes, "d2h_bytes_per_step": 8, "collate_ms_per_step": dd_collate_ms,
             "what": "dataset resident in HBM (arena.DeviceDataset); every step: H2D of the sample ids, on-GPU collate "
                     "of a fresh random batch, train step, loss read-back"},
-        "e2e_host_stream": None if hs_steps == 0 else {
-            "value": graphs * world * hs_steps / (hs_ms * 1e-3), "unit": "graphs/s", "ms_per_step": hs_ms / hs_steps,
-            "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
-            "what": "dataset in host memory (arena.SampleArena); every step: native host collate of a fresh shuffled batch "
-                    "(background thread, pinned ring), one H2D DMA, train step, loss read-back; host-memory-bandwidth bound"},
+        "strong_scaling": None if strong_ms == 0.0 else {
+            "value": strong_graphs * args.steps / (strong_ms * 1e-3), "unit": "graphs/s",
+            "ms_per_step": strong_ms / args.steps, "global_batch": strong_graphs, "graphs_per_gpu_per_step": strong_graphs // world,
+            "what": "strong scaling: the 1-GPU global batch split over the ranks (batch resident in HBM), beside the "
+                    "weak-scaling `value`"},
         "gpu_launches": launches, "kernels_per_step": kernels_per_step,
         "execution": "one CUDA graph replay per step (GraphedTrainStep)" if graphed else "eager launches",
         "wall_s_resident": t_wall, "peak_hbm_gb": torch.cuda.max_memory_allocated() / 1e9,
