@@ -47,6 +47,9 @@ SIGNATURES = {
     "hgin_linear_bwd_post": (_i32, [_i64, _ptr, _i64, _ptr, _i64, _i32, _ptr, _ptr, _i64, _i32, _ptr, _i64, _i32, _ptr,
                                     _i32, _i32, _i32, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _ptr, _ptr,
                                     _ptr, _i64, _i32, _ptr]),
+    "hgin_linear_bwd_post_self": (_i32, [_i64, _ptr, _i64, _ptr, _i64, _i32, _ptr, _ptr, _i64, _i32, _ptr, _i32, _ptr, _i64,
+                                         _ptr, _ptr, _ptr, _ptr, _i64, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32,
+                                         _ptr]),
     "hgin_reduce_workspace_bytes": (_i64, [_i64]),
     "hgin_mape_sum": (_i32, [_i64, _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
     "hgin_sqrt_mape_bwd": (_i32, [_i64, _ptr, _ptr, _ptr, _f32, _ptr, _ptr, _ptr]),

@@ -416,7 +416,7 @@ static int32_t linear_bwd_impl(int64_t rows, const float *g, int64_t ldg, const 
     const bool tc_ok = math_mode == HGIN_MATH_TF32 && rows > 0 &&
         tcgemm::bwd_eligible(rows, g, ldg, z, ldz, act, x1, ld1, k1, k2, n, c0, c1, dx, lddx, dot_x, ld_dot) &&
         (!post || (c1 - c0 >= 16 && post->ldz % 4 == 0 && aligned16(post->z)));
-    if (rows > 0 && thin::head_bwd_eligible(x1, ld1, k1, k2, n, c0, c1, dx, lddx, dot_x, W) && !ddot &&
+    if (rows > 0 && thin::head_bwd_eligible(x1, ld1, k1, k2, n, c0, c1, dx, lddx, dot_x, W) && !ddot && !(post && post->self_eps) &&
         (!post || (post->ldz % 4 == 0 && aligned16(post->z))))
         return thin::head_bwd(rows, g, ldg, z, ldz, act, alpha, x1, ld1, k1, W, dx, lddx, dW, db, dalpha, workspace,
                               post ? post->z : nullptr, post ? post->ldz : 0, post ? post->act : HGIN_ACT_NONE,
@@ -535,7 +535,7 @@ extern "C" int32_t hgin_linear_bwd_post(int64_t rows, const float *g, int64_t ld
         return linear_bwd_impl(rows, g, ldg, z, ldz, act, alpha, x1, ld1, k1, x2, ld2, k2, W, n, c0, c1, dx, lddx, nullptr,
                                0, nullptr, dW, db, dalpha, workspace, workspace_bytes, math_mode, stream, nullptr);
     }
-    tcgemm::PostArgs post{post_z, ld_post, post_act, post_alpha, post_dalpha};
+    tcgemm::PostArgs post{post_z, ld_post, post_act, post_alpha, post_dalpha, nullptr, nullptr};
     int32_t rc = linear_bwd_impl(rows, g, ldg, z, ldz, act, alpha, x1, ld1, k1, x2, ld2, k2, W, n, c0, c1, dx, lddx,
                                  nullptr, 0, nullptr, dW, db, dalpha, workspace, workspace_bytes, math_mode, stream, &post);
     if (rc != HGIN_ERR_UNSUPPORTED) return rc;
@@ -556,6 +556,28 @@ extern "C" int32_t hgin_linear_bwd_post(int64_t rows, const float *g, int64_t ld
     if (post_dalpha && (!want || rows == 0)) cudaMemsetAsync(post_dalpha, 0, sizeof(float), s);
     HGIN_CHECK_LAUNCH("hgin_linear_bwd_post");
     return HGIN_OK;
+}
+
+extern "C" int32_t hgin_linear_bwd_post_self(int64_t rows, const float *g, int64_t ldg, const float *z, int64_t ldz,
+                                             int32_t act, const float *alpha, const float *x1, int64_t ld1, int32_t k1,
+                                             const float *W, int32_t n, float *dx, int64_t lddx, float *dW, float *db,
+                                             float *dalpha, const float *post_z, int64_t ld_post, int32_t post_act,
+                                             const float *post_alpha, float *post_dalpha, const float *self_eps,
+                                             float *post_ddot, void *workspace, int64_t workspace_bytes,
+                                             int32_t math_mode, void *stream) {
+    using namespace hgin;
+    HGIN_CHECK_ARG(post_act == HGIN_ACT_PRELU || post_act == HGIN_ACT_RELU, "hgin_linear_bwd_post_self: bad post_act %d", post_act);
+    HGIN_CHECK_ARG(post_z && dx && ld_post >= k1, "hgin_linear_bwd_post_self: needs post_z [rows, k1] and dx");
+    HGIN_CHECK_ARG(post_act != HGIN_ACT_PRELU || post_alpha, "hgin_linear_bwd_post_self: PReLU needs post_alpha");
+    tcgemm::PostArgs post{post_z, ld_post, post_act, post_alpha, post_dalpha, self_eps, post_ddot};
+    // only the tensor-core input-gradient kernel carries this epilogue: other shapes / math modes return
+    // HGIN_ERR_UNSUPPORTED and the caller runs hgin_linear_bwd + hgin_gin_combine_post instead
+    const int32_t rc = linear_bwd_impl(rows, g, ldg, z, ldz, act, alpha, x1, ld1, k1, nullptr, 0, 0, W, n, 0, k1, dx, lddx,
+                                       nullptr, 0, nullptr, dW, db, dalpha, workspace, workspace_bytes, math_mode, stream,
+                                       &post);
+    if (rc == HGIN_ERR_UNSUPPORTED)
+        return fail(HGIN_ERR_UNSUPPORTED, "hgin_linear_bwd_post_self: shapes / math mode outside the tensor-core path");
+    return rc;
 }
 
 extern "C" int32_t hgin_debug_gemm_tn(int64_t rows, const float *a, int32_t n, const float *b, int32_t k, float *out,

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) transpose_cols_kernel(const float *__rest
 // Partial layout: part[cta][nn][k2 + 1] with the LAST column = db (same convention as the SIMT
 // weight-gradient partials), alpha_part[cta].
 constexpr int DZ_THREADS = 256;
-__global__ void __launch_bounds__(DZ_THREADS, 3)
+__global__ void __launch_bounds__(DZ_THREADS, 2)
 dz_prepare_kernel(int64_t rows, int n, const float *__restrict__ g, int64_t ldg, const float *__restrict__ z,
                   int64_t ldz, int act, const float *__restrict__ alpha_ptr, const float *__restrict__ x2,
                   int64_t ld2, int k2, float *__restrict__ dz, float *__restrict__ part,
@@ -91,14 +91,22 @@ dz_prepare_kernel(int64_t rows, int n, const float *__restrict__ g, int64_t ldg,
         const int64_t stride = static_cast<int64_t>(gridDim.x) * slots;
         for (int64_t m0 = static_cast<int64_t>(blockIdx.x) * slots + slot; m0 < rows; m0 += stride * RIF) {
             float4 gq[RIF], zq[RIF];
+            float xq[RIF][4];   // the rank-k2 tail's input columns, requested with the rows (not after them)
 #pragma unroll
             for (int u = 0; u < RIF; ++u) {
                 const int64_t m = m0 + u * stride;
                 gq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 zq[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) xq[u][t] = 0.f;
                 if (m < rows) {
                     gq[u] = __ldg(reinterpret_cast<const float4 *>(g + m * ldg) + cg);
                     if (act != HGIN_ACT_NONE) zq[u] = __ldg(reinterpret_cast<const float4 *>(z + m * ldz) + cg);
+                    if (want_sums) {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            if (t < k2) xq[u][t] = __ldg(x2 + m * ld2 + t);
+                    }
                 }
             }
 #pragma unroll
@@ -116,8 +124,7 @@ dz_prepare_kernel(int64_t rows, int n, const float *__restrict__ g, int64_t ldg,
                 }
                 if (write_dz) reinterpret_cast<float4 *>(dz + m * n)[cg] = make_float4(d[0], d[1], d[2], d[3]);
                 if (want_sums) {
-                    float xv[4] = {0.f, 0.f, 0.f, 0.f};
-                    for (int t = 0; t < k2; ++t) xv[t] = __ldg(x2 + m * ld2 + t);
+                    const float xv[4] = {xq[u][0], xq[u][1], xq[u][2], xq[u][3]};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         db[i] += d[i];
@@ -207,7 +214,7 @@ bool bwd_eligible(int64_t rows, const float *g, int64_t ldg, const float *z, int
            encode_fn() != nullptr;
 }
 
-static int dz_ctas() { return kNumSMs * 3; }   // 80 registers/thread: three resident CTAs per SM
+static int dz_ctas() { return kNumSMs * 2; }   // two resident CTAs per SM (the tail accumulators need > 80 registers)
 
 int64_t fwd_workspace_bytes(int k1, int n) { return align_up(static_cast<int64_t>(n) * k1 * 4, 1024) + 1024; }
 
@@ -218,7 +225,7 @@ int64_t bwd_workspace_bytes(int64_t rows, int k1, int k2, int n) {
     b += align_up(static_cast<int64_t>(dz_ctas()) * n * (k2 + 1) * 4, 1024);  // db / tail partials
     b += align_up(static_cast<int64_t>(kNumSMs) * 4 * 4, 1024);            // dalpha partials (<= 4 per CTA of the fused kernels)
     b += align_up(static_cast<int64_t>(kNumSMs) * n * k1 * 4, 1024);       // dW partials
-    b += align_up(static_cast<int64_t>(kNumSMs) * 4, 1024);                // dot partials
+    b += align_up(static_cast<int64_t>(kNumSMs) * 4 * 2, 1024);            // dot / dot2 partials
     b += align_up(static_cast<int64_t>(kNumSMs) * n * 4, 1024);            // db partials of the weight-gradient kernel
     return b + 1024;
 }
@@ -321,7 +328,8 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
     float *sum_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(dz_ctas()) * n * (k2 + 1) * 4));
     float *alpha_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(kNumSMs) * 4 * 4));
     float *dw_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(kNumSMs) * n * k1 * 4));
-    float *dot_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(kNumSMs) * 4));
+    float *dot_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(kNumSMs) * 4 * 2));
+    float *dot2_part = dot_part + kNumSMs;
     float *db_part = reinterpret_cast<float *>(carve(ws, static_cast<int64_t>(kNumSMs) * n * 4));
 
     // 0. fused single-pass backward when the shapes allow it (linear_tc_fused.cuh)
@@ -468,14 +476,18 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
         p.use_e = post_on ? 2 : (ddot != nullptr ? 1 : 0);
         const bool post_alpha = post_on && post->dalpha && post->act == HGIN_ACT_PRELU;
         p.dot_partials = (ddot || post_alpha) ? dot_part : nullptr;
+        p.self_eps = post_on ? post->self_eps : nullptr;
+        p.dot2_partials = (post_on && post->ddot) ? dot2_part : nullptr;
         const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
         gemm_nt_kernel<EPI_DX><<<grid, NT_THREADS, NtSmem::total, s>>>(tm_a, tm_b, tm_o, tm_o, tm_e, p);
         if (ddot) reduce_scalar_tc_kernel<<<1, 1024, 0, s>>>(dot_part, grid, ddot);
+        if (p.dot2_partials) reduce_scalar_tc_kernel<<<1, 1024, 0, s>>>(dot2_part, grid, post->ddot);
         if (post_alpha) reduce_scalar_tc_kernel<<<1, 1024, 0, s>>>(dot_part, grid, post->dalpha);
         else if (post && post->dalpha) cudaMemsetAsync(post->dalpha, 0, sizeof(float), s);
     } else {
         if (ddot) cudaMemsetAsync(ddot, 0, sizeof(float), s);
         if (post && post->dalpha) cudaMemsetAsync(post->dalpha, 0, sizeof(float), s);
+        if (post && post->ddot) cudaMemsetAsync(post->ddot, 0, sizeof(float), s);
     }
 
     // 3. weight gradient: dW[:, :k1] = dz^T x1 (unless step 1 already produced it)

@@ -62,6 +62,11 @@ struct NtParams {
                       // (act / alpha describe THAT layer) and dot_partials receive sum dx * min(e, 0)
     // EPI_DX
     float *dot_partials;  // [gridDim.x]
+    // EPI_DX with use_e == 2, GIN self branch riding on the epilogue (hgin_linear_bwd_post_self): the tile
+    // D = dz W is dh_self; it leaves as (1 + eps) * D * act'(e), and dot2_partials receive sum D * act(e)
+    // = d(eps) (act(e) is x_dst, the output of the layer below)
+    const float *self_eps;
+    float *dot2_partials; // [gridDim.x] or NULL
 };
 
 // Shared-memory carve-up (dynamic smem, base aligned to 1024 B by the kernel).
@@ -213,6 +218,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             named_barrier(EPI_ALL_BAR, 256);
         }
         const float alpha = (p.act == HGIN_ACT_PRELU) ? __ldg(p.alpha) : 0.0f;
+        const float self_scale = (EPI == EPI_DX && p.self_eps) ? __fadd_rn(1.0f, __ldg(p.self_eps)) : 1.0f;
+        float dot2 = 0.0f;
         // this group's staging tiles (st0: out / dx, st1: z) and epilogue-operand buffer
         const uint32_t sa0 = smem_u32(smem_stage + grp * 2 * TILE_BYTES);
         const uint32_t sa1 = sa0 + TILE_BYTES;
@@ -283,10 +290,15 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                     }
                 } else if (p.use_e == 2) {
                     // rows past the end and OOB columns: v == 0 or e == 0, so they add nothing to dot
+                    if (p.dot2_partials) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) dot2 = fmaf(v[j], act_forward(ev[j], p.act, alpha), dot2);
+                    }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        if (p.act == HGIN_ACT_PRELU && !(ev[j] > 0.f)) dot = fmaf(v[j], ev[j], dot);
-                        v[j] = act_backward(v[j], ev[j], p.act, alpha);
+                        const float rr = p.self_eps ? __fmul_rn(self_scale, v[j]) : v[j];
+                        if (p.act == HGIN_ACT_PRELU && !(ev[j] > 0.f)) dot = fmaf(rr, ev[j], dot);
+                        v[j] = act_backward(rr, ev[j], p.act, alpha);
                     }
                 }
                 // the group's staging tiles are free once its previous TMA stores have read them
@@ -316,13 +328,19 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             }
         }
         if (gt == 0) tma_store_wait<0>();
-        if (EPI == EPI_DX && p.dot_partials) {
+        if (EPI == EPI_DX && (p.dot_partials || p.dot2_partials)) {
             dot = warp_sum(dot);
+            dot2 = warp_sum(dot2);
             float *red = bias_s;  // unused by EPI_DX
-            if (lane == 0) red[grp * 4 + q] = dot;
+            if (lane == 0) {
+                red[grp * 4 + q] = dot;
+                red[8 + grp * 4 + q] = dot2;
+            }
             named_barrier(EPI_ALL_BAR, 256);
-            if (et == 0)
+            if (et == 0 && p.dot_partials)
                 p.dot_partials[blockIdx.x] = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
+            if (et == 1 && p.dot2_partials)
+                p.dot2_partials[blockIdx.x] = ((red[8] + red[9]) + (red[10] + red[11])) + ((red[12] + red[13]) + (red[14] + red[15]));
         }
     }
     tcgen05_fence_before();

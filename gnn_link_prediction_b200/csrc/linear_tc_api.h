@@ -22,6 +22,10 @@ struct PostArgs {  // activation derivative of the layer BELOW, applied to dx on
     int act;
     const float *alpha;
     float *dalpha;  // [1] out: sum dx * min(z, 0), or NULL
+    // GIN self branch on the same epilogue (hgin_linear_bwd_post_self): dx leaves as (1 + eps) * (dz W) * act'(z)
+    // and ddot = sum (dz W) * act(z); both NULL for the plain post-activation
+    const float *self_eps;
+    float *ddot;
 };
 
 bool fused_bwd_enabled();

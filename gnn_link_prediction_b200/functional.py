@@ -182,6 +182,29 @@ class HeteroConvFn(torch.autograd.Function):
                 if need[nt + 4 * si + 3] and not specs[si].concat:
                     eps_from_pass[si] = t
 
+        # A relation whose self branch is the ONLY thing type t's gradient consists of (plan == one edgeless
+        # pass; e.g. the last GIN layer) hands that pass to the epilogue of its own input-gradient GEMM
+        # (hgin_linear_bwd_post_self): dh = dz W never reaches memory.  Its source-side gradient, a gather of dh
+        # rows over the transposed CSR, is then taken as  A^T (dz W) = (A^T dz) W : the gather reads dz (which IS in
+        # memory) and one source-sized GEMM follows — same bytes for the gather, two row-sized transfers less overall.
+        self_in_gemm = {}
+        for t in types:
+            post = ctx.links_in.get(t)
+            if (post is not None and post.usable() and len(plan[t]) == 1 and plan[t][0][0] is None):
+                si = plan[t][0][1]
+                sp = specs[si]
+                h_si, W_si = saved[2 * si], params[4 * si]
+                lo = ctx.links_out.get(sp.dst)
+                g_is_dz = sp.act == ACT_NONE or (lo is not None and lo.applied)
+                # (the gather of this relation must be the only pass of its source type, so that the pre-gathered
+                # term needs no pairing with another relation's self branch)
+                src_ok = (not need_x[sp.src]) or (g_is_dz and plan[sp.src] == [(si, None)])
+                if (not sp.concat and src_ok
+                        and ops.post_self_eligible(h_si.shape[0], h_si.shape[1], W_si.shape[0], ctx.math_mode)
+                        and tuple(post.z.shape) == tuple(h_si.shape) and post.z.stride(0) % 4 == 0
+                        and post.z.data_ptr() % 16 == 0):
+                    self_in_gemm[si] = t
+
         dh_agg_of, dh_self_of = {}, {}
         for i in live:
             sp = specs[i]
@@ -213,7 +236,17 @@ class HeteroConvFn(torch.autograd.Function):
                 # x_dst was handed over as a pre-activation: materialise act(z) for the d(eps) dot product
                 dot_x = torch.where(x_dst > 0, x_dst, (lz_dst.alpha * x_dst) if lz_dst.act == ops.ACT_PRELU
                                     else torch.zeros_like(x_dst))
-            if sp.concat:
+            if i in self_in_gemm:
+                post_t = ctx.links_in[self_in_gemm[i]]
+                r = ops.linear_bwd(g, z, h, W, dx_cols=(0, k), want_dx=True, want_dw=nW, want_db=bool(nb),
+                                   want_dalpha=nalpha_here, post=post_t, self_eps=eps, want_self_ddot=bool(neps),
+                                   **common)
+                dh_agg, dh_self = None, None
+                if want_agg:      # (A^T dz) W, see above; g is dz here
+                    gz = ops.gin_combine(graph.bwd(sp.et), g, None, None, SELF_NONE)
+                    dh_agg = ops.linear_bwd(gz, None, x_src, W, act=ACT_NONE, dx_cols=(0, k), want_dx=True, want_dw=False,
+                                            want_db=False, math_mode=ctx.math_mode)["dx"]
+            elif sp.concat:
                 r = ops.linear_bwd(g, z, h, W, dx_cols=(fs, k), want_dx=want_self, dot_x=dot_x,
                                    want_dw=nW, want_db=bool(nb), want_dalpha=nalpha_here, **common)
                 dh_self = r["dx"]
@@ -231,15 +264,28 @@ class HeteroConvFn(torch.autograd.Function):
                                         None if r["dalpha"] is None else r["dalpha"].view_as(alpha),
                                         None if r["ddot"] is None else r["ddot"].view_as(eps)]
             dh_agg_of[i], dh_self_of[i] = dh_agg, dh_self
+            if i in self_in_gemm:
+                dh_self_of[i] = r["dx"]      # already (1 + eps) * dh * act'(z below): the finished gradient of type t
 
         grads_x = []
+        done_types = set(self_in_gemm.values())
         for t in types:
+            if t in done_types:
+                si = plan[t][0][1]
+                grads_x.append(dh_self_of[si])
+                continue
             post = ctx.links_in.get(t)
             dx = None
             for j, (gi, si) in enumerate(plan[t]):
                 last = j == len(plan[t]) - 1
                 s_dh = dh_self_of[si] if si is not None else None
                 s_eps = params[4 * si + 3] if si is not None else None
+                if gi is not None and gi in self_in_gemm:
+                    # already gathered ((A^T dz) W) and, by the eligibility rule, the only term of this type
+                    dx = dh_agg_of[gi]
+                    if post is not None and post.usable():
+                        dx = ops.gin_combine(None, dx, dx, None, SELF_ADD, post=post)
+                    continue
                 csr_t = graph.bwd(specs[gi].et) if gi is not None else None
                 src_rows = dh_agg_of[gi] if gi is not None else s_dh
                 want_ddot = last and si is not None and eps_from_pass.get(si) == t

@@ -240,11 +240,15 @@ def linear_fwd(x1, W, bias=None, x2=None, act=ACT_NONE, alpha=None, want_z=True,
 
 
 def linear_bwd(g, z, x1, W, x2=None, act=ACT_NONE, alpha=None, dx_cols=None, want_dx=True, dot_x=None,
-               want_dw=True, want_db=True, want_dalpha=False, math_mode=MATH_FP32, post=None):
+               want_dw=True, want_db=True, want_dalpha=False, math_mode=MATH_FP32, post=None, self_eps=None,
+               want_self_ddot=False):
     """K3.  Returns dict(dx, ddot, dW, db, dalpha) with None for what was not requested.
     dx_cols=(c0,c1) restricts the input gradient to those columns of [x1|x2].
     act=ACT_NONE: g is dz itself (z may be None).  post: a PostAct for the layer that produced the
-    dx columns — dx leaves as that layer's dz and post.dalpha is filled (no dot_x then)."""
+    dx columns — dx leaves as that layer's dz and post.dalpha is filled (no dot_x then).
+    self_eps (with post, all of x1's columns, no x2; see `post_self_eligible`): the GIN self branch rides on the same
+    epilogue — dx = (1 + eps) * (dz W) * act'(post.z), and with want_self_ddot the result carries
+    ddot = sum (dz W) * act(post.z) = d(eps) (hgin_linear_bwd_post_self)."""
     pg, ldg = _f32_matrix(g, "linear_bwd.g")
     pz, ldz = _f32_matrix(z, "linear_bwd.z")
     p1, ld1 = _f32_matrix(x1, "linear_bwd.x1")
@@ -288,6 +292,19 @@ def linear_bwd(g, z, x1, W, x2=None, act=ACT_NONE, alpha=None, dx_cols=None, wan
         if tuple(post.z.shape) != (rows, c1 - c0):
             raise HginError(f"linear_bwd: post.z is {tuple(post.z.shape)}, expected {(rows, c1 - c0)}")
         post.dalpha = torch.empty(1, dtype=torch.float32, device=dev) if post.act == ACT_PRELU else None
+        if self_eps is not None:
+            if x2 is not None or (c0, c1) != (0, k1):
+                raise HginError("linear_bwd: the self-branch epilogue needs dx over all columns of x1 and no x2")
+            sddot = torch.empty(1, dtype=torch.float32, device=dev) if want_self_ddot else None
+            with _region("linear_bwd", kernels=n_kernels + 1 + int(want_self_ddot), flops=flops, bytes=4 * rows * moved):
+                check(lib.hgin_linear_bwd_post_self(rows, pg, ldg, pz, ldz, act, _scalar(alpha, "linear_bwd.alpha"), p1,
+                                                    ld1, k1, W.data_ptr(), n, pdx, lddx, _ptr(dW), _ptr(db), _ptr(dalpha),
+                                                    ppz, ldpz, post.act, _scalar(post.alpha, "linear_bwd.post.alpha"),
+                                                    _ptr(post.dalpha), _scalar(self_eps, "linear_bwd.self_eps"),
+                                                    _ptr(sddot), ws.data_ptr(), ws_bytes, math_mode, _stream()),
+                      "hgin_linear_bwd_post_self")
+            post.applied = True
+            return {"dx": dx, "ddot": sddot, "dW": dW, "db": db, "dalpha": dalpha}
         with _region("linear_bwd", kernels=n_kernels + 1, flops=flops, bytes=4 * rows * moved):
             check(lib.hgin_linear_bwd_post(rows, pg, ldg, pz, ldz, act, _scalar(alpha, "linear_bwd.alpha"), p1, ld1, k1,
                                            p2, ld2, k2, W.data_ptr(), n, c0, c1, pdx, lddx, _ptr(dW), _ptr(db),
@@ -302,6 +319,13 @@ def linear_bwd(g, z, x1, W, x2=None, act=ACT_NONE, alpha=None, dx_cols=None, wan
                                   _ptr(db), _ptr(dalpha), ws.data_ptr(), ws_bytes, math_mode, _stream()),
               "hgin_linear_bwd")
     return {"dx": dx, "ddot": ddot, "dW": dW, "db": db, "dalpha": dalpha}
+
+
+def post_self_eligible(rows, k, n, math_mode):
+    """Shapes whose input gradient runs on the tensor-core kernel that carries the self-branch epilogue
+    (csrc/linear_tc.cu bwd_eligible; hgin_linear_bwd_post_self returns HGIN_ERR_UNSUPPORTED otherwise)."""
+    return (math_mode != MATH_FP32 and rows >= 128 and 16 <= k <= 128 and k % 16 == 0
+            and 16 <= n <= 128 and n % 16 == 0)
 
 
 def qt_baseline(p_l, avg_bw, capacity, num_paths, num_links, num_iterations=3):

@@ -197,6 +197,27 @@ int32_t hgin_linear_bwd_post(int64_t rows, const float *g, int64_t ldg, const fl
                              void *workspace, int64_t workspace_bytes, int32_t math_mode,
                              void *stream);
 
+/* hgin_linear_bwd_post_self: hgin_linear_bwd_post for a GIN layer whose ONLY contribution to the gradient of its
+ * destination type's input is its own self branch (models.py:215 `out += (1 + eps) * x_r`; e.g. the last GIN layer,
+ * whose output feeds the readout and whose source-side gradient is gathered separately).  The input gradient
+ * dh = dz W (all k1 columns; no x2) then never reaches memory:
+ *     dx          = (1 + eps) * dh * act'(post_z)         -> dz of the layer below (replaces the edgeless
+ *                                                            hgin_gin_combine_post pass: 2 row-sized transfers less)
+ *     post_dalpha = sum (1 + eps) * dh * min(post_z, 0)   (NULL to skip)
+ *     post_ddot   = sum dh * act(post_z) = d(eps)         (NULL to skip; act(post_z) IS x_dst)
+ * self_eps: device pointer to eps (NULL = 0).  Only the tensor-core input-gradient kernel carries this epilogue
+ * (HGIN_MATH_TF32 / HGIN_MATH_BF16, GEMM-sized shapes): otherwise HGIN_ERR_UNSUPPORTED is returned and nothing is
+ * enqueued — the caller then uses hgin_linear_bwd followed by hgin_gin_combine_post.
+ */
+int32_t hgin_linear_bwd_post_self(int64_t rows, const float *g, int64_t ldg, const float *z, int64_t ldz,
+                                  int32_t act, const float *alpha, const float *x1, int64_t ld1,
+                                  int32_t k1, const float *W, int32_t n, float *dx, int64_t lddx,
+                                  float *dW, float *db, float *dalpha, const float *post_z,
+                                  int64_t ld_post, int32_t post_act, const float *post_alpha,
+                                  float *post_dalpha, const float *self_eps, float *post_ddot,
+                                  void *workspace, int64_t workspace_bytes, int32_t math_mode,
+                                  void *stream);
+
 /* ---- loss: sqrt(MAPE) (train.py:12-13, 40-42) -----------------------------------------------
  * hgin_mape_sum:       sums[0] = sum_i |(pred_i - y_i) / y_i|,  sums[1] = n  (fp32, two-stage,
  *                      deterministic).  Multi-GPU: the caller all-reduces `sums`.

@@ -363,6 +363,47 @@ def test_linear_bwd_post_activation_and_dz_in_place(rows, k1, k2, n, post_act):
     assert r0["dalpha"] is None and r0["dx"] is None
 
 
+@pytest.mark.parametrize("rows,k,n", [(5000, 128, 128), (777, 64, 128), (4097, 128, 32)])
+@pytest.mark.parametrize("post_act", [ops.ACT_PRELU, ops.ACT_RELU])
+def test_linear_bwd_with_the_gin_self_branch_on_its_epilogue(rows, k, n, post_act):
+    """hgin_linear_bwd_post_self: dx = (1 + eps) * (dz W) * act'(z0), d(eps) = sum (dz W) * act(z0) and dalpha0 out of
+    the input-gradient GEMM == hgin_linear_bwd (dh to memory) followed by the edgeless hgin_gin_combine_post pass,
+    and == float64 autograd of  out = ((1 + eps) * act(z0)) W^T."""
+    g = torch.Generator().manual_seed(rows + k + n)
+    d = lambda *sh: torch.randn(*sh, generator=g, dtype=torch.float64)
+    z0 = d(rows, k).requires_grad_(True)
+    a0 = torch.tensor([0.2], dtype=torch.float64, requires_grad=True)
+    eps = torch.tensor([0.37], dtype=torch.float64, requires_grad=True)
+    W = (d(n, k) / k ** 0.5).requires_grad_(True)
+    x_dst = torch.nn.functional.prelu(z0, a0) if post_act == ops.ACT_PRELU else torch.relu(z0)
+    h = (1 + eps) * x_dst
+    dz = d(rows, n)
+    wanted = [z0, W, eps] + ([a0] if post_act == ops.ACT_PRELU else [])
+    grads = torch.autograd.grad(h @ W.t(), wanted, dz)
+    f32 = lambda t: t.detach().float().cuda().contiguous()
+    post = ops.PostAct(f32(z0), post_act, f32(a0))
+    r = ops.linear_bwd(f32(dz), None, f32(h), f32(W), act=ops.ACT_NONE, math_mode=ops.MATH_TF32, post=post,
+                       self_eps=f32(eps), want_self_ddot=True)
+    assert post.applied and ops.post_self_eligible(rows, k, n, ops.MATH_TF32)
+    _tc_close(r["dx"], grads[0])
+    _tc_close(r["dW"], grads[1])
+    scale = float((f32(dz).abs().mean() * f32(h).abs().mean()) * (rows * k) ** 0.5)     # size of such a sum of products
+    assert abs(float(r["ddot"]) - float(grads[2])) <= 2e-2 * scale
+    if post_act == ops.ACT_PRELU:
+        assert abs(float(post.dalpha) - float(grads[3])) <= 2e-2 * scale
+    # the two-pass form it replaces
+    post2 = ops.PostAct(f32(z0), post_act, f32(a0))
+    dh = ops.linear_bwd(f32(dz), None, f32(h), f32(W), act=ops.ACT_NONE, want_dw=False, want_db=False,
+                        math_mode=ops.MATH_TF32)["dx"]
+    dx2, ddot2 = ops.gin_combine(None, dh, dh, f32(eps), ops.SELF_ADD, post=post2, want_ddot=True)
+    assert torch.equal(r["dx"], dx2)                      # same products, same single rounding of (1 + eps) * dh
+    torch.testing.assert_close(r["ddot"], ddot2, rtol=1e-3, atol=1e-3 * scale)
+    # shapes outside the tensor-core path are refused, not silently computed some other way
+    with pytest.raises(ops.HginError):
+        ops.linear_bwd(f32(dz)[:, :8].contiguous(), None, f32(h), f32(W)[:8].contiguous(), act=ops.ACT_NONE,
+                       math_mode=ops.MATH_FP32, post=ops.PostAct(f32(z0), post_act, f32(a0)), self_eps=f32(eps))
+
+
 @pytest.mark.parametrize("ns,nd,e,f", [(3000, 5000, 15000, 128), (700, 90, 4000, 128), (900, 1200, 0, 64), (50, 64, 300, 8),
                                         (40, 33, 100, 5)])
 @pytest.mark.parametrize("act", [ops.ACT_PRELU, ops.ACT_RELU])
