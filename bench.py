@@ -213,7 +213,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfgC", choices=sorted(WORKLOADS) + ["cfgD", "qt"])
-    ap.add_argument("--math", default=None, choices=["fp32", "tf32"],
+    ap.add_argument("--math", default=None, choices=["fp32", "tf32", "bf16"],
                     help="dense-layer arithmetic; default tf32 tensor cores for cfgC (BASELINE configs[2] allows "
                          "reduced-precision MLP GEMMs), fp32 for cfgA")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -251,7 +251,7 @@ def main():
     from gnn_link_prediction_b200.parallel import Communicator
     comm = Communicator.from_env("nccl")
     from gnn_link_prediction_b200 import ops
-    from gnn_link_prediction_b200.models import HetroGIN, MATH_FP32, MATH_TF32
+    from gnn_link_prediction_b200.models import HetroGIN, MATH_BF16, MATH_FP32, MATH_TF32
     from gnn_link_prediction_b200.profiling import KernelTimer
     from gnn_link_prediction_b200.train import TrainStep
 
@@ -263,7 +263,7 @@ def main():
 
     torch.manual_seed(1997)
     model = HetroGIN(input_channels={"link": 7, "path": 7, "node": 3}, **model_kwargs(w)).cuda().train()
-    model.set_math_mode(MATH_TF32 if args.math == "tf32" else MATH_FP32)
+    model.set_math_mode({"tf32": MATH_TF32, "bf16": MATH_BF16, "fp32": MATH_FP32}[args.math])
     eager_step = TrainStep(model, lr=1e-3, communicator=comm)
     # launch-bound regime (cfgA): replay the whole step as one CUDA graph
     graphed = args.graph if args.graph is not None else (args.workload == "cfgA" and world == 1)
@@ -522,7 +522,9 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "graphs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": resident_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32" if args.math == "fp32" else "tf32 (dense layers; f32 aggregation and accumulation)", "data": "synthetic",
+        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32 (dense layers; f32 aggregation and accumulation)",
+                                     "bf16": "bf16 (activations / gradients stored as bf16, tcgen05 bf16 GEMMs; f32 accumulation, "
+                                             "aggregation adds, loss, optimizer)"}[args.math], "data": "synthetic",
         "config": {"workload": args.workload, "desc": w["desc"], "emb": w["emb"], "layers": w["layers"],
                    "graphs_per_gpu_per_step": graphs, "edges_per_gpu_per_step": edges,
                    "l2": "flushed between timed steps" if small else "inputs+activations larger than L2",

@@ -14,7 +14,8 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "hgin.h")
 OK = 0
 SELF_NONE, SELF_ADD, SELF_CONCAT = 0, 1, 2
 ACT_NONE, ACT_PRELU, ACT_RELU = 0, 1, 2
-MATH_FP32, MATH_TF32 = 0, 1
+MATH_FP32, MATH_TF32, MATH_BF16 = 0, 1, 2
+DTYPE_F32, DTYPE_BF16 = 0, 1
 
 _i32, _i64, _f32, _f64, _ptr = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_void_p
 
@@ -37,6 +38,8 @@ SIGNATURES = {
                                      _ptr, _i64, _i32, _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
     "hgin_gin_combine_pre": (_i32, [_i64, _ptr, _ptr, _i64, _ptr, _i64, _i32, _ptr, _i64, _i32, _ptr, _i32, _i32, _ptr, _i64,
                                     _i32, _ptr, _i32, _ptr, _ptr]),
+    "hgin_gin_combine_t": (_i32, [_i32, _i64, _ptr, _ptr, _i64, _ptr, _i64, _i32, _ptr, _i64, _i32, _ptr, _i32, _i32, _ptr,
+                                  _i64, _i32, _ptr, _i32, _ptr, _ptr, _i64, _i32, _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
     "hgin_linear_fwd_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32]),
     "hgin_linear_fwd": (_i32, [_i64, _ptr, _i64, _i32, _ptr, _i64, _i32, _ptr, _ptr, _i32, _i32, _ptr, _ptr, _i64,
                                _ptr, _i64, _i32, _ptr, _i64, _i32, _ptr]),
@@ -50,6 +53,12 @@ SIGNATURES = {
     "hgin_linear_bwd_post_self": (_i32, [_i64, _ptr, _i64, _ptr, _i64, _i32, _ptr, _ptr, _i64, _i32, _ptr, _i32, _ptr, _i64,
                                          _ptr, _ptr, _ptr, _ptr, _i64, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32,
                                          _ptr]),
+    "hgin_linear_fwd_t": (_i32, [_i32, _i32, _i64, _ptr, _i64, _i32, _ptr, _i64, _i32, _ptr, _ptr, _i32, _i32, _ptr, _ptr, _i64,
+                                 _ptr, _i64, _i32, _ptr, _i64, _i32, _ptr]),
+    "hgin_linear_bwd_t": (_i32, [_i32, _i32, _i64, _ptr, _i64, _ptr, _i64, _i32, _ptr, _ptr, _i64, _i32, _ptr, _i64, _i32, _ptr,
+                                 _i32, _i32, _i32, _ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _ptr,
+                                 _ptr, _ptr, _ptr, _ptr, _i64, _i32, _ptr]),
+    "hgin_debug_gemm_tn_bf16": (_i32, [_i64, _ptr, _i32, _ptr, _i32, _ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _ptr]),
     "hgin_reduce_workspace_bytes": (_i64, [_i64]),
     "hgin_mape_sum": (_i32, [_i64, _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
     "hgin_sqrt_mape_bwd": (_i32, [_i64, _ptr, _ptr, _ptr, _f32, _ptr, _ptr, _ptr]),

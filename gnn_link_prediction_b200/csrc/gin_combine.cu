@@ -13,69 +13,133 @@
 // Neighbour indices are fetched LPR at a time with one coalesced load and handed round by
 // shuffle; the gathers of a batch are issued back to back (UNROLL in flight) before the
 // dependent adds.
+#include <cuda_bf16.h>
+
 #include "hgin_common.cuh"
 
 namespace hgin {
 namespace {
 
-template <int VEC>
-struct Pack;
-template <>
-struct Pack<1> {
-    float v[1];
-};
-template <>
-struct Pack<4> {
-    float v[4];
-};
+using bf16 = __nv_bfloat16;
 
-template <int VEC>
-__device__ __forceinline__ Pack<VEC> load_pack(const float *p) {
-    Pack<VEC> r;
-    if constexpr (VEC == 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
-        r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
-    } else {
-        r.v[0] = __ldg(p);
-    }
-    return r;
+// Storage type T of the row matrices (x_src, x_self, post.z, out): float, or bf16 (HGIN_DTYPE_BF16: rows are
+// stored in 16 bits, every addition is still an fp32 addition in CSR order, the result is rounded once on
+// the store).  Raw<T, VEC> is what ONE vector load returns — 16 bytes for the vector variants (4 floats or
+// 8 bf16) — and stays packed in registers until it is consumed, so the gathers in flight cost the same
+// registers in both types.
+template <typename T, int VEC>
+struct Raw;
+template <>
+struct Raw<float, 1> { float v[1]; };
+template <>
+struct Raw<float, 4> { float v[4]; };
+template <>
+struct Raw<bf16, 1> { unsigned short u; };
+template <>
+struct Raw<bf16, 8> { uint4 q; };
+
+__device__ __forceinline__ void bf16x2_to_f32(uint32_t w, float &lo, float &hi) {
+    lo = __uint_as_float(w << 16);
+    hi = __uint_as_float(w & 0xffff0000u);
 }
+__device__ __forceinline__ uint32_t f32x2_to_bf16(float lo, float hi) {
+    const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&t);
+}
+
+__device__ __forceinline__ void unpack(const Raw<float, 1> &r, float (&o)[1]) { o[0] = r.v[0]; }
+__device__ __forceinline__ void unpack(const Raw<float, 4> &r, float (&o)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = r.v[i];
+}
+__device__ __forceinline__ void unpack(const Raw<bf16, 1> &r, float (&o)[1]) { o[0] = __uint_as_float(static_cast<uint32_t>(r.u) << 16); }
+__device__ __forceinline__ void unpack(const Raw<bf16, 8> &r, float (&o)[8]) {
+    bf16x2_to_f32(r.q.x, o[0], o[1]);
+    bf16x2_to_f32(r.q.y, o[2], o[3]);
+    bf16x2_to_f32(r.q.z, o[4], o[5]);
+    bf16x2_to_f32(r.q.w, o[6], o[7]);
+}
+__device__ __forceinline__ void pack(const float (&o)[1], Raw<float, 1> &r) { r.v[0] = o[0]; }
+__device__ __forceinline__ void pack(const float (&o)[4], Raw<float, 4> &r) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r.v[i] = o[i];
+}
+__device__ __forceinline__ void pack(const float (&o)[1], Raw<bf16, 1> &r) { r.u = __bfloat16_as_ushort(__float2bfloat16_rn(o[0])); }
+__device__ __forceinline__ void pack(const float (&o)[8], Raw<bf16, 8> &r) {
+    r.q.x = f32x2_to_bf16(o[0], o[1]);
+    r.q.y = f32x2_to_bf16(o[2], o[3]);
+    r.q.z = f32x2_to_bf16(o[4], o[5]);
+    r.q.w = f32x2_to_bf16(o[6], o[7]);
+}
+
+__device__ __forceinline__ Raw<float, 1> load_raw(const float *p, Raw<float, 1> *) { return {{__ldg(p)}}; }
+__device__ __forceinline__ Raw<float, 4> load_raw(const float *p, Raw<float, 4> *) {
+    const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+    return {{t.x, t.y, t.z, t.w}};
+}
+__device__ __forceinline__ Raw<bf16, 1> load_raw(const bf16 *p, Raw<bf16, 1> *) {
+    return {__ldg(reinterpret_cast<const unsigned short *>(p))};
+}
+__device__ __forceinline__ Raw<bf16, 8> load_raw(const bf16 *p, Raw<bf16, 8> *) { return {__ldg(reinterpret_cast<const uint4 *>(p))}; }
+
+// plain (coherent) loads: the accumulate path reads `out`, which this kernel also writes
+__device__ __forceinline__ Raw<float, 1> load_raw_coherent(const float *p, Raw<float, 1> *) { return {{*p}}; }
+__device__ __forceinline__ Raw<float, 4> load_raw_coherent(const float *p, Raw<float, 4> *) {
+    const float4 t = *reinterpret_cast<const float4 *>(p);
+    return {{t.x, t.y, t.z, t.w}};
+}
+__device__ __forceinline__ Raw<bf16, 1> load_raw_coherent(const bf16 *p, Raw<bf16, 1> *) {
+    return {*reinterpret_cast<const unsigned short *>(p)};
+}
+__device__ __forceinline__ Raw<bf16, 8> load_raw_coherent(const bf16 *p, Raw<bf16, 8> *) { return {*reinterpret_cast<const uint4 *>(p)}; }
 
 // Streaming variants for rows that are touched exactly once (self rows, post-activation rows, the
 // output): they must not displace the gathered source rows, which ARE reused (each link row ~35
 // times per topology), from L1.
-template <int VEC>
-__device__ __forceinline__ Pack<VEC> load_pack_stream(const float *p) {
-    Pack<VEC> r;
-    if constexpr (VEC == 4) {
-        asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-            : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3])
-            : "l"(p));
-    } else {
-        r.v[0] = __ldg(p);
-    }
+__device__ __forceinline__ Raw<float, 1> load_raw_stream(const float *p, Raw<float, 1> *) { return {{__ldg(p)}}; }
+__device__ __forceinline__ Raw<float, 4> load_raw_stream(const float *p, Raw<float, 4> *) {
+    Raw<float, 4> r;
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+        : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3])
+        : "l"(p));
+    return r;
+}
+__device__ __forceinline__ Raw<bf16, 1> load_raw_stream(const bf16 *p, Raw<bf16, 1> *t) { return load_raw(p, t); }
+__device__ __forceinline__ Raw<bf16, 8> load_raw_stream(const bf16 *p, Raw<bf16, 8> *) {
+    Raw<bf16, 8> r;
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+        : "=r"(r.q.x), "=r"(r.q.y), "=r"(r.q.z), "=r"(r.q.w)
+        : "l"(p));
     return r;
 }
 
-template <int VEC>
-__device__ __forceinline__ void store_pack_stream(float *p, const Pack<VEC> &r) {
-    if constexpr (VEC == 4) {
-        asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]),
-                     "f"(r.v[2]), "f"(r.v[3])
-                     : "memory");
-    } else {
-        p[0] = r.v[0];
-    }
+__device__ __forceinline__ void store_raw(float *p, const Raw<float, 1> &r) { p[0] = r.v[0]; }
+__device__ __forceinline__ void store_raw(float *p, const Raw<float, 4> &r) {
+    *reinterpret_cast<float4 *>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+}
+__device__ __forceinline__ void store_raw(bf16 *p, const Raw<bf16, 1> &r) { *reinterpret_cast<unsigned short *>(p) = r.u; }
+__device__ __forceinline__ void store_raw(bf16 *p, const Raw<bf16, 8> &r) { *reinterpret_cast<uint4 *>(p) = r.q; }
+__device__ __forceinline__ void store_raw_stream(float *p, const Raw<float, 1> &r) { p[0] = r.v[0]; }
+__device__ __forceinline__ void store_raw_stream(float *p, const Raw<float, 4> &r) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]),
+                 "f"(r.v[3])
+                 : "memory");
+}
+__device__ __forceinline__ void store_raw_stream(bf16 *p, const Raw<bf16, 1> &r) { store_raw(p, r); }
+__device__ __forceinline__ void store_raw_stream(bf16 *p, const Raw<bf16, 8> &r) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(r.q.x), "r"(r.q.y), "r"(r.q.z),
+                 "r"(r.q.w)
+                 : "memory");
 }
 
-template <int VEC>
-__device__ __forceinline__ void store_pack(float *p, const Pack<VEC> &r) {
-    if constexpr (VEC == 4) {
-        *reinterpret_cast<float4 *>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
-    } else {
-        p[0] = r.v[0];
-    }
+__device__ __forceinline__ float ld1(const float *p) { return __ldg(p); }
+__device__ __forceinline__ float ld1(const bf16 *p) {
+    return __uint_as_float(static_cast<uint32_t>(__ldg(reinterpret_cast<const unsigned short *>(p))) << 16);
 }
+__device__ __forceinline__ float ld1_coherent(const float *p) { return *p; }
+__device__ __forceinline__ float ld1_coherent(const bf16 *p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st1(float *p, float v) { *p = v; }
+__device__ __forceinline__ void st1(bf16 *p, float v) { *p = __float2bfloat16_rn(v); }
 
 // LPR lanes per row, VEC features per lane per chunk, NC chunks per lane:
 // covers f_src <= LPR * VEC * NC.
@@ -84,7 +148,7 @@ __device__ __forceinline__ void store_pack(float *p, const Pack<VEC> &r) {
 // writes dz directly, plus the per-CTA partial of dalpha = sum grad * min(z, 0) — the separate
 // dz = g * act'(z) pass over the row-sized tensors of the layer below disappears.
 struct PostAct {
-    const float *z;
+    const void *z;            // same storage type as the rows
     int64_t ldz;
     int act;
     const float *alpha;
@@ -106,17 +170,20 @@ struct PostAct {
 // every row address is ONE widening multiply-add (IMAD.WIDE) instead of a 64 x 64-bit product — the
 // short-row launches issue ~60 % of their scheduler slots, and integer address math was most of it.
 // FULL: f_src == LPR * VEC * NC, the feature-range predicates fold away.
-template <int VEC, int LPR, int NC, bool CONTIG, int MINB, int MODE, bool FULL>
+template <typename T, int VEC, int LPR, int NC, bool CONTIG, int MINB, int MODE, bool FULL>
 __global__ void __launch_bounds__(256, MINB)
 gin_combine_kernel(int num_rows, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                   const float *__restrict__ x_src, int ld_src, int f_src,
-                   const float *__restrict__ x_self, int ld_self, int f_self,
+                   const T *__restrict__ x_src, int ld_src, int f_src,
+                   const T *__restrict__ x_self, int ld_self, int f_self,
                    const float *__restrict__ eps_ptr, int self_mode, int accumulate,
-                   float *__restrict__ out, int ld_out, const PostAct post) {
+                   T *__restrict__ out, int ld_out, const PostAct post) {
+    using R = Raw<T, VEC>;
     // gathers in flight per lane before the dependent adds; bounded by the batch (LPR) and by
     // the register budget when a lane carries several chunks
     // (pre-activation sources need a few registers for the on-the-fly act: two gathers fewer in flight)
-    constexpr int UNROLL_MAX = (NC >= 4) ? 2 : ((NC == 2) ? 4 : ((MODE == 2 || MODE == 4) ? 6 : 8));
+    // (bf16 lanes carry 8 accumulators and unpack 8 values per gather: fewer in flight at 64 registers)
+    constexpr int UNROLL_MAX = (NC >= 4) ? 2 : ((NC == 2) ? 4 : (VEC == 8 ? ((MODE == 0 || MODE == 3) ? 6 : 4)
+                                                                          : ((MODE == 2 || MODE == 4) ? 6 : 8)));
     constexpr int UNROLL = (LPR < UNROLL_MAX) ? LPR : UNROLL_MAX;
     constexpr int ROWS_PER_WARP = 32 / LPR;
     const int lane = threadIdx.x & 31;
@@ -134,7 +201,8 @@ gin_combine_kernel(int num_rows, const int32_t *__restrict__ rowptr, const int32
     const float self_alpha = !PRE_SELF ? 1.0f : (post.self_act == HGIN_ACT_PRELU ? __ldg(post.self_alpha) : 0.0f);
     float dalpha = 0.0f, ddot = 0.0f;
     const int post_ld = static_cast<int>(post.ldz);
-    auto at = [](const float *base, int row, int ld) { return base + static_cast<int64_t>(row) * ld; };   // IMAD.WIDE
+    const T *post_z = static_cast<const T *>(post.z);
+    auto at = [](const T *base, int row, int ld) { return base + static_cast<int64_t>(row) * ld; };   // IMAD.WIDE
 
     // Row -> warp mapping.
     // CONTIG (short rows): each CTA owns a CONTIGUOUS block of rows, its warps interleaving inside it.
@@ -184,22 +252,24 @@ gin_combine_kernel(int num_rows, const int32_t *__restrict__ rowptr, const int32
         const int32_t nmine = (sub < nlen) ? __ldg(col + nbeg + sub) : -1;
         int32_t nnbeg, nnlen;
         load_bounds(row0 + 2 * stride, nnbeg, nnlen);
-        Pack<VEC> self_v[NC];
+        R self_r[NC];
         if (self_mode == HGIN_SELF_ADD && live) {
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 const int f = (c * LPR + sub) * VEC;
                 if (FULL || f < f_src)
-                    self_v[c] = CONTIG ? load_pack_stream<VEC>(at(x_self, row, ld_self) + f) : load_pack<VEC>(at(x_self, row, ld_self) + f);
+                    self_r[c] = CONTIG ? load_raw_stream(at(x_self, row, ld_self) + f, (R *)nullptr)
+                                       : load_raw(at(x_self, row, ld_self) + f, (R *)nullptr);
             }
         }
-        Pack<VEC> post_v[NC];
+        R post_r[NC];
         if (POST && post.act != HGIN_ACT_NONE && live) {
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 const int f = (c * LPR + sub) * VEC;
                 if (FULL || f < f_src)
-                    post_v[c] = CONTIG ? load_pack_stream<VEC>(at(post.z, row, post_ld) + f) : load_pack<VEC>(at(post.z, row, post_ld) + f);
+                    post_r[c] = CONTIG ? load_raw_stream(at(post_z, row, post_ld) + f, (R *)nullptr)
+                                       : load_raw(at(post_z, row, post_ld) + f, (R *)nullptr);
             }
         }
         // warp-uniform trip count so the shuffles below are always convergent
@@ -207,18 +277,18 @@ gin_combine_kernel(int num_rows, const int32_t *__restrict__ rowptr, const int32
 #pragma unroll
         for (int o = 16; o >= LPR; o >>= 1) max_len = max(max_len, __shfl_xor_sync(full, max_len, o));
 
-        Pack<VEC> acc[NC];
+        float acc[NC][VEC];
 #pragma unroll
         for (int c = 0; c < NC; ++c)
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) acc[c].v[i] = 0.0f;
+            for (int i = 0; i < VEC; ++i) acc[c][i] = 0.0f;
 
         for (int32_t base = 0; base < max_len; base += LPR) {
             // one coalesced index load per group, LPR neighbours at a time (the first batch was prefetched)
             if (base > 0) mine = (base + sub < len) ? __ldg(col + beg + base + sub) : -1;
             const int32_t batch = min(LPR, max_len - base);
             for (int32_t j0 = 0; j0 < batch; j0 += UNROLL) {
-                Pack<VEC> v[UNROLL][NC];
+                R v[UNROLL][NC];
                 int32_t nb[UNROLL];
 #pragma unroll
                 for (int u = 0; u < UNROLL; ++u) {
@@ -231,74 +301,81 @@ gin_combine_kernel(int num_rows, const int32_t *__restrict__ rowptr, const int32
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
                         const int f = (c * LPR + sub) * VEC;
-                        if (nb[u] >= 0 && (FULL || f < f_src)) {
-                            v[u][c] = load_pack<VEC>(at(x_src, nb[u], ld_src) + f);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < VEC; ++i) v[u][c].v[i] = 0.0f;
-                        }
+                        if (nb[u] >= 0 && (FULL || f < f_src)) v[u][c] = load_raw(at(x_src, nb[u], ld_src) + f, (R *)nullptr);
+                        else v[u][c] = R{};   // (zero-filled: keeps the unpack below unconditional, no spills)
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < UNROLL; ++u) {
                     if (nb[u] >= 0) {  // strictly left-to-right; skipped slots add nothing (not even +0)
 #pragma unroll
-                        for (int c = 0; c < NC; ++c)
+                        for (int c = 0; c < NC; ++c) {
+                            float t[VEC];
+                            unpack(v[u][c], t);
 #pragma unroll
                             for (int i = 0; i < VEC; ++i) {
-                                float t = v[u][c].v[i];
-                                if (PRE_SRC) t = t > 0.f ? t : src_alpha * t;   // x = act(z), on the fly
-                                acc[c].v[i] = __fadd_rn(acc[c].v[i], t);
+                                float tv = t[i];
+                                if (PRE_SRC) tv = tv > 0.f ? tv : src_alpha * tv;   // x = act(z), on the fly
+                                acc[c][i] = __fadd_rn(acc[c][i], tv);
                             }
+                        }
                     }
                 }
             }
         }
 
         if (live) {
-            float *orow = out + static_cast<int64_t>(row) * ld_out;
+            T *orow = out + static_cast<int64_t>(row) * ld_out;
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 const int f = (c * LPR + sub) * VEC;
                 if (!FULL && f >= f_src) continue;
-                Pack<VEC> r = acc[c];
+                float r[VEC];
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) r[i] = acc[c][i];
+                float sv[VEC];
                 if (self_mode == HGIN_SELF_ADD) {
+                    unpack(self_r[c], sv);
 #pragma unroll
                     for (int i = 0; i < VEC; ++i) {
-                        float xs = self_v[c].v[i];
+                        float xs = sv[i];
                         if (PRE_SELF) xs = xs > 0.f ? xs : self_alpha * xs;
-                        r.v[i] = __fadd_rn(r.v[i], __fmul_rn(ope, xs));
+                        r[i] = __fadd_rn(r[i], __fmul_rn(ope, xs));
                     }
                 }
                 if (accumulate) {
-                    const Pack<VEC> old = load_pack<VEC>(orow + f);
+                    float old[VEC];
+                    unpack(load_raw_coherent(orow + f, (R *)nullptr), old);
 #pragma unroll
-                    for (int i = 0; i < VEC; ++i) r.v[i] = __fadd_rn(old.v[i], r.v[i]);
+                    for (int i = 0; i < VEC; ++i) r[i] = __fadd_rn(old[i], r[i]);
                 }
                 if (POST && post.act != HGIN_ACT_NONE) {
+                    float pv[VEC];
+                    unpack(post_r[c], pv);
                     if (post.ddot_partials && self_mode == HGIN_SELF_ADD) {
 #pragma unroll
-                        for (int i = 0; i < VEC; ++i)
-                            ddot = fmaf(self_v[c].v[i], act_forward(post_v[c].v[i], post.act, post_alpha), ddot);
+                        for (int i = 0; i < VEC; ++i) ddot = fmaf(sv[i], act_forward(pv[i], post.act, post_alpha), ddot);
                     }
 #pragma unroll
                     for (int i = 0; i < VEC; ++i) {
-                        const float zv = post_v[c].v[i];
-                        if (post.act == HGIN_ACT_PRELU && !(zv > 0.f)) dalpha = fmaf(r.v[i], zv, dalpha);
-                        r.v[i] = act_backward(r.v[i], zv, post.act, post_alpha);
+                        const float zv = pv[i];
+                        if (post.act == HGIN_ACT_PRELU && !(zv > 0.f)) dalpha = fmaf(r[i], zv, dalpha);
+                        r[i] = act_backward(r[i], zv, post.act, post_alpha);
                     }
                 }
-                if constexpr (CONTIG) store_pack_stream<VEC>(orow + f, r);
-                else store_pack<VEC>(orow + f, r);
+                R packed;
+                pack(r, packed);
+                if constexpr (CONTIG) store_raw_stream(orow + f, packed);
+                else store_raw(orow + f, packed);
             }
             if (self_mode == HGIN_SELF_CONCAT) {
                 // [agg | (1+eps) x_self]: the self block starts at column f_src (rarely 16B aligned) -> scalar
                 for (int f = sub; f < f_self; f += LPR) {
-                    float xs = __ldg(at(x_self, row, ld_self) + f);
+                    float xs = ld1(at(x_self, row, ld_self) + f);
                     if (PRE_SELF) xs = xs > 0.f ? xs : self_alpha * xs;
                     float t = __fmul_rn(ope, xs);
-                    if (accumulate) t = __fadd_rn(orow[f_src + f], t);
-                    orow[f_src + f] = t;
+                    if (accumulate) t = __fadd_rn(ld1_coherent(orow + f_src + f), t);
+                    st1(orow + f_src + f, t);
                 }
             }
         }
@@ -329,10 +406,10 @@ __global__ void __launch_bounds__(1024) combine_reduce_scalar_kernel(const float
 
 constexpr int kMaxCombineCtas = kNumSMs * 32;
 
-template <int VEC, int LPR, int NC, bool CONTIG = false, int MINB = ((VEC * NC <= 4) ? 4 : 1)>
-int launch(int64_t num_rows64, const int32_t *rowptr, const int32_t *col, const float *x_src, int64_t ld_src64,
-           int f_src, const float *x_self, int64_t ld_self64, int f_self, const float *eps, int self_mode,
-           int accumulate, float *out, int64_t ld_out64, const PostAct *post, cudaStream_t s) {
+template <typename T, int VEC, int LPR, int NC, bool CONTIG = false, int MINB = ((NC <= 1) ? 4 : 1)>
+int launch(int64_t num_rows64, const int32_t *rowptr, const int32_t *col, const T *x_src, int64_t ld_src64,
+           int f_src, const T *x_self, int64_t ld_self64, int f_self, const float *eps, int self_mode,
+           int accumulate, T *out, int64_t ld_out64, const PostAct *post, cudaStream_t s) {
     const int num_rows = static_cast<int>(num_rows64), ld_src = static_cast<int>(ld_src64);
     const int ld_self = static_cast<int>(ld_self64), ld_out = static_cast<int>(ld_out64);
     constexpr int threads = 256;
@@ -345,7 +422,7 @@ int launch(int64_t num_rows64, const int32_t *rowptr, const int32_t *col, const 
                                                  : (post->src_act != HGIN_ACT_NONE ? 2 : 3)));
     const bool full = f_src == LPR * VEC * NC;
 #define HGIN_GO(M, F)                                                                                              \
-    gin_combine_kernel<VEC, LPR, NC, CONTIG, MINB, M, F><<<grid, threads, 0, s>>>(                                  \
+    gin_combine_kernel<T, VEC, LPR, NC, CONTIG, MINB, M, F><<<grid, threads, 0, s>>>(                               \
         num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, accumulate, out, ld_out, pa)
 #define HGIN_GO_MODE(M)          \
     do {                         \
@@ -364,20 +441,21 @@ int launch(int64_t num_rows64, const int32_t *rowptr, const int32_t *col, const 
     return grid;
 }
 
-}  // namespace
-}  // namespace hgin
+template <typename T>
+struct VecOf;
+template <>
+struct VecOf<float> { static constexpr int value = 4; };
+template <>
+struct VecOf<bf16> { static constexpr int value = 8; };
 
-namespace hgin {
-namespace {
-
-int32_t combine_dispatch(int64_t num_rows, const int32_t *rowptr, const int32_t *col, int64_t num_edges,
-                         const float *x_src, int64_t ld_src, int32_t f_src, const float *x_self, int64_t ld_self,
-                         int32_t f_self, const float *eps, int32_t self_mode, int32_t accumulate, float *out,
-                         int64_t ld_out, const float *post_z, int64_t ld_post, int32_t post_act,
-                         const float *post_alpha, float *post_dalpha, float *post_ddot, void *workspace,
-                         int64_t workspace_bytes, void *stream, const char *who, int32_t src_act = HGIN_ACT_NONE,
-                         const float *src_alpha = nullptr, int32_t self_act = HGIN_ACT_NONE,
-                         const float *self_alpha = nullptr) {
+template <typename T>
+int32_t combine_dispatch_t(int64_t num_rows, const int32_t *rowptr, const int32_t *col, int64_t num_edges,
+                           const T *x_src, int64_t ld_src, int32_t f_src, const T *x_self, int64_t ld_self,
+                           int32_t f_self, const float *eps, int32_t self_mode, int32_t accumulate, T *out,
+                           int64_t ld_out, const T *post_z, int64_t ld_post, int32_t post_act,
+                           const float *post_alpha, float *post_dalpha, float *post_ddot, void *workspace,
+                           int64_t workspace_bytes, void *stream, const char *who, int32_t src_act,
+                           const float *src_alpha, int32_t self_act, const float *self_alpha) {
     HGIN_CHECK_ARG(num_rows >= 0 && num_rows < INT32_MAX - (1 << 22), "%s: bad num_rows %lld", who, (long long)num_rows);
     HGIN_CHECK_ARG(ld_src < INT32_MAX && ld_self < INT32_MAX && ld_out < INT32_MAX && ld_post < INT32_MAX,
                    "%s: leading dimensions must fit 32 bits", who);
@@ -423,39 +501,51 @@ int32_t combine_dispatch(int64_t num_rows, const int32_t *rowptr, const int32_t 
     if (!rowptr) num_edges = 0;
 
     // 128-bit lanes need every row start 16-byte aligned.
-    bool vec4 = (f_src % 4 == 0) && (ld_src % 4 == 0) && (ld_out % 4 == 0) && aligned16(x_src) && aligned16(out);
-    if (self_mode == HGIN_SELF_ADD) vec4 = vec4 && (ld_self % 4 == 0) && aligned16(x_self);
-    if (post_on) vec4 = vec4 && (ld_post % 4 == 0) && aligned16(post_z);
+    constexpr int V = VecOf<T>::value;
+    bool vec = (f_src % V == 0) && (ld_src % V == 0) && (ld_out % V == 0) && aligned16(x_src) && aligned16(out);
+    if (self_mode == HGIN_SELF_ADD) vec = vec && (ld_self % V == 0) && aligned16(x_self);
+    if (post_on) vec = vec && (ld_post % V == 0) && aligned16(post_z);
 
     int grid = 0;
-#define HGIN_LAUNCH(V, L, N)                                                                                    \
-    grid = launch<V, L, N>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, \
-                           accumulate, out, ld_out, pp, s)
+#define HGIN_LAUNCH(VV, L, N)                                                                                      \
+    grid = launch<T, VV, L, N>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, \
+                               accumulate, out, ld_out, pp, s)
+#define HGIN_LAUNCH_CONTIG(VV, L, N)                                                                                        \
+    grid = launch<T, VV, L, N, true, 4>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, \
+                                        accumulate, out, ld_out, pp, s)
     // Lanes per row: a full warp per row suits long rows (path->link, ~36 neighbours); for short
     // rows (link->path, ~3 neighbours) the per-row latency chain rowptr -> col -> gather dominates,
     // so several rows share a warp and each lane carries more 128-bit chunks.
     const double avg_len = (num_edges >= 0 && num_rows > 0) ? static_cast<double>(num_edges) / num_rows : 1e9;
-    if (vec4) {
-        const int chunks = f_src / 4;
-        // Measured on B200 (profiles/): 2.5 M rows x ~3 neighbours, F = 128: warp/row 1.10 ms ->
-        // half-warp/row + contiguous CTA ranges + pipelined indices 0.60 ms; long rows keep warp/row.
-        int lpr = chunks <= 32 ? chunks : 32;
-        const bool short_rows = avg_len <= 8.0;
-        if ((chunks == 32 || chunks == 16) && short_rows) lpr = chunks / 2;
-        if (chunks == 32 && lpr == 16)
-            grid = launch<4, 16, 2, true, 4>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps,
-                                             self_mode, accumulate, out, ld_out, pp, s);
-        else if (chunks == 16 && lpr == 8)
-            grid = launch<4, 8, 2, true, 4>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps,
-                                            self_mode, accumulate, out, ld_out, pp, s);
-        else if (chunks <= 1) HGIN_LAUNCH(4, 1, 1);
-        else if (chunks <= 2) HGIN_LAUNCH(4, 2, 1);
-        else if (chunks <= 4) HGIN_LAUNCH(4, 4, 1);
-        else if (chunks <= 8) HGIN_LAUNCH(4, 8, 1);
-        else if (chunks <= 16) HGIN_LAUNCH(4, 16, 1);
-        else if (chunks <= 32) HGIN_LAUNCH(4, 32, 1);
-        else if (chunks <= 64) HGIN_LAUNCH(4, 32, 2);
-        else HGIN_LAUNCH(4, 32, 4);
+    const bool short_rows = avg_len <= 8.0;
+    if (vec) {
+        const int chunks = f_src / V;
+        if constexpr (V == 4) {
+            // Measured on B200 (profiles/): 2.5 M rows x ~3 neighbours, F = 128: warp/row 1.10 ms ->
+            // half-warp/row + contiguous CTA ranges + pipelined indices 0.60 ms; long rows keep warp/row.
+            if (chunks == 32 && short_rows) HGIN_LAUNCH_CONTIG(4, 16, 2);
+            else if (chunks == 16 && short_rows) HGIN_LAUNCH_CONTIG(4, 8, 2);
+            else if (chunks <= 1) HGIN_LAUNCH(4, 1, 1);
+            else if (chunks <= 2) HGIN_LAUNCH(4, 2, 1);
+            else if (chunks <= 4) HGIN_LAUNCH(4, 4, 1);
+            else if (chunks <= 8) HGIN_LAUNCH(4, 8, 1);
+            else if (chunks <= 16) HGIN_LAUNCH(4, 16, 1);
+            else if (chunks <= 32) HGIN_LAUNCH(4, 32, 1);
+            else if (chunks <= 64) HGIN_LAUNCH(4, 32, 2);
+            else HGIN_LAUNCH(4, 32, 4);
+        } else {
+            // bf16 rows: a 128-wide row is 16 chunks of 8 — half a warp per row with one chunk per lane
+            // carries as many rows per warp as the fp32 short-row variant at half the bytes.
+            if (chunks == 16 && short_rows) HGIN_LAUNCH_CONTIG(8, 16, 1);
+            else if (chunks == 8 && short_rows) HGIN_LAUNCH_CONTIG(8, 8, 1);
+            else if (chunks <= 1) HGIN_LAUNCH(8, 1, 1);
+            else if (chunks <= 2) HGIN_LAUNCH(8, 2, 1);
+            else if (chunks <= 4) HGIN_LAUNCH(8, 4, 1);
+            else if (chunks <= 8) HGIN_LAUNCH(8, 8, 1);
+            else if (chunks <= 16) HGIN_LAUNCH(8, 16, 1);
+            else if (chunks <= 32) HGIN_LAUNCH(8, 32, 1);
+            else HGIN_LAUNCH(8, 32, 2);
+        }
     } else {
         if (f_src <= 1) HGIN_LAUNCH(1, 1, 1);
         else if (f_src <= 2) HGIN_LAUNCH(1, 2, 1);
@@ -469,10 +559,33 @@ int32_t combine_dispatch(int64_t num_rows, const int32_t *rowptr, const int32_t 
         else HGIN_LAUNCH(1, 32, 16);
     }
 #undef HGIN_LAUNCH
+#undef HGIN_LAUNCH_CONTIG
     if (post.dalpha_partials && post_on) combine_reduce_scalar_kernel<<<1, 1024, 0, s>>>(post.dalpha_partials, grid, post_dalpha);
     if (post.ddot_partials && post_on) combine_reduce_scalar_kernel<<<1, 1024, 0, s>>>(post.ddot_partials, grid, post_ddot);
     HGIN_CHECK_LAUNCH(who);
     return HGIN_OK;
+}
+
+int32_t combine_dispatch(int64_t num_rows, const int32_t *rowptr, const int32_t *col, int64_t num_edges,
+                         const void *x_src, int64_t ld_src, int32_t f_src, const void *x_self, int64_t ld_self,
+                         int32_t f_self, const float *eps, int32_t self_mode, int32_t accumulate, void *out,
+                         int64_t ld_out, const void *post_z, int64_t ld_post, int32_t post_act,
+                         const float *post_alpha, float *post_dalpha, float *post_ddot, void *workspace,
+                         int64_t workspace_bytes, void *stream, const char *who, int32_t src_act = HGIN_ACT_NONE,
+                         const float *src_alpha = nullptr, int32_t self_act = HGIN_ACT_NONE,
+                         const float *self_alpha = nullptr, int32_t dtype = HGIN_DTYPE_F32) {
+    if (dtype == HGIN_DTYPE_BF16)
+        return combine_dispatch_t<bf16>(num_rows, rowptr, col, num_edges, static_cast<const bf16 *>(x_src), ld_src, f_src,
+                                        static_cast<const bf16 *>(x_self), ld_self, f_self, eps, self_mode, accumulate,
+                                        static_cast<bf16 *>(out), ld_out, static_cast<const bf16 *>(post_z), ld_post,
+                                        post_act, post_alpha, post_dalpha, post_ddot, workspace, workspace_bytes, stream,
+                                        who, src_act, src_alpha, self_act, self_alpha);
+    HGIN_CHECK_ARG(dtype == HGIN_DTYPE_F32, "%s: bad dtype %d", who, dtype);
+    return combine_dispatch_t<float>(num_rows, rowptr, col, num_edges, static_cast<const float *>(x_src), ld_src, f_src,
+                                     static_cast<const float *>(x_self), ld_self, f_self, eps, self_mode, accumulate,
+                                     static_cast<float *>(out), ld_out, static_cast<const float *>(post_z), ld_post,
+                                     post_act, post_alpha, post_dalpha, post_ddot, workspace, workspace_bytes, stream, who,
+                                     src_act, src_alpha, self_act, self_alpha);
 }
 
 }  // namespace
@@ -508,4 +621,18 @@ extern "C" int32_t hgin_gin_combine_pre(int64_t num_rows, const int32_t *rowptr,
     return hgin::combine_dispatch(num_rows, rowptr, col, num_edges, x_src, ld_src, f_src, x_self, ld_self, f_self, eps,
                                   self_mode, accumulate, out, ld_out, nullptr, 0, HGIN_ACT_NONE, nullptr, nullptr, nullptr,
                                   nullptr, 0, stream, "hgin_gin_combine_pre", src_act, src_alpha, self_act, self_alpha);
+}
+
+extern "C" int32_t hgin_gin_combine_t(int32_t dtype, int64_t num_rows, const int32_t *rowptr, const int32_t *col,
+                                      int64_t num_edges, const void *x_src, int64_t ld_src, int32_t f_src,
+                                      const void *x_self, int64_t ld_self, int32_t f_self, const float *eps,
+                                      int32_t self_mode, int32_t accumulate, void *out, int64_t ld_out, int32_t src_act,
+                                      const float *src_alpha, int32_t self_act, const float *self_alpha,
+                                      const void *post_z, int64_t ld_post, int32_t post_act, const float *post_alpha,
+                                      float *post_dalpha, float *post_ddot, void *workspace, int64_t workspace_bytes,
+                                      void *stream) {
+    return hgin::combine_dispatch(num_rows, rowptr, col, num_edges, x_src, ld_src, f_src, x_self, ld_self, f_self, eps,
+                                  self_mode, accumulate, out, ld_out, post_z, ld_post, post_act, post_alpha, post_dalpha,
+                                  post_ddot, workspace, workspace_bytes, stream, "hgin_gin_combine_t", src_act, src_alpha,
+                                  self_act, self_alpha, dtype);
 }

@@ -297,7 +297,8 @@ inline int64_t dw_splits(int64_t rows) {
 
 extern "C" int64_t hgin_linear_fwd_workspace_bytes(int64_t rows, int32_t k, int32_t n, int32_t math_mode) {
     if (rows < 0 || k <= 0 || n <= 0) return -1;
-    return math_mode == HGIN_MATH_TF32 ? hgin::tcgemm::fwd_workspace_bytes(k, n) : 0;
+    // (fp32 rows under HGIN_MATH_BF16 run the tf32 kernels; bf16 rows need half of that)
+    return math_mode != HGIN_MATH_FP32 ? hgin::tcgemm::fwd_workspace_bytes(k, n) : 0;
 }
 
 extern "C" int32_t hgin_linear_fwd(int64_t rows, const float *x1, int64_t ld1, int32_t k1, const float *x2,
@@ -310,17 +311,17 @@ extern "C" int32_t hgin_linear_fwd(int64_t rows, const float *x1, int64_t ld1, i
                    (long long)rows, k1, k2, n);
     HGIN_CHECK_ARG(act >= HGIN_ACT_NONE && act <= HGIN_ACT_RELU, "hgin_linear_fwd: bad act %d", act);
     HGIN_CHECK_ARG(act != HGIN_ACT_PRELU || alpha, "hgin_linear_fwd: PReLU needs alpha");
-    HGIN_CHECK_ARG(math_mode == HGIN_MATH_FP32 || math_mode == HGIN_MATH_TF32, "hgin_linear_fwd: bad math_mode %d", math_mode);
+    HGIN_CHECK_ARG(math_mode >= HGIN_MATH_FP32 && math_mode <= HGIN_MATH_BF16, "hgin_linear_fwd: bad math_mode %d", math_mode);
     if (rows == 0) return HGIN_OK;
     HGIN_CHECK_ARG(x1 && W && (k2 == 0 || x2) && (z || out), "hgin_linear_fwd: null pointer");
     HGIN_CHECK_ARG(ld1 >= k1 && (k2 == 0 || ld2 >= k2) && (!z || ldz >= n) && (!out || ldo >= n),
                    "hgin_linear_fwd: leading dimension too small");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (thin::head_fwd_eligible(x1, ld1, k1, k2, n) && aligned16(W))
-        return thin::head_fwd(rows, x1, ld1, k1, W, bias, act, alpha, z, ldz, out, ldo, accumulate_out, s);
-    if (thin::fwd_eligible(x1, k1, k2, n, z, ldz, out, ldo))
-        return thin::linear_fwd(rows, x1, ld1, k1, W, bias, n, act, alpha, z, ldz, out, ldo, accumulate_out, s);
-    if (math_mode == HGIN_MATH_TF32 && tcgemm::fwd_eligible(rows, x1, ld1, k1, k2, n, z, ldz, out, ldo)) {
+    if (thin::head_fwd_eligible(x1, ld1, k1, k2, n, HGIN_DTYPE_F32) && aligned16(W))
+        return thin::head_fwd(rows, x1, ld1, k1, W, bias, act, alpha, z, ldz, out, ldo, accumulate_out, HGIN_DTYPE_F32, s);
+    if (thin::fwd_eligible(x1, k1, k2, n, z, ldz, out, ldo, HGIN_DTYPE_F32))
+        return thin::linear_fwd(rows, x1, ld1, k1, W, bias, n, act, alpha, z, ldz, out, ldo, accumulate_out, HGIN_DTYPE_F32, s);
+    if (math_mode != HGIN_MATH_FP32 && tcgemm::fwd_eligible(rows, x1, ld1, k1, k2, n, z, ldz, out, ldo)) {
         if (!workspace || workspace_bytes < tcgemm::fwd_workspace_bytes(k1 + k2, n))
             return fail(HGIN_ERR_WORKSPACE_TOO_SMALL, "hgin_linear_fwd: workspace too small for the tf32 path");
         return tcgemm::linear_fwd(rows, x1, ld1, k1, x2, ld2, k2, W, bias, n, act, alpha, z, ldz, out, ldo,
@@ -355,8 +356,8 @@ static int64_t simt_bwd_workspace_bytes(int64_t rows, int32_t k, int32_t n) {
 extern "C" int64_t hgin_linear_bwd_workspace_bytes(int64_t rows, int32_t k, int32_t n, int32_t math_mode) {
     if (rows < 0 || k <= 0 || n <= 0) return -1;
     const int64_t simt = simt_bwd_workspace_bytes(rows, k, n);
-    if (math_mode != HGIN_MATH_TF32) return simt;
-    const int64_t tc = hgin::tcgemm::bwd_workspace_bytes(rows, k, k < 4 ? k : 4, n);
+    if (math_mode == HGIN_MATH_FP32) return simt;
+    const int64_t tc = hgin::tcgemm::bwd_workspace_bytes(rows, k, k < 4 ? k : 4, n);   // >= the bf16 kernels' need
     return simt > tc ? simt : tc;
 }
 
@@ -401,7 +402,7 @@ static int32_t linear_bwd_impl(int64_t rows, const float *g, int64_t ldg, const 
     HGIN_CHECK_ARG(act == HGIN_ACT_NONE || z, "hgin_linear_bwd: activation backward needs z");
     HGIN_CHECK_ARG(act != HGIN_ACT_PRELU || alpha, "hgin_linear_bwd: PReLU needs alpha");
     HGIN_CHECK_ARG(0 <= c0 && c0 <= c1 && c1 <= k, "hgin_linear_bwd: bad column range [%d,%d) of %d", c0, c1, k);
-    HGIN_CHECK_ARG(math_mode == HGIN_MATH_FP32 || math_mode == HGIN_MATH_TF32, "hgin_linear_bwd: bad math_mode %d", math_mode);
+    HGIN_CHECK_ARG(math_mode >= HGIN_MATH_FP32 && math_mode <= HGIN_MATH_BF16, "hgin_linear_bwd: bad math_mode %d", math_mode);
     HGIN_CHECK_ARG(!ddot || dot_x, "hgin_linear_bwd: ddot needs dot_x");
     HGIN_CHECK_ARG(g && W && x1 && (k2 == 0 || x2), "hgin_linear_bwd: null pointer");
     const int64_t need = hgin_linear_bwd_workspace_bytes(rows, k, n, math_mode);
@@ -413,19 +414,19 @@ static int32_t linear_bwd_impl(int64_t rows, const float *g, int64_t ldg, const 
     float *dw_partials = static_cast<float *>(workspace);
     float *scal = reinterpret_cast<float *>(static_cast<char *>(workspace) + align_up(splits * n * (k + 1) * 4, 256));
 
-    const bool tc_ok = math_mode == HGIN_MATH_TF32 && rows > 0 &&
+    const bool tc_ok = math_mode != HGIN_MATH_FP32 && rows > 0 &&
         tcgemm::bwd_eligible(rows, g, ldg, z, ldz, act, x1, ld1, k1, k2, n, c0, c1, dx, lddx, dot_x, ld_dot) &&
         (!post || (c1 - c0 >= 16 && post->ldz % 4 == 0 && aligned16(post->z)));
-    if (rows > 0 && thin::head_bwd_eligible(x1, ld1, k1, k2, n, c0, c1, dx, lddx, dot_x, W) && !ddot && !(post && post->self_eps) &&
-        (!post || (post->ldz % 4 == 0 && aligned16(post->z))))
+    if (rows > 0 && thin::head_bwd_eligible(x1, ld1, k1, k2, n, c0, c1, dx, lddx, dot_x, W, HGIN_DTYPE_F32) && !ddot &&
+        !(post && post->self_eps) && (!post || (post->ldz % 4 == 0 && aligned16(post->z))))
         return thin::head_bwd(rows, g, ldg, z, ldz, act, alpha, x1, ld1, k1, W, dx, lddx, dW, db, dalpha, workspace,
                               post ? post->z : nullptr, post ? post->ldz : 0, post ? post->act : HGIN_ACT_NONE,
-                              post ? post->alpha : nullptr, post ? post->dalpha : nullptr,
+                              post ? post->alpha : nullptr, post ? post->dalpha : nullptr, HGIN_DTYPE_F32,
                               static_cast<cudaStream_t>(stream));
     if (post && !tc_ok) return HGIN_ERR_UNSUPPORTED;   // hgin_linear_bwd_post then runs the generic form
-    if (!post && rows > 0 && thin::bwd_eligible(g, ldg, z, ldz, act, k1, k2, n, c0, c1, dx, dot_x))
+    if (!post && rows > 0 && thin::bwd_eligible(g, ldg, z, ldz, act, k1, k2, n, c0, c1, dx, dot_x, HGIN_DTYPE_F32))
         return thin::linear_bwd(rows, g, ldg, z, ldz, act, alpha, x1, ld1, k1, W, n, c0, c1, dot_x, ld_dot, ddot, dW, db,
-                                dalpha, workspace, static_cast<cudaStream_t>(stream));
+                                dalpha, workspace, HGIN_DTYPE_F32, static_cast<cudaStream_t>(stream));
     if (tc_ok) {
         return tcgemm::linear_bwd(rows, g, ldg, z, ldz, act, alpha, x1, ld1, k1, x2, ld2, k2, W, n, c0, c1, dx, lddx,
                                   dot_x, ld_dot, ddot, dW, db, dalpha, workspace, nullptr, post,
@@ -578,6 +579,152 @@ extern "C" int32_t hgin_linear_bwd_post_self(int64_t rows, const float *g, int64
     if (rc == HGIN_ERR_UNSUPPORTED)
         return fail(HGIN_ERR_UNSUPPORTED, "hgin_linear_bwd_post_self: shapes / math mode outside the tensor-core path");
     return rc;
+}
+
+// ---- typed entry points: rows stored as float or bf16 -----------------------------------------------------
+extern "C" int32_t hgin_linear_fwd_t(int32_t in_dtype, int32_t out_dtype, int64_t rows, const void *x1, int64_t ld1,
+                                     int32_t k1, const float *x2, int64_t ld2, int32_t k2, const float *W,
+                                     const float *bias, int32_t n, int32_t act, const float *alpha, void *z, int64_t ldz,
+                                     void *out, int64_t ldo, int32_t accumulate_out, void *workspace,
+                                     int64_t workspace_bytes, int32_t math_mode, void *stream) {
+    using namespace hgin;
+    if (in_dtype == HGIN_DTYPE_F32 && out_dtype == HGIN_DTYPE_F32)
+        return hgin_linear_fwd(rows, static_cast<const float *>(x1), ld1, k1, x2, ld2, k2, W, bias, n, act, alpha,
+                               static_cast<float *>(z), ldz, static_cast<float *>(out), ldo, accumulate_out, workspace,
+                               workspace_bytes, math_mode, stream);
+    HGIN_CHECK_ARG((in_dtype == HGIN_DTYPE_F32 || in_dtype == HGIN_DTYPE_BF16) && (out_dtype == HGIN_DTYPE_F32 || out_dtype == HGIN_DTYPE_BF16),
+                   "hgin_linear_fwd_t: bad dtype %d / %d", in_dtype, out_dtype);
+    HGIN_CHECK_ARG(rows >= 0 && k1 > 0 && k2 >= 0 && n > 0, "hgin_linear_fwd_t: bad sizes rows=%lld k1=%d k2=%d n=%d",
+                   (long long)rows, k1, k2, n);
+    HGIN_CHECK_ARG(act >= HGIN_ACT_NONE && act <= HGIN_ACT_RELU, "hgin_linear_fwd_t: bad act %d", act);
+    HGIN_CHECK_ARG(act != HGIN_ACT_PRELU || alpha, "hgin_linear_fwd_t: PReLU needs alpha");
+    if (rows == 0) return HGIN_OK;
+    HGIN_CHECK_ARG(x1 && W && (k2 == 0 || x2) && (z || out), "hgin_linear_fwd_t: null pointer");
+    HGIN_CHECK_ARG(ld1 >= k1 && (k2 == 0 || ld2 >= k2) && (!z || ldz >= n) && (!out || ldo >= n),
+                   "hgin_linear_fwd_t: leading dimension too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // head (n = 1): wide bf16 input, fp32 output column
+    if (in_dtype == HGIN_DTYPE_BF16 && out_dtype == HGIN_DTYPE_F32) {
+        if (thin::head_fwd_eligible(x1, ld1, k1, k2, n, HGIN_DTYPE_BF16) && aligned16(W))
+            return thin::head_fwd(rows, x1, ld1, k1, W, bias, act, alpha, static_cast<float *>(z), ldz, static_cast<float *>(out),
+                                  ldo, accumulate_out, HGIN_DTYPE_BF16, s);
+        return fail(HGIN_ERR_UNSUPPORTED, "hgin_linear_fwd_t: bf16 rows -> fp32 output is the n = 1 head only");
+    }
+    // thin (K <= 8): narrow fp32 input, wide bf16 output
+    if (in_dtype == HGIN_DTYPE_F32 && out_dtype == HGIN_DTYPE_BF16) {
+        if (thin::fwd_eligible(static_cast<const float *>(x1), k1, k2, n, z, ldz, out, ldo, HGIN_DTYPE_BF16))
+            return thin::linear_fwd(rows, static_cast<const float *>(x1), ld1, k1, W, bias, n, act, alpha, z, ldz, out, ldo,
+                                    accumulate_out, HGIN_DTYPE_BF16, s);
+        return fail(HGIN_ERR_UNSUPPORTED, "hgin_linear_fwd_t: fp32 rows -> bf16 output is the K <= 8 layer only");
+    }
+    if (tcgemm::fwd_eligible_bf16(rows, x1, ld1, k1, k2, n, z, ldz, out, ldo)) {
+        if (!workspace || workspace_bytes < tcgemm::fwd_workspace_bytes_bf16(k1 + k2, n))
+            return fail(HGIN_ERR_WORKSPACE_TOO_SMALL, "hgin_linear_fwd_t: workspace too small for the bf16 path");
+        return tcgemm::linear_fwd_bf16(rows, x1, ld1, k1, x2, ld2, k2, W, bias, n, act, alpha, z, ldz, out, ldo,
+                                       accumulate_out, workspace, s);
+    }
+    return fail(HGIN_ERR_UNSUPPORTED, "hgin_linear_fwd_t: shape outside the bf16 kernels (rows=%lld k1=%d k2=%d n=%d)",
+                (long long)rows, k1, k2, n);
+}
+
+extern "C" int32_t hgin_linear_bwd_t(int32_t g_dtype, int32_t x_dtype, int64_t rows, const void *g, int64_t ldg,
+                                     const void *z, int64_t ldz, int32_t act, const float *alpha, const void *x1,
+                                     int64_t ld1, int32_t k1, const float *x2, int64_t ld2, int32_t k2, const float *W,
+                                     int32_t n, int32_t c0, int32_t c1, void *dx, int64_t lddx, const void *dot_x,
+                                     int64_t ld_dot, float *ddot, float *dW, float *db, float *dalpha,
+                                     const void *post_z, int64_t ld_post, int32_t post_act, const float *post_alpha,
+                                     float *post_dalpha, const float *self_eps, float *post_ddot, void *workspace,
+                                     int64_t workspace_bytes, int32_t math_mode, void *stream) {
+    using namespace hgin;
+    const bool post_on = post_z != nullptr && post_act != HGIN_ACT_NONE;
+    if (g_dtype == HGIN_DTYPE_F32 && x_dtype == HGIN_DTYPE_F32) {
+        if (post_on && (self_eps || post_ddot))
+            return hgin_linear_bwd_post_self(rows, static_cast<const float *>(g), ldg, static_cast<const float *>(z), ldz, act,
+                                             alpha, static_cast<const float *>(x1), ld1, k1, W, n, static_cast<float *>(dx), lddx,
+                                             dW, db, dalpha, static_cast<const float *>(post_z), ld_post, post_act, post_alpha,
+                                             post_dalpha, self_eps, post_ddot, workspace, workspace_bytes, math_mode, stream);
+        if (post_on)
+            return hgin_linear_bwd_post(rows, static_cast<const float *>(g), ldg, static_cast<const float *>(z), ldz, act, alpha,
+                                        static_cast<const float *>(x1), ld1, k1, x2, ld2, k2, W, n, c0, c1,
+                                        static_cast<float *>(dx), lddx, dW, db, dalpha, static_cast<const float *>(post_z),
+                                        ld_post, post_act, post_alpha, post_dalpha, workspace, workspace_bytes, math_mode,
+                                        stream);
+        return hgin_linear_bwd(rows, static_cast<const float *>(g), ldg, static_cast<const float *>(z), ldz, act, alpha,
+                               static_cast<const float *>(x1), ld1, k1, x2, ld2, k2, W, n, c0, c1, static_cast<float *>(dx),
+                               lddx, static_cast<const float *>(dot_x), ld_dot, ddot, dW, db, dalpha, workspace,
+                               workspace_bytes, math_mode, stream);
+    }
+    const int k = k1 + k2;
+    HGIN_CHECK_ARG((g_dtype == HGIN_DTYPE_F32 || g_dtype == HGIN_DTYPE_BF16) && (x_dtype == HGIN_DTYPE_F32 || x_dtype == HGIN_DTYPE_BF16),
+                   "hgin_linear_bwd_t: bad dtype %d / %d", g_dtype, x_dtype);
+    HGIN_CHECK_ARG(rows >= 0 && k1 > 0 && k2 >= 0 && n > 0, "hgin_linear_bwd_t: bad sizes");
+    HGIN_CHECK_ARG(act >= HGIN_ACT_NONE && act <= HGIN_ACT_RELU, "hgin_linear_bwd_t: bad act %d", act);
+    HGIN_CHECK_ARG(act == HGIN_ACT_NONE || z, "hgin_linear_bwd_t: activation backward needs z");
+    HGIN_CHECK_ARG(act != HGIN_ACT_PRELU || alpha, "hgin_linear_bwd_t: PReLU needs alpha");
+    HGIN_CHECK_ARG(0 <= c0 && c0 <= c1 && c1 <= k, "hgin_linear_bwd_t: bad column range [%d,%d) of %d", c0, c1, k);
+    HGIN_CHECK_ARG(!ddot || dot_x, "hgin_linear_bwd_t: ddot needs dot_x");
+    HGIN_CHECK_ARG(g && W && x1 && (k2 == 0 || x2), "hgin_linear_bwd_t: null pointer");
+    HGIN_CHECK_ARG(post_act >= HGIN_ACT_NONE && post_act <= HGIN_ACT_RELU, "hgin_linear_bwd_t: bad post_act %d", post_act);
+    HGIN_CHECK_ARG(!post_on || (dx && c1 > c0 && ld_post >= c1 - c0), "hgin_linear_bwd_t: post-activation needs dx and post_z rows");
+    HGIN_CHECK_ARG(post_act != HGIN_ACT_PRELU || !post_on || post_alpha, "hgin_linear_bwd_t: PReLU needs post_alpha");
+    HGIN_CHECK_ARG(!(self_eps || post_ddot) || (post_on && k2 == 0 && c0 == 0 && c1 == k1),
+                   "hgin_linear_bwd_t: the self-branch epilogue needs a post-activation over all columns of x1");
+    const int64_t need = hgin_linear_bwd_workspace_bytes(rows, k, n, HGIN_MATH_BF16);
+    if (workspace_bytes < need || !workspace)
+        return fail(HGIN_ERR_WORKSPACE_TOO_SMALL, "hgin_linear_bwd_t: workspace %lld < %lld bytes", (long long)workspace_bytes,
+                    (long long)need);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (rows == 0) {
+        if (dW) cudaMemsetAsync(dW, 0, sizeof(float) * n * k, s);
+        if (db) cudaMemsetAsync(db, 0, sizeof(float) * n, s);
+        if (dalpha) cudaMemsetAsync(dalpha, 0, sizeof(float), s);
+        if (ddot) cudaMemsetAsync(ddot, 0, sizeof(float), s);
+        if (post_dalpha) cudaMemsetAsync(post_dalpha, 0, sizeof(float), s);
+        if (post_ddot) cudaMemsetAsync(post_ddot, 0, sizeof(float), s);
+        return HGIN_OK;
+    }
+    // head (n = 1): g / z fp32 columns, x / dx / post_z bf16
+    if (g_dtype == HGIN_DTYPE_F32 && x_dtype == HGIN_DTYPE_BF16) {
+        if (thin::head_bwd_eligible(x1, ld1, k1, k2, n, c0, c1, dx, lddx, dot_x, W, HGIN_DTYPE_BF16) && !ddot && !self_eps &&
+            !post_ddot && (!post_on || (ld_post % 4 == 0 && (reinterpret_cast<uintptr_t>(post_z) & 7u) == 0)))
+            return thin::head_bwd(rows, static_cast<const float *>(g), ldg, static_cast<const float *>(z), ldz, act, alpha, x1,
+                                  ld1, k1, W, dx, lddx, dW, db, dalpha, workspace, post_on ? post_z : nullptr, ld_post,
+                                  post_on ? post_act : HGIN_ACT_NONE, post_alpha, post_dalpha, HGIN_DTYPE_BF16, s);
+        return fail(HGIN_ERR_UNSUPPORTED, "hgin_linear_bwd_t: fp32 gradient with bf16 rows is the n = 1 head only");
+    }
+    // thin (K <= 8): g / z bf16, x / dot_x fp32, no dx
+    if (g_dtype == HGIN_DTYPE_BF16 && x_dtype == HGIN_DTYPE_F32) {
+        if (!post_on && thin::bwd_eligible(g, ldg, z, ldz, act, k1, k2, n, c0, c1, dx, static_cast<const float *>(dot_x),
+                                           HGIN_DTYPE_BF16))
+            return thin::linear_bwd(rows, g, ldg, z, ldz, act, alpha, static_cast<const float *>(x1), ld1, k1, W, n, c0, c1,
+                                    static_cast<const float *>(dot_x), ld_dot, ddot, dW, db, dalpha, workspace,
+                                    HGIN_DTYPE_BF16, s);
+        return fail(HGIN_ERR_UNSUPPORTED, "hgin_linear_bwd_t: bf16 gradient with fp32 rows is the K <= 8 layer only");
+    }
+    if (tcgemm::bwd_eligible_bf16(rows, g, ldg, z, ldz, act, x1, ld1, k1, k2, n, c0, c1, dx, lddx, dot_x, ld_dot) &&
+        (!post_on || (c1 - c0 >= 16 && ld_post % 8 == 0 && aligned16(post_z)))) {
+        tcgemm::PostArgs post{post_z, ld_post, post_act, post_alpha, post_dalpha, self_eps, post_ddot};
+        return tcgemm::linear_bwd_bf16(rows, g, ldg, z, ldz, act, alpha, x1, ld1, k1, x2, ld2, k2, W, n, c0, c1, dx, lddx,
+                                       dot_x, ld_dot, ddot, dW, db, dalpha, workspace, nullptr, post_on ? &post : nullptr, s);
+    }
+    return fail(HGIN_ERR_UNSUPPORTED, "hgin_linear_bwd_t: shape outside the bf16 kernels (rows=%lld k1=%d k2=%d n=%d)",
+                (long long)rows, k1, k2, n);
+}
+
+extern "C" int32_t hgin_debug_gemm_tn_bf16(int64_t rows, const void *a, int32_t n, const void *b, int32_t k, float *out,
+                                           void *workspace, int64_t workspace_bytes, int32_t lbo, int32_t sbo,
+                                           int32_t layout_type, int32_t k_step_bytes, void *stream) {
+    using namespace hgin;
+    HGIN_CHECK_ARG(rows > 0 && a && b && out && n >= 16 && n <= 128 && n % 16 == 0 && k >= 16 && k <= 128 && k % 16 == 0,
+                   "hgin_debug_gemm_tn_bf16: bad arguments");
+    if (!workspace || workspace_bytes < tcgemm::bwd_workspace_bytes_bf16(rows, k, 0, n))
+        return fail(HGIN_ERR_WORKSPACE_TOO_SMALL, "hgin_debug_gemm_tn_bf16: workspace too small");
+    tcgemm::TnDebug d{0, lbo < 0 ? 8192 : lbo, sbo < 0 ? 1024 : sbo, layout_type < 0 ? 2 : layout_type,
+                      k_step_bytes < 0 ? 2048 : k_step_bytes};
+    // dz = a (no activation), dW = a^T b
+    return tcgemm::linear_bwd_bf16(rows, a, n, nullptr, 0, HGIN_ACT_NONE, nullptr, b, k, k, nullptr, 0, 0, out /*W unused*/, n,
+                                   0, 0, nullptr, 0, nullptr, 0, nullptr, out, nullptr, nullptr, workspace, &d, nullptr,
+                                   static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int32_t hgin_debug_gemm_tn(int64_t rows, const float *a, int32_t n, const float *b, int32_t k, float *out,

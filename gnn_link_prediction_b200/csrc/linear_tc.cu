@@ -6,6 +6,7 @@
 #include "linear_tc.cuh"
 #include "linear_tc_fused.cuh"
 #include "linear_tc_dw.cuh"
+#include "tail_sums.cuh"
 
 namespace hgin {
 namespace tcgemm {
@@ -438,7 +439,18 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
             dz_src = g;
             dz_ld = ldg;
         }
-        if (!inplace || want_sums) {
+        if (inplace && want_sums) {     // dz is read in place by the GEMMs: only the column sums are missing
+            static bool attr = false;
+            if (!attr) {
+                cudaFuncSetAttribute(tail_sums_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+                attr = true;
+            }
+            const int slots = TAIL_THREADS / (n / 4);
+            const int ctas = static_cast<int>(ceil_div(rows, slots) < tail_ctas() ? ceil_div(rows, slots) : tail_ctas());
+            tail_sums_kernel<float><<<ctas, TAIL_THREADS, tail_smem<float>(n), s>>>(rows, n, g, ldg, x2, ld2, k2, sum_part);
+            reduce_partials_kernel<<<grid_for(n * (k2 + 1), 256, 1), 256, 0, s>>>(sum_part, ctas, n, k2, 1, dW, k, k1,
+                                                                                 db_from_mma ? nullptr : db);
+        } else if (!inplace) {
             const int tpr = n / 4, slots = DZ_THREADS / tpr;
             const int ctas = static_cast<int>(ceil_div(rows, slots) < dz_ctas() ? ceil_div(rows, slots) : dz_ctas());
             dz_prepare_kernel<<<ctas, DZ_THREADS, static_cast<size_t>(slots) * n * 5 * 4, s>>>(
@@ -461,7 +473,7 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
                   make_map(&tm_b, Wt, n, width, n, KB, width, CU_TENSOR_MAP_SWIZZLE_128B);
         // without a dx destination the store map still needs a valid (never written) target
         ok = ok && make_map(&tm_o, dx ? dx : dz, dx ? width : n, rows, dx ? lddx : n, 32, BM, CU_TENSOR_MAP_SWIZZLE_128B);
-        const float *e_src = post_on ? post->z : (dot_x ? dot_x : dz);
+        const float *e_src = post_on ? static_cast<const float *>(post->z) : (dot_x ? dot_x : dz);
         const int64_t e_ld = post_on ? post->ldz : (dot_x ? ld_dot : n);
         ok = ok && make_map(&tm_e, e_src, (post_on || dot_x) ? width : n, rows, e_ld, 32, BM, CU_TENSOR_MAP_SWIZZLE_128B);
         if (!ok) return fail(HGIN_ERR_CUDA, "hgin_linear_bwd(tf32): cuTensorMapEncodeTiled failed (dx)");

@@ -381,7 +381,7 @@ struct TnSmem {
     static constexpr int total = off_small + 32 * 8 + 64 + 1024;
 };
 
-__global__ void __launch_bounds__(THREADS, 1)
+static __global__ void __launch_bounds__(THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const TnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));

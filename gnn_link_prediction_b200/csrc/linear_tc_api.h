@@ -17,7 +17,7 @@ struct TnDebug {   // overrides of the MN-major descriptor fields (hgin_debug_ge
 };
 
 struct PostArgs {  // activation derivative of the layer BELOW, applied to dx on its way out
-    const float *z;
+    const void *z;   // rows of the same storage type as dx
     int64_t ldz;
     int act;
     const float *alpha;
@@ -47,6 +47,25 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
                    const float *W, int n, int c0, int c1, float *dx, int64_t lddx, const float *dot_x,
                    int64_t ld_dot, float *ddot, float *dW, float *db, float *dalpha, void *workspace,
                    const TnDebug *dbg, const PostArgs *post, cudaStream_t s);
+
+
+// ---- bf16 rows (HGIN_DTYPE_BF16; linear_tc_bf16.cu): x1 / z / out / g / dx / dot_x / post->z are bf16, x2, W, bias and
+// all reductions fp32 --------------------------------------------------------------------------------------------
+bool fwd_eligible_bf16(int64_t rows, const void *x1, int64_t ld1, int k1, int k2, int n, const void *z, int64_t ldz,
+                       const void *out, int64_t ldo);
+bool bwd_eligible_bf16(int64_t rows, const void *g, int64_t ldg, const void *z, int64_t ldz, int act, const void *x1,
+                       int64_t ld1, int k1, int k2, int n, int c0, int c1, const void *dx, int64_t lddx,
+                       const void *dot_x, int64_t ld_dot);
+int64_t fwd_workspace_bytes_bf16(int k1, int n);
+int64_t bwd_workspace_bytes_bf16(int64_t rows, int k1, int k2, int n);
+int32_t linear_fwd_bf16(int64_t rows, const void *x1, int64_t ld1, int k1, const float *x2, int64_t ld2, int k2,
+                        const float *W, const float *bias, int n, int act, const float *alpha, void *z, int64_t ldz,
+                        void *out, int64_t ldo, int accumulate_out, void *workspace, cudaStream_t s);
+int32_t linear_bwd_bf16(int64_t rows, const void *g, int64_t ldg, const void *z, int64_t ldz, int act,
+                        const float *alpha, const void *x1, int64_t ld1, int k1, const float *x2, int64_t ld2, int k2,
+                        const float *W, int n, int c0, int c1, void *dx, int64_t lddx, const void *dot_x,
+                        int64_t ld_dot, float *ddot, float *dW, float *db, float *dalpha, void *workspace,
+                        const TnDebug *dbg, const PostArgs *post, cudaStream_t s);
 
 }  // namespace tcgemm
 }  // namespace hgin

@@ -10,6 +10,8 @@
 //   T[n][c]  = sum_m dz[m][n] dot_x[m][c]  ->  ddot = sum_{n,c} W[n][c0 + c] T[n][c]
 // (the last equals sum_m sum_c (dz W)[m][c0+c] * dot_x[m][c] = d(eps) without materialising dz W).
 // Reductions are deterministic: lanes -> CTA (shared memory, fixed order) -> partials -> final pass.
+#include <cuda_bf16.h>
+
 #include "hgin_common.cuh"
 #include "linear_thin_api.h"
 
@@ -17,16 +19,42 @@ namespace hgin {
 namespace thin {
 namespace {
 
+using bf16 = __nv_bfloat16;
+
+// The WIDE side of these layers (z / out / g of the K <= 8 layers, x / dx of the head) is stored as float or bf16
+// (HGIN_DTYPE_*); the narrow side (K <= 8 inputs, the single head column) and all arithmetic stay fp32.
+// ldg4 / ld4 / st4: four consecutive elements as one 16-byte (float) or 8-byte (bf16) access.
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float4 ldg4(const bf16 *p) {
+    const uint2 q = __ldg(reinterpret_cast<const uint2 *>(p));
+    return make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u), __uint_as_float(q.y << 16),
+                       __uint_as_float(q.y & 0xffff0000u));
+}
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ float4 ld4(const bf16 *p) {
+    const uint2 q = *reinterpret_cast<const uint2 *>(p);
+    return make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u), __uint_as_float(q.y << 16),
+                       __uint_as_float(q.y & 0xffff0000u));
+}
+__device__ __forceinline__ void st4(float *p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ void st4(bf16 *p, float a, float b, float c, float d) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    *reinterpret_cast<uint2 *>(p) = make_uint2(*reinterpret_cast<const uint32_t *>(&lo), *reinterpret_cast<const uint32_t *>(&hi));
+}
+
 constexpr int THREADS = 256;
 constexpr int KMAX = 8;
 constexpr int DMAX = 4;                      // max dot_x columns
 constexpr int NACC = 4 * KMAX + 4 * DMAX + 4 + 1;  // per-thread accumulators: dW, T, db, dalpha = 53
 constexpr int FWD_BLK = 256;                       // rows per CTA iteration of thin_fwd (>= the most row slots a CTA has)
 
+template <typename TW>
 __global__ void __launch_bounds__(THREADS)
 thin_fwd_kernel(int64_t rows, const float *__restrict__ x, int64_t ldx, int k, const float *__restrict__ W,
                 const float *__restrict__ bias, int n, int act, const float *__restrict__ alpha_ptr,
-                float *__restrict__ z, int64_t ldz, float *__restrict__ out, int64_t ldo, int accumulate_out) {
+                TW *__restrict__ z, int64_t ldz, TW *__restrict__ out, int64_t ldo, int accumulate_out) {
     const int lpr = n >> 2;                        // lanes per row
     const int cg = threadIdx.x % lpr;              // column group: columns 4cg .. 4cg+3
     const int grp = threadIdx.x / lpr;             // row slot inside the CTA
@@ -87,17 +115,17 @@ thin_fwd_kernel(int64_t rows, const float *__restrict__ x, int64_t ldx, int k, c
                 for (int kk = 0; kk < KMAX; ++kk) s = fmaf(xv[kk], w[i][kk], s);
                 zz[i] = s + b[i];
             }
-            if (z) *reinterpret_cast<float4 *>(z + m * ldz + cg * 4) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+            if (z) st4(z + m * ldz + cg * 4, zz[0], zz[1], zz[2], zz[3]);
             if (out) {
                 float o[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) o[i] = act_forward(zz[i], act, alpha);
-                float4 *po = reinterpret_cast<float4 *>(out + m * ldo + cg * 4);
+                TW *po = out + m * ldo + cg * 4;
                 if (accumulate_out) {
-                    const float4 old = *po;
+                    const float4 old = ld4(po);
                     o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w;
                 }
-                *po = make_float4(o[0], o[1], o[2], o[3]);
+                st4(po, o[0], o[1], o[2], o[3]);
             }
         }
         __syncthreads();     // everyone is done with xs[buf] before the next iteration stages into it
@@ -143,9 +171,9 @@ __device__ __forceinline__ void thin_bwd_combine(const float (&acc)[NACC], float
 }
 
 // part[cta][n][kp], kp = k + d + 1: columns [0,k) = dW, [k, k+d) = T, k+d = db;  alpha_part[cta].
-template <bool HAS_ACT>
+template <bool HAS_ACT, typename TW>
 __global__ void __launch_bounds__(THREADS, 2)
-thin_bwd_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, const float *__restrict__ z, int64_t ldz,
+thin_bwd_kernel(int64_t rows, const TW *__restrict__ g, int64_t ldg, const TW *__restrict__ z, int64_t ldz,
                 int act, const float *__restrict__ alpha_ptr, const float *__restrict__ x, int64_t ldx, int k,
                 const float *__restrict__ dot_x, int64_t ld_dot, int d, int n, float *__restrict__ part,
                 float *__restrict__ alpha_part) {
@@ -180,8 +208,8 @@ thin_bwd_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, const fl
             gq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (HAS_ACT) zq[u] = make_float4(1.f, 1.f, 1.f, 1.f);
             if (u < rif && m < rows) {
-                gq[u] = __ldg(reinterpret_cast<const float4 *>(g + m * ldg) + cg);
-                if (HAS_ACT) zq[u] = __ldg(reinterpret_cast<const float4 *>(z + m * ldz) + cg);
+                gq[u] = ldg4(g + m * ldg + cg * 4);
+                if (HAS_ACT) zq[u] = ldg4(z + m * ldz + cg * 4);
             }
         }
         __syncthreads();                                 // the previous block's tiles have been consumed
@@ -226,22 +254,30 @@ thin_bwd_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, const fl
 }
 
 // thin_bwd for ACT_NONE (g already is dz): every warp runs its own cp.async pipeline — each thread
-// copies exactly the 16-byte pieces of g it will consume itself and the lanes of a row group copy that
-// row's x / dot_x entries — one block AHEAD into a double buffer, so no load latency sits between the
-// row blocks and no CTA barrier is needed (a row group never spans warps: n <= 128).  Dynamic shared
-// memory: 2 x blk x (n + XP + DP) floats.
-constexpr int BWD_RIF = 8;
-inline int thin_bwd_rif(int n) {
+// copies exactly the pieces of g it will consume itself and the lanes of a row group copy that
+// row's x / dot_x entries — TWO blocks ahead into a three-slot ring, so no load latency sits between the
+// row blocks and no CTA barrier is needed (a row group never spans warps: n <= 128).  Two blocks in flight
+// per CTA, two CTAs per SM: ~128 KB (fp32) / 64 KB (bf16) of g outstanding per SM; the double-buffered version
+// held half of that and ran at 2.7 TB/s.  Dynamic shared memory: NST x blk x (n x sizeof(TW) + (XP + DP) x 4).
+constexpr int BWD_NST = 3;
+inline int thin_bwd_rif(int n, int elem_bytes) {
     const int slots = THREADS / (n >> 2);
-    return BWD_RIF < 256 / slots ? BWD_RIF : 256 / slots;   // blocks of at most 256 rows: <= 94 KB of buffers
+    const int max_rows = elem_bytes == 2 ? 96 : 56;           // rows per block: three slots x two CTAs fit one SM
+    const int rif = max_rows / slots;
+    return rif < 1 ? 1 : (rif > 16 ? 16 : rif);
 }
-inline size_t thin_bwd_async_smem(int n) {
-    const int blk = (THREADS / (n >> 2)) * thin_bwd_rif(n);
-    return static_cast<size_t>(2) * blk * (n + (KMAX + 1) + (DMAX + 1)) * sizeof(float);
+inline size_t thin_bwd_async_smem(int n, int elem_bytes) {
+    const int blk = (THREADS / (n >> 2)) * thin_bwd_rif(n, elem_bytes);
+    return static_cast<size_t>(BWD_NST) * blk * (static_cast<size_t>(n) * elem_bytes + ((KMAX + 1) + (DMAX + 1)) * sizeof(float));
 }
 
-__device__ __forceinline__ void cp_async16(float *dst, const float *src) {
+// the 4 columns a thread consumes: 16 bytes of fp32, 8 bytes of bf16
+__device__ __forceinline__ void cp_async_cols4(float *dst, const float *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_cols4(bf16 *dst, const bf16 *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src)
                  : "memory");
 }
 __device__ __forceinline__ void cp_async4(float *dst, const float *src) {
@@ -249,11 +285,12 @@ __device__ __forceinline__ void cp_async4(float *dst, const float *src) {
                  : "memory");
 }
 
+template <typename TW>
 __global__ void __launch_bounds__(THREADS, 2)
-thin_bwd_async_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, const float *__restrict__ x, int64_t ldx,
+thin_bwd_async_kernel(int64_t rows, const TW *__restrict__ g, int64_t ldg, const float *__restrict__ x, int64_t ldx,
                       int k, const float *__restrict__ dot_x, int64_t ld_dot, int d, int n, int rif,
                       float *__restrict__ part) {
-    extern __shared__ __align__(16) float dyn[];
+    extern __shared__ __align__(16) uint8_t dyn_raw[];
     __shared__ float sm[THREADS * 8];
     __shared__ float red[32];
     constexpr int XP = KMAX + 1, DP = DMAX + 1;
@@ -262,21 +299,23 @@ thin_bwd_async_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, co
     const int grp = threadIdx.x / lpr;
     const int slots_per_cta = THREADS / lpr;
     const int blk = slots_per_cta * rif;
-    float *gs = dyn;                                   // [2][blk][n]
-    float *xs = gs + static_cast<size_t>(2) * blk * n; // [2][blk][XP]
-    float *ds = xs + static_cast<size_t>(2) * blk * XP;   // [2][blk][DP]
+    TW *gs = reinterpret_cast<TW *>(dyn_raw);          // [NST][blk][n]
+    float *xs = reinterpret_cast<float *>(gs + static_cast<size_t>(BWD_NST) * blk * n);   // [NST][blk][XP]
+    float *ds = xs + static_cast<size_t>(BWD_NST) * blk * XP;   // [NST][blk][DP]
     float acc[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.0f;
 
-    auto stage = [&](int buf, int64_t base) {
-        for (int u = 0; u < rif; ++u) {
-            const int r = u * slots_per_cta + grp;
-            const int64_t m = base + r;
-            if (m < rows) {
-                cp_async16(gs + (static_cast<size_t>(buf) * blk + r) * n + cg * 4, g + m * ldg + cg * 4);
-                for (int kk = cg; kk < k; kk += lpr) cp_async4(xs + (static_cast<size_t>(buf) * blk + r) * XP + kk, x + m * ldx + kk);
-                for (int c = cg; c < d; c += lpr) cp_async4(ds + (static_cast<size_t>(buf) * blk + r) * DP + c, dot_x + m * ld_dot + c);
+    auto stage = [&](int buf, int64_t base) {     // always commits a group (possibly empty): uniform group counting
+        if (base < rows) {
+            for (int u = 0; u < rif; ++u) {
+                const int r = u * slots_per_cta + grp;
+                const int64_t m = base + r;
+                if (m < rows) {
+                    cp_async_cols4(gs + (static_cast<size_t>(buf) * blk + r) * n + cg * 4, g + m * ldg + cg * 4);
+                    for (int kk = cg; kk < k; kk += lpr) cp_async4(xs + (static_cast<size_t>(buf) * blk + r) * XP + kk, x + m * ldx + kk);
+                    for (int c = cg; c < d; c += lpr) cp_async4(ds + (static_cast<size_t>(buf) * blk + r) * DP + c, dot_x + m * ld_dot + c);
+                }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -284,19 +323,16 @@ thin_bwd_async_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, co
     const int64_t step = static_cast<int64_t>(gridDim.x) * blk;
     int64_t base = static_cast<int64_t>(blockIdx.x) * blk;
     int buf = 0;
-    if (base < rows) stage(0, base);
-    for (; base < rows; base += step, buf ^= 1) {
-        if (base + step < rows) {
-            stage(buf ^ 1, base + step);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
+    stage(0, base);
+    stage(1, base + step);
+    for (; base < rows; base += step) {
+        stage((buf + 2) % BWD_NST, base + 2 * step);
+        asm volatile("cp.async.wait_group 2;" ::: "memory");   // the group of `buf` has landed
         __syncwarp();                                  // the x / dot_x entries were copied by other lanes of the row group
         for (int u = 0; u < rif; ++u) {
             const int r = u * slots_per_cta + grp;
             if (base + r >= rows) break;
-            const float4 gv = *reinterpret_cast<const float4 *>(gs + (static_cast<size_t>(buf) * blk + r) * n + cg * 4);
+            const float4 gv = ld4(gs + (static_cast<size_t>(buf) * blk + r) * n + cg * 4);
             const float dz[4] = {gv.x, gv.y, gv.z, gv.w};
             const float *xr = xs + (static_cast<size_t>(buf) * blk + r) * XP;
             const float *dr = ds + (static_cast<size_t>(buf) * blk + r) * DP;
@@ -314,8 +350,10 @@ thin_bwd_async_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, co
                 acc[48 + i] += dz[i];
             }
         }
-        __syncwarp();                                  // done with buf before the next iteration stages into it
+        __syncwarp();                                  // done with buf before a later iteration stages into it
+        buf = (buf + 1) % BWD_NST;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     thin_bwd_combine(acc, sm, red, lpr, slots_per_cta, k, d, n, part, nullptr);
 }
 
@@ -369,8 +407,9 @@ thin_scalars_kernel(const float *__restrict__ tbuf, int n, int k, int d, const f
 // ---- readout head: n = 1 output column (models.py:328), k <= 128 ---------------------------------
 // k/4 lanes per row, each owning 4 input columns: forward is a segmented dot product, backward
 // streams g, z, x once and produces dx = dz * w, dW = sum_m dz x, db, dalpha.
+template <typename TX>
 __global__ void __launch_bounds__(THREADS)
-head_fwd_kernel(int64_t rows, const float *__restrict__ x, int64_t ldx, int k, const float *__restrict__ W,
+head_fwd_kernel(int64_t rows, const TX *__restrict__ x, int64_t ldx, int k, const float *__restrict__ W,
                 const float *__restrict__ bias, int act, const float *__restrict__ alpha_ptr, float *__restrict__ z,
                 int64_t ldz, float *__restrict__ out, int64_t ldo, int accumulate_out) {
     const int lpr = k >> 2;
@@ -385,7 +424,7 @@ head_fwd_kernel(int64_t rows, const float *__restrict__ x, int64_t ldx, int k, c
         const int64_t m = it * slots + slot;
         float s = 0.0f;
         if (m < rows) {
-            const float4 xv = __ldg(reinterpret_cast<const float4 *>(x + m * ldx) + cg);
+            const float4 xv = ldg4(x + m * ldx + cg * 4);
             s = fmaf(xv.x, w.x, fmaf(xv.y, w.y, fmaf(xv.z, w.z, xv.w * w.w)));
         }
         for (int o = lpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -400,11 +439,12 @@ head_fwd_kernel(int64_t rows, const float *__restrict__ x, int64_t ldx, int k, c
     }
 }
 
+template <typename TX>
 __global__ void __launch_bounds__(THREADS)
 head_bwd_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, const float *__restrict__ z, int64_t ldz,
-                int act, const float *__restrict__ alpha_ptr, const float *__restrict__ x, int64_t ldx, int k,
-                const float *__restrict__ W, float *__restrict__ dx, int64_t lddx, float *__restrict__ part,
-                float *__restrict__ alpha_part, const float *__restrict__ pz, int64_t ldpz, int pact,
+                int act, const float *__restrict__ alpha_ptr, const TX *__restrict__ x, int64_t ldx, int k,
+                const float *__restrict__ W, TX *__restrict__ dx, int64_t lddx, float *__restrict__ part,
+                float *__restrict__ alpha_part, const TX *__restrict__ pz, int64_t ldpz, int pact,
                 const float *__restrict__ palpha_ptr, float *__restrict__ palpha_part) {
     // pz != NULL: dx leaves as dx * act'(pz) (the dz of the layer that produced x) and
     // palpha_part[cta] = sum dx * min(pz, 0) — see hgin_linear_bwd_post.
@@ -426,14 +466,14 @@ head_bwd_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, const fl
             if (cg == 0 && act == HGIN_ACT_PRELU && !(zv > 0.0f)) adal += dz * zv;
             dz = act_backward(dz, zv, act, alpha);
         }
-        const float4 xv = __ldg(reinterpret_cast<const float4 *>(x + m * ldx) + cg);
+        const float4 xv = ldg4(x + m * ldx + cg * 4);
         aw[0] = fmaf(dz, xv.x, aw[0]); aw[1] = fmaf(dz, xv.y, aw[1]);
         aw[2] = fmaf(dz, xv.z, aw[2]); aw[3] = fmaf(dz, xv.w, aw[3]);
         if (cg == 0) adb += dz;
         if (dx) {
             float o[4] = {dz * w.x, dz * w.y, dz * w.z, dz * w.w};
             if (pz) {
-                const float4 p4 = __ldg(reinterpret_cast<const float4 *>(pz + m * ldpz) + cg);
+                const float4 p4 = ldg4(pz + m * ldpz + cg * 4);
                 const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -441,7 +481,7 @@ head_bwd_kernel(int64_t rows, const float *__restrict__ g, int64_t ldg, const fl
                     o[i] = act_backward(o[i], pv[i], pact, palpha);
                 }
             }
-            reinterpret_cast<float4 *>(dx + m * lddx)[cg] = make_float4(o[0], o[1], o[2], o[3]);
+            st4(dx + m * lddx + cg * 4, o[0], o[1], o[2], o[3]);
         }
     }
 #pragma unroll
@@ -475,17 +515,21 @@ inline int thin_ctas(int64_t rows, int n, int per_sm = 4) {
 
 }  // namespace
 
-bool fwd_eligible(const float *x1, int k1, int k2, int n, const float *z, int64_t ldz, const float *out, int64_t ldo) {
-    return x1 && k2 == 0 && k1 <= KMAX && n >= 4 && n <= 128 && pow2(n) && (!z || (ldz % 4 == 0 && aligned16(z))) &&
-           (!out || (ldo % 4 == 0 && aligned16(out)));
+// rows of 4 wide-side columns must be vector-addressable: 16 B of fp32, 8 B of bf16
+inline bool wide_ok(const void *p, int64_t ld, int dtype) {
+    if (!p) return true;
+    return dtype == HGIN_DTYPE_BF16 ? (ld % 4 == 0 && (reinterpret_cast<uintptr_t>(p) & 7u) == 0) : (ld % 4 == 0 && aligned16(p));
 }
 
-bool bwd_eligible(const float *g, int64_t ldg, const float *z, int64_t ldz, int act, int k1, int k2, int n, int c0,
-                  int c1, const float *dx, const float *dot_x) {
+bool fwd_eligible(const float *x1, int k1, int k2, int n, const void *z, int64_t ldz, const void *out, int64_t ldo, int dtype) {
+    return x1 && k2 == 0 && k1 <= KMAX && n >= 4 && n <= 128 && pow2(n) && wide_ok(z, ldz, dtype) && wide_ok(out, ldo, dtype);
+}
+
+bool bwd_eligible(const void *g, int64_t ldg, const void *z, int64_t ldz, int act, int k1, int k2, int n, int c0,
+                  int c1, const void *dx, const float *dot_x, int dtype) {
     const int d = dot_x ? c1 - c0 : 0;
     return k2 == 0 && k1 <= KMAX && n >= 4 && n <= 128 && pow2(n) && dx == nullptr && d <= DMAX &&
-           (c1 == c0 || dot_x != nullptr) && ldg % 4 == 0 && aligned16(g) &&
-           (act == HGIN_ACT_NONE || (z && ldz % 4 == 0 && aligned16(z)));
+           (c1 == c0 || dot_x != nullptr) && g && wide_ok(g, ldg, dtype) && (act == HGIN_ACT_NONE || (z && wide_ok(z, ldz, dtype)));
 }
 
 int64_t bwd_workspace_bytes(int n, int k) {
@@ -496,33 +540,38 @@ int64_t bwd_workspace_bytes(int n, int k) {
 }
 
 int32_t linear_fwd(int64_t rows, const float *x, int64_t ldx, int k, const float *W, const float *bias, int n, int act,
-                   const float *alpha, float *z, int64_t ldz, float *out, int64_t ldo, int accumulate_out,
+                   const float *alpha, void *z, int64_t ldz, void *out, int64_t ldo, int accumulate_out, int dtype,
                    cudaStream_t s) {
-    thin_fwd_kernel<<<thin_ctas(rows, n), THREADS, 0, s>>>(rows, x, ldx, k, W, bias, n, act, alpha, z, ldz, out, ldo,
-                                                          accumulate_out);
+    if (dtype == HGIN_DTYPE_BF16)
+        thin_fwd_kernel<bf16><<<thin_ctas(rows, n), THREADS, 0, s>>>(rows, x, ldx, k, W, bias, n, act, alpha, static_cast<bf16 *>(z),
+                                                                    ldz, static_cast<bf16 *>(out), ldo, accumulate_out);
+    else
+        thin_fwd_kernel<float><<<thin_ctas(rows, n), THREADS, 0, s>>>(rows, x, ldx, k, W, bias, n, act, alpha, static_cast<float *>(z),
+                                                                     ldz, static_cast<float *>(out), ldo, accumulate_out);
     HGIN_CHECK_LAUNCH("hgin_linear_fwd(thin)");
     return HGIN_OK;
 }
 
-int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, int64_t ldz, int act, const float *alpha,
-                   const float *x, int64_t ldx, int k, const float *W, int n, int c0, int c1, const float *dot_x,
-                   int64_t ld_dot, float *ddot, float *dW, float *db, float *dalpha, void *workspace, cudaStream_t s) {
+template <typename TW>
+static int32_t linear_bwd_t(int64_t rows, const TW *g, int64_t ldg, const TW *z, int64_t ldz, int act, const float *alpha,
+                            const float *x, int64_t ldx, int k, const float *W, int n, int c0, int c1, const float *dot_x,
+                            int64_t ld_dot, float *ddot, float *dW, float *db, float *dalpha, void *workspace, cudaStream_t s) {
     const int d = dot_x ? c1 - c0 : 0;
     const int ctas = thin_ctas(rows, n, 2);   // 128 registers/thread: two resident CTAs per SM, one wave
     float *part = static_cast<float *>(workspace);
     float *alpha_part = part + static_cast<int64_t>(ctas) * n * (k + d + 1);
     const bool want_alpha = dalpha && act == HGIN_ACT_PRELU;
     if (act != HGIN_ACT_NONE)
-        thin_bwd_kernel<true><<<ctas, THREADS, 0, s>>>(rows, g, ldg, z, ldz, act, alpha, x, ldx, k, dot_x, ld_dot, d, n, part,
-                                                       want_alpha ? alpha_part : nullptr);
+        thin_bwd_kernel<true, TW><<<ctas, THREADS, 0, s>>>(rows, g, ldg, z, ldz, act, alpha, x, ldx, k, dot_x, ld_dot, d, n, part,
+                                                           want_alpha ? alpha_part : nullptr);
     else {
         static bool attr_set = false;
         if (!attr_set) {
-            cudaFuncSetAttribute(thin_bwd_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            cudaFuncSetAttribute(thin_bwd_async_kernel<TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
             attr_set = true;
         }
-        thin_bwd_async_kernel<<<ctas, THREADS, thin_bwd_async_smem(n), s>>>(rows, g, ldg, x, ldx, k, dot_x, ld_dot, d, n,
-                                                                             thin_bwd_rif(n), part);
+        thin_bwd_async_kernel<TW><<<ctas, THREADS, thin_bwd_async_smem(n, sizeof(TW)), s>>>(rows, g, ldg, x, ldx, k, dot_x, ld_dot, d,
+                                                                                             n, thin_bwd_rif(n, sizeof(TW)), part);
     }
     float *tbuf = alpha_part + ctas;
     const int total = n * (k + d + 1);
@@ -534,28 +583,44 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
     return HGIN_OK;
 }
 
-bool head_fwd_eligible(const float *x1, int64_t ld1, int k1, int k2, int n) {
-    return n == 1 && k2 == 0 && k1 >= 4 && k1 <= 128 && k1 % 4 == 0 && pow2(k1 >> 2) && ld1 % 4 == 0 && aligned16(x1);
+int32_t linear_bwd(int64_t rows, const void *g, int64_t ldg, const void *z, int64_t ldz, int act, const float *alpha,
+                   const float *x, int64_t ldx, int k, const float *W, int n, int c0, int c1, const float *dot_x,
+                   int64_t ld_dot, float *ddot, float *dW, float *db, float *dalpha, void *workspace, int dtype,
+                   cudaStream_t s) {
+    if (dtype == HGIN_DTYPE_BF16)
+        return linear_bwd_t<bf16>(rows, static_cast<const bf16 *>(g), ldg, static_cast<const bf16 *>(z), ldz, act, alpha, x, ldx, k,
+                                  W, n, c0, c1, dot_x, ld_dot, ddot, dW, db, dalpha, workspace, s);
+    return linear_bwd_t<float>(rows, static_cast<const float *>(g), ldg, static_cast<const float *>(z), ldz, act, alpha, x, ldx, k,
+                               W, n, c0, c1, dot_x, ld_dot, ddot, dW, db, dalpha, workspace, s);
 }
 
-bool head_bwd_eligible(const float *x1, int64_t ld1, int k1, int k2, int n, int c0, int c1, const float *dx,
-                       int64_t lddx, const float *dot_x, const float *W) {
-    return head_fwd_eligible(x1, ld1, k1, k2, n) && dot_x == nullptr && aligned16(W) &&
-           (dx == nullptr || (c0 == 0 && c1 == k1 && lddx % 4 == 0 && aligned16(dx))) && (c1 == c0 || dx != nullptr);
+bool head_fwd_eligible(const void *x1, int64_t ld1, int k1, int k2, int n, int dtype) {
+    return n == 1 && k2 == 0 && k1 >= 4 && k1 <= 128 && k1 % 4 == 0 && pow2(k1 >> 2) && x1 && wide_ok(x1, ld1, dtype);
 }
 
-int32_t head_fwd(int64_t rows, const float *x, int64_t ldx, int k, const float *W, const float *bias, int act,
-                 const float *alpha, float *z, int64_t ldz, float *out, int64_t ldo, int accumulate_out, cudaStream_t s) {
-    head_fwd_kernel<<<thin_ctas(rows, k), THREADS, 0, s>>>(rows, x, ldx, k, W, bias, act, alpha, z, ldz, out, ldo,
-                                                          accumulate_out);
+bool head_bwd_eligible(const void *x1, int64_t ld1, int k1, int k2, int n, int c0, int c1, const void *dx,
+                       int64_t lddx, const void *dot_x, const float *W, int dtype) {
+    return head_fwd_eligible(x1, ld1, k1, k2, n, dtype) && dot_x == nullptr && aligned16(W) &&
+           (dx == nullptr || (c0 == 0 && c1 == k1 && wide_ok(dx, lddx, dtype))) && (c1 == c0 || dx != nullptr);
+}
+
+int32_t head_fwd(int64_t rows, const void *x, int64_t ldx, int k, const float *W, const float *bias, int act,
+                 const float *alpha, float *z, int64_t ldz, float *out, int64_t ldo, int accumulate_out, int dtype,
+                 cudaStream_t s) {
+    if (dtype == HGIN_DTYPE_BF16)
+        head_fwd_kernel<bf16><<<thin_ctas(rows, k), THREADS, 0, s>>>(rows, static_cast<const bf16 *>(x), ldx, k, W, bias, act, alpha,
+                                                                    z, ldz, out, ldo, accumulate_out);
+    else
+        head_fwd_kernel<float><<<thin_ctas(rows, k), THREADS, 0, s>>>(rows, static_cast<const float *>(x), ldx, k, W, bias, act,
+                                                                     alpha, z, ldz, out, ldo, accumulate_out);
     HGIN_CHECK_LAUNCH("hgin_linear_fwd(head)");
     return HGIN_OK;
 }
 
 int32_t head_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, int64_t ldz, int act, const float *alpha,
-                 const float *x, int64_t ldx, int k, const float *W, float *dx, int64_t lddx, float *dW, float *db,
-                 float *dalpha, void *workspace, const float *post_z, int64_t ld_post, int post_act,
-                 const float *post_alpha, float *post_dalpha, cudaStream_t s) {
+                 const void *x, int64_t ldx, int k, const float *W, void *dx, int64_t lddx, float *dW, float *db,
+                 float *dalpha, void *workspace, const void *post_z, int64_t ld_post, int post_act,
+                 const float *post_alpha, float *post_dalpha, int dtype, cudaStream_t s) {
     const int ctas = thin_ctas(rows, k);
     float *part = static_cast<float *>(workspace);
     float *alpha_part = part + static_cast<int64_t>(ctas) * (k + 1);
@@ -564,9 +629,16 @@ int32_t head_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, int6
     const bool want_alpha = dalpha && act == HGIN_ACT_PRELU;
     const bool post_on = post_z && dx && post_act != HGIN_ACT_NONE;
     const bool want_palpha = post_on && post_dalpha && post_act == HGIN_ACT_PRELU;
-    head_bwd_kernel<<<ctas, THREADS, 0, s>>>(rows, g, ldg, z, ldz, act, alpha, x, ldx, k, W, dx, lddx, part,
-                                             want_alpha ? alpha_part : nullptr, post_on ? post_z : nullptr, ld_post,
-                                             post_act, post_alpha, want_palpha ? palpha_part : nullptr);
+    if (dtype == HGIN_DTYPE_BF16)
+        head_bwd_kernel<bf16><<<ctas, THREADS, 0, s>>>(rows, g, ldg, z, ldz, act, alpha, static_cast<const bf16 *>(x), ldx, k, W,
+                                                      static_cast<bf16 *>(dx), lddx, part, want_alpha ? alpha_part : nullptr,
+                                                      post_on ? static_cast<const bf16 *>(post_z) : nullptr, ld_post, post_act,
+                                                      post_alpha, want_palpha ? palpha_part : nullptr);
+    else
+        head_bwd_kernel<float><<<ctas, THREADS, 0, s>>>(rows, g, ldg, z, ldz, act, alpha, static_cast<const float *>(x), ldx, k, W,
+                                                       static_cast<float *>(dx), lddx, part, want_alpha ? alpha_part : nullptr,
+                                                       post_on ? static_cast<const float *>(post_z) : nullptr, ld_post, post_act,
+                                                       post_alpha, want_palpha ? palpha_part : nullptr);
     thin_finalize_kernel<<<static_cast<unsigned>(ceil_div(k + 1, 8)), 256, 0, s>>>(part, ctas, 1, k, 0, dW, db, tbuf);
     if (dalpha) thin_scalars_kernel<<<1, 256, 0, s>>>(tbuf, 1, k, 0, W, 0, nullptr, want_alpha ? alpha_part : nullptr, ctas, dalpha);
     if (post_dalpha)

@@ -18,7 +18,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
-from .ops import ACT_NONE, ACT_PRELU, ACT_RELU, MATH_FP32, SELF_ADD, SELF_CONCAT, SELF_NONE, HginError
+from .ops import ACT_NONE, ACT_PRELU, ACT_RELU, MATH_BF16, MATH_FP32, SELF_ADD, SELF_CONCAT, SELF_NONE, HginError
 
 
 class GraphCSR:
@@ -89,7 +89,7 @@ def _fold_eligible(rows, k, n, math_mode):
     """Shapes for which the backward consumes dz in place (csrc/linear_tc.cu, linear_thin.cu): only
     there does moving act'(z) into the producer of the gradient remove a pass over the rows (and
     lets d(eps) of the layer above come out of the same pass)."""
-    if math_mode != ops.MATH_TF32:
+    if math_mode not in (ops.MATH_TF32, ops.MATH_BF16):
         return False
     tensor_core = rows >= 128 and 16 <= k <= 128 and k % 16 == 0 and 16 <= n <= 128 and n % 16 == 0
     thin = k <= 8 and 4 <= n <= 128 and (n & (n - 1)) == 0      # csrc/linear_thin.cu: reads g only with ACT_NONE
@@ -115,6 +115,8 @@ class HeteroConvFn(torch.autograd.Function):
         xs = dict(zip(types, tensors[:nt]))
         params = tensors[nt:]
         training = any(ctx.needs_input_grad)
+        # HGIN_MATH_BF16: every activation this layer produces is STORED as bf16 (half the bytes per row)
+        out_dt = torch.bfloat16 if math_mode == MATH_BF16 else torch.float32
         outs, saved = {}, []
         for i, sp in enumerate(specs):
             W, b, alpha, eps = params[4 * i:4 * i + 4]
@@ -125,6 +127,8 @@ class HeteroConvFn(torch.autograd.Function):
                 pre["src_act"] = (lz_src.act, lz_src.alpha)
             if lz_dst is not None and lz_dst.lazy:
                 pre["self_act"] = (lz_dst.act, lz_dst.alpha)
+            if x_dst.dtype != x_src.dtype:      # (mixed storage types only arise outside HetroGIN.forward)
+                x_dst = x_dst.to(x_src.dtype)
             h = ops.gin_combine(graph.fwd(sp.et), x_src, x_dst, eps, SELF_CONCAT if sp.concat else SELF_ADD, **pre)
             link_ok = (training and links_out is not None and sp.act != ACT_NONE
                        and sum(1 for q in specs if q.dst == sp.dst) == 1
@@ -132,7 +136,7 @@ class HeteroConvFn(torch.autograd.Function):
             lazy = bool(link_ok and allow_lazy and ctx.needs_input_grad[7 + nt + 4 * i])
             z, o = ops.linear_fwd(h, W, b, act=sp.act, alpha=alpha, want_z=training and sp.act != ACT_NONE,
                                   out=outs.get(sp.dst), accumulate_out=sp.dst in outs, math_mode=math_mode,
-                                  want_out=not lazy)
+                                  want_out=not lazy, out_dtype=out_dt)
             outs[sp.dst] = z if lazy else o
             saved += [h if training else None, z]
             if training and ctx.needs_input_grad[7 + types.index(sp.src)]:
@@ -201,8 +205,8 @@ class HeteroConvFn(torch.autograd.Function):
                 src_ok = (not need_x[sp.src]) or (g_is_dz and plan[sp.src] == [(si, None)])
                 if (not sp.concat and src_ok
                         and ops.post_self_eligible(h_si.shape[0], h_si.shape[1], W_si.shape[0], ctx.math_mode)
-                        and tuple(post.z.shape) == tuple(h_si.shape) and post.z.stride(0) % 4 == 0
-                        and post.z.data_ptr() % 16 == 0):
+                        and tuple(post.z.shape) == tuple(h_si.shape) and post.z.dtype == h_si.dtype
+                        and (post.z.stride(0) * post.z.element_size()) % 16 == 0 and post.z.data_ptr() % 16 == 0):
                     self_in_gemm[si] = t
 
         dh_agg_of, dh_self_of = {}, {}
@@ -308,8 +312,10 @@ class LinearActFn(torch.autograd.Function):
         """link_in: ops.PostAct of the layer that produced x1 (or None); link_out: a list that receives
         this layer's own PostAct for the next layer in the chain (see HeteroConvFn)."""
         training = any(ctx.needs_input_grad)
+        # HGIN_MATH_BF16: hidden readout activations are stored as bf16; the n = 1 score column stays fp32
+        out_dt = torch.bfloat16 if (math_mode == MATH_BF16 and W.shape[0] > 1) else torch.float32
         z, out = ops.linear_fwd(x1, W, b, x2=x2, act=act, alpha=alpha, want_z=training and act != ACT_NONE,
-                                math_mode=math_mode)
+                                math_mode=math_mode, out_dtype=out_dt)
         ctx.act, ctx.math_mode = act, math_mode
         ctx.link_in, ctx.link_self = link_in, None
         if (training and link_out is not None and z is not None

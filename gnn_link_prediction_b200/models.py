@@ -24,7 +24,7 @@ from torch import Tensor
 
 from . import functional as F_
 from .functional import GraphCSR, HeteroConvFn, LinearActFn, RelationSpec
-from .ops import MATH_FP32, MATH_TF32  # noqa: F401
+from .ops import MATH_BF16, MATH_FP32, MATH_TF32  # noqa: F401
 
 
 def reset(value: Any):
@@ -211,7 +211,9 @@ class HetroGIN(torch.nn.Module):
             self.readout.append(torch.nn.Sequential(torch.nn.Linear(mlp_layers[-1], 1), head))
 
     def set_math_mode(self, mode):
-        """MATH_FP32 (parity) or MATH_TF32 (tensor cores) for every dense layer of the model."""
+        """MATH_FP32 (parity), MATH_TF32 (tcgen05 tf32 GEMMs, fp32 activations) or MATH_BF16 (activations and
+        gradients stored as bf16, tcgen05 bf16 GEMMs, fp32 accumulation / aggregation adds / loss / optimizer) for
+        every dense layer of the model."""
         self.math_mode = mode
         for m in self.modules():
             if isinstance(m, (HeteroConv, GINConv)):

@@ -11,8 +11,8 @@ import torch
 
 from . import _lib
 from .profiling import combine_bytes
-from ._lib import (ACT_NONE, ACT_PRELU, ACT_RELU, MATH_FP32, MATH_TF32, SELF_ADD, SELF_CONCAT,  # noqa: F401
-                   SELF_NONE, HginError, check)
+from ._lib import (ACT_NONE, ACT_PRELU, ACT_RELU, DTYPE_BF16, DTYPE_F32, MATH_BF16, MATH_FP32, MATH_TF32,  # noqa: F401
+                   SELF_ADD, SELF_CONCAT, SELF_NONE, HginError, check)
 
 
 TIMER = None  # set to a profiling.KernelTimer by bench.py to attribute time per kernel
@@ -54,6 +54,28 @@ def _f32_matrix(t, name):
 
 def _ptr(t):
     return 0 if t is None else t.data_ptr()
+
+
+_DTYPES = {torch.float32: DTYPE_F32, torch.bfloat16: DTYPE_BF16}
+
+
+def _matrix(t, name, dtype=None):
+    """(pointer, leading dimension in elements) of a 2-D row matrix stored as float32 or bfloat16
+    (HGIN_DTYPE_*); `dtype` pins the expected torch dtype (all row matrices of one call share it)."""
+    if t is None:
+        return 0, 0
+    if not t.is_cuda:
+        raise HginError(f"{name}: expected a CUDA tensor (there is no CPU fallback), got device {t.device}")
+    if t.dtype not in _DTYPES or t.dim() != 2:
+        raise HginError(f"{name}: expected a 2-D float32 / bfloat16 tensor, got {tuple(t.shape)} {t.dtype}")
+    if dtype is not None and t.dtype != dtype:
+        raise HginError(f"{name}: dtype {t.dtype} does not match the other row matrices of the call ({dtype})")
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        raise HginError(f"{name}: inner stride must be 1, got strides {t.stride()}")
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+    if ld < t.shape[1]:
+        raise HginError(f"{name}: row stride {ld} < width {t.shape[1]} (overlapping rows)")
+    return t.data_ptr(), ld
 
 
 def _scalar(t, name):
@@ -142,11 +164,14 @@ def gin_combine(csr, x_src, x_self=None, eps=None, self_mode=SELF_NONE, out=None
     csr=None: no edges (self term only; x_src is then only a shape donor).
     post: a PostAct — the stored result is multiplied by act'(post.z) and post.dalpha is filled.
     want_ddot (with post, SELF_ADD): returns (out, ddot) with ddot = sum x_self * act(post.z).
-    src_act / self_act: (act, alpha) when x_src / x_self hold PRE-activations (hgin_gin_combine_pre)."""
+    src_act / self_act: (act, alpha) when x_src / x_self hold PRE-activations (act applied on load).
+    Rows may be float32 or bfloat16 (all of x_src, x_self, post.z, out alike): bf16 rows are widened on load,
+    summed in fp32 in CSR order and rounded once on the store (hgin_gin_combine_t)."""
     if csr is None:
         csr = _NoEdges(x_self.shape[0])
-    ps, lds = _f32_matrix(x_src, "gin_combine.x_src")
-    pf, ldf = _f32_matrix(x_self, "gin_combine.x_self")
+    dt = x_src.dtype
+    ps, lds = _matrix(x_src, "gin_combine.x_src")
+    pf, ldf = _matrix(x_self, "gin_combine.x_self", dt)
     if x_src.shape[0] != csr.num_cols:
         raise HginError(f"gin_combine: x_src has {x_src.shape[0]} rows, CSR expects {csr.num_cols}")
     if x_self is not None and x_self.shape[0] != csr.num_rows:
@@ -157,85 +182,134 @@ def gin_combine(csr, x_src, x_self=None, eps=None, self_mode=SELF_NONE, out=None
     if out is None:
         if accumulate:
             raise HginError("gin_combine: accumulate needs an existing `out`")
-        out = torch.empty(csr.num_rows, width, dtype=torch.float32, device=x_src.device)
-    po, ldo = _f32_matrix(out, "gin_combine.out")
+        out = torch.empty(csr.num_rows, width, dtype=dt, device=x_src.device)
+    po, ldo = _matrix(out, "gin_combine.out", dt)
     if tuple(out.shape) != (csr.num_rows, width):
         raise HginError(f"gin_combine: out is {tuple(out.shape)}, expected {(csr.num_rows, width)}")
+    es = x_src.element_size()
     alg, comp = combine_bytes(csr.num_rows, csr.num_cols, csr.num_edges, f_src,
-                              f_self if self_mode != SELF_NONE else 0, width * (2 if accumulate else 1))
-    if post is not None and post.act != ACT_NONE:
-        pz, ldz = _f32_matrix(post.z, "gin_combine.post.z")
+                              f_self if self_mode != SELF_NONE else 0, width * (2 if accumulate else 1), es)
+    lib = _lib.load()
+    post_on = post is not None and post.act != ACT_NONE
+    if want_ddot and not post_on:
+        raise HginError("gin_combine: want_ddot needs a post-activation")
+    pz = ldz = 0
+    ddot = ws = None
+    ws_bytes = 0
+    kernels = 1
+    if post_on:
+        if src_act is not None or self_act is not None:
+            raise HginError("gin_combine: input activations and a post-activation cannot be combined")
+        pz, ldz = _matrix(post.z, "gin_combine.post.z", dt)
         if tuple(post.z.shape) != (csr.num_rows, f_src) or self_mode == SELF_CONCAT:
             raise HginError(f"gin_combine: post.z is {tuple(post.z.shape)}, expected {(csr.num_rows, f_src)}")
-        lib = _lib.load()
         want = post.act == ACT_PRELU
         post.dalpha = torch.empty(1, dtype=torch.float32, device=out.device) if want else None
         ddot = torch.empty(1, dtype=torch.float32, device=out.device) if want_ddot else None
         ws_bytes = lib.hgin_gin_combine_post_workspace_bytes()
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=out.device)
-        extra = 4 * csr.num_rows * f_src     # the pre-activation rows read on top of the plain pass
-        with _region("gin_combine", kernels=1 + int(want) + int(want_ddot), alg_bytes=alg + extra,
-                     compulsory_bytes=comp + extra):
-            check(lib.hgin_gin_combine_post(csr.num_rows, _ptr(csr.rowptr), _ptr(csr.col), csr.num_edges, ps, lds, f_src,
-                                            pf, ldf, f_self, _scalar(eps, "gin_combine.eps"), self_mode,
-                                            1 if accumulate else 0, po, ldo, pz, ldz, post.act,
-                                            _scalar(post.alpha, "gin_combine.post.alpha"), _ptr(post.dalpha), _ptr(ddot),
-                                            ws.data_ptr(), ws_bytes, _stream()), "hgin_gin_combine_post")
+        extra = es * csr.num_rows * f_src     # the pre-activation rows read on top of the plain pass
+        alg, comp = alg + extra, comp + extra
+        kernels = 1 + int(want) + int(want_ddot)
+    sa, sal = src_act if src_act is not None else (ACT_NONE, None)
+    fa, fal = self_act if (self_act is not None and x_self is not None) else (ACT_NONE, None)
+    with _region("gin_combine", kernels=kernels, alg_bytes=alg, compulsory_bytes=comp):
+        check(lib.hgin_gin_combine_t(_DTYPES[dt], csr.num_rows, _ptr(csr.rowptr), _ptr(csr.col), csr.num_edges, ps, lds,
+                                     f_src, pf, ldf, f_self, _scalar(eps, "gin_combine.eps"), self_mode,
+                                     1 if accumulate else 0, po, ldo, sa, _scalar(sal, "gin_combine.src_alpha"), fa,
+                                     _scalar(fal, "gin_combine.self_alpha"), pz, ldz, post.act if post_on else ACT_NONE,
+                                     _scalar(post.alpha, "gin_combine.post.alpha") if post_on else 0,
+                                     _ptr(post.dalpha) if post_on else 0, _ptr(ddot), _ptr(ws), ws_bytes, _stream()),
+              "hgin_gin_combine_t")
+    if post_on:
         post.applied = True
         return (out, ddot) if want_ddot else out
-    if want_ddot:
-        raise HginError("gin_combine: want_ddot needs a post-activation")
-    if src_act is not None or self_act is not None:
-        sa, sal = src_act if src_act is not None else (ACT_NONE, None)
-        fa, fal = self_act if (self_act is not None and x_self is not None) else (ACT_NONE, None)
-        with _region("gin_combine", kernels=1, alg_bytes=alg, compulsory_bytes=comp):
-            check(_lib.load().hgin_gin_combine_pre(csr.num_rows, _ptr(csr.rowptr), _ptr(csr.col), csr.num_edges, ps, lds,
-                                                   f_src, pf, ldf, f_self, _scalar(eps, "gin_combine.eps"), self_mode,
-                                                   1 if accumulate else 0, po, ldo, sa, _scalar(sal, "gin_combine.src_alpha"),
-                                                   fa, _scalar(fal, "gin_combine.self_alpha"), _stream()),
-                  "hgin_gin_combine_pre")
-        return out
-    with _region("gin_combine", kernels=1, alg_bytes=alg, compulsory_bytes=comp):
-        check(_lib.load().hgin_gin_combine(csr.num_rows, _ptr(csr.rowptr), _ptr(csr.col), csr.num_edges, ps, lds, f_src, pf,
-                                           ldf, f_self, _scalar(eps, "gin_combine.eps"), self_mode,
-                                           1 if accumulate else 0, po, ldo, _stream()), "hgin_gin_combine")
     return out
 
 
+def _pow2(v):
+    return v > 0 and (v & (v - 1)) == 0
+
+
+def _tc_shape(rows, k1, k2, n):
+    return rows >= 128 and 16 <= k1 <= 128 and k1 % 16 == 0 and k2 <= 4 and 16 <= n <= 128 and n % 16 == 0
+
+
+def typed_fwd_supported(in_dt, out_dt, rows, k1, k2, n):
+    """Mirror of hgin_linear_fwd_t's table for calls that involve bf16 rows (include/hgin.h)."""
+    if in_dt == torch.bfloat16 and out_dt == torch.bfloat16:
+        return _tc_shape(rows, k1, k2, n)
+    if in_dt == torch.float32 and out_dt == torch.bfloat16:          # K <= 8 layer
+        return k2 == 0 and k1 <= 8 and 4 <= n <= 128 and _pow2(n)
+    if in_dt == torch.bfloat16 and out_dt == torch.float32:          # n = 1 head
+        return n == 1 and k2 == 0 and 4 <= k1 <= 128 and k1 % 4 == 0 and _pow2(k1 >> 2)
+    return True
+
+
+def typed_bwd_supported(g_dt, x_dt, rows, k1, k2, n, c0, c1, has_dx, has_dot, has_post):
+    if g_dt == torch.bfloat16 and x_dt == torch.bfloat16:
+        w = c1 - c0
+        return _tc_shape(rows, k1, k2, n) and (w == 0 or (16 <= w <= 128 and w % 16 == 0))
+    if g_dt == torch.bfloat16 and x_dt == torch.float32:             # K <= 8 layer
+        return (k2 == 0 and k1 <= 8 and 4 <= n <= 128 and _pow2(n) and not has_dx and not has_post
+                and (c1 == c0 or has_dot) and (c1 - c0 if has_dot else 0) <= 4)
+    if g_dt == torch.float32 and x_dt == torch.bfloat16:             # n = 1 head
+        return (n == 1 and k2 == 0 and 4 <= k1 <= 128 and k1 % 4 == 0 and _pow2(k1 >> 2) and not has_dot
+                and (not has_dx or (c0 == 0 and c1 == k1)) and (c1 == c0 or has_dx))
+    return True
+
+
+def _f32(t):
+    return None if t is None else (t if t.dtype == torch.float32 else t.float())
+
+
 def linear_fwd(x1, W, bias=None, x2=None, act=ACT_NONE, alpha=None, want_z=True, out=None, accumulate_out=False,
-               math_mode=MATH_FP32, want_out=True):
+               math_mode=MATH_FP32, want_out=True, out_dtype=None):
     """K2.  z = [x1|x2] W^T + b;  out (+)= act(z).  Returns (z or None, out or None).
-    want_out=False: only z is written (the consumers apply act on load, see gin_combine src_act)."""
-    p1, ld1 = _f32_matrix(x1, "linear_fwd.x1")
-    p2, ld2 = _f32_matrix(x2, "linear_fwd.x2")
+    want_out=False: only z is written (the consumers apply act on load, see gin_combine src_act).
+    x1 may be float32 or bfloat16 rows; `out_dtype` (default: that of `out`, else of x1) is the storage type of z / out
+    (hgin_linear_fwd_t).  A bf16 combination no kernel takes runs in fp32 through casts (odd shapes only)."""
+    in_dt = x1.dtype
+    out_dt = out_dtype if out_dtype is not None else (out.dtype if out is not None else in_dt)
     rows, k1 = x1.shape
     k2 = 0 if x2 is None else x2.shape[1]
     n = W.shape[0]
+    if (in_dt != torch.float32 or out_dt != torch.float32) and not typed_fwd_supported(in_dt, out_dt, rows, k1, k2, n):
+        z32, o32 = linear_fwd(_f32(x1), W, bias, x2=x2, act=act, alpha=alpha, want_z=want_z, out=_f32(out),
+                              accumulate_out=accumulate_out, math_mode=math_mode, want_out=want_out)
+        if out is not None and o32 is not None and out.dtype != torch.float32:
+            out.copy_(o32)
+            o32 = out
+        cast = (lambda t: None if t is None else (t if t.dtype == out_dt else t.to(out_dt)))
+        return cast(z32), cast(o32)
+    p1, ld1 = _matrix(x1, "linear_fwd.x1")
+    p2, ld2 = _matrix(x2, "linear_fwd.x2", torch.float32)
     if not (W.is_cuda and W.dtype == torch.float32 and W.is_contiguous() and W.shape[1] == k1 + k2):
         raise HginError(f"linear_fwd: W must be contiguous CUDA float32 [n,{k1 + k2}], got {tuple(W.shape)}")
     if x2 is not None and x2.shape[0] != rows:
         raise HginError("linear_fwd: x1 and x2 row counts differ")
     dev = x1.device
-    z = torch.empty(rows, n, dtype=torch.float32, device=dev) if want_z else None
+    z = torch.empty(rows, n, dtype=out_dt, device=dev) if want_z else None
     if not want_out:
         if out is not None or accumulate_out or not want_z:
             raise HginError("linear_fwd: want_out=False needs want_z and no `out`")
     elif out is None:
         if accumulate_out:
             raise HginError("linear_fwd: accumulate_out needs an existing `out`")
-        out = torch.empty(rows, n, dtype=torch.float32, device=dev)
-    pz, ldz = _f32_matrix(z, "linear_fwd.z")
-    po, ldo = _f32_matrix(out, "linear_fwd.out")
+        out = torch.empty(rows, n, dtype=out_dt, device=dev)
+    pz, ldz = _matrix(z, "linear_fwd.z", out_dt)
+    po, ldo = _matrix(out, "linear_fwd.out", out_dt)
     if out is not None and tuple(out.shape) != (rows, n):
         raise HginError(f"linear_fwd: out is {tuple(out.shape)}, expected {(rows, n)}")
     lib = _lib.load()
     ws_bytes = lib.hgin_linear_fwd_workspace_bytes(rows, k1 + k2, n, math_mode)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes > 0 else None
+    ein, eout = x1.element_size(), (2 if out_dt == torch.bfloat16 else 4)
     with _region("linear_fwd", kernels=1 + (1 if ws_bytes else 0), flops=2 * rows * (k1 + k2) * n,
-                 bytes=4 * rows * (k1 + k2 + n * ((1 if want_z else 0) + (2 if accumulate_out else (1 if want_out else 0))))):
-        check(lib.hgin_linear_fwd(rows, p1, ld1, k1, p2, ld2, k2, W.data_ptr(), _ptr(bias), n, act,
-                                  _scalar(alpha, "linear_fwd.alpha"), pz, ldz, po, ldo, 1 if accumulate_out else 0,
-                                  _ptr(ws), ws_bytes, math_mode, _stream()), "hgin_linear_fwd")
+                 bytes=rows * (ein * k1 + 4 * k2 + eout * n * ((1 if want_z else 0) + (2 if accumulate_out else (1 if want_out else 0))))):
+        check(lib.hgin_linear_fwd_t(_DTYPES[in_dt], _DTYPES[out_dt], rows, p1, ld1, k1, p2, ld2, k2, W.data_ptr(), _ptr(bias),
+                                    n, act, _scalar(alpha, "linear_fwd.alpha"), pz, ldz, po, ldo, 1 if accumulate_out else 0,
+                                    _ptr(ws), ws_bytes, math_mode, _stream()), "hgin_linear_fwd_t")
     return z, out
 
 
@@ -248,12 +322,10 @@ def linear_bwd(g, z, x1, W, x2=None, act=ACT_NONE, alpha=None, dx_cols=None, wan
     dx columns — dx leaves as that layer's dz and post.dalpha is filled (no dot_x then).
     self_eps (with post, all of x1's columns, no x2; see `post_self_eligible`): the GIN self branch rides on the same
     epilogue — dx = (1 + eps) * (dz W) * act'(post.z), and with want_self_ddot the result carries
-    ddot = sum (dz W) * act(post.z) = d(eps) (hgin_linear_bwd_post_self)."""
-    pg, ldg = _f32_matrix(g, "linear_bwd.g")
-    pz, ldz = _f32_matrix(z, "linear_bwd.z")
-    p1, ld1 = _f32_matrix(x1, "linear_bwd.x1")
-    p2, ld2 = _f32_matrix(x2, "linear_bwd.x2")
-    pd, ldd = _f32_matrix(dot_x, "linear_bwd.dot_x")
+    ddot = sum (dz W) * act(post.z) = d(eps) (hgin_linear_bwd_post_self).
+    Rows may be float32 or bfloat16: g and z share one type, x1 / dx / dot_x / post.z the other (hgin_linear_bwd_t);
+    a bf16 combination no kernel takes runs in fp32 through casts (odd shapes only)."""
+    g_dt, x_dt = g.dtype, x1.dtype
     rows, k1 = x1.shape
     k2 = 0 if x2 is None else x2.shape[1]
     k = k1 + k2
@@ -263,9 +335,30 @@ def linear_bwd(g, z, x1, W, x2=None, act=ACT_NONE, alpha=None, dx_cols=None, wan
     c0, c1 = (0, k) if dx_cols is None else dx_cols
     if not (want_dx or dot_x is not None):
         c1 = c0
+    post_on = post is not None and post.act != ACT_NONE and want_dx and c1 > c0
+    if (g_dt != torch.float32 or x_dt != torch.float32) and not typed_bwd_supported(
+            g_dt, x_dt, rows, k1, k2, n, c0, c1, want_dx and c1 > c0, dot_x is not None, post_on):
+        if self_eps is not None:
+            raise HginError("linear_bwd: the self-branch epilogue exists on the tensor-core kernels only")
+        post32 = None
+        if post_on:
+            post32 = PostAct(_f32(post.z), post.act, post.alpha)
+        r = linear_bwd(_f32(g), _f32(z), _f32(x1), W, x2=x2, act=act, alpha=alpha, dx_cols=dx_cols, want_dx=want_dx,
+                       dot_x=_f32(dot_x), want_dw=want_dw, want_db=want_db, want_dalpha=want_dalpha, math_mode=math_mode,
+                       post=post32)
+        if post_on:
+            post.dalpha, post.applied = post32.dalpha, post32.applied
+        if r["dx"] is not None and x_dt != torch.float32:
+            r["dx"] = r["dx"].to(x_dt)
+        return r
+    pg, ldg = _matrix(g, "linear_bwd.g")
+    pz, ldz = _matrix(z, "linear_bwd.z", g_dt)
+    p1, ld1 = _matrix(x1, "linear_bwd.x1")
+    p2, ld2 = _matrix(x2, "linear_bwd.x2", torch.float32)
+    pd, ldd = _matrix(dot_x, "linear_bwd.dot_x", x_dt)
     dev = g.device
-    dx = torch.empty(rows, c1 - c0, dtype=torch.float32, device=dev) if (want_dx and c1 > c0) else None
-    pdx, lddx = _f32_matrix(dx, "linear_bwd.dx")
+    dx = torch.empty(rows, c1 - c0, dtype=x_dt, device=dev) if (want_dx and c1 > c0) else None
+    pdx, lddx = _matrix(dx, "linear_bwd.dx")
     if dot_x is not None and tuple(dot_x.shape) != (rows, c1 - c0):
         raise HginError(f"linear_bwd: dot_x is {tuple(dot_x.shape)}, expected {(rows, c1 - c0)}")
     ddot = torch.empty(1, dtype=torch.float32, device=dev) if dot_x is not None else None
@@ -273,7 +366,7 @@ def linear_bwd(g, z, x1, W, x2=None, act=ACT_NONE, alpha=None, dx_cols=None, wan
     db = torch.empty(n, dtype=torch.float32, device=dev) if want_db else None
     dalpha = torch.empty(1, dtype=torch.float32, device=dev) if want_dalpha else None
     lib = _lib.load()
-    ws_bytes = lib.hgin_linear_bwd_workspace_bytes(rows, k, n, math_mode)
+    ws_bytes = lib.hgin_linear_bwd_workspace_bytes(rows, k, n, math_mode if g_dt == x_dt == torch.float32 else MATH_BF16)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     flops = 2 * rows * n * ((c1 - c0) + (k + 1 if (want_dw or want_db or want_dalpha) else 0))
     reduces = want_dw or want_db or want_dalpha
@@ -282,13 +375,17 @@ def linear_bwd(g, z, x1, W, x2=None, act=ACT_NONE, alpha=None, dx_cols=None, wan
     # bytes the passes of this call move (dz pass only with an activation; dx GEMM: dz in, dx out, plus the
     # epilogue operand; dW GEMM: dz and x in; a sums-only pass over dz when the rank-k2 tail of dW is wanted)
     width = c1 - c0
-    has_e = dot_x is not None or (post is not None and post.act != ACT_NONE)
-    moved = (3 * n if act != ACT_NONE else 0) + ((n + width * (2 if has_e else 1)) if (width > 0 and dx is not None) else 0) \
-        + ((n + k) if want_dw else 0) + (n if (act == ACT_NONE and want_dw and k2 > 0) else 0)
-    if post is not None and post.act != ACT_NONE and dx is not None:
+    eg, ex = g.element_size(), x1.element_size()
+    has_e = dot_x is not None or post_on
+    moved = (3 * n * eg if act != ACT_NONE else 0) \
+        + ((n * eg + width * ex * (2 if has_e else 1)) if (width > 0 and dx is not None) else 0) \
+        + ((n * eg + k1 * ex + 4 * k2) if want_dw else 0) + (n * eg if (act == ACT_NONE and want_dw and k2 > 0) else 0)
+    ppz = ldpz = 0
+    sddot = None
+    if post_on:
         if dot_x is not None:
             raise HginError("linear_bwd: post-activation and dot_x cannot be combined")
-        ppz, ldpz = _f32_matrix(post.z, "linear_bwd.post.z")
+        ppz, ldpz = _matrix(post.z, "linear_bwd.post.z", x_dt)
         if tuple(post.z.shape) != (rows, c1 - c0):
             raise HginError(f"linear_bwd: post.z is {tuple(post.z.shape)}, expected {(rows, c1 - c0)}")
         post.dalpha = torch.empty(1, dtype=torch.float32, device=dev) if post.act == ACT_PRELU else None
@@ -296,29 +393,19 @@ def linear_bwd(g, z, x1, W, x2=None, act=ACT_NONE, alpha=None, dx_cols=None, wan
             if x2 is not None or (c0, c1) != (0, k1):
                 raise HginError("linear_bwd: the self-branch epilogue needs dx over all columns of x1 and no x2")
             sddot = torch.empty(1, dtype=torch.float32, device=dev) if want_self_ddot else None
-            with _region("linear_bwd", kernels=n_kernels + 1 + int(want_self_ddot), flops=flops, bytes=4 * rows * moved):
-                check(lib.hgin_linear_bwd_post_self(rows, pg, ldg, pz, ldz, act, _scalar(alpha, "linear_bwd.alpha"), p1,
-                                                    ld1, k1, W.data_ptr(), n, pdx, lddx, _ptr(dW), _ptr(db), _ptr(dalpha),
-                                                    ppz, ldpz, post.act, _scalar(post.alpha, "linear_bwd.post.alpha"),
-                                                    _ptr(post.dalpha), _scalar(self_eps, "linear_bwd.self_eps"),
-                                                    _ptr(sddot), ws.data_ptr(), ws_bytes, math_mode, _stream()),
-                      "hgin_linear_bwd_post_self")
-            post.applied = True
-            return {"dx": dx, "ddot": sddot, "dW": dW, "db": db, "dalpha": dalpha}
-        with _region("linear_bwd", kernels=n_kernels + 1, flops=flops, bytes=4 * rows * moved):
-            check(lib.hgin_linear_bwd_post(rows, pg, ldg, pz, ldz, act, _scalar(alpha, "linear_bwd.alpha"), p1, ld1, k1,
-                                           p2, ld2, k2, W.data_ptr(), n, c0, c1, pdx, lddx, _ptr(dW), _ptr(db),
-                                           _ptr(dalpha), ppz, ldpz, post.act, _scalar(post.alpha, "linear_bwd.post.alpha"),
-                                           _ptr(post.dalpha), ws.data_ptr(), ws_bytes, math_mode, _stream()),
-                  "hgin_linear_bwd_post")
+    elif self_eps is not None:
+        raise HginError("linear_bwd: self_eps needs a post-activation")
+    with _region("linear_bwd", kernels=n_kernels + (1 if post_on else 0) + (1 if sddot is not None else 0), flops=flops,
+                 bytes=rows * moved):
+        check(lib.hgin_linear_bwd_t(_DTYPES[g_dt], _DTYPES[x_dt], rows, pg, ldg, pz, ldz, act, _scalar(alpha, "linear_bwd.alpha"),
+                                    p1, ld1, k1, p2, ld2, k2, W.data_ptr(), n, c0, c1, pdx, lddx, pd, ldd, _ptr(ddot), _ptr(dW),
+                                    _ptr(db), _ptr(dalpha), ppz, ldpz, post.act if post_on else ACT_NONE,
+                                    _scalar(post.alpha, "linear_bwd.post.alpha") if post_on else 0,
+                                    _ptr(post.dalpha) if post_on else 0, _scalar(self_eps, "linear_bwd.self_eps"),
+                                    _ptr(sddot), ws.data_ptr(), ws_bytes, math_mode, _stream()), "hgin_linear_bwd_t")
+    if post_on:
         post.applied = True
-        return {"dx": dx, "ddot": None, "dW": dW, "db": db, "dalpha": dalpha}
-    with _region("linear_bwd", kernels=n_kernels, flops=flops, bytes=4 * rows * moved):
-        check(lib.hgin_linear_bwd(rows, pg, ldg, pz, ldz, act, _scalar(alpha, "linear_bwd.alpha"), p1, ld1, k1, p2,
-                                  ld2, k2, W.data_ptr(), n, c0, c1, pdx, lddx, pd, ldd, _ptr(ddot), _ptr(dW),
-                                  _ptr(db), _ptr(dalpha), ws.data_ptr(), ws_bytes, math_mode, _stream()),
-              "hgin_linear_bwd")
-    return {"dx": dx, "ddot": ddot, "dW": dW, "db": db, "dalpha": dalpha}
+    return {"dx": dx, "ddot": sddot if self_eps is not None else ddot, "dW": dW, "db": db, "dalpha": dalpha}
 
 
 def post_self_eligible(rows, k, n, math_mode):
@@ -369,6 +456,19 @@ def debug_gemm_tn(a, b, tma_swizzle=-1, lbo=-1, sbo=-1, layout_type=-1, k_step_b
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
     check(lib.hgin_debug_gemm_tn(rows, a.data_ptr(), n, b.data_ptr(), k, out.data_ptr(), ws.data_ptr(), ws_bytes,
                                  tma_swizzle, lbo, sbo, layout_type, k_step_bytes, _stream()), "hgin_debug_gemm_tn")
+    return out
+
+
+def debug_gemm_tn_bf16(a, b, lbo=-1, sbo=-1, layout_type=-1, k_step_bytes=-1):
+    """Diagnostics: a[rows,n]^T @ b[rows,k] (bf16 rows) through the bf16 tcgen05 MN-major kernel."""
+    rows, n = a.shape
+    k = b.shape[1]
+    lib = _lib.load()
+    out = torch.empty(n, k, dtype=torch.float32, device=a.device)
+    ws_bytes = lib.hgin_linear_bwd_workspace_bytes(rows, k, n, MATH_BF16)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
+    check(lib.hgin_debug_gemm_tn_bf16(rows, a.data_ptr(), n, b.data_ptr(), k, out.data_ptr(), ws.data_ptr(), ws_bytes,
+                                      lbo, sbo, layout_type, k_step_bytes, _stream()), "hgin_debug_gemm_tn_bf16")
     return out
 
 

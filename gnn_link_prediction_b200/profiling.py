@@ -47,11 +47,13 @@ class _Region:
         self.t.records.append((self.name, self.a, self.b, self.meta))
 
 
-def combine_bytes(num_rows, num_cols, num_edges, f_src, f_self, width):
-    """Algorithmic and compulsory bytes of one hgin_gin_combine launch:
-    B_alg = E*(F*4 + 4) + (rows+1)*4 + rows*F_self*4 + rows*F_out*4; the compulsory variant
+def combine_bytes(num_rows, num_cols, num_edges, f_src, f_self, width, elem_bytes=4):
+    """Algorithmic and compulsory bytes of one hgin_gin_combine launch, rows stored in
+    `elem_bytes` (4 = fp32, 2 = bf16), indices int32:
+    B_alg = E*(F*s + 4) + (rows+1)*4 + rows*F_self*s + rows*F_out*s; the compulsory variant
     charges each source row once (min(E, N_src)) instead of once per edge."""
-    fixed = num_edges * 4 + (num_rows + 1) * 4 + num_rows * f_self * 4 + num_rows * width * 4
-    alg = num_edges * f_src * 4 + fixed
-    compulsory = min(num_edges, num_cols) * f_src * 4 + fixed
+    s = elem_bytes
+    fixed = num_edges * 4 + (num_rows + 1) * 4 + num_rows * f_self * s + num_rows * width * s
+    alg = num_edges * f_src * s + fixed
+    compulsory = min(num_edges, num_cols) * f_src * s + fixed
     return alg, compulsory

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HGIN_VERSION 101 /* major*100 + minor */
+#define HGIN_VERSION 200 /* major*100 + minor */
 
 typedef enum hgin_status {
     HGIN_OK = 0,
@@ -49,6 +49,14 @@ typedef enum hgin_status {
 /* math modes of hgin_linear_* */
 #define HGIN_MATH_FP32 0 /* SIMT fp32 FMA: parity mode, rel 1e-5 against the CPU reference */
 #define HGIN_MATH_TF32 1 /* tcgen05 kind::tf32 tensor-core tiles, fp32 accumulate in TMEM */
+#define HGIN_MATH_BF16 2 /* activations / gradients STORED as bf16 (HGIN_DTYPE_BF16 rows), tcgen05 kind::f16 tiles on
+                          * bf16 operands, fp32 accumulate; aggregation adds, reductions, loss and Adam in fp32.
+                          * BASELINE configs[2] "bf16 MLP GEMMs", parity bar rel 1e-2 */
+
+/* storage types of the row matrices taken by the *_t entry points (weights, biases, reductions and all
+ * accumulation stay fp32) */
+#define HGIN_DTYPE_F32 0
+#define HGIN_DTYPE_BF16 1 /* rows stored as bfloat16: half the bytes per row; leading dimensions in ELEMENTS */
 
 int32_t hgin_version(void);
 const char *hgin_last_error(void);
@@ -137,6 +145,22 @@ int32_t hgin_gin_combine_pre(int64_t num_rows, const int32_t *rowptr, const int3
                              float *out, int64_t ld_out, int32_t src_act, const float *src_alpha,
                              int32_t self_act, const float *self_alpha, void *stream);
 
+/* hgin_gin_combine_t: the three entry points above in one call, on rows of storage type `dtype`
+ * (x_src, x_self, out, post_z all share it).  HGIN_DTYPE_BF16: neighbour rows are widened to fp32 as they are
+ * loaded, added left to right in fp32 exactly as in the fp32 path, and the finished row is rounded to bf16 once
+ * (round-to-nearest-even) on the store — on bf16-representable inputs the result equals the fp32 entry point's
+ * result rounded to bf16, bit for bit.  src_act / self_act (pre-activation inputs) and post_z (post-activation)
+ * are mutually exclusive as above; pass HGIN_ACT_NONE / NULL to disable either.
+ */
+int32_t hgin_gin_combine_t(int32_t dtype, int64_t num_rows, const int32_t *rowptr, const int32_t *col,
+                           int64_t num_edges, const void *x_src, int64_t ld_src, int32_t f_src,
+                           const void *x_self, int64_t ld_self, int32_t f_self, const float *eps,
+                           int32_t self_mode, int32_t accumulate, void *out, int64_t ld_out,
+                           int32_t src_act, const float *src_alpha, int32_t self_act,
+                           const float *self_alpha, const void *post_z, int64_t ld_post,
+                           int32_t post_act, const float *post_alpha, float *post_dalpha,
+                           float *post_ddot, void *workspace, int64_t workspace_bytes, void *stream);
+
 /* ---- K2: dense layer forward  z = [x1 | x2] W^T + b,  out (+)= act(z) ------------------------
  * Replaces: GINLayer.mlp = Linear + PReLU (models.py:236-239, applied at models.py:217), the
  * HeteroConv 'sum' merge over relations with the same destination type (models.py:286-298 ->
@@ -217,6 +241,37 @@ int32_t hgin_linear_bwd_post_self(int64_t rows, const float *g, int64_t ldg, con
                                   float *post_dalpha, const float *self_eps, float *post_ddot,
                                   void *workspace, int64_t workspace_bytes, int32_t math_mode,
                                   void *stream);
+
+/* ---- K2 / K3 on typed rows --------------------------------------------------------------------------
+ * hgin_linear_fwd_t / hgin_linear_bwd_t: hgin_linear_fwd and the hgin_linear_bwd family on row matrices stored as
+ * float or bf16.  W, bias, x2 (the <= 4 raw input columns of the readout), every reduction (dW, db, dalpha, ddot)
+ * and all accumulation are fp32.  Which matrices share which type:
+ *     forward   in_dtype : x1                       out_dtype : z, out
+ *     backward  g_dtype  : g, z                     x_dtype   : x1, dx, dot_x, post_z
+ * Supported combinations (anything else returns HGIN_ERR_UNSUPPORTED and enqueues nothing):
+ *     F32 / F32    the fp32 entry points above (math_mode picks SIMT fp32 or tcgen05 tf32)
+ *     BF16 / BF16  GEMM-sized layers (16 <= k1 <= 128, k1 % 16 == 0, k2 <= 4, 16 <= n <= 128, n % 16 == 0,
+ *                  rows >= 128, 16-byte aligned rows): tcgen05 kind::f16 on bf16 operands, fp32 accumulate in TMEM
+ *     forward F32 -> BF16, backward g BF16 / x F32:  the K <= 8 layers (narrow fp32 input, wide bf16 output)
+ *     forward BF16 -> F32, backward g F32 / x BF16:  the n = 1 head (wide bf16 input, one fp32 output column)
+ * hgin_linear_bwd_t carries the post-activation (post_z ...: hgin_linear_bwd_post) and the GIN self branch
+ * (self_eps, post_ddot: hgin_linear_bwd_post_self) as optional arguments: pass NULL / HGIN_ACT_NONE to disable.
+ * Workspaces: hgin_linear_{fwd,bwd}_workspace_bytes with HGIN_MATH_BF16.
+ */
+int32_t hgin_linear_fwd_t(int32_t in_dtype, int32_t out_dtype, int64_t rows, const void *x1, int64_t ld1,
+                          int32_t k1, const float *x2, int64_t ld2, int32_t k2, const float *W,
+                          const float *bias, int32_t n, int32_t act, const float *alpha, void *z,
+                          int64_t ldz, void *out, int64_t ldo, int32_t accumulate_out, void *workspace,
+                          int64_t workspace_bytes, int32_t math_mode, void *stream);
+int32_t hgin_linear_bwd_t(int32_t g_dtype, int32_t x_dtype, int64_t rows, const void *g, int64_t ldg,
+                          const void *z, int64_t ldz, int32_t act, const float *alpha, const void *x1,
+                          int64_t ld1, int32_t k1, const float *x2, int64_t ld2, int32_t k2,
+                          const float *W, int32_t n, int32_t c0, int32_t c1, void *dx, int64_t lddx,
+                          const void *dot_x, int64_t ld_dot, float *ddot, float *dW, float *db,
+                          float *dalpha, const void *post_z, int64_t ld_post, int32_t post_act,
+                          const float *post_alpha, float *post_dalpha, const float *self_eps,
+                          float *post_ddot, void *workspace, int64_t workspace_bytes, int32_t math_mode,
+                          void *stream);
 
 /* ---- loss: sqrt(MAPE) (train.py:12-13, 40-42) -----------------------------------------------
  * hgin_mape_sum:       sums[0] = sum_i |(pred_i - y_i) / y_i|,  sums[1] = n  (fp32, two-stage,
@@ -334,6 +389,11 @@ int32_t hgin_debug_gemm_tn(int64_t rows, const float *a, int32_t n, const float 
                            float *out, void *workspace, int64_t workspace_bytes, int32_t tma_swizzle,
                            int32_t lbo, int32_t sbo, int32_t layout_type, int32_t k_step_bytes,
                            void *stream);
+
+/* The same for the bf16 weight-gradient kernel (a, b: bf16 [rows, n] / [rows, k]; plain SWIZZLE_128B tensor maps). */
+int32_t hgin_debug_gemm_tn_bf16(int64_t rows, const void *a, int32_t n, const void *b, int32_t k,
+                                float *out, void *workspace, int64_t workspace_bytes, int32_t lbo,
+                                int32_t sbo, int32_t layout_type, int32_t k_step_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -466,6 +466,57 @@ def test_gin_combine_on_pre_activation_inputs(ns, nd, e, f, which, act):
         assert torch.equal(got, want)
 
 
+@pytest.mark.parametrize("ns,nd,e,f", [(3000, 5000, 15000, 128), (700, 90, 4000, 128), (900, 1200, 0, 64), (333, 257, 2000, 24),
+                                        (50, 64, 300, 16), (40, 33, 100, 5), (2000, 1500, 9000, 256)])
+@pytest.mark.parametrize("variant", ["plain", "self_add", "concat", "accumulate", "pre", "post"])
+def test_gin_combine_on_bf16_rows_equals_the_fp32_kernel_rounded_once(ns, nd, e, f, variant):
+    """HGIN_DTYPE_BF16 rows: every addition is the fp32 addition of the fp32 path (bf16 -> fp32 widening is exact),
+    and the finished row is rounded to bf16 once — so the result must equal the fp32 kernel's result on the same
+    (bf16-representable) inputs, rounded to bf16, BIT FOR BIT, in every mode."""
+    g = torch.Generator().manual_seed(ns + nd + e + f)
+    ei = torch.stack([torch.randint(0, ns, (e,), generator=g), torch.randint(0, nd, (e,), generator=g)]).cuda()
+    csr = ops.csr_build(ei, ns, nd, by="dst")
+    xs = torch.randn(ns, f, generator=g).cuda().to(torch.bfloat16)
+    xd = torch.randn(nd, f, generator=g).cuda().to(torch.bfloat16)
+    eps = torch.tensor([0.31], device="cuda")
+    a = torch.tensor([0.25], device="cuda")
+    kw, ref_kw = {}, {}
+    mode = ops.SELF_ADD
+    if variant == "plain":
+        got = ops.gin_combine(csr, xs)
+        want = ops.gin_combine(csr, xs.float())
+    elif variant == "concat":
+        got = ops.gin_combine(csr, xs, xd, eps, ops.SELF_CONCAT)
+        want = ops.gin_combine(csr, xs.float(), xd.float(), eps, ops.SELF_CONCAT)
+    elif variant == "accumulate":
+        old = torch.randn(nd, f, generator=g).cuda().to(torch.bfloat16)
+        got = ops.gin_combine(csr, xs, xd, eps, mode, out=old.clone(), accumulate=True)
+        want = ops.gin_combine(csr, xs.float(), xd.float(), eps, mode, out=old.float(), accumulate=True)
+    elif variant == "pre":
+        got = ops.gin_combine(csr, xs, xd, eps, mode, src_act=(ops.ACT_PRELU, a), self_act=(ops.ACT_RELU, None))
+        want = ops.gin_combine(csr, xs.float(), xd.float(), eps, mode, src_act=(ops.ACT_PRELU, a), self_act=(ops.ACT_RELU, None))
+    elif variant == "post":
+        z = torch.randn(nd, f, generator=g).cuda().to(torch.bfloat16)
+        p1, p2 = ops.PostAct(z, ops.ACT_PRELU, a), ops.PostAct(z.float(), ops.ACT_PRELU, a)
+        got, ddot = ops.gin_combine(csr, xs, xd, eps, mode, post=p1, want_ddot=True)
+        want, ddot_ref = ops.gin_combine(csr, xs.float(), xd.float(), eps, mode, post=p2, want_ddot=True)
+        scale = float(xd.float().abs().mean()) * (nd * f) ** 0.5
+        torch.testing.assert_close(p1.dalpha, p2.dalpha, rtol=1e-4, atol=1e-4 * scale * 10)
+        torch.testing.assert_close(ddot, ddot_ref, rtol=1e-4, atol=1e-4 * scale)
+    else:
+        got = ops.gin_combine(csr, xs, xd, eps, mode)
+        want = ops.gin_combine(csr, xs.float(), xd.float(), eps, mode)
+    assert got.dtype == torch.bfloat16
+    assert torch.equal(got, want.to(torch.bfloat16))
+
+
+def test_gin_combine_rejects_mixed_row_types():
+    csr = ops.csr_build(torch.tensor([[0, 1], [1, 0]], device="cuda"), 2, 2, by="dst")
+    x = torch.randn(2, 8, device="cuda")
+    with pytest.raises(ops.HginError):
+        ops.gin_combine(csr, x.to(torch.bfloat16), x, None, ops.SELF_ADD)
+
+
 def test_tn_descriptor_default_is_exact_layout():
     """The MN-major descriptor defaults must reproduce a^T b (tools/sweep_tn_descriptor.py finds them)."""
     g = torch.Generator().manual_seed(1)
