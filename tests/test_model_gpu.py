@@ -226,8 +226,17 @@ def test_tf32_tensor_core_mode_against_oracle(emb, layers, batch, fold, math):
     # bf16 storage (8 mantissa bits, one rounding per stored activation / gradient) on a handful of topologies: no
     # averaging over rows, so single entries sit at 1-1.5e-2 of the largest one; the Cfg-C-sized comparison
     # (tests/test_full_size_gpu.py) holds 1e-2 in norm
-    bar = 2e-2 if math == "bf16" else 1e-2
-    close(o, o_ref, rtol=1e-2, atol_rel=bar)
+    # so bf16 is held to the north star's 1e-2 in NORM (relative Frobenius error) plus a per-entry bound of 5e-2 of the
+    # largest entry (a feature whose pre-activations sit near zero flips PReLU branches on a few rows)
+    bar = 5e-2 if math == "bf16" else 1e-2
+
+    def close_mode(got, want):
+        close(got, want, rtol=1e-2, atol_rel=bar)
+        if math == "bf16":
+            w = want.detach().double()
+            assert float((got.detach().cpu().double() - w).norm()) <= 1e-2 * float(w.norm()) + 1e-12
+
+    close_mode(o, o_ref)
     torch.sqrt(mape(o, dev["path"].y.reshape(-1, 1))).backward()
     g_ref = {k: p.grad for k, p in ref.named_parameters()}
     for k, p in m.named_parameters():
@@ -239,9 +248,9 @@ def test_tf32_tensor_core_mode_against_oracle(emb, layers, batch, fold, math):
             # tf32 rounding noise (rel 2^-11 per product) is measured against the typical size of
             # such a gradient, not against its own (possibly tiny) value.
             scale = max(float(g.abs().max()) for kk, g in g_ref.items() if g is not None and g.numel() == 1)
-            assert abs(float(p.grad) - float(g_ref[k])) <= bar * scale + 1e-1 * abs(float(g_ref[k])), k
+            assert abs(float(p.grad) - float(g_ref[k])) <= min(bar, 2e-2) * scale + 1e-1 * abs(float(g_ref[k])), k
         else:
-            close(p.grad, g_ref[k], rtol=1e-2, atol_rel=bar)
+            close_mode(p.grad, g_ref[k])
 
 
 def test_device_prefetcher_yields_identical_batches():
