@@ -14,10 +14,12 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "hgin.h")
 OK = 0
 SELF_NONE, SELF_ADD, SELF_CONCAT = 0, 1, 2
 ACT_NONE, ACT_PRELU, ACT_RELU = 0, 1, 2
+ACT_LEAKY_RELU, ACT_ELU, ACT_SIGMOID, ACT_TANH, ACT_GELU, ACT_SILU, ACT_SOFTPLUS = 3, 4, 5, 6, 7, 8, 9
 MATH_FP32, MATH_TF32, MATH_BF16 = 0, 1, 2
 DTYPE_F32, DTYPE_BF16 = 0, 1
 
 _i32, _i64, _f32, _f64, _ptr = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_void_p
+_u64 = ctypes.c_uint64
 
 class CollateField(ctypes.Structure):
     """hgin_collate_field (include/hgin.h)."""
@@ -70,6 +72,20 @@ SIGNATURES = {
     "hgin_qt_baseline": (_i32, [_i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _ptr, _ptr, _ptr,
                                 _i64, _ptr]),
     "hgin_host_collate": (_i32, [_i32, _ptr, _i64, _i32, ctypes.POINTER(CollateField), _i32, _ptr, _ptr, _i32]),
+    "hgin_elementwise_workspace_bytes": (_i64, []),
+    "hgin_act_fwd": (_i32, [_i32, _i64, _i32, _ptr, _i64, _i32, _ptr, _f32, _f32, _ptr, _i64, _ptr]),
+    "hgin_act_bwd": (_i32, [_i32, _i64, _i32, _ptr, _i64, _ptr, _i64, _i32, _ptr, _f32, _f32, _ptr, _i64, _ptr, _ptr, _i64, _ptr]),
+    "hgin_dropout": (_i32, [_i32, _i64, _i32, _ptr, _i64, _f32, _u64, _u64, _ptr, _i64, _ptr]),
+    "hgin_bn_workspace_bytes": (_i64, [_i64, _i32]),
+    "hgin_bn_stats": (_i32, [_i32, _i64, _i32, _ptr, _i64, _ptr, _ptr, _i64, _ptr]),
+    "hgin_bn_finalize": (_i32, [_i32, _ptr, _f64, _f64, _i32, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "hgin_bn_act_fwd": (_i32, [_i32, _i64, _i32, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _i32, _ptr, _f32, _f32, _ptr, _i64, _ptr]),
+    "hgin_bn_act_bwd_reduce": (_i32, [_i32, _i64, _i32, _ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _i32, _ptr, _f32, _f32,
+                                      _ptr, _ptr, _i64, _ptr]),
+    "hgin_bn_act_bwd_apply": (_i32, [_i32, _i64, _i32, _ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _i32, _ptr, _f32, _f32,
+                                     _ptr, _f64, _i32, _ptr, _i64, _ptr, _ptr, _ptr, _ptr]),
+    "hgin_segment_pool": (_i32, [_i64, _ptr, _ptr, _ptr, _i64, _i32, _ptr, _ptr, _ptr]),
+    "hgin_readout_tail": (_i32, [_i64, _ptr, _i32, _i64, _ptr, _i64, _i32, _ptr, _ptr, _i32, _ptr, _i64, _ptr]),
     "hgin_set_option": (_i32, [ctypes.c_char_p, _i32]),
     "hgin_debug_gemm_tn": (_i32, [_i64, _ptr, _i32, _ptr, _i32, _ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _ptr]),
 }

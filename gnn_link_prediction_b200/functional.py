@@ -351,17 +351,57 @@ class LinearActFn(torch.autograd.Function):
         return dx1, dx2, r["dW"], r["db"], dalpha, None, None, None, None
 
 
-def activation_of(module):
-    """(ACT_* code, slope parameter) for the activations the kernels fuse."""
-    if module is None or isinstance(module, torch.nn.Identity):
-        return ACT_NONE, None
-    if isinstance(module, torch.nn.PReLU):
+class ActSpec:
+    """An activation module resolved to kernel arguments: HGIN_ACT_* code, the learnable PReLU slope (or None) and the
+    module's constructor constants p0 / p1.  `fused`: one of the three the linear kernels apply in their epilogue."""
+
+    __slots__ = ("code", "alpha", "p0", "p1")
+
+    def __init__(self, code, alpha=None, p0=0.0, p1=0.0):
+        self.code, self.alpha, self.p0, self.p1 = code, alpha, float(p0), float(p1)
+
+    @property
+    def fused(self):
+        return self.code in (ACT_NONE, ACT_PRELU, ACT_RELU)
+
+
+def act_spec_of(module) -> ActSpec:
+    """Every activation `eval(config.MLP_ACT)` / `eval(mlp_head_act)` (models.py:301, 330) can reasonably name."""
+    nn = torch.nn
+    if module is None or isinstance(module, nn.Identity):
+        return ActSpec(ACT_NONE)
+    if isinstance(module, nn.PReLU):
         if module.weight.numel() != 1:
-            raise NotImplementedError("only the single-slope torch.nn.PReLU() of the reference is fused")
-        return ACT_PRELU, module.weight
-    if isinstance(module, torch.nn.ReLU):
-        return ACT_RELU, None
-    raise NotImplementedError(f"activation {type(module).__name__} has no fused kernel (PReLU, ReLU, Identity do)")
+            raise NotImplementedError("only the single-slope torch.nn.PReLU() of the reference is supported")
+        return ActSpec(ACT_PRELU, module.weight)
+    if isinstance(module, nn.ReLU):
+        return ActSpec(ACT_RELU)
+    if isinstance(module, nn.LeakyReLU):
+        return ActSpec(ops.ACT_LEAKY_RELU, p0=module.negative_slope)
+    if isinstance(module, nn.ELU):
+        return ActSpec(ops.ACT_ELU, p0=module.alpha)
+    if isinstance(module, nn.Sigmoid):
+        return ActSpec(ops.ACT_SIGMOID)
+    if isinstance(module, nn.Tanh):
+        return ActSpec(ops.ACT_TANH)
+    if isinstance(module, nn.GELU):
+        if getattr(module, "approximate", "none") != "none":
+            raise NotImplementedError("torch.nn.GELU(approximate='tanh') has no kernel; the erf form does")
+        return ActSpec(ops.ACT_GELU)
+    if isinstance(module, nn.SiLU):
+        return ActSpec(ops.ACT_SILU)
+    if isinstance(module, nn.Softplus):
+        return ActSpec(ops.ACT_SOFTPLUS, p0=module.beta, p1=module.threshold)
+    raise NotImplementedError(f"activation {type(module).__name__} has no kernel (PReLU, ReLU, LeakyReLU, ELU, Sigmoid, Tanh, "
+                              "GELU, SiLU, Softplus and Identity do)")
+
+
+def activation_of(module):
+    """(ACT_* code, slope parameter) for the activations the LINEAR kernels fuse (GIN layers: models.py:236-239)."""
+    spec = act_spec_of(module)
+    if not spec.fused:
+        raise NotImplementedError(f"activation {type(module).__name__} is not fused into the linear kernels")
+    return spec.code, spec.alpha
 
 
 def linear_act_of(seq):
@@ -371,3 +411,103 @@ def linear_act_of(seq):
         raise NotImplementedError("fused path expects Sequential(Linear[, activation]); got " + repr(seq))
     act, alpha = activation_of(mods[1] if len(mods) == 2 else None)
     return mods[0].weight, mods[0].bias, act, alpha
+
+
+def readout_layer_of(seq):
+    """`Sequential(Linear[, BatchNorm1d][, act])` (models.py:303-330) -> (Linear, BatchNorm1d or None, ActSpec)."""
+    mods = list(seq) if isinstance(seq, torch.nn.Sequential) else [seq]
+    if not mods or not isinstance(mods[0], torch.nn.Linear):
+        raise NotImplementedError("readout layers are Sequential(Linear[, BatchNorm1d][, activation]); got " + repr(seq))
+    rest = mods[1:]
+    bn = rest.pop(0) if rest and isinstance(rest[0], torch.nn.BatchNorm1d) else None
+    if len(rest) > 1:
+        raise NotImplementedError("readout layers are Sequential(Linear[, BatchNorm1d][, activation]); got " + repr(seq))
+    return mods[0], bn, act_spec_of(rest[0] if rest else None)
+
+
+class ActFn(torch.autograd.Function):
+    """out = act(z) for an activation the linear kernels do not fuse (hgin_act_fwd / hgin_act_bwd)."""
+
+    @staticmethod
+    def forward(ctx, z, alpha, spec):
+        ctx.spec = spec
+        ctx.save_for_backward(z, alpha)
+        return ops.act_fwd(z, spec.code, alpha, spec.p0, spec.p1)
+
+    @staticmethod
+    def backward(ctx, g):
+        z, alpha = ctx.saved_tensors
+        spec = ctx.spec
+        if g.stride(-1) != 1 or g.dtype != z.dtype:
+            g = g.to(z.dtype).contiguous()
+        want_alpha = alpha is not None and ctx.needs_input_grad[1]
+        dz, dalpha = ops.act_bwd(g, z, spec.code, alpha, spec.p0, spec.p1, want_dalpha=want_alpha)
+        return (dz if ctx.needs_input_grad[0] else None), (None if dalpha is None else dalpha.view_as(alpha)), None
+
+
+class BatchNormActFn(torch.autograd.Function):
+    """out = act(BatchNorm1d(z)) (models.py:303-313).  Training mode normalises with the statistics of the GLOBAL batch:
+    under data parallelism the column sums are all-reduced (`comm`), so N ranks reproduce the single-process step on the
+    concatenated batch; the running buffers are updated in place as torch.nn.BatchNorm1d does."""
+
+    @staticmethod
+    def forward(ctx, z, gamma, beta, alpha, bn, spec, comm):
+        n = z.shape[1]
+        training = bn.training or (bn.running_mean is None and bn.running_var is None)
+        count = z.shape[0]
+        if training:
+            if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked.add_(1)
+            momentum = bn.momentum
+            if momentum is None:      # cumulative moving average (needs the host value of the counter)
+                momentum = 1.0 / float(bn.num_batches_tracked)
+            sums = ops.bn_stats(z)
+            if comm is not None and comm.world > 1:
+                comm.all_reduce_sum_(sums)
+                count = None          # global count lives in sums[2n] on the device; read lazily below
+            update = bn.training and bn.track_running_stats
+            mean, invstd = ops.bn_finalize(n, sums, bn.eps, momentum, bn.running_mean if update else None,
+                                           bn.running_var if update else None)
+            ctx.count_t = sums[2 * n:2 * n + 1] if count is None else None
+        else:
+            mean, invstd = ops.bn_finalize(n, None, bn.eps, 0.0, bn.running_mean, bn.running_var, use_running=True)
+            ctx.count_t = None
+        if count is not None and training and count < 2 and bn.training:
+            raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(z.shape)}")
+        ctx.spec, ctx.training, ctx.count, ctx.comm = spec, training, count, comm
+        ctx.save_for_backward(z, gamma, beta, alpha, mean, invstd)
+        return ops.bn_act_fwd(z, mean, invstd, gamma, beta, spec.code, alpha, spec.p0, spec.p1)
+
+    @staticmethod
+    def backward(ctx, g):
+        z, gamma, beta, alpha, mean, invstd = ctx.saved_tensors
+        spec = ctx.spec
+        if g.stride(-1) != 1 or g.dtype != z.dtype:
+            g = g.to(z.dtype).contiguous()
+        sums = ops.bn_act_bwd_reduce(g, z, mean, invstd, gamma, beta, spec.code, alpha, spec.p0, spec.p1)
+        count = ctx.count
+        if ctx.training and ctx.comm is not None and ctx.comm.world > 1:
+            ctx.comm.all_reduce_sum_(sums)
+            count = float(ctx.count_t.item())
+        nz, ng, nb, na = ctx.needs_input_grad[:4]
+        dz, dgamma, dbeta, dalpha = ops.bn_act_bwd_apply(
+            g, z, mean, invstd, gamma, beta, spec.code, sums, count, training=ctx.training, alpha=alpha, p0=spec.p0,
+            p1=spec.p1, want_dgamma=bool(ng) and gamma is not None, want_dbeta=bool(nb) and beta is not None,
+            want_dalpha=bool(na) and alpha is not None)
+        return (dz if nz else None, dgamma, dbeta, None if dalpha is None else dalpha.view_as(alpha), None, None, None)
+
+
+class DropoutFn(torch.autograd.Function):
+    """torch.nn.functional.dropout(x, p, training=True) (models.py:358-359) with a Philox mask regenerated in backward."""
+
+    @staticmethod
+    def forward(ctx, x, p, seed, offset):
+        ctx.args = (p, seed, offset)
+        return ops.dropout(x, p, seed, offset)
+
+    @staticmethod
+    def backward(ctx, g):
+        p, seed, offset = ctx.args
+        if g.stride(-1) != 1:
+            g = g.contiguous()
+        return ops.dropout(g, p, seed, offset), None, None, None

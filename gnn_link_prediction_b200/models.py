@@ -11,8 +11,10 @@ sample["path"].batch)` (train.py:34) returns `f32[N_path, 1]` with an autograd g
 Differences from the reference, all deliberate and documented in DESIGN.md:
 * relations whose output cannot reach the readout are not evaluated (the reference computes and
   discards them, SURVEY H4); their parameters keep `grad=None` either way;
-* `dropout > 0` in training mode, `mlp_bn=True`, `global_feats=True` and activations other than
-  PReLU/ReLU/None raise `NotImplementedError` instead of silently running something else;
+* `dropout > 0` draws its masks from a Philox stream of this package (hgin_dropout), not from torch's generator:
+  the reference's own CPU and CUDA masks differ from each other in the same way (parity is statistical);
+* `mlp_bn=True` under data parallelism normalises with the statistics of the GLOBAL batch (the column sums are
+  all-reduced), so N ranks reproduce the single-process step;
 * inputs must be CUDA tensors: there is no CPU path.
 """
 from __future__ import annotations
@@ -23,7 +25,8 @@ import torch
 from torch import Tensor
 
 from . import functional as F_
-from .functional import GraphCSR, HeteroConvFn, LinearActFn, RelationSpec
+from . import ops
+from .functional import ActFn, BatchNormActFn, DropoutFn, GraphCSR, HeteroConvFn, LinearActFn, RelationSpec
 from .ops import MATH_BF16, MATH_FP32, MATH_TF32  # noqa: F401
 
 
@@ -161,10 +164,6 @@ class HetroGIN(torch.nn.Module):
                  concat_path: bool, bl_features: bool, divided_features: bool, global_feats: bool,
                  mlp_layers: list, act, mlp_head_act, mlp_bn: bool):
         super().__init__()
-        if global_feats:
-            raise NotImplementedError("global_feats=True (models.py:347-352) has no fused kernel yet")
-        if mlp_bn:
-            raise NotImplementedError("mlp_bn=True (models.py:303-313) has no fused kernel yet")
         self.num_layers = message_passing_layers
         self.concat_path = concat_path
         self.bl_features = bl_features
@@ -185,7 +184,8 @@ class HetroGIN(torch.nn.Module):
         elif not self.bl_features:
             input_channels["path"] = input_channels["path"] - 1
             input_channels["link"] = input_channels["link"] - 3
-        self.global_feats_size = 0
+        self.global_feats_size = 8 if global_feats else 0    # models.py:271-274 (sic: 2 x 4 path columns)
+        self.communicator = None    # set by TrainStep: BatchNorm statistics are all-reduced over it
         self.concat_size = input_channels["path"] if concat_path else 0
 
         emb = node_embedding_size
@@ -198,17 +198,21 @@ class HetroGIN(torch.nn.Module):
             self.convs.append(HeteroConv({r: GINLayer(emb, emb) for r in self.RELATIONS}, aggr="sum"))
 
         act = eval(act)                                 # one shared activation object (models.py:301)
-        F_.activation_of(act)                           # fail at construction if it cannot be fused
+        F_.act_spec_of(act)                             # fail at construction if no kernel implements it
         width = emb + self.concat_size + self.global_feats_size
         for w in mlp_layers:
-            self.readout.append(torch.nn.Sequential(torch.nn.Linear(width, w), act))
+            if mlp_bn:                                  # models.py:303-313
+                self.readout.append(torch.nn.Sequential(torch.nn.Linear(width, w), torch.nn.BatchNorm1d(num_features=w), act))
+            else:
+                self.readout.append(torch.nn.Sequential(torch.nn.Linear(width, w), act))
             width = w
         if mlp_head_act is None:
             self.readout.append(torch.nn.Sequential(torch.nn.Linear(mlp_layers[-1], 1)))
         else:
             head = eval(mlp_head_act)
-            F_.activation_of(head)
+            F_.act_spec_of(head)
             self.readout.append(torch.nn.Sequential(torch.nn.Linear(mlp_layers[-1], 1), head))
+        self._dropout_calls = 0
 
     def set_math_mode(self, mode):
         """MATH_FP32 (parity), MATH_TF32 (tcgen05 tf32 GEMMs, fp32 activations) or MATH_BF16 (activations and
@@ -231,10 +235,10 @@ class HetroGIN(torch.nn.Module):
             needed = {t for et in live[li] for t in (et[0], et[2])}
         return live
 
-    def forward(self, x_dict, edge_index_dict, path_batch=None):
-        if self.training and self.dropout > 0:
-            raise NotImplementedError("dropout > 0 in training mode: RNG parity with the reference is impossible "
-                                      "by construction; config.json uses DROPOUT=0.0")
+    def forward(self, x_dict, edge_index_dict, path_batch=None, num_graphs=None):
+        """`num_graphs` (optional, not in the reference signature): the number of graphs in the batch when the caller
+        knows it (TrainStep does) — without it GLOBAL_FEATS reads `path_batch.max() + 1` back, as PyG's pools do."""
+        drop = self.training and self.dropout > 0
         # feature slicing, rebinding the caller's dict like models.py:333-342
         if not self.divided_features:
             x_dict["path"] = torch.cat([x_dict["path"][:, 0:3], x_dict["path"][:, 6].reshape(-1, 1)], axis=1)
@@ -252,17 +256,43 @@ class HetroGIN(torch.nn.Module):
         live = self.live_relations(graph.keys())
         # Inside this function every intermediate activation has exactly one consumer, so a layer's
         # backward may hand the layer below its dz instead of g (functional.HeteroConvFn).
-        chain = {} if (self.fold_activation_grad and torch.is_grad_enabled()) else None
+        # (a dropout between two layers is a second consumer-side op on every intermediate: no folding then)
+        chain = {} if (self.fold_activation_grad and torch.is_grad_enabled() and not drop) else None
+
+        # GLOBAL_FEATS (models.py:347-352): per-graph mean / max of the raw path columns, broadcast back per path; together
+        # with the raw columns themselves they are the constant tail of the readout input (models.py:364-369)
+        x2 = origin_path if self.concat_path else None
+        if self.global_feats:
+            if origin_path.requires_grad:
+                raise NotImplementedError("global_feats: gradients w.r.t. the raw path features are not propagated")
+            if path_batch is None:
+                raise ops.HginError("global_feats=True needs `path_batch` (collate with batch_vector=True)")
+            if num_graphs is None:
+                num_graphs = int(path_batch.max()) + 1 if path_batch.numel() else 0
+            x2 = ops.global_pool_tail(origin_path, path_batch, num_graphs, origin_path.shape[1] if self.concat_path else 0)[0]
+
         for i in range(self.num_layers):
             x_dict = self.convs[i](x_dict, graph, only=live[i], chain=chain, lazy=i < self.num_layers - 1)
-            # dropout(p=0) / eval mode is the identity (models.py:358-359)
+            if drop:   # models.py:358-359 on every output of the layer; p = 0 / eval mode is the identity
+                seed = int(torch.empty((), dtype=torch.int64).random_())      # torch's CPU generator: follows manual_seed
+                for j, k in enumerate(list(x_dict)):
+                    x_dict[k] = DropoutFn.apply(x_dict[k], float(self.dropout), seed, (self._dropout_calls << 8) | j)
+                self._dropout_calls += 1
 
         x1 = x_dict["path"]
-        x2 = origin_path if self.concat_path else None
         link = chain.get("path") if chain is not None else None
         for i, layer in enumerate(self.readout):
-            W, b, act, alpha = F_.linear_act_of(layer)
+            lin, bn, spec = F_.readout_layer_of(layer)
             nxt = [] if chain is not None else None
-            x1 = LinearActFn.apply(x1, x2 if i == 0 else None, W, b, alpha, act, self.math_mode, link, nxt)
+            if bn is None and spec.fused:
+                x1 = LinearActFn.apply(x1, x2 if i == 0 else None, lin.weight, lin.bias, spec.alpha, spec.code, self.math_mode,
+                                       link, nxt)
+            else:       # Linear -> [BatchNorm1d] -> activation as separate row passes (models.py:303-330)
+                z = LinearActFn.apply(x1, x2 if i == 0 else None, lin.weight, lin.bias, None, F_.ACT_NONE, self.math_mode,
+                                      link, None)
+                if bn is not None:
+                    x1 = BatchNormActFn.apply(z, bn.weight, bn.bias, spec.alpha, bn, spec, self.communicator)
+                else:
+                    x1 = ActFn.apply(z, spec.alpha, spec)
             link = nxt[0] if nxt else None
         return x1

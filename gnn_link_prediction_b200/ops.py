@@ -11,7 +11,8 @@ import torch
 
 from . import _lib
 from .profiling import combine_bytes
-from ._lib import (ACT_NONE, ACT_PRELU, ACT_RELU, DTYPE_BF16, DTYPE_F32, MATH_BF16, MATH_FP32, MATH_TF32,  # noqa: F401
+from ._lib import (ACT_ELU, ACT_GELU, ACT_LEAKY_RELU, ACT_SIGMOID, ACT_SILU, ACT_SOFTPLUS, ACT_TANH,  # noqa: F401
+                   ACT_NONE, ACT_PRELU, ACT_RELU, DTYPE_BF16, DTYPE_F32, MATH_BF16, MATH_FP32, MATH_TF32,  # noqa: F401
                    SELF_ADD, SELF_CONCAT, SELF_NONE, HginError, check)
 
 
@@ -413,6 +414,167 @@ def post_self_eligible(rows, k, n, math_mode):
     (csrc/linear_tc.cu bwd_eligible; hgin_linear_bwd_post_self returns HGIN_ERR_UNSUPPORTED otherwise)."""
     return (math_mode != MATH_FP32 and rows >= 128 and 16 <= k <= 128 and k % 16 == 0
             and 16 <= n <= 128 and n % 16 == 0)
+
+
+# ---- non-default branches of HetroGIN: generic activations, dropout, BatchNorm1d, global pools ---------------------
+
+def _same_shape(a, b, what):
+    if tuple(a.shape) != tuple(b.shape) or a.dtype != b.dtype:
+        raise HginError(f"{what}: shapes / dtypes differ: {tuple(a.shape)} {a.dtype} vs {tuple(b.shape)} {b.dtype}")
+
+
+def act_fwd(z, act, alpha=None, p0=0.0, p1=0.0):
+    """out = act(z) for any HGIN_ACT_* (models.py:301, 330: `eval(act)` modules the linear kernels do not fuse)."""
+    pz, ldz = _matrix(z, "act_fwd.z")
+    rows, n = z.shape
+    out = torch.empty(rows, n, dtype=z.dtype, device=z.device)
+    po, ldo = _matrix(out, "act_fwd.out")
+    with _region("act", kernels=1, bytes=2 * rows * n * z.element_size()):
+        check(_lib.load().hgin_act_fwd(_DTYPES[z.dtype], rows, n, pz, ldz, act, _scalar(alpha, "act_fwd.alpha"), float(p0),
+                                       float(p1), po, ldo, _stream()), "hgin_act_fwd")
+    return out
+
+
+def act_bwd(g, z, act, alpha=None, p0=0.0, p1=0.0, want_dalpha=False):
+    """(dz, dalpha or None):  dz = g * act'(z),  dalpha = sum g * min(z, 0)."""
+    _same_shape(g, z, "act_bwd")
+    pg, ldg = _matrix(g, "act_bwd.g")
+    pz, ldz = _matrix(z, "act_bwd.z")
+    rows, n = z.shape
+    dz = torch.empty(rows, n, dtype=z.dtype, device=z.device)
+    pd, ldd = _matrix(dz, "act_bwd.dz")
+    lib = _lib.load()
+    dalpha = torch.empty(1, dtype=torch.float32, device=z.device) if want_dalpha else None
+    ws_bytes = lib.hgin_elementwise_workspace_bytes() if want_dalpha else 0
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device) if ws_bytes else None
+    with _region("act", kernels=1 + int(want_dalpha), bytes=3 * rows * n * z.element_size()):
+        check(lib.hgin_act_bwd(_DTYPES[z.dtype], rows, n, pg, ldg, pz, ldz, act, _scalar(alpha, "act_bwd.alpha"), float(p0),
+                               float(p1), pd, ldd, _ptr(dalpha), _ptr(ws), ws_bytes, _stream()), "hgin_act_bwd")
+    return dz, dalpha
+
+
+def dropout(x, p, seed, offset=0):
+    """x * keep / (1 - p) with the Philox mask of (seed, offset); the backward pass is the same call on the gradient."""
+    px, ldx = _matrix(x, "dropout.x")
+    rows, n = x.shape
+    out = torch.empty(rows, n, dtype=x.dtype, device=x.device)
+    po, ldo = _matrix(out, "dropout.out")
+    with _region("dropout", kernels=1, bytes=2 * rows * n * x.element_size()):
+        check(_lib.load().hgin_dropout(_DTYPES[x.dtype], rows, n, px, ldx, float(p), int(seed) & (2 ** 64 - 1),
+                                       int(offset) & (2 ** 64 - 1), po, ldo, _stream()), "hgin_dropout")
+    return out
+
+
+def _vec(t, n, name):
+    if t is None:
+        return 0
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n):
+        raise HginError(f"{name}: expected a contiguous CUDA float32 vector of {n} elements")
+    return t.data_ptr()
+
+
+def bn_stats(z):
+    """float64 [2n + 1]: column sums, column sums of squares, row count (all-reduced by the caller under DP)."""
+    pz, ldz = _matrix(z, "bn_stats.z")
+    rows, n = z.shape
+    lib = _lib.load()
+    sums = torch.empty(2 * n + 1, dtype=torch.float64, device=z.device)
+    ws_bytes = lib.hgin_bn_workspace_bytes(rows, n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+    with _region("batchnorm", kernels=3, bytes=rows * n * z.element_size()):
+        check(lib.hgin_bn_stats(_DTYPES[z.dtype], rows, n, pz, ldz, sums.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
+              "hgin_bn_stats")
+    return sums
+
+
+def bn_finalize(n, sums, eps, momentum, running_mean=None, running_var=None, use_running=False):
+    """(mean, invstd) fp32 [n]; training mode also updates the running buffers in place."""
+    dev = (sums if sums is not None else running_mean).device
+    mean = torch.empty(n, dtype=torch.float32, device=dev)
+    invstd = torch.empty(n, dtype=torch.float32, device=dev)
+    with _region("batchnorm", kernels=1):
+        check(_lib.load().hgin_bn_finalize(n, _ptr(sums), float(eps), float(momentum), 1 if use_running else 0, mean.data_ptr(),
+                                           invstd.data_ptr(), _vec(running_mean, n, "bn.running_mean"),
+                                           _vec(running_var, n, "bn.running_var"), _stream()), "hgin_bn_finalize")
+    return mean, invstd
+
+
+def bn_act_fwd(z, mean, invstd, gamma, beta, act, alpha=None, p0=0.0, p1=0.0):
+    pz, ldz = _matrix(z, "bn_act_fwd.z")
+    rows, n = z.shape
+    out = torch.empty(rows, n, dtype=z.dtype, device=z.device)
+    po, ldo = _matrix(out, "bn_act_fwd.out")
+    with _region("batchnorm", kernels=1, bytes=2 * rows * n * z.element_size()):
+        check(_lib.load().hgin_bn_act_fwd(_DTYPES[z.dtype], rows, n, pz, ldz, _vec(mean, n, "bn.mean"), _vec(invstd, n, "bn.invstd"),
+                                          _vec(gamma, n, "bn.weight"), _vec(beta, n, "bn.bias"), act,
+                                          _scalar(alpha, "bn_act_fwd.alpha"), float(p0), float(p1), po, ldo, _stream()),
+              "hgin_bn_act_fwd")
+    return out
+
+
+def bn_act_bwd_reduce(g, z, mean, invstd, gamma, beta, act, alpha=None, p0=0.0, p1=0.0):
+    """float64 [2n + 1]: dbeta, dgamma, dalpha (all-reduced by the caller under DP)."""
+    _same_shape(g, z, "bn_act_bwd_reduce")
+    pg, ldg = _matrix(g, "bn_act_bwd.g")
+    pz, ldz = _matrix(z, "bn_act_bwd.z")
+    rows, n = z.shape
+    lib = _lib.load()
+    sums = torch.empty(2 * n + 1, dtype=torch.float64, device=z.device)
+    ws_bytes = lib.hgin_bn_workspace_bytes(rows, n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+    with _region("batchnorm", kernels=3, bytes=2 * rows * n * z.element_size()):
+        check(lib.hgin_bn_act_bwd_reduce(_DTYPES[z.dtype], rows, n, pg, ldg, pz, ldz, _vec(mean, n, "bn.mean"),
+                                         _vec(invstd, n, "bn.invstd"), _vec(gamma, n, "bn.weight"), _vec(beta, n, "bn.bias"), act,
+                                         _scalar(alpha, "bn_act_bwd.alpha"), float(p0), float(p1), sums.data_ptr(), ws.data_ptr(),
+                                         ws_bytes, _stream()), "hgin_bn_act_bwd_reduce")
+    return sums
+
+
+def bn_act_bwd_apply(g, z, mean, invstd, gamma, beta, act, sums, count, training=True, alpha=None, p0=0.0, p1=0.0,
+                     want_dgamma=True, want_dbeta=True, want_dalpha=False):
+    """(dz, dgamma, dbeta, dalpha) from the (global) reductions of bn_act_bwd_reduce."""
+    pg, ldg = _matrix(g, "bn_act_bwd.g")
+    pz, ldz = _matrix(z, "bn_act_bwd.z")
+    rows, n = z.shape
+    dev = z.device
+    dz = torch.empty(rows, n, dtype=z.dtype, device=dev)
+    pd, ldd = _matrix(dz, "bn_act_bwd.dz")
+    dgamma = torch.empty(n, dtype=torch.float32, device=dev) if want_dgamma else None
+    dbeta = torch.empty(n, dtype=torch.float32, device=dev) if want_dbeta else None
+    dalpha = torch.empty(1, dtype=torch.float32, device=dev) if want_dalpha else None
+    with _region("batchnorm", kernels=1, bytes=3 * rows * n * z.element_size()):
+        check(_lib.load().hgin_bn_act_bwd_apply(_DTYPES[z.dtype], rows, n, pg, ldg, pz, ldz, _vec(mean, n, "bn.mean"),
+                                                _vec(invstd, n, "bn.invstd"), _vec(gamma, n, "bn.weight"),
+                                                _vec(beta, n, "bn.bias"), act, _scalar(alpha, "bn_act_bwd.alpha"), float(p0),
+                                                float(p1), sums.data_ptr(), float(count), 1 if training else 0, pd, ldd,
+                                                _ptr(dgamma), _ptr(dbeta), _ptr(dalpha), _stream()), "hgin_bn_act_bwd_apply")
+    return dz, dgamma, dbeta, dalpha
+
+
+def global_pool_tail(x, segment_ids, num_segments, origin_cols):
+    """models.py:347-352 + the constant columns of the readout input (models.py:364-369):
+    [ x[:, :origin_cols] | mean_pool(x, segment_ids)[segment_ids] | max_pool(x, segment_ids)[segment_ids] ] as one fp32
+    matrix.  x: raw path features (no gradient), segment_ids: int64/int32 graph id per row."""
+    px, ldx = _matrix(x, "global_pool_tail.x", torch.float32)
+    rows, f = x.shape
+    if not (segment_ids.is_cuda and segment_ids.dim() == 1 and segment_ids.numel() == rows
+            and segment_ids.dtype in (torch.int64, torch.int32)):
+        raise HginError("global_pool_tail: path_batch must be a CUDA int64/int32 vector with one graph id per path")
+    segment_ids = segment_ids.contiguous()
+    ids = torch.stack((torch.arange(rows, dtype=segment_ids.dtype, device=x.device), segment_ids))
+    csr = csr_build(ids, rows, num_segments, by="dst")
+    dev = x.device
+    mean = torch.empty(num_segments, f, dtype=torch.float32, device=dev)
+    mx = torch.empty(num_segments, f, dtype=torch.float32, device=dev)
+    tail = torch.empty(rows, origin_cols + 2 * f, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    with _region("global_pool", kernels=2, bytes=rows * 4 * (f + origin_cols + 2 * f)):
+        check(lib.hgin_segment_pool(num_segments, csr.rowptr.data_ptr(), _ptr(csr.col), px, ldx, f, mean.data_ptr(),
+                                    mx.data_ptr(), _stream()), "hgin_segment_pool")
+        check(lib.hgin_readout_tail(rows, segment_ids.data_ptr(), segment_ids.element_size(), num_segments, px, ldx,
+                                    origin_cols, mean.data_ptr(), mx.data_ptr(), f, tail.data_ptr(), tail.stride(0), _stream()),
+              "hgin_readout_tail")
+    return tail, mean, mx, csr
 
 
 def qt_baseline(p_l, avg_bw, capacity, num_paths, num_links, num_iterations=3):

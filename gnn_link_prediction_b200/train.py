@@ -103,6 +103,7 @@ class TrainStep:
         self.hyper = dict(lr=lr, beta1=betas[0], beta2=betas[1], eps=eps, weight_decay=weight_decay,
                           decoupled=optimizer == "adamW")
         self.comm = communicator if communicator is not None else Communicator()
+        model.communicator = self.comm        # BatchNorm statistics (mlp_bn) are all-reduced over the same ranks
         live_mods = set()
         for li, rels in enumerate(model.live_relations(HetroGIN.RELATIONS)):
             for et in rels:
@@ -136,9 +137,12 @@ class TrainStep:
         model = self.model
         for p in self.live:
             p.grad = None
-        # the per-node graph ids are only read with GLOBAL_FEATS (unsupported here): do not force them
+        # the per-path graph ids are only read with GLOBAL_FEATS (models.py:347-352): do not force them otherwise
         graph = batch.graph if hasattr(batch, "graph") else batch.edge_index_dict   # prebuilt CSR if collated so
-        out = model(batch.x_dict, graph, dict.get(batch["path"], "batch"))
+        if getattr(model, "global_feats", False):
+            out = model(batch.x_dict, graph, batch["path"].batch, num_graphs=getattr(batch, "num_graphs", None))
+        else:
+            out = model(batch.x_dict, graph, dict.get(batch["path"], "batch"))
         y = batch["path"].y
         sums = ops.mape_sum(out.detach(), y)
         self.comm.all_reduce_sum_(sums)          # global (S, N): every rank differentiates the same loss

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HGIN_VERSION 200 /* major*100 + minor */
+#define HGIN_VERSION 210 /* major*100 + minor */
 
 typedef enum hgin_status {
     HGIN_OK = 0,
@@ -45,6 +45,15 @@ typedef enum hgin_status {
 #define HGIN_ACT_NONE 0
 #define HGIN_ACT_PRELU 1 /* single shared slope, torch.nn.PReLU() (models.py:238, config.json:27) */
 #define HGIN_ACT_RELU 2
+/* the other activations `act = eval(config.MLP_ACT)` / `eval(mlp_head_act)` can name (models.py:301, 330): taken by
+ * hgin_act_* and hgin_bn_act_* only (the hgin_linear_* kernels fuse NONE / PRELU / RELU); p0, p1 = module constants */
+#define HGIN_ACT_LEAKY_RELU 3 /* p0 = negative_slope */
+#define HGIN_ACT_ELU 4        /* p0 = alpha */
+#define HGIN_ACT_SIGMOID 5
+#define HGIN_ACT_TANH 6
+#define HGIN_ACT_GELU 7       /* erf form (approximate='none') */
+#define HGIN_ACT_SILU 8
+#define HGIN_ACT_SOFTPLUS 9   /* p0 = beta, p1 = threshold */
 
 /* math modes of hgin_linear_* */
 #define HGIN_MATH_FP32 0 /* SIMT fp32 FMA: parity mode, rel 1e-5 against the CPU reference */
@@ -370,6 +379,74 @@ int32_t hgin_qt_baseline(int64_t num_paths, int64_t num_links, int64_t num_edges
                          const float *capacity_scaled, const float *capacity_raw,
                          int32_t num_iterations, float *path_delay, float *link_out,
                          void *workspace, int64_t workspace_bytes, void *stream);
+
+/* ---- non-default branches of HetroGIN (row-streaming passes; dtype = HGIN_DTYPE_* of the row matrices) ------------
+ *
+ * hgin_act_fwd / hgin_act_bwd — replaces: the activation module applied after a readout Linear when it is not one the
+ *   linear kernels fuse (`act = eval(act)`, models.py:301, 317-330 -> torch.nn.<Module>.forward / autograd).
+ *     out = act(z);      dz = g * act'(z),  dalpha[0] = sum g * min(z, 0)  (NULL to skip; the PReLU slope gradient).
+ *   workspace (only with dalpha): hgin_elementwise_workspace_bytes().
+ *
+ * hgin_dropout — replaces: torch.nn.functional.dropout(x_dict[k], p, training) (models.py:358-359).
+ *     out[r][c] = keep(r, c) ? x[r][c] / (1 - p) : 0,  keep = (u(r, c) >= p),  u = Philox4x32-10(counter = (r * ceil(n/4) +
+ *     c/4, offset), key = seed) word c%4 scaled to [0, 1).  The backward pass is the same call on the gradient with the same
+ *     (seed, offset).  RNG streams differ from torch's by construction: parity is statistical.
+ *
+ * hgin_bn_* — replaces: torch.nn.BatchNorm1d between Linear and the activation (`mlp_bn`, models.py:303-313).
+ *   hgin_bn_stats:     sums[0:n] = column sums of z, sums[n:2n] = column sums of squares, sums[2n] = rows  (fp64,
+ *                      two-stage fixed order).  Under data parallelism the caller all-reduces `sums` (2n+1 doubles) so
+ *                      that every rank normalises with the statistics of the GLOBAL batch (= the single-process step).
+ *   hgin_bn_finalize:  mean, invstd = 1/sqrt(biased var + eps) from sums; running_mean / running_var (NULL to skip)
+ *                      updated with `momentum` and the unbiased variance as torch does.  use_running != 0 (eval mode):
+ *                      mean / invstd come from the running buffers and nothing is updated.
+ *   hgin_bn_act_fwd:   out = act(gamma * (z - mean) * invstd + beta)            (gamma / beta NULL = 1 / 0)
+ *   hgin_bn_act_bwd_reduce:  with y recomputed from z and dy = g * act'(y):  sums[0:n] = sum dy (= dbeta),
+ *                      sums[n:2n] = sum dy * xhat (= dgamma), sums[2n] = sum g * min(y, 0) (= dalpha).  All-reduced by the
+ *                      caller under data parallelism.
+ *   hgin_bn_act_bwd_apply:   dz = gamma * invstd * (dy - sums[c]/count - xhat * sums[n+c]/count)  (training != 0; count =
+ *                      GLOBAL row count) or gamma * invstd * dy (eval); writes dgamma / dbeta / dalpha (fp32, NULL to skip).
+ *   workspace: hgin_bn_workspace_bytes(rows, n).
+ *
+ * hgin_segment_pool / hgin_readout_tail — replaces: global_mean_pool / global_max_pool of the raw path features over
+ *   `path_batch` and the two torch.gather calls that broadcast them back (models.py:347-352), plus the torch.cat of the
+ *   constant readout columns (models.py:364-369).  rowptr / col: CSR of the graph ids (hgin_csr_build with
+ *   key = path_batch, other = arange; col == NULL means rows are already grouped, row id == CSR position).  Rows are added
+ *   left to right in CSR order (bit-exact with the CPU scatter_add_), mean = sum / max(count, 1).
+ *     tail[p] = [ origin[p][0:f_origin] | mean[segment_ids[p]] | max[segment_ids[p]] ],  segment ids int64 or int32.
+ */
+int64_t hgin_elementwise_workspace_bytes(void);
+int32_t hgin_act_fwd(int32_t dtype, int64_t rows, int32_t n, const void *z, int64_t ldz, int32_t act,
+                     const float *alpha, float p0, float p1, void *out, int64_t ldo, void *stream);
+int32_t hgin_act_bwd(int32_t dtype, int64_t rows, int32_t n, const void *g, int64_t ldg, const void *z,
+                     int64_t ldz, int32_t act, const float *alpha, float p0, float p1, void *dz,
+                     int64_t lddz, float *dalpha, void *workspace, int64_t workspace_bytes, void *stream);
+int32_t hgin_dropout(int32_t dtype, int64_t rows, int32_t n, const void *x, int64_t ldx, float p,
+                     uint64_t seed, uint64_t offset, void *out, int64_t ldo, void *stream);
+int64_t hgin_bn_workspace_bytes(int64_t rows, int32_t n);
+int32_t hgin_bn_stats(int32_t dtype, int64_t rows, int32_t n, const void *z, int64_t ldz, double *sums,
+                      void *workspace, int64_t workspace_bytes, void *stream);
+int32_t hgin_bn_finalize(int32_t n, const double *sums, double eps, double momentum, int32_t use_running,
+                         float *mean, float *invstd, float *running_mean, float *running_var, void *stream);
+int32_t hgin_bn_act_fwd(int32_t dtype, int64_t rows, int32_t n, const void *z, int64_t ldz,
+                        const float *mean, const float *invstd, const float *gamma, const float *beta,
+                        int32_t act, const float *alpha, float p0, float p1, void *out, int64_t ldo,
+                        void *stream);
+int32_t hgin_bn_act_bwd_reduce(int32_t dtype, int64_t rows, int32_t n, const void *g, int64_t ldg,
+                               const void *z, int64_t ldz, const float *mean, const float *invstd,
+                               const float *gamma, const float *beta, int32_t act, const float *alpha,
+                               float p0, float p1, double *sums, void *workspace, int64_t workspace_bytes,
+                               void *stream);
+int32_t hgin_bn_act_bwd_apply(int32_t dtype, int64_t rows, int32_t n, const void *g, int64_t ldg,
+                              const void *z, int64_t ldz, const float *mean, const float *invstd,
+                              const float *gamma, const float *beta, int32_t act, const float *alpha,
+                              float p0, float p1, const double *sums, double count, int32_t training,
+                              void *dz, int64_t lddz, float *dgamma, float *dbeta, float *dalpha,
+                              void *stream);
+int32_t hgin_segment_pool(int64_t segments, const int32_t *rowptr, const int32_t *col, const float *x,
+                          int64_t ldx, int32_t f, float *mean_out, float *max_out, void *stream);
+int32_t hgin_readout_tail(int64_t rows, const void *segment_ids, int32_t index_bytes, int64_t segments,
+                          const float *origin, int64_t ld_origin, int32_t f_origin, const float *mean_in,
+                          const float *max_in, int32_t f, float *tail, int64_t ld_tail, void *stream);
 
 /* ---- runtime options --------------------------------------------------------------------------
  * "fused_bwd" (0/1, default 0): HGIN_MATH_TF32 backward through the single-pass fused kernel

@@ -97,15 +97,15 @@ class HeteroConv(nn.Module):
 
 
 class HetroGIN(nn.Module):
-    """models.py:248-376 for the supported configuration family: any embedding size / layer
-    count / readout widths, `concat_path` on or off, `bl_features` / `divided_features` slicing;
-    `global_feats=False`, `mlp_bn=False`, `mlp_head_act=None`, shared-PReLU readout activation."""
+    """models.py:248-376: any embedding size / layer count / readout widths, `concat_path` on or off,
+    `bl_features` / `divided_features` slicing, `global_feats` (models.py:347-352 with PyG's global_mean_pool /
+    global_max_pool restated as scatter reductions), `mlp_bn` (models.py:303-313), any `act` / `mlp_head_act`
+    string the reference would `eval`, dropout through torch's own generator."""
 
     def __init__(self, input_channels, node_embedding_size, message_passing_layers, dropout=0.0,
                  concat_path=True, bl_features=False, divided_features=False, global_feats=False,
                  mlp_layers=(128, 32), act="torch.nn.PReLU()", mlp_head_act=None, mlp_bn=False):
         super().__init__()
-        assert not global_feats and not mlp_bn and mlp_head_act is None
         ch = dict(input_channels)                      # channel arithmetic: models.py:260-269
         if not divided_features:
             ch["path"] -= 3
@@ -119,6 +119,7 @@ class HetroGIN(nn.Module):
         self.divided_features = divided_features
         self.mlp_layers = list(mlp_layers)
         self.dropout = dropout
+        self.global_feats = global_feats
         emb = node_embedding_size
         self.convs = nn.ModuleList()
         self.convs.append(HeteroConv({r: GINLayer(ch[r[0]] + ch[r[2]], emb, concat=True) for r in RELATIONS}))
@@ -126,11 +127,17 @@ class HetroGIN(nn.Module):
             self.convs.append(HeteroConv({r: GINLayer(emb, emb) for r in RELATIONS}))
         act = eval(act)                                # ONE activation object, shared (models.py:301)
         self.readout = nn.ModuleList()
-        width = emb + (ch["path"] if concat_path else 0)
+        width = emb + (ch["path"] if concat_path else 0) + (8 if global_feats else 0)   # models.py:271-279, 317
         for w in self.mlp_layers:
-            self.readout.append(nn.Sequential(nn.Linear(width, w), act))
+            if mlp_bn:                                 # models.py:303-313
+                self.readout.append(nn.Sequential(nn.Linear(width, w), nn.BatchNorm1d(num_features=w), act))
+            else:
+                self.readout.append(nn.Sequential(nn.Linear(width, w), act))
             width = w
-        self.readout.append(nn.Sequential(nn.Linear(width, 1)))
+        if mlp_head_act is None:                       # models.py:326-330
+            self.readout.append(nn.Sequential(nn.Linear(width, 1)))
+        else:
+            self.readout.append(nn.Sequential(nn.Linear(width, 1), eval(mlp_head_act)))
 
     def forward(self, x_dict, edge_index_dict, path_batch=None):
         x_dict = dict(x_dict)
@@ -144,14 +151,33 @@ class HetroGIN(nn.Module):
             p, l = p[:, 0:6], l[:, 0:3]
         x_dict["path"], x_dict["link"] = p, l
         origin = dict(x_dict)
+        if self.global_feats:                          # models.py:347-352
+            gmean = global_mean_pool(origin["path"], path_batch)[path_batch]
+            gmax = global_max_pool(origin["path"], path_batch)[path_batch]
         for conv in self.convs:
             x_dict = conv(x_dict, edge_index_dict)
             x_dict = {k: torch.nn.functional.dropout(v, p=self.dropout, training=self.training)
                       for k, v in x_dict.items()}
-        x = torch.cat((x_dict["path"], origin["path"]), 1) if self.concat_path else x_dict["path"]
+        parts = [x_dict["path"]] + ([origin["path"]] if self.concat_path else []) + ([gmean, gmax] if self.global_feats else [])
+        x = torch.cat(parts, 1) if len(parts) > 1 else parts[0]      # models.py:362-371
         for layer in self.readout:
             x = layer(x)
         return x
+
+
+def global_mean_pool(x, batch):
+    """PyG global_mean_pool = torch_scatter.scatter(x, batch, dim=0, reduce='mean'): scatter_add_, count clamped to 1."""
+    size = int(batch.max()) + 1
+    out = scatter_sum(x, batch, size)
+    cnt = torch.zeros(size, dtype=x.dtype).scatter_add_(0, batch, torch.ones(batch.numel(), dtype=x.dtype))
+    return out / cnt.clamp_(min=1).view(-1, 1)
+
+
+def global_max_pool(x, batch):
+    """PyG global_max_pool = torch_scatter.scatter(x, batch, dim=0, reduce='max')."""
+    size = int(batch.max()) + 1
+    out = torch.full((size, x.size(1)), float("-inf"), dtype=x.dtype)
+    return out.scatter_reduce(0, batch.view(-1, 1).expand_as(x), x, reduce="amax", include_self=True)
 
 
 def mape(preds, actuals):

@@ -143,6 +143,24 @@ def main():
     model_case("L2_emb12_divided_bl", [(10, 14, 4)],
                {**base, "NODE_EMBEDDING_SIZE": 12, "MP_LAYERS": 2, "DIVIDED_FEATURES": True,
                 "BL_FEATURES": True})
+    # ---- the non-default branches of HetroGIN (models.py:301-330, 347-371) -------------------------------------------
+    # GLOBAL_FEATS only works with 4 path columns (global_feats_size is the constant 8 = 2 x 4, models.py:271-274), i.e.
+    # BL_FEATURES on and DIVIDED_FEATURES off; every other combination raises inside the reference's first readout Linear.
+    model_case("L2_emb8_globalfeats", [(10, 14, 4), (8, 7, 1), (12, 20, 3)],
+               {**base, "MP_LAYERS": 2, "BL_FEATURES": True, "GLOBAL_FEATS": True})
+    model_case("L1_emb8_globalfeats_noconcat", [(10, 14, 4), (8, 7, 1)],
+               {**base, "BL_FEATURES": True, "GLOBAL_FEATS": True, "CONCAT_PATH": False, "MLP_LAYERS": [16]})
+    model_case("L2_emb8_bn", [(10, 14, 4), (8, 7, 1), (12, 20, 3)],
+               {**base, "MP_LAYERS": 2, "MLP_BN": True, "MLP_LAYERS": [32, 16]})
+    model_case("L1_emb8_bn_leaky_headrelu", [(10, 14, 4), (8, 7, 1)],
+               {**base, "MLP_BN": True, "MLP_ACT": "torch.nn.LeakyReLU(0.1)", "MLP_HEAD_ACT": "torch.nn.ReLU()",
+                "MLP_LAYERS": [16, 8]})
+    model_case("L2_emb8_elu_softplus", [(10, 14, 4), (8, 7, 1)],
+               {**base, "MP_LAYERS": 2, "MLP_ACT": "torch.nn.ELU()", "MLP_HEAD_ACT": "torch.nn.Softplus()"})
+    model_case("L1_emb8_gelu", [(12, 20, 3)], {**base, "MLP_ACT": "torch.nn.GELU()"})
+    model_case("L1_emb8_tanh_headsigmoid", [(12, 20, 3)],
+               {**base, "MLP_ACT": "torch.nn.Tanh()", "MLP_HEAD_ACT": "torch.nn.Sigmoid()"})
+    model_case("L1_emb8_silu", [(12, 20, 3)], {**base, "MLP_ACT": "torch.nn.SiLU()"})
 
 
 if __name__ == "__main__":

@@ -35,7 +35,10 @@ def load_golden(name):
     return torch.load(os.path.join(GOLDEN, name), weights_only=False)
 
 
-MODEL_CASES = ["default", "L3_emb16", "L2_emb32_noconcat", "L2_emb8_blfeat", "L2_emb12_divided_bl"]
+# the non-default branches of HetroGIN (models.py:301-330, 347-371): global_feats, mlp_bn, other activations
+FLAG_CASES = ["L2_emb8_globalfeats", "L1_emb8_globalfeats_noconcat", "L2_emb8_bn", "L1_emb8_bn_leaky_headrelu",
+              "L2_emb8_elu_softplus", "L1_emb8_gelu", "L1_emb8_tanh_headsigmoid", "L1_emb8_silu"]
+MODEL_CASES = ["default", "L3_emb16", "L2_emb32_noconcat", "L2_emb8_blfeat", "L2_emb12_divided_bl"] + FLAG_CASES
 
 
 def config_to_kwargs(cfg):

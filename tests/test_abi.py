@@ -35,7 +35,7 @@ def test_every_declared_symbol_is_exported(built):
     raw = ctypes.CDLL(_lib.LIB_PATH)
     for name in _lib.header_functions():
         assert hasattr(raw, name), name
-    assert built.hgin_version() == 200
+    assert built.hgin_version() == 210
 
 
 def test_argument_errors_do_not_need_a_gpu(built):
