@@ -83,6 +83,11 @@ def model_case(name, topo_specs, config, steps=5):
     model = ref_train.load_model(config, datasets)          # train.py:116-137
     opt = ref_train.load_optmizer(config, model)            # train.py:140-148
     model.train()
+    if config["MODEL"] == "GAT":
+        # GATConv((-1, -1), ...) defers its Linear weights to the first forward call (models.py:417-420): one dry run
+        # materialises them (glorot draws in call order) so that the fixture can record a complete state_dict
+        with torch.no_grad():
+            model(batch.x_dict, batch.edge_index_dict, batch["path"].batch)
     fixture = {
         "config": dict(config),
         "topologies": [list(s) for s in topo_specs],
@@ -161,6 +166,16 @@ def main():
     model_case("L1_emb8_tanh_headsigmoid", [(12, 20, 3)],
                {**base, "MLP_ACT": "torch.nn.Tanh()", "MLP_HEAD_ACT": "torch.nn.Sigmoid()"})
     model_case("L1_emb8_silu", [(12, 20, 3)], {**base, "MLP_ACT": "torch.nn.SiLU()"})
+    # ---- HetroGAT (models.py:380-506) on the restated GATConv (PARITY UNPINNED, see oracle/pyg_shim) ----------------------
+    gat = {**base, "MODEL": "GAT"}
+    model_case("gat_default", [(12, 20, 3), (10, 14, 4)], gat)
+    model_case("gat_h4_emb16_noconcat", [(10, 14, 4), (8, 7, 1)],
+               {**gat, "HEADS": 4, "NODE_EMBEDDING_SIZE": 16, "CONCAT_PATH": False, "MLP_LAYERS": [24]})
+    # layers >= 1 are built for `emb` input columns while layer 0 emits emb * heads (models.py:413-428): only HEADS = 1
+    # runs with MP_LAYERS > 1
+    model_case("gat_h1_L2_emb8", [(12, 20, 3)], {**gat, "HEADS": 1, "MP_LAYERS": 2})
+    model_case("gat_h2_emb4_bl_globalfeats", [(10, 14, 4), (8, 7, 1)],
+               {**gat, "HEADS": 2, "NODE_EMBEDDING_SIZE": 4, "BL_FEATURES": True, "GLOBAL_FEATS": True})
 
 
 if __name__ == "__main__":
