@@ -511,3 +511,34 @@ class DropoutFn(torch.autograd.Function):
         if g.stride(-1) != 1:
             g = g.contiguous()
         return ops.dropout(g, p, seed, offset), None, None, None
+
+
+class GATAggregateFn(torch.autograd.Function):
+    """PyG GATConv from the attention logits on (hgin_gat_fwd / hgin_gat_bwd): out = [prev +] softmax-weighted sum of the
+    projected source rows + bias.  `prev` (optional) is the running HeteroConv sum for this destination type; it is
+    updated IN PLACE (the 'sum' merge rides on the kernel's store) and returned."""
+
+    @staticmethod
+    def forward(ctx, xs, a_src, a_dst, bias, prev, graph, et, heads, channels, slope, add_self_loops):
+        csr = graph.fwd(et)
+        out, row_max, row_sum = ops.gat_fwd(csr, xs, a_src, a_dst, bias, heads, channels, slope, add_self_loops,
+                                            out=prev, accumulate=prev is not None)
+        if prev is not None:
+            ctx.mark_dirty(prev)
+        if any(ctx.needs_input_grad):
+            graph.bwd(et)      # transposed CSR built alongside the forward work
+        ctx.graph, ctx.et, ctx.args = graph, et, (heads, channels, slope, add_self_loops)
+        ctx.save_for_backward(xs, a_src, a_dst, row_max, row_sum)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        xs, a_src, a_dst, row_max, row_sum = ctx.saved_tensors
+        heads, channels, slope, loops = ctx.args
+        if g.stride(-1) != 1:
+            g = g.contiguous()
+        d_xs, d_a_src, d_a_dst = ops.gat_bwd(ctx.graph.fwd(ctx.et), ctx.graph.bwd(ctx.et), xs, a_src, a_dst, row_max, row_sum,
+                                             g, heads, channels, slope, loops)
+        d_bias = ops.column_sums(g) if ctx.needs_input_grad[3] else None
+        d_prev = g if ctx.needs_input_grad[4] else None
+        return d_xs, d_a_src, d_a_dst, d_bias, d_prev, None, None, None, None, None, None

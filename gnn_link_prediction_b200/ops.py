@@ -577,6 +577,69 @@ def global_pool_tail(x, segment_ids, num_segments, origin_cols):
     return tail, mean, mx, csr
 
 
+# ---- graph attention (HetroGAT) -------------------------------------------------------------------------------------
+
+def _f32c(t, shape, name):
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == tuple(shape)):
+        raise HginError(f"{name}: expected a contiguous CUDA float32 tensor of shape {tuple(shape)}, got {tuple(t.shape)} {t.dtype}")
+    return t.data_ptr()
+
+
+def gat_fwd(csr, xs, a_src, a_dst, bias, heads, channels, negative_slope=0.2, add_self_loops=True, out=None, accumulate=False):
+    """PyG GATConv from the attention logits on (include/hgin.h: hgin_gat_fwd).  Returns (out, row_max, row_sum)."""
+    hc = heads * channels
+    pxs, ldxs = _matrix(xs, "gat_fwd.xs", torch.float32)
+    if tuple(xs.shape) != (csr.num_cols, hc):
+        raise HginError(f"gat_fwd: xs is {tuple(xs.shape)}, expected {(csr.num_cols, hc)}")
+    dev = xs.device
+    if out is None:
+        if accumulate:
+            raise HginError("gat_fwd: accumulate needs an existing `out`")
+        out = torch.empty(csr.num_rows, hc, dtype=torch.float32, device=dev)
+    po, ldo = _matrix(out, "gat_fwd.out", torch.float32)
+    row_max = torch.empty(csr.num_rows, heads, dtype=torch.float32, device=dev)
+    row_sum = torch.empty(csr.num_rows, heads, dtype=torch.float32, device=dev)
+    with _region("gat", kernels=1, bytes=4 * (csr.num_edges * (hc + 2 * heads) + csr.num_rows * (hc + 3 * heads))):
+        check(_lib.load().hgin_gat_fwd(csr.num_rows, _ptr(csr.rowptr), _ptr(csr.col), csr.num_cols, pxs, ldxs,
+                                       _f32c(a_src, (csr.num_cols, heads), "gat_fwd.a_src"),
+                                       _f32c(a_dst, (csr.num_rows, heads), "gat_fwd.a_dst"), _vec(bias, hc, "gat_fwd.bias"),
+                                       heads, channels, float(negative_slope), 1 if add_self_loops else 0,
+                                       1 if accumulate else 0, po, ldo, row_max.data_ptr(), row_sum.data_ptr(), _stream()),
+              "hgin_gat_fwd")
+    return out, row_max, row_sum
+
+
+def gat_bwd(csr_dst, csr_src, xs, a_src, a_dst, row_max, row_sum, g, heads, channels, negative_slope=0.2,
+            add_self_loops=True):
+    """Returns (d_xs, d_a_src, d_a_dst) for g = d loss / d out (hgin_gat_bwd)."""
+    hc = heads * channels
+    pxs, ldxs = _matrix(xs, "gat_bwd.xs", torch.float32)
+    pg, ldg = _matrix(g, "gat_bwd.g", torch.float32)
+    n_dst, n_src = csr_dst.num_rows, csr_dst.num_cols
+    if tuple(g.shape) != (n_dst, hc) or tuple(xs.shape) != (n_src, hc) or csr_src.num_rows != n_src:
+        raise HginError("gat_bwd: shapes of g / xs / the transposed CSR do not match the relation")
+    dev = xs.device
+    d_xs = torch.empty(n_src, hc, dtype=torch.float32, device=dev)
+    d_a_src = torch.empty(n_src, heads, dtype=torch.float32, device=dev)
+    d_a_dst = torch.empty(n_dst, heads, dtype=torch.float32, device=dev)
+    dot_ws = torch.empty(n_dst, heads, dtype=torch.float32, device=dev)
+    with _region("gat", kernels=2, bytes=8 * csr_dst.num_edges * (hc + 4 * heads)):
+        check(_lib.load().hgin_gat_bwd(n_dst, _ptr(csr_dst.rowptr), _ptr(csr_dst.col), n_src, _ptr(csr_src.rowptr),
+                                       _ptr(csr_src.col), pxs, ldxs, _f32c(a_src, (n_src, heads), "gat_bwd.a_src"),
+                                       _f32c(a_dst, (n_dst, heads), "gat_bwd.a_dst"),
+                                       _f32c(row_max, (n_dst, heads), "gat_bwd.row_max"),
+                                       _f32c(row_sum, (n_dst, heads), "gat_bwd.row_sum"), pg, ldg, heads, channels,
+                                       float(negative_slope), 1 if add_self_loops else 0, d_xs.data_ptr(), d_xs.stride(0),
+                                       d_a_src.data_ptr(), d_a_dst.data_ptr(), dot_ws.data_ptr(), _stream()), "hgin_gat_bwd")
+    return d_xs, d_a_src, d_a_dst
+
+
+def column_sums(x):
+    """fp32 [n] column sums of a row matrix (two-stage fp64 reduction of hgin_bn_stats)."""
+    n = x.shape[1]
+    return bn_stats(x)[:n].float()
+
+
 def qt_baseline(p_l, avg_bw, capacity, num_paths, num_links, num_iterations=3):
     """Queueing-theory baseline on a (batched) path->link relation.  p_l: CUDA int64/int32 [2,E],
     every path's edges in route order; avg_bw f32 [num_paths]; capacity f32 [num_links] (raw).

@@ -11,7 +11,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
-from .models import HetroGIN
+from .models import HetroGAT, HetroGIN
 from .parallel import Communicator
 
 
@@ -21,7 +21,7 @@ def mape(preds, actuals):
 
 
 def load_model(config, datasets):
-    """train.py:116-137 (GIN branch).  `datasets["train"][0][t]['x'].shape[1]` gives the widths."""
+    """train.py:116-137.  `datasets["train"][0][t]['x'].shape[1]` gives the widths."""
     first = datasets["train"][0]
     input_channels = {"link": first["link"]["x"].shape[1], "path": first["path"]["x"].shape[1],
                       "node": first["node"]["x"].shape[1]}
@@ -33,7 +33,12 @@ def load_model(config, datasets):
                         mlp_layers=config["MLP_LAYERS"], act=config["MLP_ACT"], mlp_bn=config["MLP_BN"],
                         mlp_head_act=config["MLP_HEAD_ACT"])
     if config["MODEL"] == "GAT":
-        raise NotImplementedError("HetroGAT (models.py:380-506) is outside the accelerated HeteroGIN path")
+        return HetroGAT(input_channels=input_channels, node_embedding_size=config["NODE_EMBEDDING_SIZE"],
+                        message_passing_layers=config["MP_LAYERS"], dropout=config["DROPOUT"], heads=config["HEADS"],
+                        concat_path=config["CONCAT_PATH"], bl_features=config["BL_FEATURES"],
+                        divided_features=config["DIVIDED_FEATURES"], global_feats=config["GLOBAL_FEATS"],
+                        mlp_layers=config["MLP_LAYERS"], act=config["MLP_ACT"], mlp_bn=config["MLP_BN"],
+                        mlp_head_act=config["MLP_HEAD_ACT"])
     raise IOError("Model not implemented")  # train.py:135
 
 

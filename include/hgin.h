@@ -448,6 +448,35 @@ int32_t hgin_readout_tail(int64_t rows, const void *segment_ids, int32_t index_b
                           const float *origin, int64_t ld_origin, int32_t f_origin, const float *mean_in,
                           const float *max_in, int32_t f, float *tail, int64_t ld_tail, void *stream);
 
+/* ---- graph attention (HetroGAT) --------------------------------------------------------------------------------
+ * Replaces: torch_geometric.nn.conv.GATConv.forward from the attention logits on (models.py:417-428 construct it, models.py:466
+ * calls it through HeteroConv) — `remove_self_loops` / `add_self_loops`, `propagate` with `message` = x_j * softmax_i(
+ * leaky_relu(alpha_j + alpha_i)) and aggr='add', `+ bias` — for bipartite inputs, concat=True, no attention dropout.
+ * The dense projections around it (lin_src, and the attention logits a_src = <lin_src(x_src), att_src> per head, a_dst
+ * likewise) are hgin_linear_fwd calls.
+ *   rowptr / col : destination-sorted CSR of the relation (hgin_csr_build, sort_row = 1); rows = destinations.
+ *   xs    [num_src, heads*channels]  projected source features;  a_src [num_src, heads], a_dst [num_rows, heads]
+ *   add_self_loops != 0: PyG's bipartite rule — edges whose source id equals their destination id are dropped and one
+ *                 loop (i, i) is appended (last in the sum) for every i < min(num_src, num_rows).
+ *   out[i] (+)= sum_j w_ij xs[j] / (sum_j w_ij + 1e-16) + bias,   w_ij = exp(e_ij - max_j e_ij)   (accumulate != 0 adds to
+ *                 `out`: the HeteroConv sum merge);  row_max / row_sum [num_rows, heads] are saved for hgin_gat_bwd.
+ * hgin_gat_bwd: g = d loss / d out.  Destination pass over the same CSR: d_a_dst [num_dst, heads] (dot_ws [num_dst, heads]
+ *   is scratch).  Source pass over the TRANSPOSED CSR (rowptr_src / col_src, sort_row = 0): d_xs [num_src, heads*channels],
+ *   d_a_src [num_src, heads].  d bias is the column sum of g (hgin_bn_stats computes it).  No atomics, nothing per edge is
+ *   stored, deterministic.  channels: a power of two in [4, 128]; heads * channels <= 512 (HGIN_ERR_UNSUPPORTED otherwise).
+ */
+int32_t hgin_gat_fwd(int64_t num_rows, const int32_t *rowptr, const int32_t *col, int64_t num_src,
+                     const float *xs, int64_t ld_xs, const float *a_src, const float *a_dst,
+                     const float *bias, int32_t heads, int32_t channels, float negative_slope,
+                     int32_t add_self_loops, int32_t accumulate, float *out, int64_t ld_out,
+                     float *row_max, float *row_sum, void *stream);
+int32_t hgin_gat_bwd(int64_t num_dst, const int32_t *rowptr_dst, const int32_t *col_dst, int64_t num_src,
+                     const int32_t *rowptr_src, const int32_t *col_src, const float *xs, int64_t ld_xs,
+                     const float *a_src, const float *a_dst, const float *row_max, const float *row_sum,
+                     const float *g, int64_t ld_g, int32_t heads, int32_t channels, float negative_slope,
+                     int32_t add_self_loops, float *d_xs, int64_t ld_dxs, float *d_a_src, float *d_a_dst,
+                     float *dot_ws, void *stream);
+
 /* ---- runtime options --------------------------------------------------------------------------
  * "fused_bwd" (0/1, default 0): HGIN_MATH_TF32 backward through the single-pass fused kernel
  * (csrc/linear_tc_fused.cuh) instead of separate passes.

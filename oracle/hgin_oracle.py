@@ -180,6 +180,92 @@ def global_max_pool(x, batch):
     return out.scatter_reduce(0, batch.view(-1, 1).expand_as(x), x, reduce="amax", include_self=True)
 
 
+class GATConv(nn.Module):
+    """PyG 2.0.2 GATConv as HetroGAT uses it (models.py:413-428): bipartite input, `concat=True`, `add_self_loops=True`,
+    `negative_slope=0.2`, no attention dropout.  PARITY UNPINNED (PyG is not vendored; restated from the published
+    algorithm).  `in_channels`: an int (one shared `lin_src is lin_dst`) or a pair of ints."""
+
+    def __init__(self, in_channels, out_channels, heads=1):
+        super().__init__()
+        self.heads, self.out_channels = heads, out_channels
+        if isinstance(in_channels, int):
+            self.lin_src = nn.Linear(in_channels, heads * out_channels, bias=False)
+            self.lin_dst = self.lin_src
+        else:
+            self.lin_src = nn.Linear(in_channels[0], heads * out_channels, bias=False)
+            self.lin_dst = nn.Linear(in_channels[1], heads * out_channels, bias=False)
+        self.att_src = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.att_dst = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.bias = nn.Parameter(torch.zeros(heads * out_channels))
+        for t in (self.lin_src.weight, self.lin_dst.weight, self.att_src, self.att_dst):   # glorot
+            bound = (6.0 / (t.size(-2) + t.size(-1))) ** 0.5
+            t.data.uniform_(-bound, bound)
+
+    def forward(self, x, edge_index):
+        x_src, x_dst = x
+        H, C = self.heads, self.out_channels
+        xs = self.lin_src(x_src).view(-1, H, C)
+        xd = self.lin_dst(x_dst).view(-1, H, C)
+        a_src = (xs * self.att_src).sum(dim=-1)
+        a_dst = (xd * self.att_dst).sum(dim=-1)
+        # remove_self_loops / add_self_loops: ids compared across the two node types, loops for i < min(N_src, N_dst)
+        keep = edge_index[0] != edge_index[1]
+        loops = torch.arange(min(xs.size(0), xd.size(0)), dtype=edge_index.dtype)
+        j = torch.cat([edge_index[0][keep], loops])
+        i = torch.cat([edge_index[1][keep], loops])
+        n = xd.size(0)
+        e = torch.nn.functional.leaky_relu(a_src.index_select(0, j) + a_dst.index_select(0, i), 0.2)
+        idx = i.view(-1, 1).expand_as(e)
+        e_max = torch.full((n, H), float("-inf")).scatter_reduce(0, idx, e, reduce="amax", include_self=True)
+        w = (e - e_max.index_select(0, i)).exp()
+        w_sum = torch.zeros(n, H).scatter_add_(0, idx, w)
+        alpha = w / (w_sum.index_select(0, i) + 1e-16)                      # torch_geometric.utils.softmax
+        msg = xs.index_select(0, j) * alpha.unsqueeze(-1)
+        out = torch.zeros(n, H, C).scatter_add_(0, i.view(-1, 1, 1).expand_as(msg), msg).view(-1, H * C)
+        out += self.bias
+        return out
+
+
+class HetroGAT(nn.Module):
+    """models.py:380-506.  Layer 0: GATConv over the raw feature widths (lazy `(-1, -1)` in the reference), `heads` heads
+    concatenated; layers >= 1: GATConv(emb, emb) with one head (so MP_LAYERS > 1 only works with HEADS = 1, as in the
+    reference).  No activation between layers.  Readout as in HetroGIN."""
+
+    def __init__(self, input_channels, node_embedding_size, message_passing_layers, dropout=0.0, heads=16,
+                 concat_path=True, bl_features=False, divided_features=False, global_feats=False,
+                 mlp_layers=(128, 32), act="torch.nn.PReLU()", mlp_head_act=None, mlp_bn=False):
+        super().__init__()
+        ch = dict(input_channels)
+        if not divided_features:
+            ch["path"] -= 3
+            ch["link"] -= 1
+        if not bl_features:
+            ch["path"] -= 1
+            ch["link"] -= 3
+        self.num_layers, self.dropout, self.concat_path, self.global_feats = message_passing_layers, dropout, concat_path, global_feats
+        self.bl_features, self.divided_features, self.mlp_layers, self.heads = bl_features, divided_features, list(mlp_layers), heads
+        emb = node_embedding_size
+        self.convs = nn.ModuleList()
+        self.convs.append(HeteroConv({r: GATConv((ch[r[0]], ch[r[2]]), emb, heads=heads) for r in RELATIONS}))
+        for _ in range(self.num_layers - 1):
+            self.convs.append(HeteroConv({r: GATConv(emb, emb) for r in RELATIONS}))
+        act = eval(act)
+        self.readout = nn.ModuleList()
+        width = emb * heads + (ch["path"] if concat_path else 0) + (8 if global_feats else 0)     # models.py:435
+        for w in self.mlp_layers:
+            if mlp_bn:
+                self.readout.append(nn.Sequential(nn.Linear(width, w), nn.BatchNorm1d(num_features=w), act))
+            else:
+                self.readout.append(nn.Sequential(nn.Linear(width, w), act))
+            width = w
+        if mlp_head_act is None:
+            self.readout.append(nn.Sequential(nn.Linear(width, 1)))
+        else:
+            self.readout.append(nn.Sequential(nn.Linear(width, 1), eval(mlp_head_act)))
+
+    forward = HetroGIN.forward        # slicing, global feats, layer loop, dropout and readout are the same code path
+
+
 def mape(preds, actuals):
     """train.py:12-13."""
     return 100.0 * torch.mean(torch.abs((preds - actuals) / actuals))

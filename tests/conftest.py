@@ -38,7 +38,19 @@ def load_golden(name):
 # the non-default branches of HetroGIN (models.py:301-330, 347-371): global_feats, mlp_bn, other activations
 FLAG_CASES = ["L2_emb8_globalfeats", "L1_emb8_globalfeats_noconcat", "L2_emb8_bn", "L1_emb8_bn_leaky_headrelu",
               "L2_emb8_elu_softplus", "L1_emb8_gelu", "L1_emb8_tanh_headsigmoid", "L1_emb8_silu"]
-MODEL_CASES = ["default", "L3_emb16", "L2_emb32_noconcat", "L2_emb8_blfeat", "L2_emb12_divided_bl"] + FLAG_CASES
+# HetroGAT (models.py:380-506) on the restated PyG GATConv
+GAT_CASES = ["gat_default", "gat_h4_emb16_noconcat", "gat_h1_L2_emb8", "gat_h2_emb4_bl_globalfeats"]
+MODEL_CASES = (["default", "L3_emb16", "L2_emb32_noconcat", "L2_emb8_blfeat", "L2_emb12_divided_bl"] + FLAG_CASES
+               + GAT_CASES)
+
+
+def build_model(module, cfg, input_channels):
+    """`module.HetroGIN` / `module.HetroGAT` (the package's models or the oracle's) for a config.json dict, as
+    train.py:116-137 builds them."""
+    kw = config_to_kwargs(cfg)
+    if cfg["MODEL"] == "GAT":
+        return module.HetroGAT(input_channels=input_channels, heads=cfg["HEADS"], **kw)
+    return module.HetroGIN(input_channels=input_channels, **kw)
 
 
 def config_to_kwargs(cfg):

@@ -170,3 +170,59 @@ def test_global_pools_unsorted_graph_ids():
     _, mean, mx, _ = ops.global_pool_tail(x.cuda(), batch.cuda(), 7, 0)
     assert torch.equal(mean.cpu(), hgin_oracle.global_mean_pool(x, batch))
     assert torch.equal(mx.cpu(), hgin_oracle.global_max_pool(x, batch))
+
+
+@pytest.mark.parametrize("heads,c", [(16, 8), (1, 8), (4, 16), (2, 4), (3, 32), (4, 128)])
+@pytest.mark.parametrize("n_src,n_dst,e", [(300, 40, 2000), (40, 300, 900), (50, 50, 0), (7, 5, 30)])
+def test_gatconv_against_the_oracle(n_src, n_dst, e, heads, c):
+    """models.GATConv (hgin_gat_fwd / hgin_gat_bwd + the projection kernels) against the oracle's restatement of PyG's
+    GATConv on a random bipartite relation: duplicate edges, edges with src id == dst id (dropped by PyG's
+    remove_self_loops), destinations without edges, the appended loops for i < min(N_src, N_dst)."""
+    from gnn_link_prediction_b200.models import GATConv
+    torch.manual_seed(heads * 100 + c + e)
+    ei = torch.stack((torch.randint(0, n_src, (e,)), torch.randint(0, n_dst, (e,))))
+    x_src, x_dst = torch.randn(n_src, 5, requires_grad=True), torch.randn(n_dst, 3, requires_grad=True)
+    ref = hgin_oracle.GATConv((5, 3), c, heads=heads)
+    with torch.no_grad():
+        ref.bias.uniform_(-0.5, 0.5)
+    mine = GATConv((5, 3), c, heads=heads)
+    mine.load_state_dict(ref.state_dict())
+    mine.cuda()
+    o_ref = ref((x_src, x_dst), ei)
+    g = torch.randn_like(o_ref)
+    o_ref.backward(g)
+    xs_c, xd_c = x_src.detach().cuda().requires_grad_(True), x_dst.detach().cuda().requires_grad_(True)
+    o = mine((xs_c, xd_c), ei.cuda())
+    o.backward(g.cuda())
+    torch.testing.assert_close(o.detach().cpu(), o_ref.detach(), rtol=2e-5, atol=2e-6)
+    torch.testing.assert_close(xs_c.grad.cpu(), x_src.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(xd_c.grad.cpu(), x_dst.grad, rtol=1e-4, atol=1e-5)
+    named = dict(ref.named_parameters())
+    for k, p in mine.named_parameters():
+        torch.testing.assert_close(p.grad.cpu(), named[k].grad, rtol=1e-4, atol=1e-5 * float(named[k].grad.abs().max()) + 1e-6)
+    # run-to-run deterministic (no atomics)
+    xs_2 = x_src.detach().cuda().requires_grad_(True)
+    mine.zero_grad()
+    o2 = mine((xs_2, x_dst.detach().cuda()), ei.cuda())
+    o2.backward(g.cuda())
+    assert torch.equal(o2, o) and torch.equal(xs_2.grad, xs_c.grad)
+
+
+def test_gatconv_shared_projection_and_unsupported_widths():
+    from gnn_link_prediction_b200.models import GATConv
+    torch.manual_seed(9)
+    ref = hgin_oracle.GATConv(8, 8)             # layers >= 1 of HetroGAT: one projection shared by both sides
+    mine = GATConv(8, 8)
+    mine.load_state_dict(ref.state_dict())
+    mine.cuda()
+    ei = torch.stack((torch.randint(0, 60, (400,)), torch.randint(0, 30, (400,))))
+    xs, xd = torch.randn(60, 8, requires_grad=True), torch.randn(30, 8, requires_grad=True)
+    o_ref = ref((xs, xd), ei)
+    o_ref.sum().backward()
+    o = mine((xs.detach().cuda(), xd.detach().cuda()), ei.cuda())
+    o.sum().backward()
+    torch.testing.assert_close(o.detach().cpu(), o_ref.detach(), rtol=2e-5, atol=2e-6)
+    torch.testing.assert_close(mine.lin_src.weight.grad.cpu(), ref.lin_src.weight.grad, rtol=1e-4, atol=1e-5)
+    bad = GATConv((3, 3), 6, heads=2).cuda()    # 6 channels per head: not a power of two
+    with pytest.raises(ops.HginError):
+        bad((torch.randn(4, 3, device="cuda"), torch.randn(4, 3, device="cuda")), torch.zeros(2, 1, dtype=torch.int64, device="cuda"))

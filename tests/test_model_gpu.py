@@ -10,9 +10,10 @@ import copy
 import pytest
 import torch
 
-from conftest import MODEL_CASES, config_to_kwargs, load_golden
+from conftest import MODEL_CASES, build_model, config_to_kwargs, load_golden
 from oracle import hgin_oracle
 from gnn_link_prediction_b200.data import Batch, CONV_EDGE_TYPES
+from gnn_link_prediction_b200 import models as _models
 from gnn_link_prediction_b200.models import GINConv, GINLayer, HeteroConv, HetroGIN
 from gnn_link_prediction_b200.synthetic import SyntheticDataset
 from gnn_link_prediction_b200.train import TrainStep, mape
@@ -48,7 +49,7 @@ def final_state_close(sd, fx):
 
 def _model_from(fx):
     in_ch = {k: v.shape[1] for k, v in fx["x_dict"].items()}
-    m = HetroGIN(input_channels=in_ch, **config_to_kwargs(fx["config"]))
+    m = build_model(_models, fx["config"], in_ch)
     m.load_state_dict(fx["state_dict"])
     return m.cuda().train()
 
@@ -100,7 +101,8 @@ def test_adam_trajectory_matches_reference_fixture(case):
     final_state_close(m.state_dict(), fx)     # (with mlp_bn this includes the running statistics and the batch counter)
 
 
-@pytest.mark.parametrize("case", ["default", "L3_emb16", "L2_emb8_globalfeats", "L2_emb8_bn", "L2_emb8_elu_softplus"])
+@pytest.mark.parametrize("case", ["default", "L3_emb16", "L2_emb8_globalfeats", "L2_emb8_bn", "L2_emb8_elu_softplus",
+                                  "gat_default", "gat_h1_L2_emb8"])
 def test_fused_train_step_matches_reference_fixture(case):
     """TrainStep (fused loss + flat bucket + hgin Adam) reproduces the reference trajectory."""
     fx = load_golden(f"model_{case}.pt")
@@ -602,7 +604,7 @@ def test_reference_loop_functions_follow_the_oracle_loop():
         want = sum(float(hgin_oracle.mape(ref(b.x_dict, b.edge_index_dict, None), b["path"].y.reshape(-1, 1)))
                    for b in DataLoader(ds, batch_size=1)) / 6
     assert abs(val - want) <= 1e-4 * abs(want)
-    with pytest.raises(NotImplementedError):
-        load_model({**config, "MODEL": "GAT"}, {"train": ds})
+    gat = load_model({**config, "MODEL": "GAT", "HEADS": 16}, {"train": ds})     # train.py:120-126
+    assert type(gat).__name__ == "HetroGAT" and gat.readout[0][0].in_features == config["NODE_EMBEDDING_SIZE"] * 16 + 3
     with pytest.raises(IOError):
         load_model({**config, "MODEL": "nope"}, {"train": ds})

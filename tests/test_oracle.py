@@ -8,13 +8,13 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import MODEL_CASES, REFERENCE, ROOT, config_to_kwargs, load_golden
+from conftest import MODEL_CASES, REFERENCE, ROOT, build_model, config_to_kwargs, load_golden
 from oracle import c_oracle, hgin_oracle
 
 
 def _oracle_model(fx):
     in_ch = {k: v.shape[1] for k, v in fx["x_dict"].items()}
-    m = hgin_oracle.HetroGIN(input_channels=in_ch, **config_to_kwargs(fx["config"]))
+    m = build_model(hgin_oracle, fx["config"], in_ch)
     m.load_state_dict(fx["state_dict"])
     m.train()
     return m
