@@ -16,6 +16,7 @@
 #include <cuda_bf16.h>
 
 #include "hgin_common.cuh"
+#include "gin_scatter_blocks.cuh"
 
 namespace hgin {
 namespace {
@@ -176,8 +177,11 @@ gin_combine_kernel(int num_rows, const int32_t *__restrict__ rowptr, const int32
                    const T *__restrict__ x_src, int ld_src, int f_src,
                    const T *__restrict__ x_self, int ld_self, int f_self,
                    const float *__restrict__ eps_ptr, int self_mode, int accumulate,
-                   T *__restrict__ out, int ld_out, const PostAct post) {
+                   T *__restrict__ out, int ld_out, const PostAct post, const int32_t *__restrict__ gate, int gate_cap) {
     using R = Raw<T, VEC>;
+    // inverse gate of scatter_blocks_kernel (gin_scatter_blocks.cuh): when the streaming kernel launched ahead of this
+    // one did the work, return at once
+    if (gate != nullptr && __ldg(gate) == 0 && __ldg(gate + 1) <= gate_cap) return;
     // gathers in flight per lane before the dependent adds; bounded by the batch (LPR) and by
     // the register budget when a lane carries several chunks
     // (pre-activation sources need a few registers for the on-the-fly act: two gathers fewer in flight)
@@ -409,7 +413,8 @@ constexpr int kMaxCombineCtas = kNumSMs * 32;
 template <typename T, int VEC, int LPR, int NC, bool CONTIG = false, int MINB = ((NC <= 1) ? 4 : 1)>
 int launch(int64_t num_rows64, const int32_t *rowptr, const int32_t *col, const T *x_src, int64_t ld_src64,
            int f_src, const T *x_self, int64_t ld_self64, int f_self, const float *eps, int self_mode,
-           int accumulate, T *out, int64_t ld_out64, const PostAct *post, cudaStream_t s) {
+           int accumulate, T *out, int64_t ld_out64, const PostAct *post, cudaStream_t s, const int32_t *gate = nullptr,
+           int gate_cap = 0) {
     const int num_rows = static_cast<int>(num_rows64), ld_src = static_cast<int>(ld_src64);
     const int ld_self = static_cast<int>(ld_self64), ld_out = static_cast<int>(ld_out64);
     constexpr int threads = 256;
@@ -423,7 +428,8 @@ int launch(int64_t num_rows64, const int32_t *rowptr, const int32_t *col, const 
     const bool full = f_src == LPR * VEC * NC;
 #define HGIN_GO(M, F)                                                                                              \
     gin_combine_kernel<T, VEC, LPR, NC, CONTIG, MINB, M, F><<<grid, threads, 0, s>>>(                               \
-        num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, accumulate, out, ld_out, pa)
+        num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, accumulate, out, ld_out, pa, \
+        gate, gate_cap)
 #define HGIN_GO_MODE(M)          \
     do {                         \
         if (full) HGIN_GO(M, true); \
@@ -455,7 +461,8 @@ int32_t combine_dispatch_t(int64_t num_rows, const int32_t *rowptr, const int32_
                            int64_t ld_out, const T *post_z, int64_t ld_post, int32_t post_act,
                            const float *post_alpha, float *post_dalpha, float *post_ddot, void *workspace,
                            int64_t workspace_bytes, void *stream, const char *who, int32_t src_act,
-                           const float *src_alpha, int32_t self_act, const float *self_alpha) {
+                           const float *src_alpha, int32_t self_act, const float *self_alpha,
+                           const int32_t *gate = nullptr, int gate_cap = 0) {
     HGIN_CHECK_ARG(num_rows >= 0 && num_rows < INT32_MAX - (1 << 22), "%s: bad num_rows %lld", who, (long long)num_rows);
     HGIN_CHECK_ARG(ld_src < INT32_MAX && ld_self < INT32_MAX && ld_out < INT32_MAX && ld_post < INT32_MAX,
                    "%s: leading dimensions must fit 32 bits", who);
@@ -509,10 +516,10 @@ int32_t combine_dispatch_t(int64_t num_rows, const int32_t *rowptr, const int32_
     int grid = 0;
 #define HGIN_LAUNCH(VV, L, N)                                                                                      \
     grid = launch<T, VV, L, N>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, \
-                               accumulate, out, ld_out, pp, s)
+                               accumulate, out, ld_out, pp, s, gate, gate_cap)
 #define HGIN_LAUNCH_CONTIG(VV, L, N)                                                                                        \
     grid = launch<T, VV, L, N, true, 4>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, \
-                                        accumulate, out, ld_out, pp, s)
+                                        accumulate, out, ld_out, pp, s, gate, gate_cap)
     // Lanes per row: a full warp per row suits long rows (path->link, ~36 neighbours); for short
     // rows (link->path, ~3 neighbours) the per-row latency chain rowptr -> col -> gather dominates,
     // so several rows share a warp and each lane carries more 128-bit chunks.
@@ -588,8 +595,100 @@ int32_t combine_dispatch(int64_t num_rows, const int32_t *rowptr, const int32_t 
                                      src_act, src_alpha, self_act, self_alpha);
 }
 
+// Streaming kernel + gated gather kernel for one long-row aggregation on a block-diagonal batch.
+template <typename T>
+int32_t combine_blocks_t(int64_t num_rows, const int32_t *rowptr, const int32_t *col, int64_t num_edges, int64_t num_in,
+                         const int32_t *rowptr_in, const int32_t *col_in, int32_t num_blocks, const int64_t *in_ptr,
+                         const int64_t *out_ptr, const int32_t *gate, const T *x_src, int64_t ld_src, int32_t f_src,
+                         const T *x_self, int64_t ld_self, const float *eps, int32_t self_mode, int32_t accumulate, T *out,
+                         int64_t ld_out, int32_t src_act, const float *src_alpha, int32_t self_act, const float *self_alpha,
+                         void *stream) {
+    const char *who = "hgin_gin_combine_blocks_t";
+    constexpr int elem = static_cast<int>(sizeof(T));
+    HGIN_CHECK_ARG(num_blocks > 0 && in_ptr && out_ptr && gate && rowptr && col && rowptr_in && col_in, "%s: null pointer", who);
+    if (!(f_src % (16 / elem) == 0 && f_src >= 32 && f_src <= 128 && ld_src == f_src && ld_out % 4 == 0 && ld_out >= f_src &&
+          (self_mode == HGIN_SELF_NONE || (self_mode == HGIN_SELF_ADD && ld_self % 4 == 0 && ld_self >= f_src)) &&
+          aligned16(x_src) && aligned16(out) && aligned16(x_self) && num_rows < INT32_MAX && num_in < INT32_MAX))
+        return fail(HGIN_ERR_UNSUPPORTED, "%s: needs contiguous input rows of 32..128 features (16-byte multiples), SELF_NONE / "
+                    "SELF_ADD, 16-byte aligned rows", who);
+    HGIN_CHECK_ARG(src_act >= HGIN_ACT_NONE && src_act <= HGIN_ACT_RELU && self_act >= HGIN_ACT_NONE && self_act <= HGIN_ACT_RELU &&
+                   (src_act != HGIN_ACT_PRELU || src_alpha) && (self_act != HGIN_ACT_PRELU || self_alpha), "%s: input activation", who);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    scatter::SbParams p{};
+    p.num_blocks = num_blocks;
+    p.in_ptr = in_ptr;
+    p.out_ptr = out_ptr;
+    p.rowptr = rowptr_in;
+    p.col = col_in;
+    p.gate = gate;
+    p.cap_rows = scatter::capacity_rows(f_src, elem);
+    p.x_in = x_src;
+    p.f = f_src;
+    p.x_self = x_self;
+    p.ld_self = static_cast<int>(ld_self);
+    p.eps = eps;
+    p.self_mode = self_mode;
+    p.accumulate = accumulate;
+    p.out = out;
+    p.ld_out = static_cast<int>(ld_out);
+    p.in_act = src_act;
+    p.in_alpha = src_alpha;
+    p.self_act = self_act;
+    p.self_alpha = self_alpha;
+    p.stages = scatter::stages_for(f_src, elem);
+    p.stage_bytes = scatter::stage_bytes_for(f_src, elem);
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[elem == 2]) {
+        cudaFuncSetAttribute(scatter::scatter_blocks_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter::SB_SMEM);
+        attr_set[elem == 2] = true;
+    }
+    const int grid = num_blocks < kNumSMs ? num_blocks : kNumSMs;
+    scatter::scatter_blocks_kernel<T><<<grid, scatter::SB_THREADS, scatter::SB_SMEM, s>>>(p);
+    HGIN_CHECK_LAUNCH(who);
+    // the gather kernel behind it, with the inverse gate
+    return combine_dispatch_t<T>(num_rows, rowptr, col, num_edges, x_src, ld_src, f_src, x_self, ld_self, f_src, eps, self_mode,
+                                 accumulate, out, ld_out, nullptr, 0, HGIN_ACT_NONE, nullptr, nullptr, nullptr, nullptr, 0, stream,
+                                 who, src_act, src_alpha, self_act, self_alpha, gate, p.cap_rows);
+}
+
 }  // namespace
 }  // namespace hgin
+
+extern "C" int32_t hgin_block_gate(int64_t rows_a, const int32_t *rowptr_a, const int32_t *col_a, int64_t rows_b,
+                                   const int32_t *rowptr_b, const int32_t *col_b, int32_t num_blocks, const int64_t *in_ptr,
+                                   const int64_t *out_ptr, int32_t *gate, void *stream) {
+    using namespace hgin;
+    HGIN_CHECK_ARG(rows_a >= 0 && rows_b >= 0 && num_blocks >= 0 && gate, "hgin_block_gate: bad arguments");
+    HGIN_CHECK_ARG(num_blocks == 0 || (in_ptr && out_ptr), "hgin_block_gate: null block pointers");
+    HGIN_CHECK_ARG((rows_a == 0 || rowptr_a) && (rows_b == 0 || rowptr_b), "hgin_block_gate: null row pointers");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaMemsetAsync(gate, 0, 2 * sizeof(int32_t), s);
+    const int64_t work = rows_a > rows_b ? rows_a : rows_b;
+    scatter::block_gate_kernel<<<grid_for(work > 0 ? work : 1, 256, 8), 256, 0, s>>>(rows_a, rowptr_a, col_a, rows_b, rowptr_b, col_b,
+                                                                                    num_blocks, in_ptr, out_ptr, gate);
+    HGIN_CHECK_LAUNCH("hgin_block_gate");
+    return HGIN_OK;
+}
+
+extern "C" int32_t hgin_gin_combine_blocks_t(int32_t dtype, int64_t num_rows, const int32_t *rowptr, const int32_t *col,
+                                             int64_t num_edges, int64_t num_in, const int32_t *rowptr_in, const int32_t *col_in,
+                                             int32_t num_blocks, const int64_t *in_ptr, const int64_t *out_ptr, const int32_t *gate,
+                                             const void *x_src, int64_t ld_src, int32_t f_src, const void *x_self, int64_t ld_self,
+                                             const float *eps, int32_t self_mode, int32_t accumulate, void *out, int64_t ld_out,
+                                             int32_t src_act, const float *src_alpha, int32_t self_act, const float *self_alpha,
+                                             void *stream) {
+    using namespace hgin;
+    if (dtype == HGIN_DTYPE_BF16)
+        return combine_blocks_t<bf16>(num_rows, rowptr, col, num_edges, num_in, rowptr_in, col_in, num_blocks, in_ptr, out_ptr, gate,
+                                      static_cast<const bf16 *>(x_src), ld_src, f_src, static_cast<const bf16 *>(x_self), ld_self,
+                                      eps, self_mode, accumulate, static_cast<bf16 *>(out), ld_out, src_act, src_alpha, self_act,
+                                      self_alpha, stream);
+    HGIN_CHECK_ARG(dtype == HGIN_DTYPE_F32, "hgin_gin_combine_blocks_t: bad dtype %d", dtype);
+    return combine_blocks_t<float>(num_rows, rowptr, col, num_edges, num_in, rowptr_in, col_in, num_blocks, in_ptr, out_ptr, gate,
+                                   static_cast<const float *>(x_src), ld_src, f_src, static_cast<const float *>(x_self), ld_self,
+                                   eps, self_mode, accumulate, static_cast<float *>(out), ld_out, src_act, src_alpha, self_act,
+                                   self_alpha, stream);
+}
 
 extern "C" int32_t hgin_gin_combine(int64_t num_rows, const int32_t *rowptr, const int32_t *col, int64_t num_edges,
                                     const float *x_src, int64_t ld_src, int32_t f_src, const float *x_self, int64_t ld_self,

@@ -232,7 +232,8 @@ class Batch(HeteroData):
         if not ets:
             return self.edge_index_dict
         num_nodes = {nt: self[nt]["x"].shape[0] for nt in self.node_types}
-        return GraphCSR.from_prebuilt({et: self[et] for et in ets}, num_nodes)
+        blocks = {nt: self[nt]["ptr"] for nt in self.node_types if "ptr" in self[nt]}     # block-diagonal structure
+        return GraphCSR.from_prebuilt({et: self[et] for et in ets}, num_nodes, blocks)
 
 
 class DataLoader:

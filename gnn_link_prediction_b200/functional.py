@@ -26,16 +26,19 @@ class GraphCSR:
     aggregation) and, on demand, the source-sorted transpose (backward gather).  Built on the GPU
     by K0 from the COO `edge_index_dict` the reference passes around (train.py:34)."""
 
-    def __init__(self, edge_index_dict, num_nodes):
+    def __init__(self, edge_index_dict, num_nodes, blocks=None):
         self.edge_index_dict = dict(edge_index_dict)
         self.num_nodes = dict(num_nodes)
         self._by_dst, self._by_src = {}, {}
+        # block-diagonal batches: node type -> int64 [B + 1] device vector of first rows per sample (PyG's `ptr`)
+        self.blocks = dict(blocks) if blocks else {}
+        self._plans = {}
 
     @classmethod
-    def from_prebuilt(cls, stores, num_nodes):
+    def from_prebuilt(cls, stores, num_nodes, blocks=None):
         """From CSR tensors already on the device (`data.Batch.from_data_list(csr=True)`): stores[et]
         holds int32 `csr_{dst,src}_{rowptr,col}`; no K0 launch happens for these relations."""
-        g = cls({et: st.get("edge_index") for et, st in stores.items()}, num_nodes)
+        g = cls({et: st.get("edge_index") for et, st in stores.items()}, num_nodes, blocks)
         for et, st in stores.items():
             n_src, n_dst = num_nodes[et[0]], num_nodes[et[2]]
             e = st["csr_dst_col"].shape[0]
@@ -67,6 +70,26 @@ class GraphCSR:
             self._by_src[et] = ops.csr_build(self.edge_index_dict[et], self.num_nodes[et[0]],
                                              self.num_nodes[et[2]], by="src")
         return self._by_src[et]
+
+    def stream_plan(self, et, side):
+        """ops.StreamPlan for the aggregation that writes rows of et's destination type (side 'fwd': the forward K1 pass)
+        or of its source type (side 'bwd': the transposed K4 gather) — or None when the batch has no block tables or the
+        rows are short (the gather kernel is the right schedule for ~3 neighbours per row).  The gate is computed once."""
+        key = (tuple(et), side)
+        if not ops.STREAM_LONG_ROWS and key not in self._plans:
+            return None
+        if key not in self._plans:
+            plan = None
+            t_out, t_in = (et[2], et[0]) if side == "fwd" else (et[0], et[2])
+            p_in, p_out = self.blocks.get(t_in), self.blocks.get(t_out)
+            if (p_in is not None and p_out is not None and p_in.is_cuda and p_in.dtype == torch.int64
+                    and p_in.numel() == p_out.numel() and p_in.numel() >= 2):
+                csr_out, csr_in = (self.fwd(et), self.bwd(et)) if side == "fwd" else (self.bwd(et), self.fwd(et))
+                if csr_out.num_rows > 0 and csr_out.num_edges > 8 * csr_out.num_rows:
+                    plan = ops.StreamPlan(csr_in, p_in.contiguous(), p_out.contiguous(),
+                                          ops.block_gate(csr_out, csr_in, p_in.contiguous(), p_out.contiguous()))
+            self._plans[key] = plan
+        return self._plans[key]
 
     def validate(self):
         for c in list(self._by_dst.values()) + list(self._by_src.values()):
@@ -129,7 +152,8 @@ class HeteroConvFn(torch.autograd.Function):
                 pre["self_act"] = (lz_dst.act, lz_dst.alpha)
             if x_dst.dtype != x_src.dtype:      # (mixed storage types only arise outside HetroGIN.forward)
                 x_dst = x_dst.to(x_src.dtype)
-            h = ops.gin_combine(graph.fwd(sp.et), x_src, x_dst, eps, SELF_CONCAT if sp.concat else SELF_ADD, **pre)
+            h = ops.gin_combine(graph.fwd(sp.et), x_src, x_dst, eps, SELF_CONCAT if sp.concat else SELF_ADD,
+                                stream=None if sp.concat else graph.stream_plan(sp.et, "fwd"), **pre)
             link_ok = (training and links_out is not None and sp.act != ACT_NONE
                        and sum(1 for q in specs if q.dst == sp.dst) == 1
                        and _fold_eligible(h.shape[0], h.shape[1], W.shape[0], math_mode))
@@ -247,7 +271,7 @@ class HeteroConvFn(torch.autograd.Function):
                                    **common)
                 dh_agg, dh_self = None, None
                 if want_agg:      # (A^T dz) W, see above; g is dz here
-                    gz = ops.gin_combine(graph.bwd(sp.et), g, None, None, SELF_NONE)
+                    gz = ops.gin_combine(graph.bwd(sp.et), g, None, None, SELF_NONE, stream=graph.stream_plan(sp.et, "bwd"))
                     dh_agg = ops.linear_bwd(gz, None, x_src, W, act=ACT_NONE, dx_cols=(0, k), want_dx=True, want_dw=False,
                                             want_db=False, math_mode=ctx.math_mode)["dx"]
             elif sp.concat:
@@ -293,8 +317,10 @@ class HeteroConvFn(torch.autograd.Function):
                 csr_t = graph.bwd(specs[gi].et) if gi is not None else None
                 src_rows = dh_agg_of[gi] if gi is not None else s_dh
                 want_ddot = last and si is not None and eps_from_pass.get(si) == t
+                plan_t = graph.stream_plan(specs[gi].et, "bwd") if (gi is not None and not (last and post is not None)) else None
                 res = ops.gin_combine(csr_t, src_rows, s_dh, s_eps, SELF_ADD if si is not None else SELF_NONE, out=dx,
-                                      accumulate=dx is not None, post=post if last else None, want_ddot=want_ddot)
+                                      accumulate=dx is not None, post=post if last else None, want_ddot=want_ddot,
+                                      stream=plan_t)
                 if want_ddot:
                     dx, ddot = res
                     grads_p[4 * si + 3] = ddot.view_as(s_eps)

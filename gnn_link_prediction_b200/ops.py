@@ -159,13 +159,51 @@ class _NoEdges:
         self.num_rows, self.num_cols, self.num_edges, self.rowptr, self.col = num_rows, num_rows, 0, None, None
 
 
+class StreamPlan:
+    """What hgin_gin_combine_blocks_t needs on top of the output-major CSR: the input-major CSR of the same relation, the
+    block tables of the two node types (`ptr` vectors of the batch, int64 on the device) and the gate computed once per
+    batch by hgin_block_gate (functional.GraphCSR.stream_plan builds and caches it)."""
+
+    __slots__ = ("csr_in", "in_ptr", "out_ptr", "gate", "num_blocks")
+
+    def __init__(self, csr_in, in_ptr, out_ptr, gate):
+        self.csr_in, self.in_ptr, self.out_ptr, self.gate = csr_in, in_ptr, out_ptr, gate
+        self.num_blocks = in_ptr.numel() - 1
+
+
+def block_gate(csr_out, csr_in, in_ptr, out_ptr):
+    """int32 [2] on the device: violations (0 = the streaming schedule is bit-identical to the gather), max output rows of a
+    block (include/hgin.h: hgin_block_gate)."""
+    for t in (in_ptr, out_ptr):
+        if not (t.is_cuda and t.dtype == torch.int64 and t.is_contiguous() and t.dim() == 1):
+            raise HginError("block_gate: block tables must be contiguous CUDA int64 vectors")
+    if in_ptr.numel() != out_ptr.numel() or in_ptr.numel() < 2:
+        raise HginError("block_gate: block tables of the two node types differ in length")
+    gate = torch.empty(2, dtype=torch.int32, device=in_ptr.device)
+    with _region("csr_build", kernels=1, bytes=8 * csr_out.num_edges):
+        check(_lib.load().hgin_block_gate(csr_out.num_rows, _ptr(csr_out.rowptr), _ptr(csr_out.col), csr_in.num_rows,
+                                          _ptr(csr_in.rowptr), _ptr(csr_in.col), in_ptr.numel() - 1, in_ptr.data_ptr(),
+                                          out_ptr.data_ptr(), gate.data_ptr(), _stream()), "hgin_block_gate")
+    return gate
+
+
+# Opt-in (measured and rejected as the default, DESIGN.md "Long rows"): long-row aggregations of block-diagonal batches
+# through the input-major streaming kernel.  Bit-identical to the gather kernel, but every edge costs a 512-byte
+# read-modify-write of shared memory (3 x E x F x 4 B = 11 GB per path->link launch against ~36 TB/s of aggregate
+# shared-memory bandwidth, a 310 us floor before any latency) where the gather kernel keeps its accumulators in
+# registers and is bound by L2->SM bandwidth (336 us): 1.5 ms against 0.34-0.44 ms per launch at Cfg-C.
+STREAM_LONG_ROWS = False
+
+
 def gin_combine(csr, x_src, x_self=None, eps=None, self_mode=SELF_NONE, out=None, accumulate=False, post=None,
-                want_ddot=False, src_act=None, self_act=None):
+                want_ddot=False, src_act=None, self_act=None, stream=None):
     """K1/K4.  out[r] (+)= sum_{e in row r} x_src[col[e]]  {+ | concat}  (1+eps) * x_self[r].
     csr=None: no edges (self term only; x_src is then only a shape donor).
     post: a PostAct — the stored result is multiplied by act'(post.z) and post.dalpha is filled.
     want_ddot (with post, SELF_ADD): returns (out, ddot) with ddot = sum x_self * act(post.z).
     src_act / self_act: (act, alpha) when x_src / x_self hold PRE-activations (act applied on load).
+    stream: a StreamPlan — the batch is block-diagonal and this is a long-row aggregation: input-major streaming kernel
+    with the gather kernel behind an inverse device-side gate (same bits either way; hgin_gin_combine_blocks_t).
     Rows may be float32 or bfloat16 (all of x_src, x_self, post.z, out alike): bf16 rows are widened on load,
     summed in fp32 in CSR order and rounded once on the store (hgin_gin_combine_t)."""
     if csr is None:
@@ -214,6 +252,19 @@ def gin_combine(csr, x_src, x_self=None, eps=None, self_mode=SELF_NONE, out=None
         kernels = 1 + int(want) + int(want_ddot)
     sa, sal = src_act if src_act is not None else (ACT_NONE, None)
     fa, fal = self_act if (self_act is not None and x_self is not None) else (ACT_NONE, None)
+    if (stream is not None and STREAM_LONG_ROWS and not post_on and self_mode in (SELF_NONE, SELF_ADD) and csr.rowptr is not None
+            and 32 <= f_src <= 128 and f_src % (16 // es) == 0 and x_src.shape[0] > 1 and lds == f_src and ldo % 4 == 0
+            and (x_self is None or ldf % 4 == 0) and x_src.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0
+            and (x_self is None or x_self.data_ptr() % 16 == 0)):
+        cin = stream.csr_in
+        with _region("gin_combine", kernels=2, alg_bytes=alg, compulsory_bytes=comp):
+            check(lib.hgin_gin_combine_blocks_t(_DTYPES[dt], csr.num_rows, _ptr(csr.rowptr), _ptr(csr.col), csr.num_edges,
+                                                cin.num_rows, _ptr(cin.rowptr), _ptr(cin.col), stream.num_blocks,
+                                                stream.in_ptr.data_ptr(), stream.out_ptr.data_ptr(), stream.gate.data_ptr(),
+                                                ps, lds, f_src, pf, ldf, _scalar(eps, "gin_combine.eps"), self_mode,
+                                                1 if accumulate else 0, po, ldo, sa, _scalar(sal, "gin_combine.src_alpha"), fa,
+                                                _scalar(fal, "gin_combine.self_alpha"), _stream()), "hgin_gin_combine_blocks_t")
+        return out
     with _region("gin_combine", kernels=kernels, alg_bytes=alg, compulsory_bytes=comp):
         check(lib.hgin_gin_combine_t(_DTYPES[dt], csr.num_rows, _ptr(csr.rowptr), _ptr(csr.col), csr.num_edges, ps, lds,
                                      f_src, pf, ldf, f_self, _scalar(eps, "gin_combine.eps"), self_mode,

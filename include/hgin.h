@@ -116,6 +116,35 @@ int32_t hgin_gin_combine(int64_t num_rows, const int32_t *rowptr, const int32_t 
                          const float *eps, int32_t self_mode, int32_t accumulate,
                          float *out, int64_t ld_out, void *stream);
 
+/* ---- K1 / K4 for long rows on block-diagonal batches: input-major streaming -------------------------------------------
+ * Same result as hgin_gin_combine_t (bit for bit), different schedule (csrc/gin_scatter_blocks.cuh): a batch of topology
+ * samples is block-diagonal — block b owns input rows [in_ptr[b], in_ptr[b+1]) and output rows [out_ptr[b], out_ptr[b+1])
+ * (PyG's `ptr` vectors of the two node types) — so one CTA per block keeps the block's output rows as fp32 accumulators
+ * in shared memory and streams the block's input rows ONCE, in order, through a ring of bulk copies: every input row
+ * crosses HBM exactly once instead of ~2.9 times through L2 (path->link rows have ~36 neighbours).
+ *   hgin_block_gate: once per batch and relation.  gate[0] = number of violations (a row of the output-major CSR_A whose
+ *     neighbours are not in non-decreasing order — then ascending-input order would differ from the stable edge order of the
+ *     reference's scatter_add_ —, an edge of the input-major CSR_B that leaves its block, block tables that do not cover the
+ *     rows); gate[1] = largest number of output rows of a block.
+ *   hgin_gin_combine_blocks_t: launches the streaming kernel, which runs only if gate[0] == 0 and gate[1] fits its
+ *     accumulator tile, and behind it the gather kernel of hgin_gin_combine_t with the inverse gate: a static, capturable
+ *     launch sequence with exactly one of the two doing the work.  (rowptr, col) = CSR_A, rows = outputs, as for
+ *     hgin_gin_combine_t; (rowptr_in, col_in) = CSR_B, rows = inputs.  Input rows must be contiguous (ld_src == f_src),
+ *     32 <= f_src <= 128; SELF_NONE or SELF_ADD; src_act / self_act as in hgin_gin_combine_pre.  HGIN_ERR_UNSUPPORTED
+ *     otherwise (the caller then uses hgin_gin_combine_t).
+ */
+int32_t hgin_block_gate(int64_t rows_a, const int32_t *rowptr_a, const int32_t *col_a, int64_t rows_b,
+                        const int32_t *rowptr_b, const int32_t *col_b, int32_t num_blocks,
+                        const int64_t *in_ptr, const int64_t *out_ptr, int32_t *gate, void *stream);
+int32_t hgin_gin_combine_blocks_t(int32_t dtype, int64_t num_rows, const int32_t *rowptr, const int32_t *col,
+                                  int64_t num_edges, int64_t num_in, const int32_t *rowptr_in,
+                                  const int32_t *col_in, int32_t num_blocks, const int64_t *in_ptr,
+                                  const int64_t *out_ptr, const int32_t *gate, const void *x_src,
+                                  int64_t ld_src, int32_t f_src, const void *x_self, int64_t ld_self,
+                                  const float *eps, int32_t self_mode, int32_t accumulate, void *out,
+                                  int64_t ld_out, int32_t src_act, const float *src_alpha, int32_t self_act,
+                                  const float *self_alpha, void *stream);
+
 /* ---- K4 with the activation derivative of the layer below ("post-activation") ---------------
  * Replaces: the first op of the NEXT autograd node on the way down, PReLU.backward of the layer
  * whose output this gradient is for (models.py:238 -> at::prelu_backward).  The row result r of

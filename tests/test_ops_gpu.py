@@ -580,3 +580,95 @@ def test_head_layer(k):
     torch.testing.assert_close(r["dW"].cpu().double(), W.grad, rtol=RTOL, atol=ATOL * rows ** 0.5)
     torch.testing.assert_close(r["db"].cpu().double(), b.grad, rtol=RTOL, atol=ATOL * rows ** 0.5)
     torch.testing.assert_close(r["dx"].cpu().double(), xr.grad, rtol=RTOL, atol=ATOL)
+
+
+def _block_diagonal_relation(sizes_in, sizes_out, deg, seed, sort_rows=True):
+    """A block-diagonal bipartite relation: block b has sizes_in[b] input rows and sizes_out[b] output rows, every input row
+    sends `deg`-ish edges to random output rows of ITS block; COO grouped by input row (as the reference ships it)."""
+    g = torch.Generator().manual_seed(seed)
+    src, dst = [], []
+    i0 = o0 = 0
+    for ni, no in zip(sizes_in, sizes_out):
+        if ni and no:
+            k = torch.randint(1, 2 * deg, (ni,), generator=g)
+            s = torch.repeat_interleave(torch.arange(ni), k) + i0
+            d = torch.randint(0, no, (int(k.sum()),), generator=g) + o0
+            src.append(s), dst.append(d)
+        i0, o0 = i0 + ni, o0 + no
+    ei = torch.stack((torch.cat(src), torch.cat(dst)))
+    if not sort_rows:       # shuffle the edge order: stable destination order is then NOT ascending in the input id
+        ei = ei[:, torch.randperm(ei.shape[1], generator=g)]
+    ptr_in = torch.tensor([0] + list(torch.tensor(sizes_in).cumsum(0)), dtype=torch.int64)
+    ptr_out = torch.tensor([0] + list(torch.tensor(sizes_out).cumsum(0)), dtype=torch.int64)
+    return ei, ptr_in, ptr_out
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("f", [128, 64, 32])
+@pytest.mark.parametrize("case", ["plain", "self_add", "accumulate", "pre_act", "unsorted", "oversize_block", "ragged"])
+def test_streaming_long_row_aggregation_is_bit_identical_to_the_gather(case, f, dtype, monkeypatch):
+    """hgin_gin_combine_blocks_t (input-major streaming over a block-diagonal batch, csrc/gin_scatter_blocks.cuh) against
+    hgin_gin_combine_t on the same inputs: torch.equal in every mode it takes, including the two gated fall-backs (edge
+    order not ascending within output rows; a block with more output rows than the accumulator tile holds)."""
+    from gnn_link_prediction_b200.functional import GraphCSR
+    monkeypatch.setattr(ops, "STREAM_LONG_ROWS", True)      # opt-in schedule (the gather kernel is the default)
+    if case == "oversize_block":
+        sizes_in, sizes_out = [300, 40000, 500], [20, 3000, 30]
+    elif case == "ragged":
+        sizes_in, sizes_out = [1, 0, 77, 33, 0, 5, 1000], [3, 4, 1, 40, 0, 2, 130]
+    else:
+        sizes_in, sizes_out = [700, 650, 900, 31, 64], [60, 50, 80, 7, 33]
+    ei, ptr_in, ptr_out = _block_diagonal_relation(sizes_in, sizes_out, 3, 5, sort_rows=case != "unsorted")
+    n_in, n_out = int(ptr_in[-1]), int(ptr_out[-1])
+    et = ("a", "to", "b")
+    graph = GraphCSR({et: ei.cuda()}, {"a": n_in, "b": n_out}, blocks={"a": ptr_in.cuda(), "b": ptr_out.cuda()})
+    plan = graph.stream_plan(et, "fwd")
+    assert plan is not None
+    gate = plan.gate.cpu()
+    assert (int(gate[0]) == 0) == (case != "unsorted") and int(gate[1]) == max(sizes_out)
+    torch.manual_seed(1)
+    x = torch.randn(n_in, f, device="cuda").to(dtype)
+    xs = torch.randn(n_out, f, device="cuda").to(dtype)
+    eps = torch.tensor([0.3], device="cuda")
+    alpha = torch.tensor([0.25], device="cuda")
+    kw = {}
+    if case in ("self_add", "accumulate", "pre_act", "ragged"):
+        kw.update(x_self=xs, eps=eps, self_mode=ops.SELF_ADD)
+    if case == "pre_act":
+        kw.update(src_act=(ops.ACT_PRELU, alpha), self_act=(ops.ACT_RELU, None))
+
+    def run(stream):
+        out = None
+        if case == "accumulate":
+            out = torch.full((n_out, f), 0.5, device="cuda").to(dtype)
+        return ops.gin_combine(graph.fwd(et), x, out=out, accumulate=out is not None, stream=stream, **kw)
+
+    want = run(None)
+    got = run(plan)
+    assert torch.equal(got, want)
+    # and the transposed direction (the K4 pass): outputs are the `a` rows, inputs the `b` rows
+    plan_t = graph.stream_plan(et, "bwd")
+    if plan_t is not None:      # only long rows get a plan
+        g = torch.randn(n_out, f, device="cuda").to(dtype)
+        assert torch.equal(ops.gin_combine(graph.bwd(et), g, stream=plan_t), ops.gin_combine(graph.bwd(et), g))
+
+
+def test_streaming_plan_only_for_long_rows_and_block_tables(monkeypatch):
+    from gnn_link_prediction_b200.functional import GraphCSR
+    et = ("a", "to", "b")
+    ei, ptr_in, ptr_out = _block_diagonal_relation([200, 300], [20, 30], 3, 0)
+    off = GraphCSR({et: ei.cuda()}, {"a": 500, "b": 50}, blocks={"a": ptr_in.cuda(), "b": ptr_out.cuda()})
+    assert off.stream_plan(et, "fwd") is None                    # opt-in: off by default
+    monkeypatch.setattr(ops, "STREAM_LONG_ROWS", True)
+    ei, ptr_in, ptr_out = _block_diagonal_relation([200, 300], [20, 30], 3, 0)
+    et = ("a", "to", "b")
+    no_blocks = GraphCSR({et: ei.cuda()}, {"a": 500, "b": 50})
+    assert no_blocks.stream_plan(et, "fwd") is None
+    with_blocks = GraphCSR({et: ei.cuda()}, {"a": 500, "b": 50}, blocks={"a": ptr_in.cuda(), "b": ptr_out.cuda()})
+    assert with_blocks.stream_plan(et, "fwd") is not None        # ~30 inputs per output row
+    assert with_blocks.stream_plan(et, "bwd") is None            # ~3 outputs per input row: the gather kernel's case
+    # an edge that leaves its block closes the gate (the gather kernel then does the work)
+    bad = ei.clone()
+    bad[1, 0] = 45
+    g = GraphCSR({et: bad.cuda()}, {"a": 500, "b": 50}, blocks={"a": ptr_in.cuda(), "b": ptr_out.cuda()})
+    assert int(g.stream_plan(et, "fwd").gate[0]) > 0
