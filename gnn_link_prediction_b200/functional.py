@@ -512,7 +512,11 @@ class BatchNormActFn(torch.autograd.Function):
             g = g.to(z.dtype).contiguous()
         sums = ops.bn_act_bwd_reduce(g, z, mean, invstd, gamma, beta, spec.code, alpha, spec.p0, spec.p1)
         count = ctx.count
+        local = None
         if ctx.training and ctx.comm is not None and ctx.comm.world > 1:
+            # dz needs the GLOBAL reductions; the parameter gradients leave as this rank's PARTIAL sums, because the
+            # step all-reduces the flat gradient bucket with SUM afterwards (parallel.py)
+            local = sums.clone()
             ctx.comm.all_reduce_sum_(sums)
             count = float(ctx.count_t.item())
         nz, ng, nb, na = ctx.needs_input_grad[:4]
@@ -520,6 +524,11 @@ class BatchNormActFn(torch.autograd.Function):
             g, z, mean, invstd, gamma, beta, spec.code, sums, count, training=ctx.training, alpha=alpha, p0=spec.p0,
             p1=spec.p1, want_dgamma=bool(ng) and gamma is not None, want_dbeta=bool(nb) and beta is not None,
             want_dalpha=bool(na) and alpha is not None)
+        if local is not None:
+            n = z.shape[1]
+            dbeta = None if dbeta is None else local[:n].float()
+            dgamma = None if dgamma is None else local[n:2 * n].float()
+            dalpha = None if dalpha is None else local[2 * n:2 * n + 1].float()
         return (dz if nz else None, dgamma, dbeta, None if dalpha is None else dalpha.view_as(alpha), None, None, None)
 
 

@@ -125,21 +125,58 @@ class TrainStep:
         for p in self.live:
             offsets.append(n)
             n += (p.numel() + align - 1) // align * align
+        self.offsets = offsets
         self.flat_p = torch.zeros(n, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.grad_views = []
+        self.grad_views = [self.flat_g[off:off + p.numel()].view_as(p) for p, off in zip(self.live, offsets)]
+        self._adopt()
+
+    def _adopt(self):
+        """Make every live parameter a view of the flat bucket (copying its current values in)."""
         with torch.no_grad():
-            for p, off in zip(self.live, offsets):   # parameters become views of the flat bucket
-                self.flat_p[off:off + p.numel()].copy_(p.reshape(-1))
-                p.data = self.flat_p[off:off + p.numel()].view_as(p)
-                self.grad_views.append(self.flat_g[off:off + p.numel()].view_as(p))
+            for p, off in zip(self.live, self.offsets):
+                view = self.flat_p[off:off + p.numel()]
+                if p.data_ptr() != view.data_ptr():
+                    view.copy_(p.detach().reshape(-1).to(self.flat_p.device))
+                    p.data = view.view_as(p)
+
+    def _check_aliasing(self):
+        """The reference's save_best_model (train.py:155-160) does model.to('cpu') ... .cuda(), which gives every
+        parameter fresh storage: Adam would then update the bucket while the model stopped learning.  Detected here
+        (a pointer comparison per parameter) and repaired by re-adopting the parameters' current values."""
+        base, esz = self.flat_p.data_ptr(), self.flat_p.element_size()
+        for p, off in zip(self.live, self.offsets):
+            if p.data_ptr() != base + off * esz:
+                if p.device != self.flat_p.device:
+                    raise ops.HginError("TrainStep: a model parameter left the GPU (model.cpu()?); move the model back "
+                                        "with model.cuda() before the next step")
+                self._adopt()
+                return
+
+    def state_dict(self):
+        """Optimizer state of the fused Adam (the model's own state_dict holds the parameters): resume with
+        `TrainStep(model, ...).load_state_dict(sd)` after `model.load_state_dict(...)`."""
+        return {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "step": self.step_count.clone(),
+                "hyper": dict(self.hyper), "numel": self.flat_p.numel()}
+
+    def load_state_dict(self, sd):
+        if int(sd["numel"]) != self.flat_p.numel():
+            raise ValueError(f"TrainStep.load_state_dict: bucket of {sd['numel']} floats does not match this model's "
+                             f"{self.flat_p.numel()}")
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.step_count.copy_(sd["step"])
+        self.hyper.update(sd["hyper"])
+        self._adopt()
+        return self
 
     def __call__(self, batch):
         """`batch` already resident on the GPU.  Returns a CUDA tensor [mape, sqrt(mape)] (global)."""
         model = self.model
+        self._check_aliasing()
         for p in self.live:
             p.grad = None
         # the per-path graph ids are only read with GLOBAL_FEATS (models.py:347-352): do not force them otherwise
@@ -153,7 +190,10 @@ class TrainStep:
         self.comm.all_reduce_sum_(sums)          # global (S, N): every rank differentiates the same loss
         loss_out, dpred = ops.sqrt_mape_bwd(out.detach(), y, sums)
         out.backward(dpred)
-        torch._foreach_copy_(self.grad_views, [p.grad for p in self.live])   # gather into the flat bucket
+        # gather into the flat bucket (a live parameter the batch gave no gradient — a relation without edges —
+        # contributes zeros, as torch.optim.Adam would skip it only when grad is None on EVERY rank)
+        grads = [p.grad if p.grad is not None else torch.zeros_like(v) for p, v in zip(self.live, self.grad_views)]
+        torch._foreach_copy_(self.grad_views, grads)
         self.comm.all_reduce_sum_(self.flat_g)   # SUM of partial gradients (no division by world size)
         ops.increment(self.step_count)
         ops.adam_step(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, self.step_count, **self.hyper)
@@ -212,6 +252,8 @@ class GraphedTrainStep:
 
     def __init__(self, step: TrainStep, edge_bucket=8192, max_graphs=4, warmup=2):
         if step.comm.world > 1:
+            # tried in round 2 (two B200s): capturing the step's two NCCL all-reduces with the kernels left one rank
+            # blocked inside the collective after the other failed in capture; not enabled.  Multi-GPU runs use TrainStep.
             raise NotImplementedError("GraphedTrainStep: capture of the NCCL all-reduces is not enabled; "
                                       "use TrainStep for multi-GPU runs")
         self.step, self.edge_bucket, self.max_graphs, self.warmup = step, edge_bucket, max_graphs, warmup

@@ -608,3 +608,39 @@ def test_reference_loop_functions_follow_the_oracle_loop():
     assert type(gat).__name__ == "HetroGAT" and gat.readout[0][0].in_features == config["NODE_EMBEDDING_SIZE"] * 16 + 3
     with pytest.raises(IOError):
         load_model({**config, "MODEL": "nope"}, {"train": ds})
+
+
+def test_trainstep_survives_cpu_round_trip_and_resumes_from_its_state():
+    """The reference's save_best_model (train.py:155-160) moves the model to the CPU and back, which detaches every
+    parameter from TrainStep's flat bucket; the step notices and re-adopts them.  state_dict / load_state_dict carry the
+    fused Adam's moments, so a resumed run continues the same trajectory."""
+    kw = dict(node_embedding_size=8, message_passing_layers=2, dropout=0.0, concat_path=True, bl_features=False,
+              divided_features=False, global_feats=False, mlp_layers=[16], act="torch.nn.PReLU()", mlp_head_act=None,
+              mlp_bn=False)
+    ds = SyntheticDataset(3, num_nodes=10, num_links=14, num_topologies=2)
+    batch = Batch.from_data_list([ds[i] for i in range(3)]).cuda()
+
+    def fresh():
+        torch.manual_seed(5)
+        return HetroGIN({"link": 7, "path": 7, "node": 3}, **kw).cuda().train()
+
+    ref_model = fresh()
+    ref_step = TrainStep(ref_model)
+    want = [float(ref_step(batch)[0]) for _ in range(6)]
+
+    model = fresh()
+    step = TrainStep(model)
+    got = [float(step(batch)[0]) for _ in range(3)]
+    model.to("cpu")
+    model.cuda()                                   # fresh storage for every parameter
+    got += [float(step(batch)[0]) for _ in range(3)]
+    assert got == want
+    # resume: new objects, parameters from the model's state_dict, moments from the step's
+    model2 = fresh()
+    step2 = TrainStep(model2)
+    half = fresh()
+    half_step = TrainStep(half)
+    first = [float(half_step(batch)[0]) for _ in range(3)]
+    model2.load_state_dict(half.state_dict())
+    step2.load_state_dict(half_step.state_dict())
+    assert first + [float(step2(batch)[0]) for _ in range(3)] == want
