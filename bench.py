@@ -563,6 +563,19 @@ def main():
                                                 "kernels_per_step": a["kernels_per_step"], "dtype": a["dtype"]}}
         except Exception as exc:   # the default line must not depend on the extra run
             line["other_workloads"] = {"cfgA": {"error": repr(exc)[:200]}}
+        # the same Cfg-C workload in the bf16 storage mode (BASELINE configs[2] "bf16 MLP GEMMs"): a second line BESIDE
+        # the tf32 one, with its own roofline, measured by the same script in its own process
+        if args.math != "bf16":
+            try:
+                torch.cuda.empty_cache()
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", "cfgC", "--math", "bf16",
+                                    "--no-cpu-baseline", "--no-extra", "--steps", str(args.steps), "--warmup", str(args.warmup)],
+                                   capture_output=True, text=True, timeout=300)
+                b = json.loads(r.stdout.strip().splitlines()[-1])
+                line["other_workloads"]["cfgC_bf16"] = {k: b[k] for k in ("value", "unit", "ms_per_step", "dtype", "e2e", "roofline",
+                                                                          "edges_per_s", "kernels_per_step", "peak_hbm_gb")}
+            except Exception as exc:
+                line["other_workloads"]["cfgC_bf16"] = {"error": repr(exc)[:200]}
     print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
