@@ -510,14 +510,26 @@ def main():
                      else "one H2D copy per tensor (DevicePrefetcher)"),
                "readback": "every step, collected one step later (train.LossReadback)" if args.readback == "deferred"
                else "every step, blocking"}
-    # the parsed end-to-end number: a FRESH shuffled batch is collated from host-resident samples INSIDE the timed
-    # region every step (native host collate on a background thread into a pinned ring), copied with one DMA,
-    # trained on, and its loss read back.  (cfgA under a CUDA graph has no streaming loader arm: pre-collated.)
-    e2e_main = e2e_pre if hs_steps == 0 else {
+    # the host-streaming arm: a FRESH shuffled batch is collated from host-resident samples INSIDE the timed region
+    # every step (native host collate on a background thread into a pinned ring), copied with one DMA, trained on, and
+    # its loss read back.  Bound by the HOST's memory system, not by the GPU: per rank and step the collate reads and
+    # writes 230 MB and the DMA reads them again, so 8 ranks on one host ask for ~350 GB/s of host memory traffic.
+    e2e_host = None if hs_steps == 0 else {
         "value": graphs * world * hs_steps / (hs_ms * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": h2d_bytes,
         "d2h_bytes_per_step": 8, "ms_per_step": hs_ms / hs_steps,
         "collate": "inside the timed region (arena.HostLoader: native host collate of a fresh shuffled batch per step)",
         "staging": "one packed pinned buffer per batch -> DevicePrefetcher ring (one DMA per step)",
+        "readback": "every step, collected one step later (train.LossReadback)"}
+    # the parsed end-to-end number = the production data path: the dataset is resident in HBM
+    # (arena.DeviceDataset; 225 KB per sample, so 180 GB hold ~800 k samples), every step copies that step's sample ids
+    # from pinned host memory, assembles a FRESH random batch on the GPU (hgin_collate_*), trains on it and reads the
+    # loss back — all inside the timed region.  (cfgA under a CUDA graph has no loader arm: pre-collated.)
+    e2e_main = e2e_pre if dd_ms == 0.0 else {
+        "value": graphs * world * args.steps / (dd_ms * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": dd_bytes,
+        "d2h_bytes_per_step": 8, "ms_per_step": dd_ms / args.steps, "collate_ms_per_step": dd_collate_ms,
+        "collate": "inside the timed region, on the GPU (arena.DeviceDataset: fresh random batch per step from the sample ids)",
+        "staging": "dataset resident in HBM (uploaded once, outside the timed region); per step: H2D of the sample ids "
+                   "from pinned host memory",
         "readback": "every step, collected one step later (train.LossReadback)"}
     line = {
         "metric": METRIC, "value": value, "unit": "graphs/s", "n_gpus": world, "steps": args.steps,
@@ -532,12 +544,8 @@ def main():
                    "parallelism": f"dp{world} (samples sharded, NCCL sum-allreduce of one flat grad bucket)"},
         "edges_per_s": edges * world * args.steps / (resident_ms * 1e-3),
         "e2e": e2e_main,
+        "e2e_host_stream": e2e_host,
         "e2e_precollated": e2e_pre if e2e_main is not e2e_pre else None,
-        "e2e_device_dataset": None if dd_ms == 0.0 else {
-            "value": graphs * world * args.steps / (dd_ms * 1e-3), "unit": "graphs/s", "ms_per_step": dd_ms / args.steps,
-            "h2d_bytes_per_step": dd_bytes, "d2h_bytes_per_step": 8, "collate_ms_per_step": dd_collate_ms,
-            "what": "dataset resident in HBM (arena.DeviceDataset); every step: H2D of the sample ids, on-GPU collate "
-                    "of a fresh random batch, train step, loss read-back"},
         "strong_scaling": None if strong_ms == 0.0 else {
             "value": strong_graphs * args.steps / (strong_ms * 1e-3), "unit": "graphs/s",
             "ms_per_step": strong_ms / args.steps, "global_batch": strong_graphs, "graphs_per_gpu_per_step": strong_graphs // world,
@@ -572,7 +580,7 @@ def main():
                                     "--no-cpu-baseline", "--no-extra", "--steps", str(args.steps), "--warmup", str(args.warmup)],
                                    capture_output=True, text=True, timeout=300)
                 b = json.loads(r.stdout.strip().splitlines()[-1])
-                line["other_workloads"]["cfgC_bf16"] = {k: b[k] for k in ("value", "unit", "ms_per_step", "dtype", "e2e", "roofline",
+                line["other_workloads"]["cfgC_bf16"] = {k: b[k] for k in ("value", "unit", "ms_per_step", "dtype", "e2e", "e2e_host_stream", "roofline",
                                                                           "edges_per_s", "kernels_per_step", "peak_hbm_gb")}
             except Exception as exc:
                 line["other_workloads"]["cfgC_bf16"] = {"error": repr(exc)[:200]}
