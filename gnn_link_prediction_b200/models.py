@@ -293,6 +293,7 @@ class _HetroBase(torch.nn.Module):
             self.readout.append(torch.nn.Sequential(torch.nn.Linear(mlp_layers[-1], 1), head))
         self._dropout_calls = 0
         self.communicator = None    # set by TrainStep: BatchNorm statistics are all-reduced over it
+        self._edges_validated = False
 
     def set_math_mode(self, mode):
         """MATH_FP32 (parity), MATH_TF32 (tcgen05 tf32 GEMMs, fp32 activations) or MATH_BF16 (activations and
@@ -316,6 +317,15 @@ class _HetroBase(torch.nn.Module):
             live[li] = [et for et in present if et[2] in needed]
             needed = {t for et in live[li] for t in (et[0], et[2])}
         return live
+
+    def _validate_once(self, graph, was_coo):
+        """PyG raises on an edge_index that points outside its node sets; hgin_csr_build drops such edges and raises a
+        device-side flag instead (no sync in the step).  The flag is read back ONCE per model, after the first forward
+        call on a COO `edge_index_dict` (one synchronisation), so that a corrupt dataset is reported, not absorbed."""
+        if was_coo and not self._edges_validated:
+            self._edges_validated = True
+            if not torch.cuda.is_current_stream_capturing():
+                graph.validate()
 
     def _slice_inputs(self, x_dict):
         """Feature slicing, rebinding the caller's dict like models.py:333-342."""
@@ -427,6 +437,7 @@ class HetroGIN(_HetroBase):
             x_dict = self.convs[i](x_dict, graph, only=live[i], chain=chain, lazy=i < self.num_layers - 1)
             if drop:
                 x_dict = self._dropout_outputs(x_dict)
+        self._validate_once(graph, graph is not edge_index_dict)
         link = chain.get("path") if chain is not None else None
         return self._run_readout(x_dict["path"], x2, link, chain is not None)
 
@@ -477,4 +488,5 @@ class HetroGAT(_HetroBase):
             x_dict = self.convs[i](x_dict, graph, only=live[i])
             if self.training and self.dropout > 0:
                 x_dict = self._dropout_outputs(x_dict)
+        self._validate_once(graph, graph is not edge_index_dict)
         return self._run_readout(x_dict["path"], x2, None, False)

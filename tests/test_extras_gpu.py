@@ -226,3 +226,24 @@ def test_gatconv_shared_projection_and_unsupported_widths():
     bad = GATConv((3, 3), 6, heads=2).cuda()    # 6 channels per head: not a power of two
     with pytest.raises(ops.HginError):
         bad((torch.randn(4, 3, device="cuda"), torch.randn(4, 3, device="cuda")), torch.zeros(2, 1, dtype=torch.int64, device="cuda"))
+
+
+def test_batchnorm_on_bf16_rows():
+    torch.manual_seed(6)
+    n = 64
+    z = (1.5 * torch.randn(3000, n) - 0.3).bfloat16()
+    g = torch.randn(3000, n).bfloat16()
+    bn_ref = torch.nn.BatchNorm1d(n)
+    zr = z.float().requires_grad_(True)
+    out_ref = torch.nn.functional.leaky_relu(bn_ref(zr), 0.1)
+    out_ref.backward(g.float())
+    bn = torch.nn.BatchNorm1d(n).cuda()
+    spec = F_.act_spec_of(torch.nn.LeakyReLU(0.1))
+    zc = z.cuda().requires_grad_(True)
+    out = F_.BatchNormActFn.apply(zc, bn.weight, bn.bias, None, bn, spec, None)
+    assert out.dtype == torch.bfloat16
+    out.backward(g.cuda())
+    torch.testing.assert_close(out.float().cpu(), out_ref.detach(), rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(zc.grad.float().cpu(), zr.grad, rtol=2e-2, atol=2e-3)
+    torch.testing.assert_close(bn.weight.grad.cpu(), bn_ref.weight.grad, rtol=1e-3, atol=1e-2)
+    torch.testing.assert_close(bn.running_var.cpu(), bn_ref.running_var, rtol=1e-4, atol=1e-5)

@@ -644,3 +644,65 @@ def test_trainstep_survives_cpu_round_trip_and_resumes_from_its_state():
     model2.load_state_dict(half.state_dict())
     step2.load_state_dict(half_step.state_dict())
     assert first + [float(step2(batch)[0]) for _ in range(3)] == want
+
+
+def test_out_of_range_edges_are_reported_on_the_first_forward():
+    """PyG raises on an edge_index that leaves its node sets; the drop-in reads K0's device-side flag once."""
+    kw = dict(node_embedding_size=8, message_passing_layers=1, dropout=0.0, concat_path=True, bl_features=False,
+              divided_features=False, global_feats=False, mlp_layers=[8], act="torch.nn.PReLU()", mlp_head_act=None,
+              mlp_bn=False)
+    ds = SyntheticDataset(1, num_nodes=8, num_links=9)
+    dev = Batch.from_data_list([ds[0]]).cuda()
+    ei = dict(dev.edge_index_dict)
+    bad = ei[("link", "includes", "path")].clone()
+    bad[1, 0] = 10 ** 6
+    ei[("link", "includes", "path")] = bad
+    m = HetroGIN({"link": 7, "path": 7, "node": 3}, **kw).cuda()
+    with pytest.raises(IndexError):
+        m(dev.x_dict, ei, None)
+    ok = HetroGIN({"link": 7, "path": 7, "node": 3}, **kw).cuda()
+    ok(Batch.from_data_list([ds[0]]).cuda().x_dict, dev.edge_index_dict, None)      # a clean batch passes
+
+
+@pytest.mark.parametrize("math", ["tf32", "bf16"])
+def test_non_default_flags_in_the_tensor_core_modes(math):
+    """global_feats + mlp_bn + a non-fused activation with the tensor-core math modes (the 12-column readout tail and the
+    BatchNorm / activation row passes on fp32 or bf16 rows) against the fp32 oracle at the reduced-precision bar."""
+    from gnn_link_prediction_b200 import models as _m
+    kw = dict(node_embedding_size=64, message_passing_layers=2, dropout=0.0, concat_path=True, bl_features=True,
+              divided_features=False, global_feats=True, mlp_layers=[64, 32], act="torch.nn.ELU()", mlp_head_act=None,
+              mlp_bn=True)
+    ds = SyntheticDataset(4, num_topologies=2)
+    samples = [ds[i] for i in range(4)]
+    cpu_batch = Batch.from_data_list(samples)
+    torch.manual_seed(3)
+    ref = hgin_oracle.HetroGIN(input_channels={"link": 7, "path": 7, "node": 3}, **kw)
+    m = HetroGIN(input_channels={"link": 7, "path": 7, "node": 3}, **kw)
+    m.load_state_dict(ref.state_dict())
+    m.cuda().train().set_math_mode(_m.MATH_TF32 if math == "tf32" else _m.MATH_BF16)
+    y = cpu_batch["path"].y.reshape(-1, 1)
+    o_ref = ref(cpu_batch.x_dict, cpu_batch.edge_index_dict, cpu_batch["path"].batch)
+    torch.sqrt(hgin_oracle.mape(o_ref, y)).backward()
+    dev = Batch.from_data_list(samples, index_dtype=torch.int32, edge_types=CONV_EDGE_TYPES).cuda()
+    o = m(dev.x_dict, dev.edge_index_dict, dev["path"].batch)
+    torch.sqrt(mape(o, dev["path"].y.reshape(-1, 1))).backward()
+    tol = 1e-2 if math == "tf32" else 3e-2
+
+    def rel(a, b):
+        b = b.detach().double()
+        return float((a.detach().cpu().double() - b).norm() / (b.norm() + 1e-30))
+
+    assert rel(o, o_ref) <= tol
+    g_ref = {k: p.grad for k, p in ref.named_parameters()}
+    gmax = max(float(g.norm()) for g in g_ref.values() if g is not None)
+    for k, p in m.named_parameters():
+        assert (p.grad is None) == (g_ref[k] is None), k
+        if p.grad is None:
+            continue
+        if p.numel() == 1:      # d(eps), d(alpha): cancelling sums, held against the typical size of such gradients
+            scale = max(float(g.abs().max()) for g in g_ref.values() if g is not None and g.numel() == 1)
+            assert abs(float(p.grad) - float(g_ref[k])) <= 3 * tol * scale + 1e-1 * abs(float(g_ref[k])), k
+        elif float(g_ref[k].norm()) > 1e-4 * gmax:      # (zero-gradient biases before a BatchNorm: noise)
+            assert rel(p.grad, g_ref[k]) <= 3 * tol, k
+    for k in ("readout.0.1.running_mean", "readout.0.1.running_var"):
+        assert rel(m.state_dict()[k], ref.state_dict()[k]) <= tol, k
