@@ -93,6 +93,9 @@ SIGNATURES = {
                             _ptr, _ptr]),
     "hgin_gat_bwd": (_i32, [_i64, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _f32,
                             _i32, _ptr, _i64, _ptr, _ptr, _ptr, _ptr]),
+    "hgin_small_step_workspace_bytes": (_i64, [_i64]),
+    "hgin_small_step": (_i32, [_i64, _ptr, _ptr, _ptr, _i64, _i32, _ptr, _ptr, _i64, _i32, _ptr, _ptr, _i32, _i32, _i32, _i32]
+                        + [_ptr] * 11 + [_ptr] * 11 + [_ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
     "hgin_set_option": (_i32, [ctypes.c_char_p, _i32]),
     "hgin_debug_gemm_tn": (_i32, [_i64, _ptr, _i32, _ptr, _i32, _ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _ptr]),
 }

@@ -691,6 +691,52 @@ def column_sums(x):
     return bn_stats(x)[:n].float()
 
 
+def small_step(csr, x_path, path_cols, x_link, link_cols, y, params, grads, concat_path, want_out=False):
+    """One forward + loss + backward of config.json's model family in three kernels (include/hgin.h: hgin_small_step).
+    params / grads: dicts with keys W0 b0 a0 eps0 W1 b1 aR W2 b2 W3 b3 (gradients: same shapes, written in place).
+    Returns (loss_out [mape, sqrt(mape)], sums [S, N], out or None)."""
+    import ctypes
+    for t, name in ((x_path, "x_path"), (x_link, "x_link")):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1):
+            raise HginError(f"small_step: {name} must be a CUDA float32 matrix with unit inner stride")
+    y = y.reshape(-1)
+    if not (y.is_cuda and y.dtype == torch.float32 and y.is_contiguous() and y.numel() == x_path.shape[0]):
+        raise HginError("small_step: y must be a contiguous CUDA float32 vector with one entry per path")
+    if csr.num_rows != x_path.shape[0] or csr.num_cols != x_link.shape[0]:
+        raise HginError("small_step: the CSR does not match the feature matrices")
+    keys = ("W0", "b0", "a0", "eps0", "W1", "b1", "aR", "W2", "b2", "W3", "b3")
+    for k in keys:
+        for d, what in ((params, "parameter"), (grads, "gradient")):
+            t = d[k]
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise HginError(f"small_step: {what} {k} must be a contiguous CUDA float32 tensor")
+        if params[k].numel() != grads[k].numel():
+            raise HginError(f"small_step: gradient of {k} has the wrong size")
+    emb, n1, n2 = params["W0"].shape[0], params["W1"].shape[0], params["W2"].shape[0]
+    fp, fl = len(path_cols), len(link_cols)
+    if params["W0"].shape[1] != fl + fp or params["W1"].shape[1] != emb + (fp if concat_path else 0) \
+            or params["W2"].shape[1] != n1 or params["W3"].numel() != n2:
+        raise HginError("small_step: parameter shapes do not form the GIN layer + 3-layer readout chain")
+    dev = x_path.device
+    lib = _lib.load()
+    np_ = x_path.shape[0]
+    ws_bytes = lib.hgin_small_step_workspace_bytes(np_)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    sums = torch.empty(2, dtype=torch.float32, device=dev)
+    loss_out = torch.empty(2, dtype=torch.float32, device=dev)
+    out = torch.empty(np_, dtype=torch.float32, device=dev) if want_out else None
+    pc = (ctypes.c_int32 * 8)(*(list(path_cols) + [0] * (8 - fp)))
+    lc = (ctypes.c_int32 * 8)(*(list(link_cols) + [0] * (8 - fl)))
+    with _region("small_step", kernels=3, flops=6 * np_ * (emb * (fl + fp) + n1 * (emb + fp) + n1 * n2 + n2)):
+        check(lib.hgin_small_step(np_, _ptr(csr.rowptr), _ptr(csr.col), x_path.data_ptr(), x_path.stride(0), fp,
+                                  ctypes.cast(pc, ctypes.c_void_p), x_link.data_ptr(), x_link.stride(0), fl,
+                                  ctypes.cast(lc, ctypes.c_void_p), y.data_ptr(), emb, n1, n2, 1 if concat_path else 0,
+                                  *[params[k].data_ptr() for k in keys], *[grads[k].data_ptr() for k in keys],
+                                  sums.data_ptr(), loss_out.data_ptr(), _ptr(out), ws.data_ptr(), ws_bytes, _stream()),
+              "hgin_small_step")
+    return loss_out, sums, out
+
+
 def qt_baseline(p_l, avg_bw, capacity, num_paths, num_links, num_iterations=3):
     """Queueing-theory baseline on a (batched) path->link relation.  p_l: CUDA int64/int32 [2,E],
     every path's edges in route order; avg_bw f32 [num_paths]; capacity f32 [num_links] (raw).

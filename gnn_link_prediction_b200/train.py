@@ -101,7 +101,7 @@ class TrainStep:
     """
 
     def __init__(self, model: HetroGIN, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
-                 optimizer="adam", communicator=None):
+                 optimizer="adam", communicator=None, fused_small=True):
         if optimizer not in ("adam", "adamW"):
             raise NotImplementedError("TrainStep fuses Adam/AdamW; use train_one_epoch with torch.optim.SGD")
         self.model = model
@@ -133,6 +133,66 @@ class TrainStep:
         self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
         self.grad_views = [self.flat_g[off:off + p.numel()].view_as(p) for p, off in zip(self.live, offsets)]
         self._adopt()
+        self._small = self._small_plan() if fused_small else None
+
+    SMALL_RELATION = ("link", "includes", "path")
+
+    def _small_plan(self):
+        """config.json's model family (one message-passing layer, Linear-PReLU-Linear-PReLU-Linear readout with one shared
+        slope, no BatchNorm / global features / dropout) on one GPU: the whole forward + loss + backward runs as
+        hgin_small_step (three kernels instead of ~25).  Returns the parameter / gradient tables or None."""
+        m = self.model
+        if not isinstance(m, HetroGIN) or self.comm.world > 1 or m.num_layers != 1 or m.global_feats or m.dropout > 0:
+            return None
+        if m.math_mode not in (ops.MATH_FP32, ops.MATH_TF32) or len(m.readout) != 3:
+            return None
+        key = "__".join(self.SMALL_RELATION)
+        if key not in m.convs[0].convs:
+            return None
+        layer = m.convs[0].convs[key]
+        seqs = [layer.mlp, m.readout[0], m.readout[1], m.readout[2]]
+        if [len(q) for q in seqs] != [2, 2, 2, 1]:
+            return None
+        if not all(isinstance(q[0], torch.nn.Linear) for q in seqs):
+            return None
+        acts = [layer.mlp[1], m.readout[0][1], m.readout[1][1]]
+        if not all(isinstance(a, torch.nn.PReLU) and a.weight.numel() == 1 for a in acts) or acts[1] is not acts[2]:
+            return None
+        if not m.divided_features:
+            pc = [0, 1, 2] + ([6] if m.bl_features else [])
+            lc = [0, 1, 2] + ([4, 5, 6] if m.bl_features else [])
+        elif m.bl_features:
+            pc, lc = list(range(7)), list(range(7))
+        else:
+            return None
+        W0, W1, W2, W3 = layer.mlp[0].weight, m.readout[0][0].weight, m.readout[1][0].weight, m.readout[2][0].weight
+        emb, n1, n2 = W0.shape[0], W1.shape[0], W2.shape[0]
+        concat = bool(m.concat_path)
+        if (W0.shape[1] != len(lc) + len(pc) or W1.shape[1] != emb + (len(pc) if concat else 0) or W3.shape[0] != 1
+                or emb > 32 or emb + len(pc) > 32 or n1 > 128 or n2 > 32):
+            return None
+        params = {"W0": W0, "b0": layer.mlp[0].bias, "a0": acts[0].weight, "eps0": layer.conv.eps,
+                  "W1": W1, "b1": m.readout[0][0].bias, "aR": acts[1].weight, "W2": W2, "b2": m.readout[1][0].bias,
+                  "W3": W3, "b3": m.readout[2][0].bias}
+        view_of = {id(p): v for p, v in zip(self.live, self.grad_views)}
+        if any(id(p) not in view_of for p in params.values()) or len(view_of) != len(params):
+            return None
+        return {"params": params, "grads": {k: view_of[id(p)] for k, p in params.items()}, "path_cols": pc, "link_cols": lc,
+                "concat": concat}
+
+    def _small_call(self, batch):
+        from .functional import GraphCSR
+        plan = self._small
+        graph = batch.graph if hasattr(batch, "graph") else batch.edge_index_dict
+        if not isinstance(graph, GraphCSR):
+            graph = GraphCSR(graph, {t: batch[t]["x"].shape[0] for t in ("path", "link", "node") if "x" in batch[t]})
+        loss_out, _, _ = ops.small_step(graph.fwd(self.SMALL_RELATION), batch["path"]["x"], plan["path_cols"], batch["link"]["x"],
+                                        plan["link_cols"], batch["path"].y, plan["params"], plan["grads"], plan["concat"])
+        for p, v in zip(self.live, self.grad_views):
+            p.grad = v                 # the gradients ARE the bucket slices: no gather copy
+        ops.increment(self.step_count)
+        ops.adam_step(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, self.step_count, **self.hyper)
+        return loss_out
 
     def _adopt(self):
         """Make every live parameter a view of the flat bucket (copying its current values in)."""
@@ -177,6 +237,9 @@ class TrainStep:
         """`batch` already resident on the GPU.  Returns a CUDA tensor [mape, sqrt(mape)] (global)."""
         model = self.model
         self._check_aliasing()
+        if (self._small is not None and model.training and self.SMALL_RELATION in batch.edge_types
+                and model.math_mode in (ops.MATH_FP32, ops.MATH_TF32)):
+            return self._small_call(batch)
         for p in self.live:
             p.grad = None
         # the per-path graph ids are only read with GLOBAL_FEATS (models.py:347-352): do not force them otherwise

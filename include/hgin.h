@@ -506,6 +506,33 @@ int32_t hgin_gat_bwd(int64_t num_dst, const int32_t *rowptr_dst, const int32_t *
                      int32_t add_self_loops, float *d_xs, int64_t ld_dxs, float *d_a_src, float *d_a_dst,
                      float *dot_ws, void *stream);
 
+/* ---- the whole train step of config.json's model in three kernels (launch-bound regime) ---------------------------------
+ * Replaces: one iteration of train.py:31-44 — HetroGIN.forward (models.py:332-376), mape + sqrt (train.py:12-13, 40-42),
+ * loss.backward() — for the model family of config.json: MP_LAYERS = 1 (only link -> path reaches the readout), GIN layer
+ * with concat=True, readout Linear-PReLU-Linear-PReLU-Linear with ONE shared PReLU slope, no BatchNorm / global features /
+ * dropout.  After the neighbour sum the network is row-local in the path rows, so the forward is recomputed in the
+ * backward kernel instead of being stored, and the weight gradients are accumulated in registers per CTA (fixed ownership,
+ * no atomics, deterministic).  The optimizer step stays hgin_adam_step.
+ *   rowptr / col      destination-sorted CSR of ('link', 'includes', 'path')
+ *   x_path / x_link   RAW feature matrices (7 columns in the reference); *_cols_host: HOST arrays naming the f_path / f_link
+ *                     columns the model slices out (models.py:333-342), e.g. {0,1,2}
+ *   W0 [emb, f_link + f_path], b0, alpha0, eps0: the GIN layer;  W1 [n1, emb + (concat_path ? f_path : 0)], b1, W2 [n2, n1],
+ *   b2, W3 [1, n2], b3, alpha_r: the readout.  d*: gradients, same shapes.  sums [2] = (sum |(out - y)/y|, N);
+ *   loss_out [2] = (mape, sqrt(mape));  out [num_paths] (NULL to skip): the scores.
+ * Limits: f_path, f_link <= 8; emb <= 32; emb + f_path <= 32; n1 <= 128; n2 <= 32 (HGIN_ERR_UNSUPPORTED otherwise).
+ */
+int64_t hgin_small_step_workspace_bytes(int64_t num_paths);
+int32_t hgin_small_step(int64_t num_paths, const int32_t *rowptr, const int32_t *col, const float *x_path,
+                        int64_t ld_path, int32_t f_path, const int32_t *path_cols_host, const float *x_link,
+                        int64_t ld_link, int32_t f_link, const int32_t *link_cols_host, const float *y,
+                        int32_t emb, int32_t n1, int32_t n2, int32_t concat_path, const float *W0,
+                        const float *b0, const float *alpha0, const float *eps0, const float *W1,
+                        const float *b1, const float *alpha_r, const float *W2, const float *b2,
+                        const float *W3, const float *b3, float *dW0, float *db0, float *dalpha0,
+                        float *deps0, float *dW1, float *db1, float *dalpha_r, float *dW2, float *db2,
+                        float *dW3, float *db3, float *sums, float *loss_out, float *out, void *workspace,
+                        int64_t workspace_bytes, void *stream);
+
 /* ---- runtime options --------------------------------------------------------------------------
  * "fused_bwd" (0/1, default 0): HGIN_MATH_TF32 backward through the single-pass fused kernel
  * (csrc/linear_tc_fused.cuh) instead of separate passes.

@@ -706,3 +706,56 @@ def test_non_default_flags_in_the_tensor_core_modes(math):
             assert rel(p.grad, g_ref[k]) <= 3 * tol, k
     for k in ("readout.0.1.running_mean", "readout.0.1.running_var"):
         assert rel(m.state_dict()[k], ref.state_dict()[k]) <= tol, k
+
+
+@pytest.mark.parametrize("variant", ["default", "noconcat", "blfeat", "emb16_mlp64x16"])
+def test_three_kernel_step_of_the_default_model_family(variant):
+    """hgin_small_step (config.json's model: one GIN layer + 3-layer readout, the whole forward + loss + backward in three
+    kernels) against the layer-by-layer TrainStep on the same batch: loss, every gradient, and a 4-step trajectory."""
+    kw = dict(node_embedding_size=8, message_passing_layers=1, dropout=0.0, concat_path=True, bl_features=False,
+              divided_features=False, global_feats=False, mlp_layers=[128, 32], act="torch.nn.PReLU()", mlp_head_act=None,
+              mlp_bn=False)
+    kw.update({"default": {}, "noconcat": dict(concat_path=False), "blfeat": dict(bl_features=True),
+               "emb16_mlp64x16": dict(node_embedding_size=16, mlp_layers=[64, 16])}[variant])
+    ds = SyntheticDataset(5, num_nodes=12, num_links=20, num_topologies=3)
+    batch = Batch.from_data_list([ds[i] for i in range(5)]).cuda()
+
+    def fresh(fused):
+        torch.manual_seed(21)
+        m = HetroGIN({"link": 7, "path": 7, "node": 3}, **kw).cuda().train()
+        with torch.no_grad():      # non-trivial eps / slopes
+            m.convs[0].convs["link__includes__path"].conv.eps.fill_(0.2)
+            m.readout[0][1].weight.fill_(0.1)
+        return m, TrainStep(m, fused_small=fused)
+
+    m_ref, s_ref = fresh(False)
+    m_new, s_new = fresh(True)
+    assert s_new._small is not None and s_ref._small is None
+    l_ref = [s_ref(batch).clone() for _ in range(1)]
+    l_new = [s_new(batch).clone() for _ in range(1)]
+    torch.testing.assert_close(l_new[0], l_ref[0], rtol=1e-5, atol=0)
+    g_scale = float(s_ref.flat_g.abs().max())
+    torch.testing.assert_close(s_new.flat_g, s_ref.flat_g, rtol=1e-4, atol=1e-6 * g_scale)
+    for k, p in m_new.named_parameters():       # live parameters expose their gradient, dead ones stay None
+        q = dict(m_ref.named_parameters())[k]
+        assert (p.grad is None) == (q.grad is None), k
+    for _ in range(3):
+        a, b = s_new(batch), s_ref(batch)
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=0)
+    torch.testing.assert_close(s_new.flat_p, s_ref.flat_p, rtol=1e-3, atol=1e-5)
+    # run-to-run deterministic
+    m2, s2 = fresh(True)
+    for _ in range(4):
+        s2(batch)
+    assert torch.equal(s2.flat_p, s_new.flat_p)
+
+
+def test_three_kernel_step_is_not_used_outside_its_family():
+    base = dict(node_embedding_size=8, message_passing_layers=1, dropout=0.0, concat_path=True, bl_features=False,
+                divided_features=False, global_feats=False, mlp_layers=[128, 32], act="torch.nn.PReLU()", mlp_head_act=None,
+                mlp_bn=False)
+    for change in (dict(message_passing_layers=2), dict(mlp_bn=True), dict(act="torch.nn.ELU()"), dict(mlp_layers=[64]),
+                   dict(mlp_layers=[256, 32]), dict(mlp_head_act="torch.nn.ReLU()"), dict(dropout=0.1),
+                   dict(global_feats=True, bl_features=True)):
+        m = HetroGIN({"link": 7, "path": 7, "node": 3}, **{**base, **change}).cuda().train()
+        assert TrainStep(m)._small is None, change
