@@ -55,9 +55,12 @@ struct SmallParams {
 };
 
 struct SmallSmem {
-    float W1[SS_MAX_K1][SS_MAX_N1];        // [k][n]
-    float W2kn[SS_MAX_N1][SS_MAX_N2];      // [k][n]
-    float W2nk[SS_MAX_N2][SS_MAX_N1];      // [n][k]
+    // every contraction reads BOTH operands four elements at a time along the contraction index (one LDS.128 of the
+    // weights feeds 4 x R FMAs, one broadcast LDS.128 of the activations 4 x 4): row pitches of 36 / 132 floats spread
+    // the lanes' rows over the banks
+    float W1nk[SS_MAX_N1][SS_MAX_K1 + 4];  // [n][k]   z1 (contract k), d e (contract n, 4 k at a time)
+    float W2nk[SS_MAX_N2][SS_MAX_N1 + 4];  // [n][k]   z2 (contract k)
+    float W2kn[SS_MAX_N1][SS_MAX_N2 + 4];  // [k][n]   d a1 (contract n)
     float W0[SS_MAX_EMB][SS_MAX_K0 + 1];   // [n][k] (+1: no bank conflicts across n)
     float b1[SS_MAX_N1], b2[SS_MAX_N2], b0[SS_MAX_EMB], W3[SS_MAX_N2];
     // row staging
@@ -98,10 +101,10 @@ __device__ void load_weights(const SmallParams &p, SmallSmem &s) {
     const int k1 = p.emb + (p.concat ? p.fp : 0), k0 = p.fl + p.fp;
     stage<SS_MAX_K1 * SS_MAX_N1>(
         [&](int i) { const int k = i / SS_MAX_N1, n = i % SS_MAX_N1; return (k < k1 && n < p.n1) ? __ldg(p.W1 + n * k1 + k) : 0.f; },
-        [&](int i, float v) { s.W1[i / SS_MAX_N1][i % SS_MAX_N1] = v; });
+        [&](int i, float v) { s.W1nk[i % SS_MAX_N1][i / SS_MAX_N1] = v; });
     stage<SS_MAX_N1 * SS_MAX_N2>(
         [&](int i) { const int k = i / SS_MAX_N2, n = i % SS_MAX_N2; return (k < p.n1 && n < p.n2) ? __ldg(p.W2 + n * p.n1 + k) : 0.f; },
-        [&](int i, float v) { s.W2kn[i / SS_MAX_N2][i % SS_MAX_N2] = v; });
+        [&](int i, float v) { s.W2kn[i / SS_MAX_N2][i % SS_MAX_N2] = v; });      // (pad columns are never read)
     stage<SS_MAX_N2 * SS_MAX_N1>(
         [&](int i) { const int n = i / SS_MAX_N1, k = i % SS_MAX_N1; return (k < p.n1 && n < p.n2) ? __ldg(p.W2 + n * p.n1 + k) : 0.f; },
         [&](int i, float v) { s.W2nk[i / SS_MAX_N1][i % SS_MAX_N1] = v; });
@@ -155,11 +158,34 @@ struct RowBatch {
     float z0[SS_R], z1[SS_R][4], z2[SS_R], a2[SS_R], out[SS_R];
 };
 
+// The gather chain rowptr -> col -> x_link is three dependent (cold: DRAM) latencies and bounds the kernel, not the FMAs
+// (ncu: the store of the gathered columns into the scratch is the top stall).  So the row bounds are requested two
+// batches ahead and the first 16 neighbour ids one batch ahead; only the x_link fetch itself stays exposed.
+template <int SS_R>
+struct GatherPre {
+    int e0[SS_R], len[SS_R], nb[SS_R];
+};
+template <int SS_R>
+__device__ __forceinline__ void pre_bounds(const SmallParams &p, int row0, int end, GatherPre<SS_R> &g) {
+#pragma unroll
+    for (int q = 0; q < SS_R; ++q) {
+        const int row = min(row0 + q, p.np - 1);
+        const bool on = row0 < end;            // (whole batch past the CTA's range: nothing to fetch)
+        g.e0[q] = on ? __ldg(p.rowptr + row) : 0;
+        g.len[q] = on ? __ldg(p.rowptr + row + 1) - g.e0[q] : 0;
+    }
+}
+template <int SS_R>
+__device__ __forceinline__ void pre_cols(const SmallParams &p, int lane, GatherPre<SS_R> &g) {
+#pragma unroll
+    for (int q = 0; q < SS_R; ++q) g.nb[q] = (lane < 16 && lane < g.len[q]) ? __ldg(p.col + g.e0[q] + lane) : -1;
+}
+
 // Forward of SS_R path rows (tile slots r0 .. r0 + SS_R - 1; rows past `np` are clamped to the last row and masked by the
 // caller) by one warp; stages H, Xin, A1.  Returns the pre-activations the backward needs.
 template <int SS_R, class D>
 __device__ __forceinline__ RowBatch<SS_R> rows_forward(const SmallParams &p, const D &d, SmallSmem &s, int row0, int r0, int lane,
-                                                       float ope, float a0, float aR, float b3) {
+                                                       float ope, float a0, float aR, float b3, const GatherPre<SS_R> &pre) {
     RowBatch<SS_R> st;
     const int k0 = d.k0(), k1 = d.k1();
     int rows[SS_R];
@@ -173,8 +199,8 @@ __device__ __forceinline__ RowBatch<SS_R> rows_forward(const SmallParams &p, con
     int e0[SS_R], len[SS_R];
 #pragma unroll
     for (int q = 0; q < SS_R; ++q) {
-        e0[q] = __ldg(p.rowptr + rows[q]);
-        len[q] = __ldg(p.rowptr + rows[q] + 1) - e0[q];
+        e0[q] = pre.e0[q];
+        len[q] = pre.len[q];
     }
     float hv[SS_R];
 #pragma unroll
@@ -185,7 +211,8 @@ __device__ __forceinline__ RowBatch<SS_R> rows_forward(const SmallParams &p, con
     for (int base = 0; base < max_len; base += 16) {
         int nb[SS_R];
 #pragma unroll
-        for (int q = 0; q < SS_R; ++q) nb[q] = (lane < 16 && base + lane < len[q]) ? __ldg(p.col + e0[q] + base + lane) : -1;
+        for (int q = 0; q < SS_R; ++q)
+            nb[q] = base == 0 ? pre.nb[q] : ((lane < 16 && base + lane < len[q]) ? __ldg(p.col + e0[q] + base + lane) : -1);
 #pragma unroll
         for (int q = 0; q < SS_R; ++q) {
             if (nb[q] >= 0) {
@@ -235,15 +262,16 @@ __device__ __forceinline__ RowBatch<SS_R> rows_forward(const SmallParams &p, con
 #pragma unroll
         for (int j = 0; j < 4; ++j) st.z1[q][j] = s.b1[lane + 32 * j];
 #pragma unroll
-    for (int k = 0; k < k1; ++k) {
-        float w[4];
+    for (int k = 0; k < k1; k += 4) {          // (Xin and W1nk are zero beyond k1)
+        float4 w[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) w[j] = s.W1[k][lane + 32 * j];
+        for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const float4 *>(&s.W1nk[lane + 32 * j][k]);
 #pragma unroll
         for (int q = 0; q < SS_R; ++q) {
-            const float x = s.Xin[r0 + q][k];
+            const float4 x = *reinterpret_cast<const float4 *>(&s.Xin[r0 + q][k]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) st.z1[q][j] = fmaf(x, w[j], st.z1[q][j]);
+            for (int j = 0; j < 4; ++j)
+                st.z1[q][j] = fmaf(x.w, w[j].w, fmaf(x.z, w[j].z, fmaf(x.y, w[j].y, fmaf(x.x, w[j].x, st.z1[q][j]))));
         }
     }
 #pragma unroll
@@ -251,18 +279,20 @@ __device__ __forceinline__ RowBatch<SS_R> rows_forward(const SmallParams &p, con
 #pragma unroll
         for (int j = 0; j < 4; ++j) s.A1[r0 + q][lane + 32 * j] = (lane + 32 * j) < d.n1() ? prelu(st.z1[q][j], aR) : 0.f;
     __syncwarp();
-    // z2: two partial chains per row (even / odd k): 2 * SS_R independent FMA chains
+    // z2: two partial chains per row (k mod 8 < 4 / >= 4): 2 * SS_R independent FMA chains
     float ze[SS_R], zo[SS_R];
 #pragma unroll
     for (int q = 0; q < SS_R; ++q) { ze[q] = s.b2[lane]; zo[q] = 0.f; }
 #pragma unroll 4
-    for (int k = 0; k < SS_MAX_N1; k += 2) {      // (A1 and W2kn are zero beyond n1)
-        const float w0 = s.W2kn[k][lane], w1 = s.W2kn[k + 1][lane];
+    for (int k = 0; k < SS_MAX_N1; k += 8) {      // (A1 and W2nk are zero beyond n1)
+        const float4 w0 = *reinterpret_cast<const float4 *>(&s.W2nk[lane][k]);
+        const float4 w1 = *reinterpret_cast<const float4 *>(&s.W2nk[lane][k + 4]);
 #pragma unroll
         for (int q = 0; q < SS_R; ++q) {
-            const float2 a = *reinterpret_cast<const float2 *>(&s.A1[r0 + q][k]);
-            ze[q] = fmaf(a.x, w0, ze[q]);
-            zo[q] = fmaf(a.y, w1, zo[q]);
+            const float4 a = *reinterpret_cast<const float4 *>(&s.A1[r0 + q][k]);
+            const float4 b = *reinterpret_cast<const float4 *>(&s.A1[r0 + q][k + 4]);
+            ze[q] = fmaf(a.w, w0.w, fmaf(a.z, w0.z, fmaf(a.y, w0.y, fmaf(a.x, w0.x, ze[q]))));
+            zo[q] = fmaf(b.w, w1.w, fmaf(b.z, w1.z, fmaf(b.y, w1.y, fmaf(b.x, w1.x, zo[q]))));
         }
     }
     float part[SS_R];
@@ -295,17 +325,25 @@ small_fwd_loss_kernel(const SmallParams p, float *__restrict__ partial_s, float 
     const D d(p);
     extern __shared__ __align__(16) uint8_t raw[];
     SmallSmem &s = *reinterpret_cast<SmallSmem *>(raw);
-    load_weights(p, s);
-    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float ope = __fadd_rn(1.0f, __ldg(p.eps0)), a0 = __ldg(p.a0), aR = __ldg(p.aR), b3 = __ldg(p.b3);
-    float sum = 0.f;
     int beg, end;
     cta_rows(p, beg, end);
+    GatherPre<SS_R> g1, g2;      // (requested before the weights: the two latencies overlap)
+    pre_bounds<SS_R>(p, beg + warp * SS_R, end, g1);
+    pre_bounds<SS_R>(p, beg + TILE + warp * SS_R, end, g2);
+    const float ope = __fadd_rn(1.0f, __ldg(p.eps0)), a0 = __ldg(p.a0), aR = __ldg(p.aR), b3 = __ldg(p.b3);
+    load_weights(p, s);
+    pre_cols<SS_R>(p, lane, g1);
+    __syncthreads();
+    float sum = 0.f;
     for (int t0 = beg; t0 < end; t0 += TILE) {
         const int r0 = warp * SS_R, row0 = t0 + r0;
+        const GatherPre<SS_R> cur = g1;
+        g1 = g2;
+        pre_bounds<SS_R>(p, t0 + 2 * TILE + r0, end, g2);
+        pre_cols<SS_R>(p, lane, g1);
         if (row0 >= end) continue;
-        const RowBatch<SS_R> st = rows_forward<SS_R, D>(p, d, s, row0, r0, lane, ope, a0, aR, b3);
+        const RowBatch<SS_R> st = rows_forward<SS_R, D>(p, d, s, row0, r0, lane, ope, a0, aR, b3, cur);
 #pragma unroll
         for (int q = 0; q < SS_R; ++q) {
             if (row0 + q < end) {
@@ -369,11 +407,19 @@ small_bwd_kernel(const SmallParams p, const float *__restrict__ partial_s, int n
 
     int beg, end;
     cta_rows(p, beg, end);
+    GatherPre<SS_R> g1, g2;
+    pre_bounds<SS_R>(p, beg + warp * SS_R, end, g1);
+    pre_bounds<SS_R>(p, beg + TILE + warp * SS_R, end, g2);
+    pre_cols<SS_R>(p, lane, g1);
     for (int t0 = beg; t0 < end; t0 += TILE) {
         const int rows_here = min(TILE, end - t0);
         const int r0 = warp * SS_R, row0 = t0 + r0;
+        const GatherPre<SS_R> cur = g1;
+        g1 = g2;
+        pre_bounds<SS_R>(p, t0 + 2 * TILE + r0, end, g2);
+        pre_cols<SS_R>(p, lane, g1);
         if (row0 < end) {
-            const RowBatch<SS_R> st = rows_forward<SS_R, D>(p, d, s, row0, r0, lane, ope, a0, aR, b3);
+            const RowBatch<SS_R> st = rows_forward<SS_R, D>(p, d, s, row0, r0, lane, ope, a0, aR, b3, cur);
             float g[SS_R];
 #pragma unroll
             for (int q = 0; q < SS_R; ++q) {
@@ -395,16 +441,17 @@ small_bwd_kernel(const SmallParams p, const float *__restrict__ partial_s, int n
             for (int q = 0; q < SS_R; ++q)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dz1[q][j] = 0.f;
-#pragma unroll 4
-            for (int n = 0; n < d.n2(); ++n) {
-                float w[4];
+#pragma unroll 2
+            for (int n = 0; n < SS_MAX_N2; n += 4) {      // (Dz2 is zero beyond n2)
+                float4 w[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) w[j] = s.W2nk[n][lane + 32 * j];
+                for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const float4 *>(&s.W2kn[lane + 32 * j][n]);
 #pragma unroll
                 for (int q = 0; q < SS_R; ++q) {
-                    const float dv = s.Dz2[r0 + q][n];
+                    const float4 dv = *reinterpret_cast<const float4 *>(&s.Dz2[r0 + q][n]);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) dz1[q][j] = fmaf(dv, w[j], dz1[q][j]);
+                    for (int j = 0; j < 4; ++j)
+                        dz1[q][j] = fmaf(dv.w, w[j].w, fmaf(dv.z, w[j].z, fmaf(dv.y, w[j].y, fmaf(dv.x, w[j].x, dz1[q][j]))));
                 }
             }
 #pragma unroll
@@ -422,24 +469,35 @@ small_bwd_kernel(const SmallParams p, const float *__restrict__ partial_s, int n
 #pragma unroll
             for (int q = 0; q < SS_R; ++q) de[q] = 0.f;
 #pragma unroll
-            for (int j = 0; j < d.emb(); ++j) {
-                float part[SS_R];
-                float w[4];
+            for (int j4 = 0; j4 < d.emb(); j4 += 4) {      // four input columns j at a time
+                float part[SS_R][4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) w[i] = s.W1[j][lane + 32 * i];
+                for (int q = 0; q < SS_R; ++q)
 #pragma unroll
-                for (int q = 0; q < SS_R; ++q) {
-                    part[q] = 0.f;
+                    for (int c = 0; c < 4; ++c) part[q][c] = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) part[q] = fmaf(dz1[q][i], w[i], part[q]);
+                for (int i = 0; i < 4; ++i) {
+                    const float4 w = *reinterpret_cast<const float4 *>(&s.W1nk[lane + 32 * i][j4]);
+#pragma unroll
+                    for (int q = 0; q < SS_R; ++q) {
+                        part[q][0] = fmaf(dz1[q][i], w.x, part[q][0]);
+                        part[q][1] = fmaf(dz1[q][i], w.y, part[q][1]);
+                        part[q][2] = fmaf(dz1[q][i], w.z, part[q][2]);
+                        part[q][3] = fmaf(dz1[q][i], w.w, part[q][3]);
+                    }
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-                    for (int q = 0; q < SS_R; ++q) part[q] += __shfl_xor_sync(0xffffffffu, part[q], o);
-                if (lane == j) {
+                    for (int q = 0; q < SS_R; ++q)
 #pragma unroll
-                    for (int q = 0; q < SS_R; ++q) de[q] = part[q];
+                        for (int c = 0; c < 4; ++c) part[q][c] += __shfl_xor_sync(0xffffffffu, part[q][c], o);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (lane == j4 + c) {
+#pragma unroll
+                        for (int q = 0; q < SS_R; ++q) de[q] = part[q][c];
+                    }
                 }
             }
 #pragma unroll
