@@ -315,6 +315,82 @@ def _f32(t):
     return None if t is None else (t if t.dtype == torch.float32 else t.float())
 
 
+TILE = 128      # the tcgen05 kernels take 16 <= K, N <= 128 (W resident in shared memory); wider layers are tiled here
+
+
+def _tiled_shape(rows, k1, k2, n, math_mode):
+    """Layers wider than one tensor-core tile (hidden 256): run as 128-blocks of the tcgen05 kernels instead of falling to
+    the fp32 SIMT engine.  Block partial sums over K are added by a torch op (glue), the activation is a row pass."""
+    return (math_mode != MATH_FP32 and rows >= 128 and (k1 > TILE or n > TILE) and k1 % 16 == 0 and n % 16 == 0
+            and k1 <= 1024 and n <= 1024 and k2 <= 4)
+
+
+def _blocks(width):
+    return [slice(b, min(b + TILE, width)) for b in range(0, width, TILE)]
+
+
+def _linear_fwd_tiled(x1, W, bias, x2, act, alpha, want_z, out, accumulate_out, math_mode, want_out, out_dt):
+    rows, k1 = x1.shape
+    n = W.shape[0]
+    z = torch.empty(rows, n, dtype=out_dt, device=x1.device)
+    for nb in _blocks(n):
+        for i, kb in enumerate(_blocks(k1)):
+            first = i == 0
+            Wb = W[nb, kb] if (not first or x2 is None) else torch.cat((W[nb, kb], W[nb, k1:]), 1)     # the x2 columns ride on block 0
+            _, part = linear_fwd(x1[:, kb], Wb.contiguous(), bias[nb].contiguous() if (first and bias is not None) else None,
+                                 x2=x2 if first else None, act=ACT_NONE, want_z=False, out=z[:, nb] if first else None,
+                                 math_mode=math_mode, out_dtype=out_dt)
+            if not first:
+                z[:, nb].add_(part)
+    if act == ACT_NONE:
+        res = z
+    else:
+        res = act_fwd(z, act, alpha) if want_out else None
+    if want_out and out is not None:
+        if accumulate_out:
+            out.add_(res)
+        else:
+            out.copy_(res)
+        res = out
+    return (z if (want_z or not want_out) and act != ACT_NONE else (z if want_z else None)), res
+
+
+def _linear_bwd_tiled(g, z, x1, W, x2, act, alpha, want_dx, dot_x, want_dw, want_db, want_dalpha, math_mode):
+    rows, k1 = x1.shape
+    k2 = 0 if x2 is None else x2.shape[1]
+    n = W.shape[0]
+    dalpha = None
+    if act != ACT_NONE:
+        dz, dalpha = act_bwd(g, z, act, alpha, want_dalpha=want_dalpha and act == ACT_PRELU)
+        if want_dalpha and dalpha is None:
+            dalpha = torch.zeros(1, dtype=torch.float32, device=g.device)
+    else:
+        dz = g
+    db = column_sums(dz) if want_db else None
+    dW = torch.empty(n, k1 + k2, dtype=torch.float32, device=g.device) if want_dw else None
+    dx = torch.empty(rows, k1, dtype=x1.dtype, device=g.device) if want_dx else None
+    for i, kb in enumerate(_blocks(k1)):
+        width = kb.stop - kb.start
+        for j, nb in enumerate(_blocks(n)):
+            tail = x2 if (i == 0 and want_dw) else None
+            Wb = W[nb, kb] if tail is None else torch.cat((W[nb, kb], W[nb, k1:]), 1)
+            r = linear_bwd(dz[:, nb], None, x1[:, kb], Wb.contiguous(), x2=tail, act=ACT_NONE, dx_cols=(0, width), want_dx=want_dx,
+                           want_dw=want_dw, want_db=False, math_mode=math_mode)
+            if want_dw:
+                dW[nb, kb] = r["dW"][:, :width]
+                if tail is not None:
+                    dW[nb, k1:] = r["dW"][:, width:]
+            if want_dx:
+                if j == 0:
+                    dx[:, kb] = r["dx"]
+                else:
+                    dx[:, kb] += r["dx"]
+    ddot = None
+    if dot_x is not None:
+        ddot = (dx.float() * dot_x.float()).sum().reshape(1)
+    return {"dx": dx, "ddot": ddot, "dW": dW, "db": db, "dalpha": dalpha}
+
+
 def linear_fwd(x1, W, bias=None, x2=None, act=ACT_NONE, alpha=None, want_z=True, out=None, accumulate_out=False,
                math_mode=MATH_FP32, want_out=True, out_dtype=None):
     """K2.  z = [x1|x2] W^T + b;  out (+)= act(z).  Returns (z or None, out or None).
@@ -326,6 +402,8 @@ def linear_fwd(x1, W, bias=None, x2=None, act=ACT_NONE, alpha=None, want_z=True,
     rows, k1 = x1.shape
     k2 = 0 if x2 is None else x2.shape[1]
     n = W.shape[0]
+    if _tiled_shape(rows, k1, k2, n, math_mode) and (in_dt == out_dt or in_dt == torch.float32):
+        return _linear_fwd_tiled(x1, W, bias, x2, act, alpha, want_z, out, accumulate_out, math_mode, want_out, out_dt)
     if (in_dt != torch.float32 or out_dt != torch.float32) and not typed_fwd_supported(in_dt, out_dt, rows, k1, k2, n):
         z32, o32 = linear_fwd(_f32(x1), W, bias, x2=x2, act=act, alpha=alpha, want_z=want_z, out=_f32(out),
                               accumulate_out=accumulate_out, math_mode=math_mode, want_out=want_out)
@@ -388,6 +466,9 @@ def linear_bwd(g, z, x1, W, x2=None, act=ACT_NONE, alpha=None, dx_cols=None, wan
     if not (want_dx or dot_x is not None):
         c1 = c0
     post_on = post is not None and post.act != ACT_NONE and want_dx and c1 > c0
+    if (_tiled_shape(rows, k1, k2, n, math_mode) and not post_on and self_eps is None and g_dt == x_dt
+            and (c1 == c0 or (c0, c1) == (0, k1))):
+        return _linear_bwd_tiled(g, z, x1, W, x2, act, alpha, want_dx and c1 > c0, dot_x, want_dw, want_db, want_dalpha, math_mode)
     if (g_dt != torch.float32 or x_dt != torch.float32) and not typed_bwd_supported(
             g_dt, x_dt, rows, k1, k2, n, c0, c1, want_dx and c1 > c0, dot_x is not None, post_on):
         if self_eps is not None:

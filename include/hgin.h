@@ -57,7 +57,8 @@ typedef enum hgin_status {
 
 /* math modes of hgin_linear_* */
 #define HGIN_MATH_FP32 0 /* SIMT fp32 FMA: parity mode, rel 1e-5 against the CPU reference */
-#define HGIN_MATH_TF32 1 /* tcgen05 kind::tf32 tensor-core tiles, fp32 accumulate in TMEM */
+#define HGIN_MATH_TF32 1 /* tcgen05 kind::tf32 tensor-core tiles, fp32 accumulate in TMEM (16 <= K, N <= 128 per call;
+                          * the host side tiles wider layers into 128-blocks of the same kernels) */
 #define HGIN_MATH_BF16 2 /* activations / gradients STORED as bf16 (HGIN_DTYPE_BF16 rows), tcgen05 kind::f16 tiles on
                           * bf16 operands, fp32 accumulate; aggregation adds, reductions, loss and Adam in fp32.
                           * BASELINE configs[2] "bf16 MLP GEMMs", parity bar rel 1e-2 */

@@ -759,3 +759,38 @@ def test_three_kernel_step_is_not_used_outside_its_family():
                    dict(global_feats=True, bl_features=True)):
         m = HetroGIN({"link": 7, "path": 7, "node": 3}, **{**base, **change}).cuda().train()
         assert TrainStep(m)._small is None, change
+
+
+@pytest.mark.parametrize("math", ["tf32", "bf16"])
+def test_hidden_256_model_runs_on_the_tensor_cores(math):
+    """NODE_EMBEDDING_SIZE = 256: every GIN / readout layer is wider than one tcgen05 tile and runs as 128-blocks."""
+    from gnn_link_prediction_b200 import models as _m
+    kw = dict(node_embedding_size=256, message_passing_layers=2, dropout=0.0, concat_path=True, bl_features=False,
+              divided_features=False, global_feats=False, mlp_layers=[128, 32], act="torch.nn.PReLU()", mlp_head_act=None,
+              mlp_bn=False)
+    ds = SyntheticDataset(3, num_topologies=2)
+    samples = [ds[i] for i in range(3)]
+    cpu_batch = Batch.from_data_list(samples)
+    torch.manual_seed(4)
+    ref = hgin_oracle.HetroGIN(input_channels={"link": 7, "path": 7, "node": 3}, **kw)
+    m = HetroGIN(input_channels={"link": 7, "path": 7, "node": 3}, **kw)
+    m.load_state_dict(ref.state_dict())
+    m.cuda().train().set_math_mode(_m.MATH_TF32 if math == "tf32" else _m.MATH_BF16)
+    y = cpu_batch["path"].y.reshape(-1, 1)
+    o_ref = ref(cpu_batch.x_dict, cpu_batch.edge_index_dict, None)
+    torch.sqrt(hgin_oracle.mape(o_ref, y)).backward()
+    dev = Batch.from_data_list(samples, index_dtype=torch.int32, edge_types=CONV_EDGE_TYPES).cuda()
+    o = m(dev.x_dict, dev.edge_index_dict, None)
+    torch.sqrt(mape(o, dev["path"].y.reshape(-1, 1))).backward()
+    tol = 1e-2 if math == "tf32" else 3e-2
+
+    def rel(a, b):
+        b = b.detach().double()
+        return float((a.detach().cpu().double() - b).norm() / (b.norm() + 1e-30))
+
+    assert rel(o, o_ref) <= tol
+    g_ref = {k: p.grad for k, p in ref.named_parameters()}
+    for k, p in m.named_parameters():
+        assert (p.grad is None) == (g_ref[k] is None), k
+        if p.grad is not None and p.numel() > 1:
+            assert rel(p.grad, g_ref[k]) <= 3 * tol, k

@@ -672,3 +672,38 @@ def test_streaming_plan_only_for_long_rows_and_block_tables(monkeypatch):
     bad[1, 0] = 45
     g = GraphCSR({et: bad.cuda()}, {"a": 500, "b": 50}, blocks={"a": ptr_in.cuda(), "b": ptr_out.cuda()})
     assert int(g.stream_plan(et, "fwd").gate[0]) > 0
+
+
+@pytest.mark.parametrize("math", ["tf32", "bf16"])
+@pytest.mark.parametrize("k,n,k2", [(256, 256, 0), (256, 128, 3), (128, 256, 0), (384, 192, 0)])
+def test_layers_wider_than_one_tensor_core_tile_run_as_128_blocks(k, n, k2, math):
+    """hidden 256: ops.linear_fwd / linear_bwd tile K and N into 128-blocks of the tcgen05 kernels (instead of falling to
+    the fp32 SIMT engine); checked against fp64 at the reduced-precision bar."""
+    torch.manual_seed(k + n)
+    mode = ops.MATH_TF32 if math == "tf32" else ops.MATH_BF16
+    dt = torch.float32 if math == "tf32" else torch.bfloat16
+    rows = 1000
+    x = torch.randn(rows, k, device="cuda").to(dt)
+    x2 = torch.randn(rows, k2, device="cuda") if k2 else None
+    W = torch.randn(n, k + k2, device="cuda") / (k ** 0.5)
+    b = torch.randn(n, device="cuda")
+    alpha = torch.tensor([0.25], device="cuda")
+    g = torch.randn(rows, n, device="cuda").to(dt)
+    xin = torch.cat((x.double(), x2.double()), 1) if k2 else x.double()
+    z_ref = xin @ W.double().t() + b.double()
+    o_ref = torch.where(z_ref > 0, z_ref, 0.25 * z_ref)
+    z, o = ops.linear_fwd(x, W, b, x2=x2, act=ops.ACT_PRELU, alpha=alpha, want_z=True, math_mode=mode, out_dtype=dt)
+    tol = 5e-3 if math == "tf32" else 3e-2
+
+    def rel(a, r):
+        return float((a.double() - r).norm() / r.norm())
+
+    assert rel(z, z_ref) < tol and rel(o, o_ref) < tol
+    r = ops.linear_bwd(g, z, x, W, x2=x2, act=ops.ACT_PRELU, alpha=alpha, dx_cols=(0, k), want_dx=True, want_dw=True,
+                       want_db=True, want_dalpha=True, math_mode=mode)
+    dz_ref = g.double() * torch.where(z.double() > 0, 1.0, 0.25)
+    assert rel(r["dx"], dz_ref @ W.double()[:, :k]) < tol
+    assert rel(r["dW"], dz_ref.t() @ xin) < tol
+    assert rel(r["db"], dz_ref.sum(0)) < tol
+    da_ref = (g.double() * torch.clamp(z.double(), max=0)).sum()
+    assert abs(float(r["dalpha"]) - float(da_ref)) < tol * float((g.double() * z.double()).abs().sum()) ** 0.5 + tol * abs(float(da_ref))
