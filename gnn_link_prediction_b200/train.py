@@ -315,8 +315,9 @@ class GraphedTrainStep:
 
     def __init__(self, step: TrainStep, edge_bucket=8192, max_graphs=4, warmup=2):
         if step.comm.world > 1:
-            # tried in round 2 (two B200s): capturing the step's two NCCL all-reduces with the kernels left one rank
-            # blocked inside the collective after the other failed in capture; not enabled.  Multi-GPU runs use TrainStep.
+            # tried twice in round 2 on two B200s (default capture mode, then capture_error_mode="thread_local" so that
+            # NCCL's watchdog thread may query events while this thread captures): both runs ended with the ranks blocked
+            # inside the captured collectives.  Not enabled; multi-GPU runs use TrainStep's eager launches.
             raise NotImplementedError("GraphedTrainStep: capture of the NCCL all-reduces is not enabled; "
                                       "use TrainStep for multi-GPU runs")
         self.step, self.edge_bucket, self.max_graphs, self.warmup = step, edge_bucket, max_graphs, warmup
