@@ -754,7 +754,7 @@ def gat_bwd(csr_dst, csr_src, xs, a_src, a_dst, row_max, row_sum, g, heads, chan
     d_xs = torch.empty(n_src, hc, dtype=torch.float32, device=dev)
     d_a_src = torch.empty(n_src, heads, dtype=torch.float32, device=dev)
     d_a_dst = torch.empty(n_dst, heads, dtype=torch.float32, device=dev)
-    dot_ws = torch.empty(n_dst, heads, dtype=torch.float32, device=dev)
+    dot_ws = torch.empty(n_dst, heads, 4, dtype=torch.float32, device=dev)      # (a_dst, max, 1/sum, D) records
     with _region("gat", kernels=2, bytes=8 * csr_dst.num_edges * (hc + 4 * heads)):
         check(_lib.load().hgin_gat_bwd(n_dst, _ptr(csr_dst.rowptr), _ptr(csr_dst.col), n_src, _ptr(csr_src.rowptr),
                                        _ptr(csr_src.col), pxs, ldxs, _f32c(a_src, (n_src, heads), "gat_bwd.a_src"),

@@ -490,8 +490,8 @@ int32_t hgin_readout_tail(int64_t rows, const void *segment_ids, int32_t index_b
  *                 loop (i, i) is appended (last in the sum) for every i < min(num_src, num_rows).
  *   out[i] (+)= sum_j w_ij xs[j] / (sum_j w_ij + 1e-16) + bias,   w_ij = exp(e_ij - max_j e_ij)   (accumulate != 0 adds to
  *                 `out`: the HeteroConv sum merge);  row_max / row_sum [num_rows, heads] are saved for hgin_gat_bwd.
- * hgin_gat_bwd: g = d loss / d out.  Destination pass over the same CSR: d_a_dst [num_dst, heads] (dot_ws [num_dst, heads]
- *   is scratch).  Source pass over the TRANSPOSED CSR (rowptr_src / col_src, sort_row = 0): d_xs [num_src, heads*channels],
+ * hgin_gat_bwd: g = d loss / d out.  Destination pass over the same CSR: d_a_dst [num_dst, heads] (dot_ws: 16 * num_dst * heads bytes of
+ *   16-byte-aligned scratch: one (a_dst, row max, 1 / row sum, softmax dot) record per destination and head, read by the source pass).  Source pass over the TRANSPOSED CSR (rowptr_src / col_src, sort_row = 0): d_xs [num_src, heads*channels],
  *   d_a_src [num_src, heads].  d bias is the column sum of g (hgin_bn_stats computes it).  No atomics, nothing per edge is
  *   stored, deterministic.  channels: a power of two in [4, 128]; heads * channels <= 512 (HGIN_ERR_UNSUPPORTED otherwise).
  */
@@ -505,7 +505,7 @@ int32_t hgin_gat_bwd(int64_t num_dst, const int32_t *rowptr_dst, const int32_t *
                      const float *a_src, const float *a_dst, const float *row_max, const float *row_sum,
                      const float *g, int64_t ld_g, int32_t heads, int32_t channels, float negative_slope,
                      int32_t add_self_loops, float *d_xs, int64_t ld_dxs, float *d_a_src, float *d_a_dst,
-                     float *dot_ws, void *stream);
+                     void *dot_ws, void *stream);
 
 /* ---- the whole train step of config.json's model in three kernels (launch-bound regime) ---------------------------------
  * Replaces: one iteration of train.py:31-44 — HetroGIN.forward (models.py:332-376), mape + sqrt (train.py:12-13, 40-42),
