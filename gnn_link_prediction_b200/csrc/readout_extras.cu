@@ -226,14 +226,35 @@ bn_stats_kernel(int64_t rows, int n, const T *__restrict__ z, int64_t ldz, doubl
     for (int j = 0; j < kBnCols; ++j) s[j] = ss[j] = 0.0;
     const int64_t per = (rows + gridDim.x - 1) / gridDim.x;
     const int64_t r0 = per * blockIdx.x, r1 = (r0 + per < rows) ? r0 + per : rows;
-    for (int64_t r = r0 + threadIdx.y; r < r1; r += kBnRowsY) {
+    // four rows per iteration with all loads issued first: one 4-byte load per thread in flight ran at 2.2 TB/s
+    constexpr int RU = 4;
+    int64_t r = r0 + threadIdx.y;
+    for (; r + (RU - 1) * kBnRowsY < r1; r += RU * kBnRowsY) {
+        float v[RU][kBnCols];
+#pragma unroll
+        for (int u = 0; u < RU; ++u)
+#pragma unroll
+            for (int j = 0; j < kBnCols; ++j) {
+                const int c = threadIdx.x + 32 * j;
+                v[u][j] = c < n ? ld1<T>(z + (r + u * kBnRowsY) * ldz + c) : 0.f;
+            }
+#pragma unroll
+        for (int u = 0; u < RU; ++u)
+#pragma unroll
+            for (int j = 0; j < kBnCols; ++j) {
+                const double d = static_cast<double>(v[u][j]);
+                s[j] += d;
+                ss[j] = fma(d, d, ss[j]);
+            }
+    }
+    for (; r < r1; r += kBnRowsY) {
 #pragma unroll
         for (int j = 0; j < kBnCols; ++j) {
             const int c = threadIdx.x + 32 * j;
             if (c < n) {
-                const double v = static_cast<double>(ld1<T>(z + r * ldz + c));
-                s[j] += v;
-                ss[j] = fma(v, v, ss[j]);
+                const double d = static_cast<double>(ld1<T>(z + r * ldz + c));
+                s[j] += d;
+                ss[j] = fma(d, d, ss[j]);
             }
         }
     }
