@@ -162,29 +162,45 @@ dz_prepare_kernel(int64_t rows, int n, const float *__restrict__ g, int64_t ldg,
 
 // out[nn][col0 + k] (ld = ldw) = sum_p part[p][nn][k] for k < kcols; the optional extra column
 // (index kcols) goes to db.
+static inline int reduce_grid(int64_t total) {
+    const int64_t want = (total + 31) / 32;
+    return static_cast<int>(want < 1 ? 1 : (want > kNumSMs * 8 ? kNumSMs * 8 : want));
+}
+
+// One CTA per 32 consecutive elements (grid-stride over such groups): warp w adds the partials w, w + 8, ... with the lanes on
+// consecutive elements (coalesced, the loads of a warp independent), the eight sums are combined in a fixed order.  (A thread
+// per element walking all ~148 partials was a chain of ~37 dependent steps: 14.5 us per call, 22 calls per Cfg-C step.)
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const float *__restrict__ part, int num_part, int n, int kcols, int has_db_col,
                        float *__restrict__ dW, int ldw, int col0, float *__restrict__ db) {
+    __shared__ float red[8][32];
     const int kp = kcols + (has_db_col ? 1 : 0);
     const int64_t total = static_cast<int64_t>(n) * kp;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        int pp = 0;
-        for (; pp + 3 < num_part; pp += 4) {   // four independent chains, fixed association
-            s0 += part[static_cast<int64_t>(pp) * total + i];
-            s1 += part[static_cast<int64_t>(pp + 1) * total + i];
-            s2 += part[static_cast<int64_t>(pp + 2) * total + i];
-            s3 += part[static_cast<int64_t>(pp + 3) * total + i];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t g0 = static_cast<int64_t>(blockIdx.x) * 32; g0 < total; g0 += static_cast<int64_t>(gridDim.x) * 32) {
+        const int64_t i = g0 + lane;
+        float s0 = 0.f, s1 = 0.f;
+        if (i < total) {
+            int pp = warp;
+            for (; pp + 8 < num_part; pp += 16) {      // two independent chains per warp
+                s0 += part[static_cast<int64_t>(pp) * total + i];
+                s1 += part[static_cast<int64_t>(pp + 8) * total + i];
+            }
+            if (pp < num_part) s0 += part[static_cast<int64_t>(pp) * total + i];
         }
-        for (; pp < num_part; ++pp) s0 += part[static_cast<int64_t>(pp) * total + i];
-        const float s = (s0 + s1) + (s2 + s3);
-        const int nn = static_cast<int>(i / kp), k = static_cast<int>(i % kp);
-        if (has_db_col && k == kcols) {
-            if (db) db[nn] = s;
-        } else if (dW) {
-            dW[static_cast<int64_t>(nn) * ldw + col0 + k] = s;
+        red[warp][lane] = s0 + s1;
+        __syncthreads();
+        if (warp == 0 && i < total) {
+            const float s = ((red[0][lane] + red[1][lane]) + (red[2][lane] + red[3][lane])) +
+                            ((red[4][lane] + red[5][lane]) + (red[6][lane] + red[7][lane]));
+            const int nn = static_cast<int>(i / kp), k = static_cast<int>(i % kp);
+            if (has_db_col && k == kcols) {
+                if (db) db[nn] = s;
+            } else if (dW) {
+                dW[static_cast<int64_t>(nn) * ldw + col0 + k] = s;
+            }
         }
+        __syncthreads();
     }
 }
 
@@ -369,9 +385,9 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
         p.sum_partials = sum_part;
         p.alpha_partials = alpha_part;
         bwd_fused_kernel<<<grid, FUSED_THREADS, FusedSmem::total, s>>>(tm_g, tm_z, tm_wt, tm_h, tm_dx, tm_e, p);
-        reduce_partials_kernel<<<grid_for(n * k1, 256, 2), 256, 0, s>>>(dw_part, grid, n, k1, 0, dW, k, 0, nullptr);
+        reduce_partials_kernel<<<reduce_grid(n * k1), 256, 0, s>>>(dw_part, grid, n, k1, 0, dW, k, 0, nullptr);
         if (db || k2 > 0)
-            reduce_partials_kernel<<<grid_for(n * (k2 + 1), 256, 1), 256, 0, s>>>(sum_part, grid, n, k2, 1, dW, k, k1, db);
+            reduce_partials_kernel<<<reduce_grid(n * (k2 + 1)), 256, 0, s>>>(sum_part, grid, n, k2, 1, dW, k, k1, db);
         if (dalpha) {
             if (act == HGIN_ACT_PRELU) reduce_scalar_tc_kernel<<<1, 1024, 0, s>>>(alpha_part, grid * 4, dalpha);
             else cudaMemsetAsync(dalpha, 0, sizeof(float), s);
@@ -411,9 +427,9 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
         p.alpha_partials = alpha_part;
         const int grid = static_cast<int>(ceil_div(rows, p.rows_per_cta));
         dw_fused_kernel<<<grid, DW_THREADS, DwSmem::total, s>>>(tm_g, tm_z, tm_h, tm_dz, p);
-        reduce_partials_kernel<<<grid_for(n * k1, 256, 2), 256, 0, s>>>(dw_part, grid, n, k1, 0, dW, k, 0, nullptr);
+        reduce_partials_kernel<<<reduce_grid(n * k1), 256, 0, s>>>(dw_part, grid, n, k1, 0, dW, k, 0, nullptr);
         if (db || k2 > 0)
-            reduce_partials_kernel<<<grid_for(n * (k2 + 1), 256, 1), 256, 0, s>>>(sum_part, grid, n, k2, 1, dW, k, k1, db);
+            reduce_partials_kernel<<<reduce_grid(n * (k2 + 1)), 256, 0, s>>>(sum_part, grid, n, k2, 1, dW, k, k1, db);
         if (dalpha) {
             if (act == HGIN_ACT_PRELU) reduce_scalar_tc_kernel<<<1, 1024, 0, s>>>(alpha_part, grid * 4, dalpha);
             else cudaMemsetAsync(dalpha, 0, sizeof(float), s);
@@ -448,7 +464,7 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
             const int slots = TAIL_THREADS / (n / 4);
             const int ctas = static_cast<int>(ceil_div(rows, slots) < tail_ctas() ? ceil_div(rows, slots) : tail_ctas());
             tail_sums_kernel<float><<<ctas, TAIL_THREADS, tail_smem<float>(n), s>>>(rows, n, g, ldg, x2, ld2, k2, sum_part);
-            reduce_partials_kernel<<<grid_for(n * (k2 + 1), 256, 1), 256, 0, s>>>(sum_part, ctas, n, k2, 1, dW, k, k1,
+            reduce_partials_kernel<<<reduce_grid(n * (k2 + 1)), 256, 0, s>>>(sum_part, ctas, n, k2, 1, dW, k, k1,
                                                                                  db_from_mma ? nullptr : db);
         } else if (!inplace) {
             const int tpr = n / 4, slots = DZ_THREADS / tpr;
@@ -457,7 +473,7 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
                 rows, n, g, ldg, z, ldz, act, alpha, x2, ld2, k2, dz, sum_part, want_alpha ? alpha_part : nullptr, want_sums,
                 inplace ? 0 : 1);
             if (want_sums && ((db && !db_from_mma) || tail))
-                reduce_partials_kernel<<<grid_for(n * (k2 + 1), 256, 1), 256, 0, s>>>(sum_part, ctas, n, k2, 1, dW, k, k1,
+                reduce_partials_kernel<<<reduce_grid(n * (k2 + 1)), 256, 0, s>>>(sum_part, ctas, n, k2, 1, dW, k, k1,
                                                                                      db_from_mma ? nullptr : db);
             if (want_alpha) reduce_scalar_tc_kernel<<<1, 1024, 0, s>>>(alpha_part, ctas, dalpha);
         }
@@ -523,8 +539,8 @@ int32_t linear_bwd(int64_t rows, const float *g, int64_t ldg, const float *z, in
         p.k_step_bytes = dbg ? dbg->k_step_bytes : 1024;
         const int grid = static_cast<int>(ceil_div(rows, p.rows_per_cta));
         gemm_tn_kernel<<<grid, THREADS, TnSmem::total, s>>>(tm_a, tm_b, p);
-        reduce_partials_kernel<<<grid_for(n * k1, 256, 2), 256, 0, s>>>(dw_part, grid, n, k1, 0, dW, k, 0, nullptr);
-        if (db_from_mma) reduce_partials_kernel<<<1, 256, 0, s>>>(db_part, grid, n, 0, 1, nullptr, 0, 0, db);
+        reduce_partials_kernel<<<reduce_grid(n * k1), 256, 0, s>>>(dw_part, grid, n, k1, 0, dW, k, 0, nullptr);
+        if (db_from_mma) reduce_partials_kernel<<<reduce_grid(n), 256, 0, s>>>(db_part, grid, n, 0, 1, nullptr, 0, 0, db);
     }
     HGIN_CHECK_LAUNCH("hgin_linear_bwd(tf32)");
     return HGIN_OK;
