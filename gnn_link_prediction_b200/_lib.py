@@ -96,6 +96,8 @@ SIGNATURES = {
     "hgin_small_step_workspace_bytes": (_i64, [_i64]),
     "hgin_small_step": (_i32, [_i64, _ptr, _ptr, _ptr, _i64, _i32, _ptr, _ptr, _i64, _i32, _ptr, _ptr, _i32, _i32, _i32, _i32]
                         + [_ptr] * 11 + [_ptr] * 11 + [_ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
+    "hgin_small_step_phase": (_i32, [_i32, _i64, _ptr, _ptr, _ptr, _i64, _i32, _ptr, _ptr, _i64, _i32, _ptr, _ptr, _i32, _i32, _i32, _i32]
+                              + [_ptr] * 11 + [_ptr] * 11 + [_ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
     "hgin_set_option": (_i32, [ctypes.c_char_p, _i32]),
     "hgin_debug_gemm_tn": (_i32, [_i64, _ptr, _i32, _ptr, _i32, _ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _i32, _ptr]),
 }

@@ -376,22 +376,28 @@ small_bwd_kernel(const SmallParams p, const float *__restrict__ partial_s, int n
     const float ope = __fadd_rn(1.0f, __ldg(p.eps0)), a0 = __ldg(p.a0), aR = __ldg(p.aR), b3 = __ldg(p.b3);
     // S = sum |(out - y) / y| over all rows: every CTA adds the forward kernel's per-CTA partials itself, in the same fixed
     // order (lane l takes partials l, l + 32, ..., then a butterfly), so no launch sits between forward and backward
+    // (num_partial_s == 0: data-parallel step — `sums` already holds the GLOBAL (S, N), all-reduced by the caller)
     if (warp == 0) {
         float tsum = 0.f;
         for (int i = lane; i < num_partial_s; i += 32) tsum += partial_s[i];
         tsum = warp_sum_all(tsum);
-        if (lane == 0) s.red[0][0] = tsum;
+        if (lane == 0) {
+            s.red[0][0] = num_partial_s > 0 ? tsum : sums[0];
+            s.red[0][1] = num_partial_s > 0 ? static_cast<float>(p.np) : sums[1];
+        }
     }
     __syncthreads();
-    const float S = s.red[0][0], N = static_cast<float>(p.np);
+    const float S = s.red[0][0], N = s.red[0][1];
     __syncthreads();
     // seed of d sqrt(100 S / N) / d out_i  (hgin_sqrt_mape_bwd)
     const float mape = 100.0f * (S / N);
     const float L = sqrtf(mape);
     const float cseed = 50.0f / (N * L);
     if (blockIdx.x == 0 && t == 0) {
-        sums[0] = S;
-        sums[1] = N;
+        if (num_partial_s > 0) {
+            sums[0] = S;
+            sums[1] = N;
+        }
         loss_out[0] = mape;
         loss_out[1] = L;
     }
@@ -568,6 +574,17 @@ small_bwd_kernel(const SmallParams p, const float *__restrict__ partial_s, int n
     }
 }
 
+// data-parallel forward phase: this rank's (S, N) from the forward kernel's partials, to be all-reduced by the caller
+__global__ void small_local_sums_kernel(const float *__restrict__ partial_s, int count, int np, float *__restrict__ sums) {
+    float t = 0.f;
+    for (int i = threadIdx.x; i < count; i += 32) t += partial_s[i];
+    t = warp_sum_all(t);
+    if (threadIdx.x == 0) {
+        sums[0] = t;
+        sums[1] = static_cast<float>(np);
+    }
+}
+
 struct SmallGrads {
     float *dW0, *db0, *da0, *deps0, *dW1, *db1, *daR, *dW2, *db2, *dW3, *db3;
 };
@@ -627,7 +644,7 @@ extern "C" int64_t hgin_small_step_workspace_bytes(int64_t num_paths) {
     return align_up(static_cast<int64_t>(small_ctas(num_paths)) * P_TOTAL * 4, 256) + 4096;
 }
 
-extern "C" int32_t hgin_small_step(int64_t num_paths, const int32_t *rowptr, const int32_t *col, const float *x_path,
+static int32_t small_step_impl(int phase, int64_t num_paths, const int32_t *rowptr, const int32_t *col, const float *x_path,
                                    int64_t ld_path, int32_t f_path, const int32_t *path_cols_host, const float *x_link,
                                    int64_t ld_link, int32_t f_link, const int32_t *link_cols_host, const float *y, int32_t emb,
                                    int32_t n1, int32_t n2, int32_t concat_path, const float *W0, const float *b0,
@@ -687,10 +704,14 @@ extern "C" int32_t hgin_small_step(int64_t num_paths, const int32_t *rowptr, con
         if (cost < best_cost) { best_cost = cost; best_r = r; }
     }
     const bool is_default = emb == 8 && f_link == 3 && f_path == 3 && n1 == 128 && n2 == 32 && concat_path;
+    // phase 0: the whole step; 1: forward + this rank's (S, N) only; 2: backward with the global (S, N) given in `sums`
 #define HGIN_SMALL(R, D)                                                                                     \
     do {                                                                                                     \
-        small_fwd_loss_kernel<R, D><<<ctas, SS_THREADS, sizeof(SmallSmem), s>>>(p, partial_s, out);          \
-        small_bwd_kernel<R, D><<<ctas, SS_THREADS, sizeof(SmallSmem), s>>>(p, partial_s, ctas, sums, loss_out, partials); \
+        if (phase != 2) small_fwd_loss_kernel<R, D><<<ctas, SS_THREADS, sizeof(SmallSmem), s>>>(p, partial_s, out); \
+        if (phase == 1) small_local_sums_kernel<<<1, 32, 0, s>>>(partial_s, ctas, p.np, sums);               \
+        if (phase != 1)                                                                                      \
+            small_bwd_kernel<R, D><<<ctas, SS_THREADS, sizeof(SmallSmem), s>>>(p, partial_s, phase == 0 ? ctas : 0, sums, \
+                                                                                loss_out, partials);          \
     } while (0)
 #define HGIN_SMALL_R(D)                     \
     do {                                    \
@@ -702,8 +723,42 @@ extern "C" int32_t hgin_small_step(int64_t num_paths, const int32_t *rowptr, con
     else HGIN_SMALL_R(DynDims);
 #undef HGIN_SMALL_R
 #undef HGIN_SMALL
-    const SmallGrads g{dW0, db0, dalpha0, deps0, dW1, db1, dalpha_r, dW2, db2, dW3, db3};
-    small_reduce_kernel<<<static_cast<int>(ceil_div(P_TOTAL, 32)), 256, 0, s>>>(partials, ctas, emb, k0, k1, n1, n2, g);
+    if (phase != 1) {
+        const SmallGrads g{dW0, db0, dalpha0, deps0, dW1, db1, dalpha_r, dW2, db2, dW3, db3};
+        small_reduce_kernel<<<static_cast<int>(ceil_div(P_TOTAL, 32)), 256, 0, s>>>(partials, ctas, emb, k0, k1, n1, n2, g);
+    }
     HGIN_CHECK_LAUNCH("hgin_small_step");
     return HGIN_OK;
+}
+
+extern "C" int32_t hgin_small_step(int64_t num_paths, const int32_t *rowptr, const int32_t *col, const float *x_path,
+                                   int64_t ld_path, int32_t f_path, const int32_t *path_cols_host, const float *x_link,
+                                   int64_t ld_link, int32_t f_link, const int32_t *link_cols_host, const float *y, int32_t emb,
+                                   int32_t n1, int32_t n2, int32_t concat_path, const float *W0, const float *b0,
+                                   const float *alpha0, const float *eps0, const float *W1, const float *b1,
+                                   const float *alpha_r, const float *W2, const float *b2, const float *W3, const float *b3,
+                                   float *dW0, float *db0, float *dalpha0, float *deps0, float *dW1, float *db1, float *dalpha_r,
+                                   float *dW2, float *db2, float *dW3, float *db3, float *sums, float *loss_out, float *out,
+                                   void *workspace, int64_t workspace_bytes, void *stream) {
+    return small_step_impl(0, num_paths, rowptr, col, x_path, ld_path, f_path, path_cols_host, x_link, ld_link, f_link,
+                           link_cols_host, y, emb, n1, n2, concat_path, W0, b0, alpha0, eps0, W1, b1, alpha_r, W2, b2, W3, b3, dW0,
+                           db0, dalpha0, deps0, dW1, db1, dalpha_r, dW2, db2, dW3, db3, sums, loss_out, out, workspace,
+                           workspace_bytes, stream);
+}
+
+extern "C" int32_t hgin_small_step_phase(int32_t phase, int64_t num_paths, const int32_t *rowptr, const int32_t *col,
+                                         const float *x_path, int64_t ld_path, int32_t f_path, const int32_t *path_cols_host,
+                                         const float *x_link, int64_t ld_link, int32_t f_link, const int32_t *link_cols_host,
+                                         const float *y, int32_t emb, int32_t n1, int32_t n2, int32_t concat_path,
+                                         const float *W0, const float *b0, const float *alpha0, const float *eps0,
+                                         const float *W1, const float *b1, const float *alpha_r, const float *W2,
+                                         const float *b2, const float *W3, const float *b3, float *dW0, float *db0,
+                                         float *dalpha0, float *deps0, float *dW1, float *db1, float *dalpha_r, float *dW2,
+                                         float *db2, float *dW3, float *db3, float *sums, float *loss_out, float *out,
+                                         void *workspace, int64_t workspace_bytes, void *stream) {
+    HGIN_CHECK_ARG(phase == 1 || phase == 2, "hgin_small_step_phase: phase must be 1 (forward) or 2 (backward)");
+    return small_step_impl(phase, num_paths, rowptr, col, x_path, ld_path, f_path, path_cols_host, x_link, ld_link, f_link,
+                           link_cols_host, y, emb, n1, n2, concat_path, W0, b0, alpha0, eps0, W1, b1, alpha_r, W2, b2, W3, b3, dW0,
+                           db0, dalpha0, deps0, dW1, db1, dalpha_r, dW2, db2, dW3, db3, sums, loss_out, out, workspace,
+                           workspace_bytes, stream);
 }

@@ -772,10 +772,12 @@ def column_sums(x):
     return bn_stats(x)[:n].float()
 
 
-def small_step(csr, x_path, path_cols, x_link, link_cols, y, params, grads, concat_path, want_out=False):
+def small_step(csr, x_path, path_cols, x_link, link_cols, y, params, grads, concat_path, want_out=False, phase=0, sums=None):
     """One forward + loss + backward of config.json's model family in three kernels (include/hgin.h: hgin_small_step).
     params / grads: dicts with keys W0 b0 a0 eps0 W1 b1 aR W2 b2 W3 b3 (gradients: same shapes, written in place).
-    Returns (loss_out [mape, sqrt(mape)], sums [S, N], out or None)."""
+    Returns (loss_out [mape, sqrt(mape)], sums [S, N], out or None).
+    phase 1 / 2 (data parallelism, hgin_small_step_phase): 1 = forward only, `sums` = this rank's (S, N), to be all-reduced;
+    2 = backward with the global `sums` passed back in."""
     import ctypes
     for t, name in ((x_path, "x_path"), (x_link, "x_link")):
         if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1):
@@ -803,18 +805,25 @@ def small_step(csr, x_path, path_cols, x_link, link_cols, y, params, grads, conc
     np_ = x_path.shape[0]
     ws_bytes = lib.hgin_small_step_workspace_bytes(np_)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    sums = torch.empty(2, dtype=torch.float32, device=dev)
+    if phase == 2:
+        if sums is None or not (sums.is_cuda and sums.dtype == torch.float32 and sums.numel() == 2):
+            raise HginError("small_step: phase 2 needs the all-reduced (S, N) in `sums`")
+    else:
+        sums = torch.empty(2, dtype=torch.float32, device=dev)
     loss_out = torch.empty(2, dtype=torch.float32, device=dev)
     out = torch.empty(np_, dtype=torch.float32, device=dev) if want_out else None
     pc = (ctypes.c_int32 * 8)(*(list(path_cols) + [0] * (8 - fp)))
     lc = (ctypes.c_int32 * 8)(*(list(link_cols) + [0] * (8 - fl)))
-    with _region("small_step", kernels=3, flops=6 * np_ * (emb * (fl + fp) + n1 * (emb + fp) + n1 * n2 + n2)):
-        check(lib.hgin_small_step(np_, _ptr(csr.rowptr), _ptr(csr.col), x_path.data_ptr(), x_path.stride(0), fp,
-                                  ctypes.cast(pc, ctypes.c_void_p), x_link.data_ptr(), x_link.stride(0), fl,
-                                  ctypes.cast(lc, ctypes.c_void_p), y.data_ptr(), emb, n1, n2, 1 if concat_path else 0,
-                                  *[params[k].data_ptr() for k in keys], *[grads[k].data_ptr() for k in keys],
-                                  sums.data_ptr(), loss_out.data_ptr(), _ptr(out), ws.data_ptr(), ws_bytes, _stream()),
-              "hgin_small_step")
+    args = (np_, _ptr(csr.rowptr), _ptr(csr.col), x_path.data_ptr(), x_path.stride(0), fp, ctypes.cast(pc, ctypes.c_void_p),
+            x_link.data_ptr(), x_link.stride(0), fl, ctypes.cast(lc, ctypes.c_void_p), y.data_ptr(), emb, n1, n2,
+            1 if concat_path else 0, *[params[k].data_ptr() for k in keys], *[grads[k].data_ptr() for k in keys],
+            sums.data_ptr(), loss_out.data_ptr(), _ptr(out), ws.data_ptr(), ws_bytes, _stream())
+    with _region("small_step", kernels=3 if phase == 0 else 2, flops=(6 if phase == 0 else (2 if phase == 1 else 6)) * np_ * (
+            emb * (fl + fp) + n1 * (emb + fp) + n1 * n2 + n2)):
+        if phase == 0:
+            check(lib.hgin_small_step(*args), "hgin_small_step")
+        else:
+            check(lib.hgin_small_step_phase(phase, *args), "hgin_small_step_phase")
     return loss_out, sums, out
 
 

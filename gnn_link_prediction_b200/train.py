@@ -139,10 +139,10 @@ class TrainStep:
 
     def _small_plan(self):
         """config.json's model family (one message-passing layer, Linear-PReLU-Linear-PReLU-Linear readout with one shared
-        slope, no BatchNorm / global features / dropout) on one GPU: the whole forward + loss + backward runs as
-        hgin_small_step (three kernels instead of ~25).  Returns the parameter / gradient tables or None."""
+        slope, no BatchNorm / global features / dropout): the whole forward + loss + backward runs as hgin_small_step
+        (three kernels instead of ~25; under data parallelism split around the all-reduce of the loss statistics).  Returns the parameter / gradient tables or None."""
         m = self.model
-        if not isinstance(m, HetroGIN) or self.comm.world > 1 or m.num_layers != 1 or m.global_feats or m.dropout > 0:
+        if not isinstance(m, HetroGIN) or m.num_layers != 1 or m.global_feats or m.dropout > 0:
             return None
         if m.math_mode not in (ops.MATH_FP32, ops.MATH_TF32) or len(m.readout) != 3:
             return None
@@ -186,8 +186,17 @@ class TrainStep:
         graph = batch.graph if hasattr(batch, "graph") else batch.edge_index_dict
         if not isinstance(graph, GraphCSR):
             graph = GraphCSR(graph, {t: batch[t]["x"].shape[0] for t in ("path", "link", "node") if "x" in batch[t]})
-        loss_out, _, _ = ops.small_step(graph.fwd(self.SMALL_RELATION), batch["path"]["x"], plan["path_cols"], batch["link"]["x"],
-                                        plan["link_cols"], batch["path"].y, plan["params"], plan["grads"], plan["concat"])
+        args = (graph.fwd(self.SMALL_RELATION), batch["path"]["x"], plan["path_cols"], batch["link"]["x"], plan["link_cols"],
+                batch["path"].y, plan["params"], plan["grads"], plan["concat"])
+        if self.comm.world > 1:
+            # every rank differentiates the same GLOBAL sqrt(100 * S / N): forward, all-reduce (S, N), backward, then SUM of
+            # the partial gradients over the flat bucket (parallel.py)
+            _, sums, _ = ops.small_step(*args, phase=1)
+            self.comm.all_reduce_sum_(sums)
+            loss_out, _, _ = ops.small_step(*args, phase=2, sums=sums)
+            self.comm.all_reduce_sum_(self.flat_g)
+        else:
+            loss_out, _, _ = ops.small_step(*args)
         for p, v in zip(self.live, self.grad_views):
             p.grad = v                 # the gradients ARE the bucket slices: no gather copy
         ops.increment(self.step_count)

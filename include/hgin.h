@@ -521,6 +521,9 @@ int32_t hgin_gat_bwd(int64_t num_dst, const int32_t *rowptr_dst, const int32_t *
  *   b2, W3 [1, n2], b3, alpha_r: the readout.  d*: gradients, same shapes.  sums [2] = (sum |(out - y)/y|, N);
  *   loss_out [2] = (mape, sqrt(mape));  out [num_paths] (NULL to skip): the scores.
  * Limits: f_path, f_link <= 8; emb <= 32; emb + f_path <= 32; n1 <= 128; n2 <= 32 (HGIN_ERR_UNSUPPORTED otherwise).
+ * hgin_small_step_phase: the same step split around the loss statistics, for data parallelism (the loss is
+ *   sqrt of a GLOBAL mean).  phase 1: forward, `sums` = this rank's (S, N) — the caller all-reduces it;  phase 2: backward
+ *   with `sums` holding the global (S, N), gradients = this rank's partial sums — the caller all-reduces the bucket.
  */
 int64_t hgin_small_step_workspace_bytes(int64_t num_paths);
 int32_t hgin_small_step(int64_t num_paths, const int32_t *rowptr, const int32_t *col, const float *x_path,
@@ -533,6 +536,17 @@ int32_t hgin_small_step(int64_t num_paths, const int32_t *rowptr, const int32_t 
                         float *deps0, float *dW1, float *db1, float *dalpha_r, float *dW2, float *db2,
                         float *dW3, float *db3, float *sums, float *loss_out, float *out, void *workspace,
                         int64_t workspace_bytes, void *stream);
+int32_t hgin_small_step_phase(int32_t phase, int64_t num_paths, const int32_t *rowptr, const int32_t *col,
+                              const float *x_path, int64_t ld_path, int32_t f_path,
+                              const int32_t *path_cols_host, const float *x_link, int64_t ld_link,
+                              int32_t f_link, const int32_t *link_cols_host, const float *y, int32_t emb,
+                              int32_t n1, int32_t n2, int32_t concat_path, const float *W0, const float *b0,
+                              const float *alpha0, const float *eps0, const float *W1, const float *b1,
+                              const float *alpha_r, const float *W2, const float *b2, const float *W3,
+                              const float *b3, float *dW0, float *db0, float *dalpha0, float *deps0,
+                              float *dW1, float *db1, float *dalpha_r, float *dW2, float *db2, float *dW3,
+                              float *db3, float *sums, float *loss_out, float *out, void *workspace,
+                              int64_t workspace_bytes, void *stream);
 
 /* ---- runtime options --------------------------------------------------------------------------
  * "fused_bwd" (0/1, default 0): HGIN_MATH_TF32 backward through the single-pass fused kernel

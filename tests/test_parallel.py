@@ -122,6 +122,8 @@ VARIANTS = {
     # mlp_bn: BatchNorm statistics must be those of the GLOBAL batch (column sums all-reduced) for N ranks to equal one;
     # global_feats: per-graph pools are local to a sample, so sharding by sample leaves them unchanged
     "gin_bn_globalfeats": dict(mlp_bn=True, global_feats=True, bl_features=True),
+    # config.json's own model: the three-kernel step (hgin_small_step) split around the all-reduce of the loss statistics
+    "gin_default_small_step": dict(node_embedding_size=8, message_passing_layers=1, mlp_layers=[128, 32]),
     # (HetroGAT is NOT in this list: PyG's bipartite add_self_loops rule — GATConv drops edges whose source id equals
     # their destination id and adds (i, i) for i < min(N_src, N_dst), ids taken across node types — makes its output a
     # function of the batch composition, so a sharded step cannot equal the single-process one by construction.)
