@@ -153,7 +153,7 @@ class HeteroConvFn(torch.autograd.Function):
             if x_dst.dtype != x_src.dtype:      # (mixed storage types only arise outside HetroGIN.forward)
                 x_dst = x_dst.to(x_src.dtype)
             h = ops.gin_combine(graph.fwd(sp.et), x_src, x_dst, eps, SELF_CONCAT if sp.concat else SELF_ADD,
-                                stream=None if sp.concat else graph.stream_plan(sp.et, "fwd"), **pre)
+                                block_plan=None if sp.concat else graph.stream_plan(sp.et, "fwd"), **pre)
             link_ok = (training and links_out is not None and sp.act != ACT_NONE
                        and sum(1 for q in specs if q.dst == sp.dst) == 1
                        and _fold_eligible(h.shape[0], h.shape[1], W.shape[0], math_mode))
@@ -271,7 +271,7 @@ class HeteroConvFn(torch.autograd.Function):
                                    **common)
                 dh_agg, dh_self = None, None
                 if want_agg:      # (A^T dz) W, see above; g is dz here
-                    gz = ops.gin_combine(graph.bwd(sp.et), g, None, None, SELF_NONE, stream=graph.stream_plan(sp.et, "bwd"))
+                    gz = ops.gin_combine(graph.bwd(sp.et), g, None, None, SELF_NONE, block_plan=graph.stream_plan(sp.et, "bwd"))
                     dh_agg = ops.linear_bwd(gz, None, x_src, W, act=ACT_NONE, dx_cols=(0, k), want_dx=True, want_dw=False,
                                             want_db=False, math_mode=ctx.math_mode)["dx"]
             elif sp.concat:
@@ -320,7 +320,7 @@ class HeteroConvFn(torch.autograd.Function):
                 plan_t = graph.stream_plan(specs[gi].et, "bwd") if (gi is not None and not (last and post is not None)) else None
                 res = ops.gin_combine(csr_t, src_rows, s_dh, s_eps, SELF_ADD if si is not None else SELF_NONE, out=dx,
                                       accumulate=dx is not None, post=post if last else None, want_ddot=want_ddot,
-                                      stream=plan_t)
+                                      block_plan=plan_t)
                 if want_ddot:
                     dx, ddot = res
                     grads_p[4 * si + 3] = ddot.view_as(s_eps)

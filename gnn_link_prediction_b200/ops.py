@@ -196,13 +196,13 @@ STREAM_LONG_ROWS = False
 
 
 def gin_combine(csr, x_src, x_self=None, eps=None, self_mode=SELF_NONE, out=None, accumulate=False, post=None,
-                want_ddot=False, src_act=None, self_act=None, stream=None):
+                want_ddot=False, src_act=None, self_act=None, block_plan=None):
     """K1/K4.  out[r] (+)= sum_{e in row r} x_src[col[e]]  {+ | concat}  (1+eps) * x_self[r].
     csr=None: no edges (self term only; x_src is then only a shape donor).
     post: a PostAct — the stored result is multiplied by act'(post.z) and post.dalpha is filled.
     want_ddot (with post, SELF_ADD): returns (out, ddot) with ddot = sum x_self * act(post.z).
     src_act / self_act: (act, alpha) when x_src / x_self hold PRE-activations (act applied on load).
-    stream: a StreamPlan — the batch is block-diagonal and this is a long-row aggregation: input-major streaming kernel
+    block_plan: a StreamPlan — the batch is block-diagonal and this is a long-row aggregation: input-major streaming kernel
     with the gather kernel behind an inverse device-side gate (same bits either way; hgin_gin_combine_blocks_t).
     Rows may be float32 or bfloat16 (all of x_src, x_self, post.z, out alike): bf16 rows are widened on load,
     summed in fp32 in CSR order and rounded once on the store (hgin_gin_combine_t)."""
@@ -252,15 +252,16 @@ def gin_combine(csr, x_src, x_self=None, eps=None, self_mode=SELF_NONE, out=None
         kernels = 1 + int(want) + int(want_ddot)
     sa, sal = src_act if src_act is not None else (ACT_NONE, None)
     fa, fal = self_act if (self_act is not None and x_self is not None) else (ACT_NONE, None)
-    if (stream is not None and STREAM_LONG_ROWS and not post_on and self_mode in (SELF_NONE, SELF_ADD) and csr.rowptr is not None
+    if (block_plan is not None and STREAM_LONG_ROWS and not post_on and self_mode in (SELF_NONE, SELF_ADD) and csr.rowptr is not None
             and 32 <= f_src <= 128 and f_src % (16 // es) == 0 and x_src.shape[0] > 1 and lds == f_src and ldo % 4 == 0
             and (x_self is None or ldf % 4 == 0) and x_src.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0
             and (x_self is None or x_self.data_ptr() % 16 == 0)):
-        cin = stream.csr_in
+        cin = block_plan.csr_in
         with _region("gin_combine", kernels=2, alg_bytes=alg, compulsory_bytes=comp):
             check(lib.hgin_gin_combine_blocks_t(_DTYPES[dt], csr.num_rows, _ptr(csr.rowptr), _ptr(csr.col), csr.num_edges,
-                                                cin.num_rows, _ptr(cin.rowptr), _ptr(cin.col), stream.num_blocks,
-                                                stream.in_ptr.data_ptr(), stream.out_ptr.data_ptr(), stream.gate.data_ptr(),
+                                                cin.num_rows, _ptr(cin.rowptr), _ptr(cin.col), block_plan.num_blocks,
+                                                block_plan.in_ptr.data_ptr(), block_plan.out_ptr.data_ptr(),
+                                                block_plan.gate.data_ptr(),
                                                 ps, lds, f_src, pf, ldf, _scalar(eps, "gin_combine.eps"), self_mode,
                                                 1 if accumulate else 0, po, ldo, sa, _scalar(sal, "gin_combine.src_alpha"), fa,
                                                 _scalar(fal, "gin_combine.self_alpha"), _stream()), "hgin_gin_combine_blocks_t")

@@ -641,7 +641,7 @@ def test_streaming_long_row_aggregation_is_bit_identical_to_the_gather(case, f, 
         out = None
         if case == "accumulate":
             out = torch.full((n_out, f), 0.5, device="cuda").to(dtype)
-        return ops.gin_combine(graph.fwd(et), x, out=out, accumulate=out is not None, stream=stream, **kw)
+        return ops.gin_combine(graph.fwd(et), x, out=out, accumulate=out is not None, block_plan=stream, **kw)
 
     want = run(None)
     got = run(plan)
@@ -650,7 +650,7 @@ def test_streaming_long_row_aggregation_is_bit_identical_to_the_gather(case, f, 
     plan_t = graph.stream_plan(et, "bwd")
     if plan_t is not None:      # only long rows get a plan
         g = torch.randn(n_out, f, device="cuda").to(dtype)
-        assert torch.equal(ops.gin_combine(graph.bwd(et), g, stream=plan_t), ops.gin_combine(graph.bwd(et), g))
+        assert torch.equal(ops.gin_combine(graph.bwd(et), g, block_plan=plan_t), ops.gin_combine(graph.bwd(et), g))
 
 
 def test_streaming_plan_only_for_long_rows_and_block_tables(monkeypatch):
