@@ -9,7 +9,8 @@
 // Eager execution is 25 launches of a few microseconds each (0.30 ms per step even as one CUDA-graph replay, most of it
 // in the SIMT weight-gradient kernels and their partial reductions).  Here:
 //   small_fwd_loss_kernel   forward of every row, per-CTA partial of sum |(out - y) / y|          (train.py:12-13)
-//   small_bwd_kernel        S = sum of the partials (every CTA, same fixed order); forward RECOMPUTED per row (nothing was stored), backward per row, weight gradients
+//   small_bwd_kernel        S = sum of the partials (every CTA, same fixed order); per row the forward's pre-activations
+//                           are reloaded (1 KB per row, L2-resident), backward per row, weight gradients
 //                           accumulated in registers over the CTA's row tiles (each thread owns fixed dW elements, so no
 //                           atomics and a fixed order), per-CTA partials
 //   small_reduce_kernel     partials -> the parameters' gradient tensors (fixed order over CTAs)
@@ -311,6 +312,53 @@ __device__ __forceinline__ RowBatch<SS_R> rows_forward(const SmallParams &p, con
     return st;
 }
 
+// What the forward kernel leaves per row for the backward kernel (1 KB, L2-resident at config.json's sizes): the three
+// pre-activations, the readout input and the GIN layer input.  The backward kernel then reloads 8 coalesced words per lane
+// and row instead of repeating the gather and the three contractions (the recompute was ~1/3 of the backward kernel).
+constexpr int A_Z1 = 0, A_Z2 = 128, A_Z0 = 160, A_XIN = 192, A_H = 224, A_OUT = 240, A_ROW = 256;
+
+template <int SS_R>
+__device__ __forceinline__ void rows_store(const SmallSmem &s, const RowBatch<SS_R> &st, float *__restrict__ act, int row0, int end,
+                                           int r0, int lane) {
+#pragma unroll
+    for (int q = 0; q < SS_R; ++q) {
+        if (row0 + q >= end) continue;
+        float *a = act + static_cast<int64_t>(row0 + q) * A_ROW;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[A_Z1 + lane + 32 * j] = st.z1[q][j];
+        a[A_Z2 + lane] = st.z2[q];
+        a[A_Z0 + lane] = st.z0[q];
+        a[A_XIN + lane] = s.Xin[r0 + q][lane];
+        if (lane < SS_MAX_K0) a[A_H + lane] = s.H[r0 + q][lane];
+        if (lane == 0) a[A_OUT] = st.out[q];
+    }
+}
+
+template <int SS_R, class D>
+__device__ __forceinline__ RowBatch<SS_R> rows_reload(const D &d, SmallSmem &s, const float *__restrict__ act, int row0, int np,
+                                                      int r0, int lane, float aR) {
+    RowBatch<SS_R> st;
+#pragma unroll
+    for (int q = 0; q < SS_R; ++q) {
+        const float *a = act + static_cast<int64_t>(min(row0 + q, np - 1)) * A_ROW;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st.z1[q][j] = __ldg(a + A_Z1 + lane + 32 * j);
+        st.z2[q] = __ldg(a + A_Z2 + lane);
+        st.z0[q] = __ldg(a + A_Z0 + lane);
+        s.Xin[r0 + q][lane] = __ldg(a + A_XIN + lane);
+        if (lane < SS_MAX_K0) s.H[r0 + q][lane] = __ldg(a + A_H + lane);
+        st.out[q] = __ldg(a + A_OUT);
+    }
+#pragma unroll
+    for (int q = 0; q < SS_R; ++q) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s.A1[r0 + q][lane + 32 * j] = (lane + 32 * j) < d.n1() ? prelu(st.z1[q][j], aR) : 0.f;
+        st.a2[q] = lane < d.n2() ? prelu(st.z2[q], aR) : 0.f;
+    }
+    __syncwarp();
+    return st;
+}
+
 // CTA c owns the contiguous rows [c * rows_per_cta, (c + 1) * rows_per_cta): cost is proportional to rows, not to tiles
 __device__ __forceinline__ void cta_rows(const SmallParams &p, int &beg, int &end) {
     const int per = (p.np + gridDim.x - 1) / gridDim.x;
@@ -320,7 +368,7 @@ __device__ __forceinline__ void cta_rows(const SmallParams &p, int &beg, int &en
 
 template <int SS_R, class D>
 __global__ void __launch_bounds__(SS_THREADS, 2)
-small_fwd_loss_kernel(const SmallParams p, float *__restrict__ partial_s, float *__restrict__ out) {
+small_fwd_loss_kernel(const SmallParams p, float *__restrict__ partial_s, float *__restrict__ out, float *__restrict__ act) {
     constexpr int TILE = SS_WARPS * SS_R;
     const D d(p);
     extern __shared__ __align__(16) uint8_t raw[];
@@ -344,6 +392,7 @@ small_fwd_loss_kernel(const SmallParams p, float *__restrict__ partial_s, float 
         pre_cols<SS_R>(p, lane, g1);
         if (row0 >= end) continue;
         const RowBatch<SS_R> st = rows_forward<SS_R, D>(p, d, s, row0, r0, lane, ope, a0, aR, b3, cur);
+        rows_store<SS_R>(s, st, act, row0, end, r0, lane);
 #pragma unroll
         for (int q = 0; q < SS_R; ++q) {
             if (row0 + q < end) {
@@ -365,7 +414,7 @@ small_fwd_loss_kernel(const SmallParams p, float *__restrict__ partial_s, float 
 template <int SS_R, class D>
 __global__ void __launch_bounds__(SS_THREADS, 2)
 small_bwd_kernel(const SmallParams p, const float *__restrict__ partial_s, int num_partial_s, float *__restrict__ sums,
-                 float *__restrict__ loss_out, float *__restrict__ partials) {
+                 float *__restrict__ loss_out, float *__restrict__ partials, const float *__restrict__ act) {
     constexpr int TILE = SS_WARPS * SS_R;
     const D d(p);
     extern __shared__ __align__(16) uint8_t raw[];
@@ -373,7 +422,7 @@ small_bwd_kernel(const SmallParams p, const float *__restrict__ partial_s, int n
     load_weights(p, s);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
-    const float ope = __fadd_rn(1.0f, __ldg(p.eps0)), a0 = __ldg(p.a0), aR = __ldg(p.aR), b3 = __ldg(p.b3);
+    const float a0 = __ldg(p.a0), aR = __ldg(p.aR);
     // S = sum |(out - y) / y| over all rows: every CTA adds the forward kernel's per-CTA partials itself, in the same fixed
     // order (lane l takes partials l, l + 32, ..., then a butterfly), so no launch sits between forward and backward
     // (num_partial_s == 0: data-parallel step — `sums` already holds the GLOBAL (S, N), all-reduced by the caller)
@@ -413,19 +462,11 @@ small_bwd_kernel(const SmallParams p, const float *__restrict__ partial_s, int n
 
     int beg, end;
     cta_rows(p, beg, end);
-    GatherPre<SS_R> g1, g2;
-    pre_bounds<SS_R>(p, beg + warp * SS_R, end, g1);
-    pre_bounds<SS_R>(p, beg + TILE + warp * SS_R, end, g2);
-    pre_cols<SS_R>(p, lane, g1);
     for (int t0 = beg; t0 < end; t0 += TILE) {
         const int rows_here = min(TILE, end - t0);
         const int r0 = warp * SS_R, row0 = t0 + r0;
-        const GatherPre<SS_R> cur = g1;
-        g1 = g2;
-        pre_bounds<SS_R>(p, t0 + 2 * TILE + r0, end, g2);
-        pre_cols<SS_R>(p, lane, g1);
         if (row0 < end) {
-            const RowBatch<SS_R> st = rows_forward<SS_R, D>(p, d, s, row0, r0, lane, ope, a0, aR, b3, cur);
+            const RowBatch<SS_R> st = rows_reload<SS_R, D>(d, s, act, row0, p.np, r0, lane, aR);
             float g[SS_R];
 #pragma unroll
             for (int q = 0; q < SS_R; ++q) {
@@ -528,11 +569,20 @@ small_bwd_kernel(const SmallParams p, const float *__restrict__ partial_s, int n
         // outer products over the staged rows (slots of warps that had no rows hold stale data: bounded by rows_here)
         for (int r = 0; r < rows_here; ++r) {
             const float a = s.A1[r][k2];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) acc2[i] = fmaf(s.Dz2[r][n2base + i], a, acc2[i]);
             const float dv = s.Dz1[r][n1];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) acc1[i] = fmaf(dv, s.Xin[r][k1base + i], acc1[i]);
+            for (int i4 = 0; i4 < 16; i4 += 4) {          // the broadcast operands four at a time (LDS.128)
+                const float4 dz = *reinterpret_cast<const float4 *>(&s.Dz2[r][n2base + i4]);
+                const float4 xi = *reinterpret_cast<const float4 *>(&s.Xin[r][k1base + i4]);
+                acc2[i4 + 0] = fmaf(dz.x, a, acc2[i4 + 0]);
+                acc2[i4 + 1] = fmaf(dz.y, a, acc2[i4 + 1]);
+                acc2[i4 + 2] = fmaf(dz.z, a, acc2[i4 + 2]);
+                acc2[i4 + 3] = fmaf(dz.w, a, acc2[i4 + 3]);
+                acc1[i4 + 0] = fmaf(dv, xi.x, acc1[i4 + 0]);
+                acc1[i4 + 1] = fmaf(dv, xi.y, acc1[i4 + 1]);
+                acc1[i4 + 2] = fmaf(dv, xi.z, acc1[i4 + 2]);
+                acc1[i4 + 3] = fmaf(dv, xi.w, acc1[i4 + 3]);
+            }
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const int idx = t + i * SS_THREADS;
@@ -641,7 +691,7 @@ inline int small_ctas(int64_t np) {      // two CTAs per SM (100 KB of shared me
 using namespace hgin;
 
 extern "C" int64_t hgin_small_step_workspace_bytes(int64_t num_paths) {
-    return align_up(static_cast<int64_t>(small_ctas(num_paths)) * P_TOTAL * 4, 256) + 4096;
+    return align_up(static_cast<int64_t>(small_ctas(num_paths)) * P_TOTAL * 4, 256) + 4096 + num_paths * A_ROW * 4;
 }
 
 static int32_t small_step_impl(int phase, int64_t num_paths, const int32_t *rowptr, const int32_t *col, const float *x_path,
@@ -695,6 +745,8 @@ static int32_t small_step_impl(int phase, int64_t num_paths, const int32_t *rowp
     const int ctas = small_ctas(num_paths);
     float *partials = static_cast<float *>(workspace);
     float *partial_s = partials + static_cast<int64_t>(ctas) * P_TOTAL;
+    float *act = reinterpret_cast<float *>(static_cast<uint8_t *>(workspace) +
+                                           align_up(static_cast<int64_t>(ctas) * P_TOTAL * 4, 256) + 4096);
     // rows a warp carries together: whole rounds of 8 * R rows over each CTA's range, weighted by the (sub-linear) cost of a round
     const int64_t per = ceil_div(num_paths, ctas);
     int best_r = 4;
@@ -707,11 +759,11 @@ static int32_t small_step_impl(int phase, int64_t num_paths, const int32_t *rowp
     // phase 0: the whole step; 1: forward + this rank's (S, N) only; 2: backward with the global (S, N) given in `sums`
 #define HGIN_SMALL(R, D)                                                                                     \
     do {                                                                                                     \
-        if (phase != 2) small_fwd_loss_kernel<R, D><<<ctas, SS_THREADS, sizeof(SmallSmem), s>>>(p, partial_s, out); \
+        if (phase != 2) small_fwd_loss_kernel<R, D><<<ctas, SS_THREADS, sizeof(SmallSmem), s>>>(p, partial_s, out, act); \
         if (phase == 1) small_local_sums_kernel<<<1, 32, 0, s>>>(partial_s, ctas, p.np, sums);               \
         if (phase != 1)                                                                                      \
             small_bwd_kernel<R, D><<<ctas, SS_THREADS, sizeof(SmallSmem), s>>>(p, partial_s, phase == 0 ? ctas : 0, sums, \
-                                                                                loss_out, partials);          \
+                                                                                loss_out, partials, act);     \
     } while (0)
 #define HGIN_SMALL_R(D)                     \
     do {                                    \

@@ -773,12 +773,14 @@ def column_sums(x):
     return bn_stats(x)[:n].float()
 
 
-def small_step(csr, x_path, path_cols, x_link, link_cols, y, params, grads, concat_path, want_out=False, phase=0, sums=None):
+def small_step(csr, x_path, path_cols, x_link, link_cols, y, params, grads, concat_path, want_out=False, phase=0, sums=None,
+               workspace=None):
     """One forward + loss + backward of config.json's model family in three kernels (include/hgin.h: hgin_small_step).
     params / grads: dicts with keys W0 b0 a0 eps0 W1 b1 aR W2 b2 W3 b3 (gradients: same shapes, written in place).
-    Returns (loss_out [mape, sqrt(mape)], sums [S, N], out or None).
+    Returns (loss_out [mape, sqrt(mape)], sums [S, N], out or None, workspace).
     phase 1 / 2 (data parallelism, hgin_small_step_phase): 1 = forward only, `sums` = this rank's (S, N), to be all-reduced;
-    2 = backward with the global `sums` passed back in."""
+    2 = backward with the global `sums` AND the forward call's `workspace` (it holds the per-row pre-activations) passed
+    back in."""
     import ctypes
     for t, name in ((x_path, "x_path"), (x_link, "x_link")):
         if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1):
@@ -805,11 +807,14 @@ def small_step(csr, x_path, path_cols, x_link, link_cols, y, params, grads, conc
     lib = _lib.load()
     np_ = x_path.shape[0]
     ws_bytes = lib.hgin_small_step_workspace_bytes(np_)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     if phase == 2:
         if sums is None or not (sums.is_cuda and sums.dtype == torch.float32 and sums.numel() == 2):
             raise HginError("small_step: phase 2 needs the all-reduced (S, N) in `sums`")
+        if workspace is None or workspace.numel() < ws_bytes:
+            raise HginError("small_step: phase 2 needs the workspace of the phase-1 call")
+        ws = workspace
     else:
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         sums = torch.empty(2, dtype=torch.float32, device=dev)
     loss_out = torch.empty(2, dtype=torch.float32, device=dev)
     out = torch.empty(np_, dtype=torch.float32, device=dev) if want_out else None
@@ -825,7 +830,7 @@ def small_step(csr, x_path, path_cols, x_link, link_cols, y, params, grads, conc
             check(lib.hgin_small_step(*args), "hgin_small_step")
         else:
             check(lib.hgin_small_step_phase(phase, *args), "hgin_small_step_phase")
-    return loss_out, sums, out
+    return loss_out, sums, out, ws
 
 
 def qt_baseline(p_l, avg_bw, capacity, num_paths, num_links, num_iterations=3):

@@ -191,12 +191,12 @@ class TrainStep:
         if self.comm.world > 1:
             # every rank differentiates the same GLOBAL sqrt(100 * S / N): forward, all-reduce (S, N), backward, then SUM of
             # the partial gradients over the flat bucket (parallel.py)
-            _, sums, _ = ops.small_step(*args, phase=1)
+            _, sums, _, ws = ops.small_step(*args, phase=1)
             self.comm.all_reduce_sum_(sums)
-            loss_out, _, _ = ops.small_step(*args, phase=2, sums=sums)
+            loss_out = ops.small_step(*args, phase=2, sums=sums, workspace=ws)[0]
             self.comm.all_reduce_sum_(self.flat_g)
         else:
-            loss_out, _, _ = ops.small_step(*args)
+            loss_out = ops.small_step(*args)[0]
         for p, v in zip(self.live, self.grad_views):
             p.grad = v                 # the gradients ARE the bucket slices: no gather copy
         ops.increment(self.step_count)

@@ -523,7 +523,9 @@ int32_t hgin_gat_bwd(int64_t num_dst, const int32_t *rowptr_dst, const int32_t *
  * Limits: f_path, f_link <= 8; emb <= 32; emb + f_path <= 32; n1 <= 128; n2 <= 32 (HGIN_ERR_UNSUPPORTED otherwise).
  * hgin_small_step_phase: the same step split around the loss statistics, for data parallelism (the loss is
  *   sqrt of a GLOBAL mean).  phase 1: forward, `sums` = this rank's (S, N) — the caller all-reduces it;  phase 2: backward
- *   with `sums` holding the global (S, N), gradients = this rank's partial sums — the caller all-reduces the bucket.
+ *   with `sums` holding the global (S, N) and the SAME workspace as the phase-1 call (it holds the per-row pre-activations
+ *   the forward kernel left for the backward kernel, 1 KB per path), gradients = this rank's partial sums — the caller
+ *   all-reduces the bucket.
  */
 int64_t hgin_small_step_workspace_bytes(int64_t num_paths);
 int32_t hgin_small_step(int64_t num_paths, const int32_t *rowptr, const int32_t *col, const float *x_path,
