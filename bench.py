@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — HeteroGIN train-step throughput on B200 (see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfgC|cfgA|cfgD] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfgC|cfgA|cfgD|qt|gat] [--impl reference]
 
 One "step" = one pass of the hot path over one batch of synthetic datanet-shaped samples:
 CSR build -> L heterogeneous GIN layers -> readout -> sqrt(MAPE) -> backward -> Adam
@@ -212,7 +212,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfgC", choices=sorted(WORKLOADS) + ["cfgD", "qt"])
+    ap.add_argument("--workload", default="cfgC", choices=sorted(WORKLOADS) + ["cfgD", "qt", "gat"])
     ap.add_argument("--math", default=None, choices=["fp32", "tf32", "bf16"],
                     help="dense-layer arithmetic; default tf32 tensor cores for cfgC (BASELINE configs[2] allows "
                          "reduced-precision MLP GEMMs), fp32 for cfgA")
@@ -239,6 +239,9 @@ def main():
     if args.workload == "qt":
         import bench_qt
         return bench_qt.main(args)
+    if args.workload == "gat":
+        import bench_gat
+        return bench_gat.main(args)
     w = WORKLOADS[args.workload]
     if args.math is None:
         args.math = "tf32" if args.workload == "cfgC" else "fp32"
