@@ -330,9 +330,10 @@ class _HetroBase(torch.nn.Module):
     def _slice_inputs(self, x_dict):
         """Feature slicing, rebinding the caller's dict like models.py:333-342."""
         if not self.divided_features:
-            x_dict["path"] = torch.cat([x_dict["path"][:, 0:3], x_dict["path"][:, 6].reshape(-1, 1)], axis=1)
-            x_dict["link"] = torch.cat([x_dict["link"][:, 0:3], x_dict["link"][:, 4:7]], axis=1)
-            if not self.bl_features:
+            if self.bl_features:
+                x_dict["path"] = torch.cat([x_dict["path"][:, 0:3], x_dict["path"][:, 6].reshape(-1, 1)], axis=1)
+                x_dict["link"] = torch.cat([x_dict["link"][:, 0:3], x_dict["link"][:, 4:7]], axis=1)
+            else:   # cat(...)[:, 0:3] of the reference == the first three raw columns: a view (row pitch 7), no copy
                 x_dict["path"] = x_dict["path"][:, 0:3]
                 x_dict["link"] = x_dict["link"][:, 0:3]
         elif not self.bl_features:
