@@ -42,6 +42,9 @@ SIGNATURES = {
                                     _i32, _ptr, _i32, _ptr, _ptr]),
     "hgin_gin_combine_t": (_i32, [_i32, _i64, _ptr, _ptr, _i64, _ptr, _i64, _i32, _ptr, _i64, _i32, _ptr, _i32, _i32, _ptr,
                                   _i64, _i32, _ptr, _i32, _ptr, _ptr, _i64, _i32, _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
+    "hgin_gin_combine_table_t": (_i32, [_i32, _i64, _ptr, _ptr, _i64, _i32, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _ptr, _i64, _i32,
+                                        _ptr, _i32, _i32, _ptr, _i64, _i32, _ptr, _i32, _ptr, _ptr, _i64, _i32, _ptr, _ptr, _ptr,
+                                        _ptr, _i64, _ptr]),
     "hgin_block_gate": (_i32, [_i64, _ptr, _ptr, _i64, _ptr, _ptr, _i32, _ptr, _ptr, _ptr, _ptr]),
     "hgin_gin_combine_blocks_t": (_i32, [_i32, _i64, _ptr, _ptr, _i64, _i64, _ptr, _ptr, _i32, _ptr, _ptr, _ptr, _ptr, _i64, _i32,
                                          _ptr, _i64, _ptr, _i32, _i32, _ptr, _i64, _i32, _ptr, _i32, _ptr, _ptr]),

@@ -171,24 +171,58 @@ struct PostAct {
 // every row address is ONE widening multiply-add (IMAD.WIDE) instead of a 64 x 64-bit product — the
 // short-row launches issue ~60 % of their scheduler slots, and integer address math was most of it.
 // FULL: f_src == LPR * VEC * NC, the feature-range predicates fold away.
-template <typename T, int VEC, int LPR, int NC, bool CONTIG, int MINB, int MODE, bool FULL>
-__global__ void __launch_bounds__(256, MINB)
+// Block-diagonal batches (one block per topology sample): block b owns source rows [in_ptr[b], in_ptr[b+1]) and output rows
+// [out_ptr[b], out_ptr[b+1]).  gate: the counters of block_gate_kernel (gin_scatter_blocks.cuh).  gate_mode selects which
+// schedule the counters must allow for this launch to be SKIPPED (the other kernel of the pair does the work then):
+//   1  input-major streaming (scatter_blocks_kernel): containment, ascending rows, output rows of a block <= gate_cap
+//   2  the TABLE variant of this kernel: containment, source rows of a block <= gate_cap
+struct BlockInfo {
+    int num_blocks;
+    const int64_t *in_ptr;
+    const int64_t *out_ptr;
+    const int32_t *gate;
+    int gate_cap;
+    int gate_mode;
+};
+__device__ __forceinline__ bool gate_allows(const BlockInfo &b) {
+    if (b.gate == nullptr) return false;
+    if (__ldg(b.gate) != 0) return false;
+    if (b.gate_mode == 1) return __ldg(b.gate + 3) == 0 && __ldg(b.gate + 1) <= b.gate_cap;
+    return __ldg(b.gate + 2) <= b.gate_cap;
+}
+
+// TABLE (short rows on block-diagonal batches; the north star's "neighbour rows staged through shared memory"): one
+// 1024-thread CTA per SM takes one block at a time, copies the block's source rows (200 link rows = 100 KB in fp32) into
+// shared memory once — applying the source pre-activation there, once per source row instead of once per gathered
+// element — and every gather of the block's ~2450 output rows is then a shared-memory load: no L1/L2 gather traffic, no
+// col -> gather latency through L2; the kernel is left with the streaming of the self / post / output rows.  Same CSR,
+// same order of additions: bit-identical to the global-gather variant, which runs behind the inverse gate otherwise.
+template <typename T, int VEC, int LPR, int NC, bool CONTIG, int MINB, int MODE, bool FULL, bool TABLE = false>
+__global__ void __launch_bounds__(TABLE ? 1024 : 256, MINB)
 gin_combine_kernel(int num_rows, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                    const T *__restrict__ x_src, int ld_src, int f_src,
                    const T *__restrict__ x_self, int ld_self, int f_self,
                    const float *__restrict__ eps_ptr, int self_mode, int accumulate,
-                   T *__restrict__ out, int ld_out, const PostAct post, const int32_t *__restrict__ gate, int gate_cap) {
+                   T *__restrict__ out, int ld_out, const PostAct post, const BlockInfo blk) {
     using R = Raw<T, VEC>;
-    // inverse gate of scatter_blocks_kernel (gin_scatter_blocks.cuh): when the streaming kernel launched ahead of this
-    // one did the work, return at once
-    if (gate != nullptr && __ldg(gate) == 0 && __ldg(gate + 1) <= gate_cap) return;
+    // exactly one kernel of a (TABLE / streaming, global-gather) pair does the work; the other leaves zero partials
+    if (TABLE ? !gate_allows(blk) : gate_allows(blk)) {
+        if (MODE == 1 && threadIdx.x == 0) {
+            if (post.dalpha_partials) post.dalpha_partials[blockIdx.x] = 0.0f;
+            if (post.ddot_partials) post.ddot_partials[blockIdx.x] = 0.0f;
+        }
+        return;
+    }
+    extern __shared__ __align__(16) uint8_t table_raw[];
+    T *table = reinterpret_cast<T *>(table_raw);
     // gathers in flight per lane before the dependent adds; bounded by the batch (LPR) and by
     // the register budget when a lane carries several chunks
     // (pre-activation sources need a few registers for the on-the-fly act: two gathers fewer in flight)
     // (bf16 lanes carry 8 accumulators and unpack 8 values per gather: fewer in flight at 64 registers)
     constexpr int UNROLL_MAX = (NC >= 4) ? 2 : ((NC == 2) ? 4 : (VEC == 8 ? ((MODE == 0 || MODE == 3) ? 6 : 4)
                                                                           : ((MODE == 2 || MODE == 4) ? 6 : 8)));
-    constexpr int UNROLL = (LPR < UNROLL_MAX) ? LPR : UNROLL_MAX;
+    // (TABLE: gathers are shared-memory loads, two in flight cover their latency — and the 1024-thread CTA has 64 registers)
+    constexpr int UNROLL = TABLE ? ((NC >= 2) ? (MODE == 1 ? 1 : 2) : 4) : ((LPR < UNROLL_MAX) ? LPR : UNROLL_MAX);
     constexpr int ROWS_PER_WARP = 32 / LPR;
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPR;   // lane inside the row group
@@ -217,7 +251,11 @@ gin_combine_kernel(int num_rows, const int32_t *__restrict__ rowptr, const int32
     //   that the tail is spread evenly.
     const int warps_per_cta = blockDim.x >> 5;
     int cta_beg, cta_end, stride;
-    if (CONTIG) {
+    int tbl0 = 0;     // first source row held by the table
+    if (TABLE) {
+        cta_beg = cta_end = 0;
+        stride = warps_per_cta * ROWS_PER_WARP;
+    } else if (CONTIG) {
         const int unit = warps_per_cta * ROWS_PER_WARP;
         const int rows_per_cta = ((num_rows + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) + unit - 1) / unit * unit;
         const int64_t b64 = static_cast<int64_t>(blockIdx.x) * rows_per_cta;
@@ -234,6 +272,28 @@ gin_combine_kernel(int num_rows, const int32_t *__restrict__ rowptr, const int32
     // three memory latencies; with ~3 neighbours per row (link->path) that chain, not bandwidth,
     // bounds the kernel.  So the row bounds are fetched two iterations ahead and the first batch of
     // neighbour indices one iteration ahead, leaving only the gather itself exposed.
+    for (int bi = TABLE ? static_cast<int>(blockIdx.x) : 0; bi < (TABLE ? blk.num_blocks : 1); bi += TABLE ? static_cast<int>(gridDim.x) : 1) {
+    if constexpr (TABLE) {
+        tbl0 = static_cast<int>(__ldg(blk.in_ptr + bi));
+        const int tbl_rows = static_cast<int>(__ldg(blk.in_ptr + bi + 1)) - tbl0;
+        cta_beg = static_cast<int>(__ldg(blk.out_ptr + bi));
+        cta_end = static_cast<int>(__ldg(blk.out_ptr + bi + 1));
+        __syncthreads();                       // the previous block's gathers are done with the table
+        const int ppr = f_src / VEC;           // (TABLE launches are full-width vector launches: f_src % VEC == 0)
+        for (int i = threadIdx.x; i < tbl_rows * ppr; i += blockDim.x) {
+            const int r = i / ppr, c = (i - r * ppr) * VEC;
+            R v = load_raw(at(x_src, tbl0 + r, ld_src) + c, (R *)nullptr);
+            if (PRE_SRC) {                     // act(z) once per source element (the gathers then add plain values)
+                float t[VEC];
+                unpack(v, t);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) t[k] = t[k] > 0.f ? t[k] : src_alpha * t[k];
+                pack(t, v);
+            }
+            store_raw(table + r * f_src + c, v);
+        }
+        __syncthreads();
+    }
     int row0 = cta_beg + static_cast<int>(threadIdx.x >> 5) * ROWS_PER_WARP;
     auto load_bounds = [&](int r0, int32_t &b, int32_t &l) {
         const int r = r0 + grp;
@@ -305,8 +365,12 @@ gin_combine_kernel(int num_rows, const int32_t *__restrict__ rowptr, const int32
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
                         const int f = (c * LPR + sub) * VEC;
-                        if (nb[u] >= 0 && (FULL || f < f_src)) v[u][c] = load_raw(at(x_src, nb[u], ld_src) + f, (R *)nullptr);
-                        else v[u][c] = R{};   // (zero-filled: keeps the unpack below unconditional, no spills)
+                        if (nb[u] >= 0 && (FULL || f < f_src)) {
+                            if constexpr (TABLE) v[u][c] = load_raw_coherent(table + (nb[u] - tbl0) * f_src + f, (R *)nullptr);
+                            else v[u][c] = load_raw(at(x_src, nb[u], ld_src) + f, (R *)nullptr);
+                        } else {
+                            v[u][c] = R{};   // (zero-filled: keeps the unpack below unconditional, no spills)
+                        }
                     }
                 }
 #pragma unroll
@@ -319,7 +383,7 @@ gin_combine_kernel(int num_rows, const int32_t *__restrict__ rowptr, const int32
 #pragma unroll
                             for (int i = 0; i < VEC; ++i) {
                                 float tv = t[i];
-                                if (PRE_SRC) tv = tv > 0.f ? tv : src_alpha * tv;   // x = act(z), on the fly
+                                if (PRE_SRC && !TABLE) tv = tv > 0.f ? tv : src_alpha * tv;   // x = act(z), on the fly
                                 acc[c][i] = __fadd_rn(acc[c][i], tv);
                             }
                         }
@@ -386,6 +450,7 @@ gin_combine_kernel(int num_rows, const int32_t *__restrict__ rowptr, const int32
         beg = nbeg; len = nlen; mine = nmine;
         nbeg = nnbeg; nlen = nnlen;
     }
+    }   // blocks (TABLE) / single pass
     if (POST && (post.dalpha_partials || post.ddot_partials)) {   // fixed association: lanes -> warps -> CTA partial
         __shared__ float red[32];
         if (post.dalpha_partials) {
@@ -408,28 +473,39 @@ __global__ void __launch_bounds__(1024) combine_reduce_scalar_kernel(const float
     if (threadIdx.x == 0) out[0] = s;
 }
 
-constexpr int kMaxCombineCtas = kNumSMs * 32;
+constexpr int kMaxCombineCtas = kNumSMs * 33;      // 32 waves of the gather kernel + one wave of its TABLE twin
+constexpr int kTableSmem = 220 * 1024;              // source rows of one block held in shared memory by the TABLE variant
 
-template <typename T, int VEC, int LPR, int NC, bool CONTIG = false, int MINB = ((NC <= 1) ? 4 : 1)>
+template <typename T, int VEC, int LPR, int NC, bool CONTIG = false, int MINB = ((NC <= 1) ? 4 : 1), bool TABLE = false>
 int launch(int64_t num_rows64, const int32_t *rowptr, const int32_t *col, const T *x_src, int64_t ld_src64,
            int f_src, const T *x_self, int64_t ld_self64, int f_self, const float *eps, int self_mode,
-           int accumulate, T *out, int64_t ld_out64, const PostAct *post, cudaStream_t s, const int32_t *gate = nullptr,
-           int gate_cap = 0) {
+           int accumulate, T *out, int64_t ld_out64, const PostAct *post, cudaStream_t s, const BlockInfo blk = BlockInfo{}) {
     const int num_rows = static_cast<int>(num_rows64), ld_src = static_cast<int>(ld_src64);
     const int ld_self = static_cast<int>(ld_self64), ld_out = static_cast<int>(ld_out64);
-    constexpr int threads = 256;
-    constexpr int rows_per_cta = (threads / 32) * (32 / LPR);
+    constexpr int threads = TABLE ? 1024 : 256;
+    constexpr int rows_per_cta = (256 / 32) * (32 / LPR);
     // Grid-stride over rows with whole waves of CTAs: enough CTAs (32 per SM) that the hardware
     // scheduler evens out the heavy-tailed row lengths of the path->link relation.
-    const int grid = grid_for(num_rows, rows_per_cta, 32);
+    // TABLE: one persistent CTA per SM, blocks dealt round-robin.
+    const int grid = TABLE ? kNumSMs : grid_for(num_rows, rows_per_cta, 32);
+    const size_t smem = TABLE ? static_cast<size_t>(kTableSmem) : 0;
     const PostAct pa = post ? *post : PostAct{};
     const int mode = !post ? 0 : (post->z ? 1 : ((post->src_act != HGIN_ACT_NONE && post->self_act != HGIN_ACT_NONE) ? 4
                                                  : (post->src_act != HGIN_ACT_NONE ? 2 : 3)));
     const bool full = f_src == LPR * VEC * NC;
 #define HGIN_GO(M, F)                                                                                              \
-    gin_combine_kernel<T, VEC, LPR, NC, CONTIG, MINB, M, F><<<grid, threads, 0, s>>>(                               \
-        num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, accumulate, out, ld_out, pa, \
-        gate, gate_cap)
+    do {                                                                                                           \
+        auto kfn = gin_combine_kernel<T, VEC, LPR, NC, CONTIG, TABLE ? 1 : MINB, M, F, TABLE>;                     \
+        if (TABLE) {                                                                                               \
+            static bool attr_set = false;                                                                          \
+            if (!attr_set) {                                                                                       \
+                cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableSmem);                \
+                attr_set = true;                                                                                   \
+            }                                                                                                      \
+        }                                                                                                          \
+        kfn<<<grid, threads, smem, s>>>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps,   \
+                                        self_mode, accumulate, out, ld_out, pa, blk);                               \
+    } while (0)
 #define HGIN_GO_MODE(M)          \
     do {                         \
         if (full) HGIN_GO(M, true); \
@@ -462,7 +538,7 @@ int32_t combine_dispatch_t(int64_t num_rows, const int32_t *rowptr, const int32_
                            const float *post_alpha, float *post_dalpha, float *post_ddot, void *workspace,
                            int64_t workspace_bytes, void *stream, const char *who, int32_t src_act,
                            const float *src_alpha, int32_t self_act, const float *self_alpha,
-                           const int32_t *gate = nullptr, int gate_cap = 0) {
+                           const BlockInfo blk_in = BlockInfo{}, bool table = false) {
     HGIN_CHECK_ARG(num_rows >= 0 && num_rows < INT32_MAX - (1 << 22), "%s: bad num_rows %lld", who, (long long)num_rows);
     HGIN_CHECK_ARG(ld_src < INT32_MAX && ld_self < INT32_MAX && ld_out < INT32_MAX && ld_post < INT32_MAX,
                    "%s: leading dimensions must fit 32 bits", who);
@@ -516,10 +592,25 @@ int32_t combine_dispatch_t(int64_t num_rows, const int32_t *rowptr, const int32_
     int grid = 0;
 #define HGIN_LAUNCH(VV, L, N)                                                                                      \
     grid = launch<T, VV, L, N>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, \
-                               accumulate, out, ld_out, pp, s, gate, gate_cap)
+                               accumulate, out, ld_out, pp, s, table ? BlockInfo{} : blk_in)
 #define HGIN_LAUNCH_CONTIG(VV, L, N)                                                                                        \
-    grid = launch<T, VV, L, N, true, 4>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode, \
-                                        accumulate, out, ld_out, pp, s, gate, gate_cap)
+    do {                                                                                                                    \
+        if (table) {    /* the TABLE twin first (one wave), then the global-gather kernel behind the inverse gate */         \
+            BlockInfo bt = blk_in;                                                                                          \
+            bt.gate_mode = 2;                                                                                               \
+            bt.gate_cap = kTableSmem / (f_src * static_cast<int>(sizeof(T)));                                               \
+            launch<T, VV, L, N, true, 1, true>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps,      \
+                                               self_mode, accumulate, out, ld_out, pp, s, bt);                              \
+            PostAct behind = post;                                                                                          \
+            if (behind.dalpha_partials) behind.dalpha_partials += kNumSMs;                                                  \
+            if (behind.ddot_partials) behind.ddot_partials += kNumSMs;                                                      \
+            grid = kNumSMs + launch<T, VV, L, N, true, 4>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, \
+                                                          eps, self_mode, accumulate, out, ld_out, pp ? &behind : nullptr, s, bt); \
+        } else {                                                                                                            \
+            grid = launch<T, VV, L, N, true, 4>(num_rows, rowptr, col, x_src, ld_src, f_src, x_self, ld_self, f_self, eps,      \
+                                                self_mode, accumulate, out, ld_out, pp, s, blk_in);                          \
+        }                                                                                                                   \
+    } while (0)
     // Lanes per row: a full warp per row suits long rows (path->link, ~36 neighbours); for short
     // rows (link->path, ~3 neighbours) the per-row latency chain rowptr -> col -> gather dominates,
     // so several rows share a warp and each lane carries more 128-bit chunks.
@@ -580,19 +671,20 @@ int32_t combine_dispatch(int64_t num_rows, const int32_t *rowptr, const int32_t 
                          const float *post_alpha, float *post_dalpha, float *post_ddot, void *workspace,
                          int64_t workspace_bytes, void *stream, const char *who, int32_t src_act = HGIN_ACT_NONE,
                          const float *src_alpha = nullptr, int32_t self_act = HGIN_ACT_NONE,
-                         const float *self_alpha = nullptr, int32_t dtype = HGIN_DTYPE_F32) {
+                         const float *self_alpha = nullptr, int32_t dtype = HGIN_DTYPE_F32,
+                         const BlockInfo blk = BlockInfo{}, bool table = false) {
     if (dtype == HGIN_DTYPE_BF16)
         return combine_dispatch_t<bf16>(num_rows, rowptr, col, num_edges, static_cast<const bf16 *>(x_src), ld_src, f_src,
                                         static_cast<const bf16 *>(x_self), ld_self, f_self, eps, self_mode, accumulate,
                                         static_cast<bf16 *>(out), ld_out, static_cast<const bf16 *>(post_z), ld_post,
                                         post_act, post_alpha, post_dalpha, post_ddot, workspace, workspace_bytes, stream,
-                                        who, src_act, src_alpha, self_act, self_alpha);
+                                        who, src_act, src_alpha, self_act, self_alpha, blk, table);
     HGIN_CHECK_ARG(dtype == HGIN_DTYPE_F32, "%s: bad dtype %d", who, dtype);
     return combine_dispatch_t<float>(num_rows, rowptr, col, num_edges, static_cast<const float *>(x_src), ld_src, f_src,
                                      static_cast<const float *>(x_self), ld_self, f_self, eps, self_mode, accumulate,
                                      static_cast<float *>(out), ld_out, static_cast<const float *>(post_z), ld_post,
                                      post_act, post_alpha, post_dalpha, post_ddot, workspace, workspace_bytes, stream, who,
-                                     src_act, src_alpha, self_act, self_alpha);
+                                     src_act, src_alpha, self_act, self_alpha, blk, table);
 }
 
 // Streaming kernel + gated gather kernel for one long-row aggregation on a block-diagonal batch.
@@ -648,7 +740,8 @@ int32_t combine_blocks_t(int64_t num_rows, const int32_t *rowptr, const int32_t 
     // the gather kernel behind it, with the inverse gate
     return combine_dispatch_t<T>(num_rows, rowptr, col, num_edges, x_src, ld_src, f_src, x_self, ld_self, f_src, eps, self_mode,
                                  accumulate, out, ld_out, nullptr, 0, HGIN_ACT_NONE, nullptr, nullptr, nullptr, nullptr, 0, stream,
-                                 who, src_act, src_alpha, self_act, self_alpha, gate, p.cap_rows);
+                                 who, src_act, src_alpha, self_act, self_alpha,
+                                 BlockInfo{num_blocks, in_ptr, out_ptr, gate, p.cap_rows, 1});
 }
 
 }  // namespace
@@ -662,7 +755,7 @@ extern "C" int32_t hgin_block_gate(int64_t rows_a, const int32_t *rowptr_a, cons
     HGIN_CHECK_ARG(num_blocks == 0 || (in_ptr && out_ptr), "hgin_block_gate: null block pointers");
     HGIN_CHECK_ARG((rows_a == 0 || rowptr_a) && (rows_b == 0 || rowptr_b), "hgin_block_gate: null row pointers");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    cudaMemsetAsync(gate, 0, 2 * sizeof(int32_t), s);
+    cudaMemsetAsync(gate, 0, 4 * sizeof(int32_t), s);
     const int64_t work = rows_a > rows_b ? rows_a : rows_b;
     scatter::block_gate_kernel<<<grid_for(work > 0 ? work : 1, 256, 8), 256, 0, s>>>(rows_a, rowptr_a, col_a, rows_b, rowptr_b, col_b,
                                                                                     num_blocks, in_ptr, out_ptr, gate);
@@ -688,6 +781,23 @@ extern "C" int32_t hgin_gin_combine_blocks_t(int32_t dtype, int64_t num_rows, co
                                    static_cast<const float *>(x_src), ld_src, f_src, static_cast<const float *>(x_self), ld_self,
                                    eps, self_mode, accumulate, static_cast<float *>(out), ld_out, src_act, src_alpha, self_act,
                                    self_alpha, stream);
+}
+
+extern "C" int32_t hgin_gin_combine_table_t(int32_t dtype, int64_t num_rows, const int32_t *rowptr, const int32_t *col,
+                                            int64_t num_edges, int32_t num_blocks, const int64_t *in_ptr,
+                                            const int64_t *out_ptr, const int32_t *gate, const void *x_src, int64_t ld_src,
+                                            int32_t f_src, const void *x_self, int64_t ld_self, int32_t f_self,
+                                            const float *eps, int32_t self_mode, int32_t accumulate, void *out, int64_t ld_out,
+                                            int32_t src_act, const float *src_alpha, int32_t self_act, const float *self_alpha,
+                                            const void *post_z, int64_t ld_post, int32_t post_act, const float *post_alpha,
+                                            float *post_dalpha, float *post_ddot, void *workspace, int64_t workspace_bytes,
+                                            void *stream) {
+    using namespace hgin;
+    HGIN_CHECK_ARG(num_blocks > 0 && in_ptr && out_ptr && gate && rowptr && col, "hgin_gin_combine_table_t: null pointer");
+    return combine_dispatch(num_rows, rowptr, col, num_edges, x_src, ld_src, f_src, x_self, ld_self, f_self, eps, self_mode,
+                            accumulate, out, ld_out, post_z, ld_post, post_act, post_alpha, post_dalpha, post_ddot, workspace,
+                            workspace_bytes, stream, "hgin_gin_combine_table_t", src_act, src_alpha, self_act, self_alpha, dtype,
+                            BlockInfo{num_blocks, in_ptr, out_ptr, gate, 0, 2}, true);
 }
 
 extern "C" int32_t hgin_gin_combine(int64_t num_rows, const int32_t *rowptr, const int32_t *col, int64_t num_edges,

@@ -49,7 +49,7 @@ struct SbParams {
     const int64_t *out_ptr;   // [num_blocks + 1] first OUTPUT row of every block
     const int32_t *rowptr;    // CSR_B: rows = input rows, cols = output rows
     const int32_t *col;
-    const int32_t *gate;      // [2]: violations, max output rows per block
+    const int32_t *gate;      // [4]: see block_gate_kernel
     int cap_rows;
     const void *x_in;         // [N_in, f] contiguous rows
     int f;
@@ -119,7 +119,7 @@ template <typename T>
 __global__ void __launch_bounds__(SB_THREADS, 1) scatter_blocks_kernel(const SbParams p) {
     // gate: streaming is only bit-identical to the gather kernel when CSR_A's rows are ascending, and only possible
     // when every block's output rows fit the accumulator tile
-    if (__ldg(p.gate) != 0 || __ldg(p.gate + 1) > p.cap_rows) return;
+    if (__ldg(p.gate) != 0 || __ldg(p.gate + 3) != 0 || __ldg(p.gate + 1) > p.cap_rows) return;
 
     extern __shared__ __align__(128) uint8_t smem[];
     float *acc = reinterpret_cast<float *>(smem);
@@ -253,21 +253,22 @@ __global__ void __launch_bounds__(SB_THREADS, 1) scatter_blocks_kernel(const SbP
     }
 }
 
-// gate[0] += number of violations: rows of CSR_A (rows = outputs) whose neighbour list is not non-decreasing, and edges
-// of CSR_B (rows = inputs) that leave their block;  gate[1] = max output rows of a block.  (gate is zeroed by the caller.)
+// gate[0] += edges of CSR_B (rows = inputs) that leave their block, block tables that do not cover the rows;
+// gate[1] = max output rows of a block;  gate[2] = max input rows of a block;
+// gate[3] += rows of CSR_A (rows = outputs) whose neighbour list is not non-decreasing.  (gate is zeroed by the caller.)
 __global__ void block_gate_kernel(int64_t rows_a, const int32_t *__restrict__ rowptr_a, const int32_t *__restrict__ col_a,
                                   int64_t rows_b, const int32_t *__restrict__ rowptr_b, const int32_t *__restrict__ col_b,
                                   int num_blocks, const int64_t *__restrict__ in_ptr, const int64_t *__restrict__ out_ptr,
                                   int32_t *gate) {
     const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    int bad = 0;
+    int bad = 0, unsorted = 0;
     for (int64_t r = tid; r < rows_a; r += stride) {
         const int b = __ldg(rowptr_a + r), e = __ldg(rowptr_a + r + 1);
         int prev = -1;
         for (int i = b; i < e; ++i) {
             const int c = __ldg(col_a + i);
-            bad += c < prev;
+            unsorted += c < prev;
             prev = c;
         }
     }
@@ -287,12 +288,15 @@ __global__ void block_gate_kernel(int64_t rows_a, const int32_t *__restrict__ ro
             bad += (c < o0 || c >= o1);
         }
     }
-    for (int64_t i = tid; i < num_blocks; i += stride)
+    for (int64_t i = tid; i < num_blocks; i += stride) {
         atomicMax(gate + 1, static_cast<int>(__ldg(out_ptr + i + 1) - __ldg(out_ptr + i)));
+        atomicMax(gate + 2, static_cast<int>(__ldg(in_ptr + i + 1) - __ldg(in_ptr + i)));
+    }
     if (tid == 0 && (num_blocks == 0 || __ldg(in_ptr + num_blocks) != rows_b || __ldg(out_ptr + num_blocks) != rows_a ||
                      __ldg(in_ptr) != 0 || __ldg(out_ptr) != 0))
         bad += 1;
     if (bad) atomicAdd(gate, bad);     // integer counters: order-free
+    if (unsorted) atomicAdd(gate + 3, unsorted);
 }
 
 inline int stage_bytes_for(int f, int elem) { return SB_STAGE_ROWS * f * elem; }

@@ -73,19 +73,24 @@ class GraphCSR:
 
     def stream_plan(self, et, side):
         """ops.StreamPlan for the aggregation that writes rows of et's destination type (side 'fwd': the forward K1 pass)
-        or of its source type (side 'bwd': the transposed K4 gather) — or None when the batch has no block tables or the
-        rows are short (the gather kernel is the right schedule for ~3 neighbours per row).  The gate is computed once."""
+        or of its source type (side 'bwd': the transposed K4 gather) — or None when the batch has no block tables.  Short
+        rows (~3 neighbours: link->path) take the shared-memory table variant, long rows the (opt-in) streaming kernel;
+        ops.gin_combine picks by row length.  The gate is computed once per batch and relation side."""
         key = (tuple(et), side)
-        if not ops.STREAM_LONG_ROWS and key not in self._plans:
-            return None
+        if not (ops.STREAM_LONG_ROWS or ops.TABLE_SHORT_ROWS):
+            return None                  # both block-diagonal schedules are opt-in (measured: DESIGN.md "Long rows" / "Short rows")
         if key not in self._plans:
             plan = None
             t_out, t_in = (et[2], et[0]) if side == "fwd" else (et[0], et[2])
             p_in, p_out = self.blocks.get(t_in), self.blocks.get(t_out)
             if (p_in is not None and p_out is not None and p_in.is_cuda and p_in.dtype == torch.int64
                     and p_in.numel() == p_out.numel() and p_in.numel() >= 2):
+                other = self._by_src if side == "fwd" else self._by_dst
+                if et not in other and not torch.is_grad_enabled():
+                    return None          # inference: not worth building the second orientation for the gate
                 csr_out, csr_in = (self.fwd(et), self.bwd(et)) if side == "fwd" else (self.bwd(et), self.fwd(et))
-                if csr_out.num_rows > 0 and csr_out.num_edges > 8 * csr_out.num_rows:
+                long_rows = csr_out.num_edges > 8 * csr_out.num_rows
+                if csr_out.num_rows > 0 and (ops.STREAM_LONG_ROWS if long_rows else ops.TABLE_SHORT_ROWS):
                     plan = ops.StreamPlan(csr_in, p_in.contiguous(), p_out.contiguous(),
                                           ops.block_gate(csr_out, csr_in, p_in.contiguous(), p_out.contiguous()))
             self._plans[key] = plan
@@ -317,7 +322,7 @@ class HeteroConvFn(torch.autograd.Function):
                 csr_t = graph.bwd(specs[gi].et) if gi is not None else None
                 src_rows = dh_agg_of[gi] if gi is not None else s_dh
                 want_ddot = last and si is not None and eps_from_pass.get(si) == t
-                plan_t = graph.stream_plan(specs[gi].et, "bwd") if (gi is not None and not (last and post is not None)) else None
+                plan_t = graph.stream_plan(specs[gi].et, "bwd") if gi is not None else None
                 res = ops.gin_combine(csr_t, src_rows, s_dh, s_eps, SELF_ADD if si is not None else SELF_NONE, out=dx,
                                       accumulate=dx is not None, post=post if last else None, want_ddot=want_ddot,
                                       block_plan=plan_t)

@@ -172,14 +172,14 @@ class StreamPlan:
 
 
 def block_gate(csr_out, csr_in, in_ptr, out_ptr):
-    """int32 [2] on the device: violations (0 = the streaming schedule is bit-identical to the gather), max output rows of a
-    block (include/hgin.h: hgin_block_gate)."""
+    """int32 [4] on the device: containment violations, max output rows of a block, max input rows of a block, output rows
+    with a non-ascending neighbour list (include/hgin.h: hgin_block_gate)."""
     for t in (in_ptr, out_ptr):
         if not (t.is_cuda and t.dtype == torch.int64 and t.is_contiguous() and t.dim() == 1):
             raise HginError("block_gate: block tables must be contiguous CUDA int64 vectors")
     if in_ptr.numel() != out_ptr.numel() or in_ptr.numel() < 2:
         raise HginError("block_gate: block tables of the two node types differ in length")
-    gate = torch.empty(2, dtype=torch.int32, device=in_ptr.device)
+    gate = torch.empty(4, dtype=torch.int32, device=in_ptr.device)
     with _region("csr_build", kernels=1, bytes=8 * csr_out.num_edges):
         check(_lib.load().hgin_block_gate(csr_out.num_rows, _ptr(csr_out.rowptr), _ptr(csr_out.col), csr_in.num_rows,
                                           _ptr(csr_in.rowptr), _ptr(csr_in.col), in_ptr.numel() - 1, in_ptr.data_ptr(),
@@ -193,6 +193,14 @@ def block_gate(csr_out, csr_in, in_ptr, out_ptr):
 # shared-memory bandwidth, a 310 us floor before any latency) where the gather kernel keeps its accumulators in
 # registers and is bound by L2->SM bandwidth (336 us): 1.5 ms against 0.34-0.44 ms per launch at Cfg-C.
 STREAM_LONG_ROWS = False
+
+# Opt-in (measured at parity, DESIGN.md "Short rows"): short-row aggregations of block-diagonal batches through the
+# shared-memory table variant (hgin_gin_combine_table_t) — the source rows of one topology sample staged in shared memory
+# once, every gather a shared-memory load.  Bit-identical rows; at Cfg-C 6.05 ms of aggregation per tf32 step against
+# 5.92 ms and 4.89 against 4.90 ms in bf16: the contiguous row ranges of the default kernel already keep a sample's 100 KB of
+# link rows in L1, and both variants are bound by the self / post / output rows they stream, so the default stays the
+# kernel without the extra gate and skipped-twin launches.
+TABLE_SHORT_ROWS = False
 
 
 def gin_combine(csr, x_src, x_self=None, eps=None, self_mode=SELF_NONE, out=None, accumulate=False, post=None,
@@ -266,6 +274,22 @@ def gin_combine(csr, x_src, x_self=None, eps=None, self_mode=SELF_NONE, out=None
                                                 1 if accumulate else 0, po, ldo, sa, _scalar(sal, "gin_combine.src_alpha"), fa,
                                                 _scalar(fal, "gin_combine.self_alpha"), _stream()), "hgin_gin_combine_blocks_t")
         return out
+    if (block_plan is not None and TABLE_SHORT_ROWS and csr.rowptr is not None and csr.col is not None and csr.num_rows > 0
+            and csr.num_edges <= 8 * csr.num_rows and f_src * es in (256, 512) and self_mode != SELF_CONCAT):
+        with _region("gin_combine", kernels=kernels + 1, alg_bytes=alg, compulsory_bytes=comp):
+            check(lib.hgin_gin_combine_table_t(_DTYPES[dt], csr.num_rows, _ptr(csr.rowptr), _ptr(csr.col), csr.num_edges,
+                                               block_plan.num_blocks, block_plan.in_ptr.data_ptr(),
+                                               block_plan.out_ptr.data_ptr(), block_plan.gate.data_ptr(), ps, lds,
+                                               f_src, pf, ldf, f_self, _scalar(eps, "gin_combine.eps"), self_mode,
+                                               1 if accumulate else 0, po, ldo, sa, _scalar(sal, "gin_combine.src_alpha"), fa,
+                                               _scalar(fal, "gin_combine.self_alpha"), pz, ldz,
+                                               post.act if post_on else ACT_NONE,
+                                               _scalar(post.alpha, "gin_combine.post.alpha") if post_on else 0,
+                                               _ptr(post.dalpha) if post_on else 0, _ptr(ddot), _ptr(ws), ws_bytes, _stream()),
+                  "hgin_gin_combine_table_t")
+        if post_on:
+            post.applied = True
+        return (out, ddot) if want_ddot else out
     with _region("gin_combine", kernels=kernels, alg_bytes=alg, compulsory_bytes=comp):
         check(lib.hgin_gin_combine_t(_DTYPES[dt], csr.num_rows, _ptr(csr.rowptr), _ptr(csr.col), csr.num_edges, ps, lds,
                                      f_src, pf, ldf, f_self, _scalar(eps, "gin_combine.eps"), self_mode,

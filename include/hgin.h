@@ -123,11 +123,11 @@ int32_t hgin_gin_combine(int64_t num_rows, const int32_t *rowptr, const int32_t 
  * (PyG's `ptr` vectors of the two node types) — so one CTA per block keeps the block's output rows as fp32 accumulators
  * in shared memory and streams the block's input rows ONCE, in order, through a ring of bulk copies: every input row
  * crosses HBM exactly once instead of ~2.9 times through L2 (path->link rows have ~36 neighbours).
- *   hgin_block_gate: once per batch and relation.  gate[0] = number of violations (a row of the output-major CSR_A whose
- *     neighbours are not in non-decreasing order — then ascending-input order would differ from the stable edge order of the
- *     reference's scatter_add_ —, an edge of the input-major CSR_B that leaves its block, block tables that do not cover the
- *     rows); gate[1] = largest number of output rows of a block.
- *   hgin_gin_combine_blocks_t: launches the streaming kernel, which runs only if gate[0] == 0 and gate[1] fits its
+ *   hgin_block_gate: once per batch and relation, gate is int32[4].  gate[0] = containment violations (an edge of the
+ *     input-major CSR_B that leaves its block, block tables that do not cover the rows); gate[1] / gate[2] = largest number
+ *     of output / input rows of a block; gate[3] = rows of the output-major CSR_A whose neighbours are not in non-decreasing
+ *     order (then ascending-input order would differ from the stable edge order of the reference's scatter_add_).
+ *   hgin_gin_combine_blocks_t: launches the streaming kernel, which runs only if gate[0] == gate[3] == 0 and gate[1] fits its
  *     accumulator tile, and behind it the gather kernel of hgin_gin_combine_t with the inverse gate: a static, capturable
  *     launch sequence with exactly one of the two doing the work.  (rowptr, col) = CSR_A, rows = outputs, as for
  *     hgin_gin_combine_t; (rowptr_in, col_in) = CSR_B, rows = inputs.  Input rows must be contiguous (ld_src == f_src),
@@ -199,6 +199,26 @@ int32_t hgin_gin_combine_t(int32_t dtype, int64_t num_rows, const int32_t *rowpt
                            const float *self_alpha, const void *post_z, int64_t ld_post,
                            int32_t post_act, const float *post_alpha, float *post_dalpha,
                            float *post_ddot, void *workspace, int64_t workspace_bytes, void *stream);
+
+/* hgin_gin_combine_table_t: hgin_gin_combine_t for SHORT rows on a block-diagonal batch (the link->path aggregation of
+ * models.py:211-217 and the backward of path->link: ~3 neighbours per row, all inside the row's own topology sample).
+ * One 1024-thread CTA per SM takes a block at a time, stages the block's source rows (200 link rows = 100 KB fp32) in
+ * shared memory once — applying src_act there, once per source element — and every gather is a shared-memory load.
+ * Same CSR, same left-to-right additions: rows are bit-identical to hgin_gin_combine_t (post_dalpha / post_ddot are sums
+ * over a different CTA partition: equal to fp32 rounding).  The kernel runs only if gate (hgin_block_gate) reports
+ * containment (gate[0] == 0) and the source rows of every block fit (gate[2] * f_src * elem <= 220 KB); the kernel of
+ * hgin_gin_combine_t follows behind the inverse gate, so the launch sequence is static and capturable.  Shapes without a
+ * staged variant (rows that are not short, widths other than 64 / 128, unaligned rows) run hgin_gin_combine_t's kernel only.
+ */
+int32_t hgin_gin_combine_table_t(int32_t dtype, int64_t num_rows, const int32_t *rowptr, const int32_t *col,
+                                 int64_t num_edges, int32_t num_blocks, const int64_t *in_ptr,
+                                 const int64_t *out_ptr, const int32_t *gate, const void *x_src, int64_t ld_src,
+                                 int32_t f_src, const void *x_self, int64_t ld_self, int32_t f_self,
+                                 const float *eps, int32_t self_mode, int32_t accumulate, void *out,
+                                 int64_t ld_out, int32_t src_act, const float *src_alpha, int32_t self_act,
+                                 const float *self_alpha, const void *post_z, int64_t ld_post,
+                                 int32_t post_act, const float *post_alpha, float *post_dalpha,
+                                 float *post_ddot, void *workspace, int64_t workspace_bytes, void *stream);
 
 /* ---- K2: dense layer forward  z = [x1 | x2] W^T + b,  out (+)= act(z) ------------------------
  * Replaces: GINLayer.mlp = Linear + PReLU (models.py:236-239, applied at models.py:217), the

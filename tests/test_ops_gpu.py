@@ -625,7 +625,8 @@ def test_streaming_long_row_aggregation_is_bit_identical_to_the_gather(case, f, 
     plan = graph.stream_plan(et, "fwd")
     assert plan is not None
     gate = plan.gate.cpu()
-    assert (int(gate[0]) == 0) == (case != "unsorted") and int(gate[1]) == max(sizes_out)
+    assert int(gate[0]) == 0 and (int(gate[3]) == 0) == (case != "unsorted")
+    assert int(gate[1]) == max(sizes_out) and int(gate[2]) == max(sizes_in)
     torch.manual_seed(1)
     x = torch.randn(n_in, f, device="cuda").to(dtype)
     xs = torch.randn(n_out, f, device="cuda").to(dtype)
@@ -653,6 +654,73 @@ def test_streaming_long_row_aggregation_is_bit_identical_to_the_gather(case, f, 
         assert torch.equal(ops.gin_combine(graph.bwd(et), g, block_plan=plan_t), ops.gin_combine(graph.bwd(et), g))
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("f", [128, 64])
+@pytest.mark.parametrize("case", ["plain", "self_add", "accumulate", "pre_act", "post", "post_relu", "oversize_block", "leaky_block",
+                                  "ragged", "many_blocks"])
+def test_short_row_table_aggregation_is_bit_identical_to_the_gather(case, f, dtype, monkeypatch):
+    """hgin_gin_combine_table_t (source rows of a block staged in shared memory, one CTA per SM) against hgin_gin_combine_t on
+    the same inputs: torch.equal on the rows in every mode, including the gated fall-backs (a block whose source rows do not
+    fit the table; an edge that leaves its block); the PReLU-slope and eps sums to fp32 rounding."""
+    from gnn_link_prediction_b200.functional import GraphCSR
+    monkeypatch.setattr(ops, "TABLE_SHORT_ROWS", True)      # opt-in schedule (the global-gather kernel is the default)
+    if case == "oversize_block":
+        sizes_in, sizes_out = [20, 3000, 30], [300, 4000, 500]
+    elif case == "ragged":
+        sizes_in, sizes_out = [3, 4, 1, 40, 0, 2, 130], [1, 0, 77, 33, 0, 5, 1000]
+    elif case == "many_blocks":
+        sizes_in, sizes_out = [200] * 400, [611] * 400
+    else:
+        sizes_in, sizes_out = [60, 50, 80, 7, 33], [700, 650, 900, 31, 64]
+    # relation a -> b where every a row has ~3 b-neighbours of its own block: the transposed gather (rows = a) is the short side
+    ei, ptr_a, ptr_b = _block_diagonal_relation(sizes_out, sizes_in, 3, 11)
+    if case == "leaky_block":
+        ei[1, 5] = int(ptr_b[-1]) - 1
+    n_a, n_b = int(ptr_a[-1]), int(ptr_b[-1])
+    et = ("a", "to", "b")
+    graph = GraphCSR({et: ei.cuda()}, {"a": n_a, "b": n_b}, blocks={"a": ptr_a.cuda(), "b": ptr_b.cuda()})
+    plan = graph.stream_plan(et, "bwd")          # outputs = a rows (short), inputs = b rows
+    assert plan is not None
+    gate = plan.gate.cpu()
+    assert (int(gate[0]) == 0) == (case != "leaky_block") and int(gate[2]) == max(sizes_in)
+    csr = graph.bwd(et)
+    assert csr.num_edges <= 8 * csr.num_rows
+    torch.manual_seed(2)
+    x = torch.randn(n_b, f, device="cuda").to(dtype)
+    xs = torch.randn(n_a, f, device="cuda").to(dtype)
+    z = torch.randn(n_a, f, device="cuda").to(dtype)
+    eps = torch.tensor([0.3], device="cuda")
+    alpha = torch.tensor([0.25], device="cuda")
+    kw = {}
+    if case in ("self_add", "accumulate", "pre_act", "ragged", "post", "post_relu", "many_blocks"):
+        kw.update(x_self=xs, eps=eps, self_mode=ops.SELF_ADD)
+    if case in ("pre_act", "many_blocks"):
+        kw.update(src_act=(ops.ACT_PRELU, alpha), self_act=(ops.ACT_RELU, None))
+
+    def run(p):
+        out = None
+        if case == "accumulate":
+            out = torch.full((n_a, f), 0.5, device="cuda").to(dtype)
+        post = None
+        if case == "post":
+            post = ops.PostAct(z, ops.ACT_PRELU, alpha)
+        if case == "post_relu":
+            post = ops.PostAct(z, ops.ACT_RELU, None)
+        res = ops.gin_combine(csr, x, out=out, accumulate=out is not None, block_plan=p, post=post,
+                              want_ddot=post is not None, **kw)
+        if post is not None:
+            return res[0], res[1], post.dalpha
+        return res, None, None
+
+    want, ddot_w, dal_w = run(None)
+    got, ddot_g, dal_g = run(plan)
+    assert torch.equal(got, want)
+    if ddot_w is not None:
+        torch.testing.assert_close(ddot_g, ddot_w, rtol=1e-4, atol=1e-2)
+    if dal_w is not None:
+        torch.testing.assert_close(dal_g, dal_w, rtol=1e-4, atol=1e-2)
+
+
 def test_streaming_plan_only_for_long_rows_and_block_tables(monkeypatch):
     from gnn_link_prediction_b200.functional import GraphCSR
     et = ("a", "to", "b")
@@ -667,6 +735,9 @@ def test_streaming_plan_only_for_long_rows_and_block_tables(monkeypatch):
     with_blocks = GraphCSR({et: ei.cuda()}, {"a": 500, "b": 50}, blocks={"a": ptr_in.cuda(), "b": ptr_out.cuda()})
     assert with_blocks.stream_plan(et, "fwd") is not None        # ~30 inputs per output row
     assert with_blocks.stream_plan(et, "bwd") is None            # ~3 outputs per input row: the gather kernel's case
+    monkeypatch.setattr(ops, "TABLE_SHORT_ROWS", True)
+    again = GraphCSR({et: ei.cuda()}, {"a": 500, "b": 50}, blocks={"a": ptr_in.cuda(), "b": ptr_out.cuda()})
+    assert again.stream_plan(et, "bwd") is not None              # ... unless the shared-memory table variant is opted in
     # an edge that leaves its block closes the gate (the gather kernel then does the work)
     bad = ei.clone()
     bad[1, 0] = 45
