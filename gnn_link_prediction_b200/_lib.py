@@ -45,6 +45,8 @@ SIGNATURES = {
     "hgin_gin_combine_table_t": (_i32, [_i32, _i64, _ptr, _ptr, _i64, _i32, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _ptr, _i64, _i32,
                                         _ptr, _i32, _i32, _ptr, _i64, _i32, _ptr, _i32, _ptr, _ptr, _i64, _i32, _ptr, _ptr, _ptr,
                                         _ptr, _i64, _ptr]),
+    "hgin_gin_combine_staged_t": (_i32, [_i32, _i64, _ptr, _ptr, _i64, _i32, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _ptr, _i64, _ptr,
+                                         _i32, _i32, _ptr, _i64, _i32, _ptr, _i32, _ptr, _ptr]),
     "hgin_block_gate": (_i32, [_i64, _ptr, _ptr, _i64, _ptr, _ptr, _i32, _ptr, _ptr, _ptr, _ptr]),
     "hgin_gin_combine_blocks_t": (_i32, [_i32, _i64, _ptr, _ptr, _i64, _i64, _ptr, _ptr, _i32, _ptr, _ptr, _ptr, _ptr, _i64, _i32,
                                          _ptr, _i64, _ptr, _i32, _i32, _ptr, _i64, _i32, _ptr, _i32, _ptr, _ptr]),

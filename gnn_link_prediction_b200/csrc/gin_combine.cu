@@ -16,7 +16,10 @@
 #include <cuda_bf16.h>
 
 #include "hgin_common.cuh"
+#include <cstdlib>
+
 #include "gin_scatter_blocks.cuh"
+#include "gin_stage_blocks.cuh"
 
 namespace hgin {
 namespace {
@@ -744,8 +747,85 @@ int32_t combine_blocks_t(int64_t num_rows, const int32_t *rowptr, const int32_t 
                                  BlockInfo{num_blocks, in_ptr, out_ptr, gate, p.cap_rows, 1});
 }
 
+// Staged-source kernel + gated gather kernel for one long-row aggregation on a block-diagonal batch.
+template <typename T>
+int32_t combine_staged_t(int64_t num_rows, const int32_t *rowptr, const int32_t *col, int64_t num_edges, int32_t num_blocks,
+                         const int64_t *in_ptr, const int64_t *out_ptr, const int32_t *gate, const T *x_src, int64_t ld_src,
+                         int32_t f_src, const T *x_self, int64_t ld_self, const float *eps, int32_t self_mode, int32_t accumulate,
+                         T *out, int64_t ld_out, int32_t src_act, const float *src_alpha, int32_t self_act,
+                         const float *self_alpha, void *stream) {
+    const char *who = "hgin_gin_combine_staged_t";
+    constexpr int elem = static_cast<int>(sizeof(T));
+    HGIN_CHECK_ARG(num_blocks > 0 && in_ptr && out_ptr && gate && rowptr && col, "%s: null pointer", who);
+    if (!(f_src % (16 / elem) == 0 && f_src >= 16 && f_src <= 128 && ld_src == f_src && ld_out % 4 == 0 && ld_out >= f_src &&
+          (self_mode == HGIN_SELF_NONE || (self_mode == HGIN_SELF_ADD && ld_self % 4 == 0 && ld_self >= f_src)) &&
+          aligned16(x_src) && aligned16(out) && aligned16(x_self) && num_rows < INT32_MAX && num_edges > 0 && num_edges < INT32_MAX))
+        return fail(HGIN_ERR_UNSUPPORTED, "%s: needs contiguous input rows of 16..128 features (16-byte multiples), SELF_NONE / "
+                    "SELF_ADD, 16-byte aligned rows, at least one edge", who);
+    HGIN_CHECK_ARG(src_act >= HGIN_ACT_NONE && src_act <= HGIN_ACT_RELU && self_act >= HGIN_ACT_NONE && self_act <= HGIN_ACT_RELU &&
+                   (src_act != HGIN_ACT_PRELU || src_alpha) && (self_act != HGIN_ACT_PRELU || self_alpha), "%s: input activation", who);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    staged::SgParams p{};
+    p.num_blocks = num_blocks;
+    p.in_ptr = in_ptr;
+    p.out_ptr = out_ptr;
+    p.rowptr = rowptr;
+    p.col = col;
+    p.num_edges = static_cast<int>(num_edges);
+    p.gate = gate;
+    p.x_in = x_src;
+    p.f = f_src;
+    p.x_self = x_self;
+    p.ld_self = static_cast<int>(ld_self);
+    p.eps = eps;
+    p.self_mode = self_mode;
+    p.accumulate = accumulate;
+    p.out = out;
+    p.ld_out = static_cast<int>(ld_out);
+    p.in_act = src_act;
+    p.in_alpha = src_alpha;
+    p.self_act = self_act;
+    p.self_alpha = self_alpha;
+    const char *dbg = getenv("HGIN_SG_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[elem == 2]) {
+        cudaFuncSetAttribute(staged::stage_blocks_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, staged::SG_SMEM);
+        cudaFuncSetAttribute(staged::stage_blocks_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, staged::SG_SMEM);
+        attr_set[elem == 2] = true;
+    }
+    const int grid = num_blocks < kNumSMs ? num_blocks : kNumSMs;
+    if (src_act != HGIN_ACT_NONE) staged::stage_blocks_kernel<T, true><<<grid, staged::SG_THREADS, staged::SG_SMEM, s>>>(p);
+    else staged::stage_blocks_kernel<T, false><<<grid, staged::SG_THREADS, staged::SG_SMEM, s>>>(p);
+    HGIN_CHECK_LAUNCH(who);
+    // the gather kernel behind it, with the inverse gate
+    return combine_dispatch_t<T>(num_rows, rowptr, col, num_edges, x_src, ld_src, f_src, x_self, ld_self, f_src, eps, self_mode,
+                                 accumulate, out, ld_out, nullptr, 0, HGIN_ACT_NONE, nullptr, nullptr, nullptr, nullptr, 0, stream,
+                                 who, src_act, src_alpha, self_act, self_alpha,
+                                 BlockInfo{num_blocks, in_ptr, out_ptr, gate, staged::SG_CAP_ROWS, 1});
+}
+
 }  // namespace
 }  // namespace hgin
+
+extern "C" int32_t hgin_gin_combine_staged_t(int32_t dtype, int64_t num_rows, const int32_t *rowptr, const int32_t *col,
+                                             int64_t num_edges, int32_t num_blocks, const int64_t *in_ptr, const int64_t *out_ptr,
+                                             const int32_t *gate, const void *x_src, int64_t ld_src, int32_t f_src,
+                                             const void *x_self, int64_t ld_self, const float *eps, int32_t self_mode,
+                                             int32_t accumulate, void *out, int64_t ld_out, int32_t src_act, const float *src_alpha,
+                                             int32_t self_act, const float *self_alpha, void *stream) {
+    using namespace hgin;
+    if (dtype == HGIN_DTYPE_BF16)
+        return combine_staged_t<bf16>(num_rows, rowptr, col, num_edges, num_blocks, in_ptr, out_ptr, gate,
+                                      static_cast<const bf16 *>(x_src), ld_src, f_src, static_cast<const bf16 *>(x_self), ld_self,
+                                      eps, self_mode, accumulate, static_cast<bf16 *>(out), ld_out, src_act, src_alpha, self_act,
+                                      self_alpha, stream);
+    HGIN_CHECK_ARG(dtype == HGIN_DTYPE_F32, "hgin_gin_combine_staged_t: bad dtype %d", dtype);
+    return combine_staged_t<float>(num_rows, rowptr, col, num_edges, num_blocks, in_ptr, out_ptr, gate,
+                                   static_cast<const float *>(x_src), ld_src, f_src, static_cast<const float *>(x_self), ld_self,
+                                   eps, self_mode, accumulate, static_cast<float *>(out), ld_out, src_act, src_alpha, self_act,
+                                   self_alpha, stream);
+}
 
 extern "C" int32_t hgin_block_gate(int64_t rows_a, const int32_t *rowptr_a, const int32_t *col_a, int64_t rows_b,
                                    const int32_t *rowptr_b, const int32_t *col_b, int32_t num_blocks, const int64_t *in_ptr,

@@ -77,7 +77,7 @@ class GraphCSR:
         rows (~3 neighbours: link->path) take the shared-memory table variant, long rows the (opt-in) streaming kernel;
         ops.gin_combine picks by row length.  The gate is computed once per batch and relation side."""
         key = (tuple(et), side)
-        if not (ops.STREAM_LONG_ROWS or ops.TABLE_SHORT_ROWS):
+        if not (ops.STREAM_LONG_ROWS or ops.STAGE_LONG_ROWS or ops.TABLE_SHORT_ROWS):
             return None                  # both block-diagonal schedules are opt-in (measured: DESIGN.md "Long rows" / "Short rows")
         if key not in self._plans:
             plan = None
@@ -90,7 +90,7 @@ class GraphCSR:
                     return None          # inference: not worth building the second orientation for the gate
                 csr_out, csr_in = (self.fwd(et), self.bwd(et)) if side == "fwd" else (self.bwd(et), self.fwd(et))
                 long_rows = csr_out.num_edges > 8 * csr_out.num_rows
-                if csr_out.num_rows > 0 and (ops.STREAM_LONG_ROWS if long_rows else ops.TABLE_SHORT_ROWS):
+                if csr_out.num_rows > 0 and ((ops.STREAM_LONG_ROWS or ops.STAGE_LONG_ROWS) if long_rows else ops.TABLE_SHORT_ROWS):
                     plan = ops.StreamPlan(csr_in, p_in.contiguous(), p_out.contiguous(),
                                           ops.block_gate(csr_out, csr_in, p_in.contiguous(), p_out.contiguous()))
             self._plans[key] = plan

@@ -194,6 +194,12 @@ def block_gate(csr_out, csr_in, in_ptr, out_ptr):
 # registers and is bound by L2->SM bandwidth (336 us): 1.5 ms against 0.34-0.44 ms per launch at Cfg-C.
 STREAM_LONG_ROWS = False
 
+# Opt-in (measured, DESIGN.md "Long rows"): long-row aggregations of block-diagonal batches through the staged-source kernel
+# (hgin_gin_combine_staged_t): register accumulators, the block's source rows streamed ONCE through two shared-memory stages
+# (csrc/gin_stage_blocks.cuh).  Bit-identical; 424 us against 364 us per Cfg-C path->link launch in fp32 and 339 against
+# 247 us in bf16 (tools/staged_probe.py): the per-row list walk costs more issue slots than the L2 re-reads it removes.
+STAGE_LONG_ROWS = False
+
 # Opt-in (measured at parity, DESIGN.md "Short rows"): short-row aggregations of block-diagonal batches through the
 # shared-memory table variant (hgin_gin_combine_table_t) — the source rows of one topology sample staged in shared memory
 # once, every gather a shared-memory load.  Bit-identical rows; at Cfg-C 6.05 ms of aggregation per tf32 step against
@@ -260,6 +266,18 @@ def gin_combine(csr, x_src, x_self=None, eps=None, self_mode=SELF_NONE, out=None
         kernels = 1 + int(want) + int(want_ddot)
     sa, sal = src_act if src_act is not None else (ACT_NONE, None)
     fa, fal = self_act if (self_act is not None and x_self is not None) else (ACT_NONE, None)
+    if (block_plan is not None and STAGE_LONG_ROWS and not STREAM_LONG_ROWS and not post_on and self_mode in (SELF_NONE, SELF_ADD)
+            and csr.rowptr is not None and csr.num_edges > 8 * csr.num_rows and 16 <= f_src <= 128 and f_src % (16 // es) == 0
+            and lds == f_src and ldo % 4 == 0 and (x_self is None or ldf % 4 == 0) and x_src.data_ptr() % 16 == 0
+            and out.data_ptr() % 16 == 0 and (x_self is None or x_self.data_ptr() % 16 == 0)):
+        with _region("gin_combine", kernels=2, alg_bytes=alg, compulsory_bytes=comp):
+            check(lib.hgin_gin_combine_staged_t(_DTYPES[dt], csr.num_rows, _ptr(csr.rowptr), _ptr(csr.col), csr.num_edges,
+                                                block_plan.num_blocks, block_plan.in_ptr.data_ptr(),
+                                                block_plan.out_ptr.data_ptr(), block_plan.gate.data_ptr(),
+                                                ps, lds, f_src, pf, ldf, _scalar(eps, "gin_combine.eps"), self_mode,
+                                                1 if accumulate else 0, po, ldo, sa, _scalar(sal, "gin_combine.src_alpha"), fa,
+                                                _scalar(fal, "gin_combine.self_alpha"), _stream()), "hgin_gin_combine_staged_t")
+        return out
     if (block_plan is not None and STREAM_LONG_ROWS and not post_on and self_mode in (SELF_NONE, SELF_ADD) and csr.rowptr is not None
             and 32 <= f_src <= 128 and f_src % (16 // es) == 0 and x_src.shape[0] > 1 and lds == f_src and ldo % 4 == 0
             and (x_self is None or ldf % 4 == 0) and x_src.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0

@@ -200,6 +200,26 @@ int32_t hgin_gin_combine_t(int32_t dtype, int64_t num_rows, const int32_t *rowpt
                            int32_t post_act, const float *post_alpha, float *post_dalpha,
                            float *post_ddot, void *workspace, int64_t workspace_bytes, void *stream);
 
+/* hgin_gin_combine_staged_t: K1 / K4 for LONG rows on a block-diagonal batch (the path->link aggregation of
+ * models.py:211-217 and the backward of link->path: ~36 neighbours per row, every source row gathered ~2.9 times).
+ * One CTA per SM takes a block at a time, keeps the block's output rows (<= 224) as fp32 accumulators in registers and
+ * streams the block's source rows ONCE, in ascending order, through two shared-memory stages filled by cp.async.bulk;
+ * the neighbours of a row that fall inside the staged chunk (a prefix of what is left of its ascending list) are added
+ * left to right from shared memory (csrc/gin_stage_blocks.cuh).  Same CSR, same order of additions: bit-identical to
+ * hgin_gin_combine_t.  The kernel runs only if gate (hgin_block_gate) reports containment (gate[0] == 0), ascending
+ * neighbour lists (gate[3] == 0) and gate[1] <= 224; the kernel of hgin_gin_combine_t follows behind the inverse gate
+ * (a static, capturable launch sequence).  Input rows must be contiguous (ld_src == f_src), 16 <= f_src <= 128;
+ * SELF_NONE or SELF_ADD; src_act / self_act as in hgin_gin_combine_pre.  HGIN_ERR_UNSUPPORTED otherwise (the caller
+ * then uses hgin_gin_combine_t).
+ */
+int32_t hgin_gin_combine_staged_t(int32_t dtype, int64_t num_rows, const int32_t *rowptr, const int32_t *col,
+                                  int64_t num_edges, int32_t num_blocks, const int64_t *in_ptr,
+                                  const int64_t *out_ptr, const int32_t *gate, const void *x_src,
+                                  int64_t ld_src, int32_t f_src, const void *x_self, int64_t ld_self,
+                                  const float *eps, int32_t self_mode, int32_t accumulate, void *out,
+                                  int64_t ld_out, int32_t src_act, const float *src_alpha, int32_t self_act,
+                                  const float *self_alpha, void *stream);
+
 /* hgin_gin_combine_table_t: hgin_gin_combine_t for SHORT rows on a block-diagonal batch (the link->path aggregation of
  * models.py:211-217 and the backward of path->link: ~3 neighbours per row, all inside the row's own topology sample).
  * One 1024-thread CTA per SM takes a block at a time, stages the block's source rows (200 link rows = 100 KB fp32) in

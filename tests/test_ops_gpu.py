@@ -605,17 +605,24 @@ def _block_diagonal_relation(sizes_in, sizes_out, deg, seed, sort_rows=True):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("f", [128, 64, 32])
-@pytest.mark.parametrize("case", ["plain", "self_add", "accumulate", "pre_act", "unsorted", "oversize_block", "ragged"])
-def test_streaming_long_row_aggregation_is_bit_identical_to_the_gather(case, f, dtype, monkeypatch):
+@pytest.mark.parametrize("case", ["plain", "self_add", "accumulate", "pre_act", "unsorted", "oversize_block", "ragged",
+                                  "many_blocks"])
+@pytest.mark.parametrize("schedule", ["staged", "streaming"])
+def test_streaming_long_row_aggregation_is_bit_identical_to_the_gather(case, f, dtype, schedule, monkeypatch):
     """hgin_gin_combine_blocks_t (input-major streaming over a block-diagonal batch, csrc/gin_scatter_blocks.cuh) against
     hgin_gin_combine_t on the same inputs: torch.equal in every mode it takes, including the two gated fall-backs (edge
     order not ascending within output rows; a block with more output rows than the accumulator tile holds)."""
     from gnn_link_prediction_b200.functional import GraphCSR
-    monkeypatch.setattr(ops, "STREAM_LONG_ROWS", True)      # opt-in schedule (the gather kernel is the default)
+    # staged: source rows through shared memory, accumulators in registers (hgin_gin_combine_staged_t);
+    # streaming: the opt-in input-major schedule with shared-memory accumulators (hgin_gin_combine_blocks_t)
+    monkeypatch.setattr(ops, "STREAM_LONG_ROWS", schedule == "streaming")
+    monkeypatch.setattr(ops, "STAGE_LONG_ROWS", schedule == "staged")
     if case == "oversize_block":
         sizes_in, sizes_out = [300, 40000, 500], [20, 3000, 30]
     elif case == "ragged":
         sizes_in, sizes_out = [1, 0, 77, 33, 0, 5, 1000], [3, 4, 1, 40, 0, 2, 130]
+    elif case == "many_blocks":      # more blocks than SMs: every CTA walks several blocks through its two stages
+        sizes_in, sizes_out = [700, 0, 1100, 217] * 100, [100, 3, 224, 9] * 100
     else:
         sizes_in, sizes_out = [700, 650, 900, 31, 64], [60, 50, 80, 7, 33]
     ei, ptr_in, ptr_out = _block_diagonal_relation(sizes_in, sizes_out, 3, 5, sort_rows=case != "unsorted")
@@ -633,9 +640,9 @@ def test_streaming_long_row_aggregation_is_bit_identical_to_the_gather(case, f, 
     eps = torch.tensor([0.3], device="cuda")
     alpha = torch.tensor([0.25], device="cuda")
     kw = {}
-    if case in ("self_add", "accumulate", "pre_act", "ragged"):
+    if case in ("self_add", "accumulate", "pre_act", "ragged", "many_blocks"):
         kw.update(x_self=xs, eps=eps, self_mode=ops.SELF_ADD)
-    if case == "pre_act":
+    if case in ("pre_act", "many_blocks"):
         kw.update(src_act=(ops.ACT_PRELU, alpha), self_act=(ops.ACT_RELU, None))
 
     def run(stream):
