@@ -587,6 +587,19 @@ def main():
                                                                           "edges_per_s", "kernels_per_step", "peak_hbm_gb")}
             except Exception as exc:
                 line["other_workloads"]["cfgC_bf16"] = {"error": repr(exc)[:200]}
+        # and the same tf32 step captured once and replayed as ONE CUDA graph (train.GraphedTrainStep; single GPU only —
+        # NCCL inside the capture blocked twice, DESIGN.md §7 — so the headline stays on eager launches, which scale out)
+        if not graphed:
+            try:
+                torch.cuda.empty_cache()
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", "cfgC", "--math", args.math, "--graph",
+                                    "--no-cpu-baseline", "--no-extra", "--steps", str(args.steps), "--warmup", str(args.warmup)],
+                                   capture_output=True, text=True, timeout=300)
+                g = json.loads(r.stdout.strip().splitlines()[-1])
+                line["other_workloads"]["cfgC_graph_replay"] = {k: g[k] for k in ("value", "unit", "ms_per_step", "dtype", "e2e",
+                                                                                  "execution", "kernels_per_step")}
+            except Exception as exc:
+                line["other_workloads"]["cfgC_graph_replay"] = {"error": repr(exc)[:200]}
     print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
