@@ -222,7 +222,7 @@ gin_combine_kernel(int num_rows, const int32_t *__restrict__ rowptr, const int32
     // the register budget when a lane carries several chunks
     // (pre-activation sources need a few registers for the on-the-fly act: two gathers fewer in flight)
     // (bf16 lanes carry 8 accumulators and unpack 8 values per gather: fewer in flight at 64 registers)
-    constexpr int UNROLL_MAX = (NC >= 4) ? 2 : ((NC == 2) ? 4 : (VEC == 8 ? ((MODE == 0 || MODE == 3) ? 6 : 4)
+    constexpr int UNROLL_MAX = (NC >= 4) ? 2 : ((NC == 2) ? 4 : (VEC == 8 ? ((MODE == 0 || MODE == 3) ? (CONTIG ? 4 : 6) : 4)
                                                                           : ((MODE == 2 || MODE == 4) ? 6 : 8)));
     // (TABLE: gathers are shared-memory loads, two in flight cover their latency — and the 1024-thread CTA has 64 registers)
     constexpr int UNROLL = TABLE ? ((NC >= 2) ? (MODE == 1 ? 1 : 2) : 4) : ((LPR < UNROLL_MAX) ? LPR : UNROLL_MAX);
@@ -241,9 +241,17 @@ gin_combine_kernel(int num_rows, const int32_t *__restrict__ rowptr, const int32
     const float src_alpha = !PRE_SRC ? 1.0f : (post.src_act == HGIN_ACT_PRELU ? __ldg(post.src_alpha) : 0.0f);
     const float self_alpha = !PRE_SELF ? 1.0f : (post.self_act == HGIN_ACT_PRELU ? __ldg(post.self_alpha) : 0.0f);
     float dalpha = 0.0f, ddot = 0.0f;
-    const int post_ld = static_cast<int>(post.ldz);
     const T *post_z = static_cast<const T *>(post.z);
-    auto at = [](const T *base, int row, int ld) { return base + static_cast<int64_t>(row) * ld; };   // IMAD.WIDE
+    // Row addresses: base + row * (row pitch in BYTES), both factors unsigned 32-bit, so that every address is ONE
+    // IMAD.WIDE.U32 with the 64-bit base as its addend (rows are >= 0 where an address is formed; the dispatch bounds
+    // the pitches).  The signed element-index form cost four instructions per gather, in a kernel that is issue-bound.
+    auto at = [](const T *base, int row, uint32_t pitch) {
+        return reinterpret_cast<const T *>(reinterpret_cast<const char *>(base) + static_cast<uint64_t>(static_cast<uint32_t>(row)) * pitch);
+    };
+    const uint32_t pitch_src = static_cast<uint32_t>(ld_src) * static_cast<uint32_t>(sizeof(T));
+    const uint32_t pitch_self = static_cast<uint32_t>(ld_self) * static_cast<uint32_t>(sizeof(T));
+    const uint32_t pitch_post = static_cast<uint32_t>(post.ldz) * static_cast<uint32_t>(sizeof(T));
+    const uint32_t pitch_out = static_cast<uint32_t>(ld_out) * static_cast<uint32_t>(sizeof(T));
 
     // Row -> warp mapping.
     // CONTIG (short rows): each CTA owns a CONTIGUOUS block of rows, its warps interleaving inside it.
@@ -285,7 +293,7 @@ gin_combine_kernel(int num_rows, const int32_t *__restrict__ rowptr, const int32
         const int ppr = f_src / VEC;           // (TABLE launches are full-width vector launches: f_src % VEC == 0)
         for (int i = threadIdx.x; i < tbl_rows * ppr; i += blockDim.x) {
             const int r = i / ppr, c = (i - r * ppr) * VEC;
-            R v = load_raw(at(x_src, tbl0 + r, ld_src) + c, (R *)nullptr);
+            R v = load_raw(at(x_src + c, tbl0 + r, pitch_src), (R *)nullptr);
             if (PRE_SRC) {                     // act(z) once per source element (the gathers then add plain values)
                 float t[VEC];
                 unpack(v, t);
@@ -310,13 +318,13 @@ gin_combine_kernel(int num_rows, const int32_t *__restrict__ rowptr, const int32
     int32_t beg, len, nbeg, nlen;
     load_bounds(row0, beg, len);
     load_bounds(row0 + stride, nbeg, nlen);
-    int32_t mine = (sub < len) ? __ldg(col + beg + sub) : -1;
+    int32_t mine = (sub < len) ? __ldg(col + (beg + sub)) : -1;
 
     for (; row0 < cta_end; row0 += stride) {
         const int row = row0 + grp;
         const bool live = row < cta_end;
         // issue the prefetches for the following rows before touching this row's data
-        const int32_t nmine = (sub < nlen) ? __ldg(col + nbeg + sub) : -1;
+        const int32_t nmine = (sub < nlen) ? __ldg(col + (nbeg + sub)) : -1;
         int32_t nnbeg, nnlen;
         load_bounds(row0 + 2 * stride, nnbeg, nnlen);
         R self_r[NC];
@@ -325,8 +333,8 @@ gin_combine_kernel(int num_rows, const int32_t *__restrict__ rowptr, const int32
             for (int c = 0; c < NC; ++c) {
                 const int f = (c * LPR + sub) * VEC;
                 if (FULL || f < f_src)
-                    self_r[c] = CONTIG ? load_raw_stream(at(x_self, row, ld_self) + f, (R *)nullptr)
-                                       : load_raw(at(x_self, row, ld_self) + f, (R *)nullptr);
+                    self_r[c] = CONTIG ? load_raw_stream(at(x_self + f, row, pitch_self), (R *)nullptr)
+                                       : load_raw(at(x_self + f, row, pitch_self), (R *)nullptr);
             }
         }
         R post_r[NC];
@@ -335,8 +343,8 @@ gin_combine_kernel(int num_rows, const int32_t *__restrict__ rowptr, const int32
             for (int c = 0; c < NC; ++c) {
                 const int f = (c * LPR + sub) * VEC;
                 if (FULL || f < f_src)
-                    post_r[c] = CONTIG ? load_raw_stream(at(post_z, row, post_ld) + f, (R *)nullptr)
-                                       : load_raw(at(post_z, row, post_ld) + f, (R *)nullptr);
+                    post_r[c] = CONTIG ? load_raw_stream(at(post_z + f, row, pitch_post), (R *)nullptr)
+                                       : load_raw(at(post_z + f, row, pitch_post), (R *)nullptr);
             }
         }
         // warp-uniform trip count so the shuffles below are always convergent
@@ -352,16 +360,21 @@ gin_combine_kernel(int num_rows, const int32_t *__restrict__ rowptr, const int32
 
         for (int32_t base = 0; base < max_len; base += LPR) {
             // one coalesced index load per group, LPR neighbours at a time (the first batch was prefetched)
-            if (base > 0) mine = (base + sub < len) ? __ldg(col + beg + base + sub) : -1;
+            if (base > 0) mine = (base + sub < len) ? __ldg(col + (beg + base + sub)) : -1;
             const int32_t batch = min(LPR, max_len - base);
             for (int32_t j0 = 0; j0 < batch; j0 += UNROLL) {
                 R v[UNROLL][NC];
                 int32_t nb[UNROLL];
 #pragma unroll
                 for (int u = 0; u < UNROLL; ++u) {
-                    // (j0+u) % LPR keeps the source lane in range; out-of-batch slots are masked by nb < 0
-                    const int32_t s = __shfl_sync(full, mine, grp * LPR + ((j0 + u) % LPR));
-                    nb[u] = (j0 + u < batch) ? s : -1;
+                    if constexpr (LPR % UNROLL == 0) {
+                        // slot j0 + u < LPR: lanes past the row's end hold -1 already (batch <= max_len - base), no mask needed
+                        nb[u] = __shfl_sync(full, mine, grp * LPR + j0 + u);
+                    } else {
+                        // (j0+u) % LPR keeps the source lane in range; out-of-batch slots are masked by nb < 0
+                        const int32_t s = __shfl_sync(full, mine, grp * LPR + ((j0 + u) % LPR));
+                        nb[u] = (j0 + u < batch) ? s : -1;
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < UNROLL; ++u) {
@@ -370,7 +383,7 @@ gin_combine_kernel(int num_rows, const int32_t *__restrict__ rowptr, const int32
                         const int f = (c * LPR + sub) * VEC;
                         if (nb[u] >= 0 && (FULL || f < f_src)) {
                             if constexpr (TABLE) v[u][c] = load_raw_coherent(table + (nb[u] - tbl0) * f_src + f, (R *)nullptr);
-                            else v[u][c] = load_raw(at(x_src, nb[u], ld_src) + f, (R *)nullptr);
+                            else v[u][c] = load_raw(at(x_src + f, nb[u], pitch_src), (R *)nullptr);
                         } else {
                             v[u][c] = R{};   // (zero-filled: keeps the unpack below unconditional, no spills)
                         }
@@ -396,7 +409,7 @@ gin_combine_kernel(int num_rows, const int32_t *__restrict__ rowptr, const int32
         }
 
         if (live) {
-            T *orow = out + static_cast<int64_t>(row) * ld_out;
+            T *orow = const_cast<T *>(at(out, row, pitch_out));
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 const int f = (c * LPR + sub) * VEC;
@@ -442,7 +455,7 @@ gin_combine_kernel(int num_rows, const int32_t *__restrict__ rowptr, const int32
             if (self_mode == HGIN_SELF_CONCAT) {
                 // [agg | (1+eps) x_self]: the self block starts at column f_src (rarely 16B aligned) -> scalar
                 for (int f = sub; f < f_self; f += LPR) {
-                    float xs = ld1(at(x_self, row, ld_self) + f);
+                    float xs = ld1(at(x_self + f, row, pitch_self));
                     if (PRE_SELF) xs = xs > 0.f ? xs : self_alpha * xs;
                     float t = __fmul_rn(ope, xs);
                     if (accumulate) t = __fadd_rn(ld1_coherent(orow + f_src + f), t);
@@ -490,7 +503,8 @@ int launch(int64_t num_rows64, const int32_t *rowptr, const int32_t *col, const 
     // Grid-stride over rows with whole waves of CTAs: enough CTAs (32 per SM) that the hardware
     // scheduler evens out the heavy-tailed row lengths of the path->link relation.
     // TABLE: one persistent CTA per SM, blocks dealt round-robin.
-    const int grid = TABLE ? kNumSMs : grid_for(num_rows, rows_per_cta, 32);
+    static const int waves_probe = getenv("HGIN_PROBE_WAVES") ? atoi(getenv("HGIN_PROBE_WAVES")) : 0;   // EXPERIMENT
+    const int grid = TABLE ? kNumSMs : grid_for(num_rows, rows_per_cta, (CONTIG && waves_probe > 0) ? waves_probe : 32);
     const size_t smem = TABLE ? static_cast<size_t>(kTableSmem) : 0;
     const PostAct pa = post ? *post : PostAct{};
     const int mode = !post ? 0 : (post->z ? 1 : ((post->src_act != HGIN_ACT_NONE && post->self_act != HGIN_ACT_NONE) ? 4
