@@ -26,18 +26,20 @@ def main():
         m = re.match(r"\s*Function : (\S+)", line)
         if m:
             cur = m.group(1)
+            while cur in kernels:            # the same instantiation emitted by two translation units: keep both
+                cur += "'"
             kernels[cur] = collections.Counter()
             continue
         if cur is None:
             continue
-        m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+        m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P(?:\d+|T)\s+)?([A-Z0-9_.]+)", line)
         if m:
             op = m.group(1)
             kernels[cur]["total"] += 1
             for k in KEYS:
                 if op.startswith(k):
                     kernels[cur][k] += 1
-    demangled = subprocess.run(["cu++filt"] + list(kernels), capture_output=True, text=True).stdout.splitlines()
+    demangled = subprocess.run(["cu++filt"] + [k.rstrip("'") for k in kernels], capture_output=True, text=True).stdout.splitlines()
     print(f"# {os.path.relpath(so, ROOT)}: architectures {archs}; {len(kernels)} kernels")
     print("# " + " | ".join(["instr"] + KEYS + ["kernel"]))
     tot = collections.Counter()
